@@ -1,0 +1,128 @@
+// TEST INFRASTRUCTURE ONLY -- never linked into the product library.
+//
+// A tiny CPU emulation of the CUDA execution model, good enough to run the engine's kernel *bodies*
+// (the same templates nvcc compiles for sm_100a) inside the CPU test-suite: one OS thread per CUDA
+// thread of a block, a std::barrier for __syncthreads(), blocks executed one after another.
+// It exists because the development container has no GPU: index maps, twiddle tables and the autosort
+// scatter are checked here against the double-precision oracle before GPU minutes are spent, and the
+// shared-memory access log lets the tests assert "bank-conflict free" per configuration.
+#pragma once
+#include <algorithm>
+#include <barrier>
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <thread>
+#include <vector>
+
+struct float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(16) double2 { double x, y; };
+
+namespace b2emu {
+struct idx3 { unsigned x, y, z; };
+struct SmemRec { uint32_t addr; uint16_t bytes; uint16_t store; };
+struct State {
+    idx3 blockDim{1, 1, 1}, gridDim{1, 1, 1};
+    std::barrier<>* bar = nullptr;
+    unsigned char* smem = nullptr;
+    bool log = false;
+    std::vector<std::vector<SmemRec>> recs;  // per thread (block 0 only)
+};
+inline State& st() { static State s; return s; }
+inline thread_local idx3 t_threadIdx{0, 0, 0};
+inline thread_local idx3 t_blockIdx{0, 0, 0};
+
+inline void syncthreads() { st().bar->arrive_and_wait(); }
+inline void log_access(const void* base, size_t index, size_t elem_bytes, bool store) {
+    State& s = st();
+    if (!s.log || t_blockIdx.x != 0) return;
+    (void)base;
+    s.recs[t_threadIdx.x].push_back(SmemRec{(uint32_t)(index * elem_bytes), (uint16_t)elem_bytes, (uint16_t)store});
+}
+
+struct ConflictReport {
+    double worst = 1.0;     // worst wavefronts/ideal over all warp-wide accesses
+    double mean = 1.0;      // traffic-weighted mean
+    size_t accesses = 0;
+};
+
+// Analyse the log of block 0: for every warp and every k-th shared access, count the wavefronts the
+// 32-bank x 4-byte crossbar needs (64-bit accesses are served per half-warp, 128-bit per quarter-warp).
+inline ConflictReport analyse(unsigned nthreads) {
+    State& s = st();
+    ConflictReport rep;
+    double tot_act = 0, tot_ideal = 0;
+    for (unsigned w0 = 0; w0 < nthreads; w0 += 32) {
+        unsigned lanes = std::min(32u, nthreads - w0);
+        size_t nacc = s.recs[w0].size();
+        bool uniform = true;
+        for (unsigned l = 0; l < lanes; ++l) uniform &= (s.recs[w0 + l].size() == nacc);
+        if (!uniform) continue;  // divergent (guarded) access sequence: skip this warp
+        for (size_t i = 0; i < nacc; ++i) {
+            unsigned bytes = s.recs[w0][i].bytes;
+            unsigned per_phase = bytes == 4 ? 32 : (bytes == 8 ? 16 : 8);
+            unsigned wave = 0, ideal = 0;
+            for (unsigned p0 = 0; p0 < lanes; p0 += per_phase) {
+                // distinct 4-byte words per bank
+                std::vector<std::vector<uint32_t>> bank(32);
+                for (unsigned l = p0; l < std::min(lanes, p0 + per_phase); ++l) {
+                    const SmemRec& r = s.recs[w0 + l][i];
+                    for (unsigned b = 0; b < r.bytes; b += 4) {
+                        uint32_t word = (r.addr + b) / 4;
+                        auto& v = bank[word % 32];
+                        if (std::find(v.begin(), v.end(), word) == v.end()) v.push_back(word);
+                    }
+                }
+                unsigned deg = 0;
+                for (auto& v : bank) deg = std::max<unsigned>(deg, (unsigned)v.size());
+                wave += deg;
+                ideal += 1;
+            }
+            double ratio = (double)wave / ideal;
+            rep.worst = std::max(rep.worst, ratio);
+            tot_act += wave;
+            tot_ideal += ideal;
+            rep.accesses++;
+        }
+    }
+    rep.mean = tot_ideal > 0 ? tot_act / tot_ideal : 1.0;
+    return rep;
+}
+
+// run f(smem) for every thread of every block
+template <class F>
+inline void launch(unsigned grid, unsigned block, size_t smem_bytes, F&& f, bool log = false) {
+    State& s = st();
+    s.blockDim = {block, 1, 1};
+    s.gridDim = {grid, 1, 1};
+    std::vector<unsigned char> smem(smem_bytes + 64);
+    s.smem = smem.data();
+    std::barrier<> bar((std::ptrdiff_t)block);
+    s.bar = &bar;
+    s.log = log;
+    s.recs.assign(block, {});
+    std::vector<std::thread> th;
+    th.reserve(block);
+    for (unsigned t = 0; t < block; ++t) {
+        th.emplace_back([&, t]() {
+            t_threadIdx = {t, 0, 0};
+            for (unsigned b = 0; b < grid; ++b) {
+                t_blockIdx = {b, 0, 0};
+                f(s.smem);
+                s.bar->arrive_and_wait();
+            }
+        });
+    }
+    for (auto& x : th) x.join();
+    s.bar = nullptr;
+}
+}  // namespace b2emu
+
+#define threadIdx (::b2emu::t_threadIdx)
+#define blockIdx (::b2emu::t_blockIdx)
+#define blockDim (::b2emu::st().blockDim)
+#define gridDim (::b2emu::st().gridDim)
+#define __syncthreads() ::b2emu::syncthreads()
+#define B2_SMEM_LD(sm, i) (::b2emu::log_access((sm), (size_t)(i), sizeof((sm)[0]), false), (sm)[(i)])
+#define B2_SMEM_ST(sm, i, v) (::b2emu::log_access((sm), (size_t)(i), sizeof((sm)[0]), true), (void)((sm)[(i)] = (v)))

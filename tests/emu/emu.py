@@ -1,0 +1,51 @@
+"""ctypes front-end of the CPU kernel-body emulation (tests only; see cuda_emu.h)."""
+import ctypes, os, subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+KIND_ROWS, KIND_ROWS_TOUT, KIND_COLS = 0, 1, 2
+OP_TW, OP_SCALE = 1, 2
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "_build", "libb200fft_emu.so")
+        srcs = [os.path.join(_HERE, f) for f in ("emu_driver.cpp", "cuda_emu.h")]
+        csrc = os.path.join(_HERE, "..", "..", "vkfft_b200", "csrc")
+        srcs += [os.path.join(csrc, f) for f in os.listdir(csrc)]
+        if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+            subprocess.check_call([os.path.join(_HERE, "build.sh")])
+        _LIB = ctypes.CDLL(so)
+        _LIB.emu_run_pass.restype = ctypes.c_int
+    return _LIB
+
+
+def kernels():
+    L = lib()
+    out = []
+    buf = (ctypes.c_int * 19)()
+    for i in range(L.emu_kernel_count()):
+        L.emu_kernel_info(i, buf)
+        v = list(buf)
+        out.append(dict(kind=v[0], prec=v[1], n=v[2], inv=v[3], ops=v[4], threads=v[5], q=v[6], tpl=v[7], v=v[8],
+                        smem=v[9], ns=v[10], radices=v[11:11 + v[10]]))
+    return out
+
+
+def run_pass(kind, prec, n, inv, ops, inp, out, G, nb=(1, 1, 1), in_es=1, out_es=1, in_gs=None, out_gs=None,
+             in_bs=(0, 0, 0), out_bs=(0, 0, 0), twM=0, tw_line0=0, scale=1.0, log=False):
+    L = lib()
+    nbA = (ctypes.c_uint * 3)(*nb)
+    ibs = (ctypes.c_longlong * 3)(*in_bs)
+    obs = (ctypes.c_longlong * 3)(*out_bs)
+    rep = (ctypes.c_double * 3)()
+    rc = L.emu_run_pass(kind, prec, n, inv, ops, inp.ctypes.data_as(ctypes.c_void_p),
+                        out.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint(G), nbA,
+                        ctypes.c_longlong(in_es), ctypes.c_longlong(out_es), ctypes.c_longlong(in_gs),
+                        ctypes.c_longlong(out_gs), ibs, obs, ctypes.c_ulonglong(twM), ctypes.c_uint(tw_line0),
+                        ctypes.c_double(scale), int(log), rep)
+    if rc != 0:
+        raise RuntimeError(f"emu_run_pass rc={rc}")
+    return dict(worst=rep[0], mean=rep[1], accesses=rep[2])

@@ -1,0 +1,53 @@
+// TEST INFRASTRUCTURE ONLY: runs the engine's kernel bodies on the CPU emulation (see cuda_emu.h).
+// Built by tests/emu/build.sh into tests/emu/_build/libb200fft_emu.so and driven from pytest via ctypes.
+#include "kernel_inst.cuh"
+#include "kernel_list.def"
+#include "lut.h"
+
+#include <cstdio>
+#include <vector>
+
+using namespace b200fft;
+
+extern "C" int emu_kernel_count() { return b2_kernel_count(); }
+extern "C" int emu_kernel_info(int i, int* out /*kind,prec,n,inv,ops,threads,q,tpl,v,smem,ns,r0..r7*/) {
+    const b2_kernel_info* k = b2_kernel_at(i);
+    int v[] = {k->kind, k->prec, k->n, k->inv, k->ops, k->threads, k->q, k->tpl, k->v, k->smem_bytes, k->ns};
+    for (int j = 0; j < 11; ++j) out[j] = v[j];
+    for (int j = 0; j < 8; ++j) out[11 + j] = k->radices[j];
+    return 0;
+}
+
+// Run one pass.  `in`/`out` are host arrays of complex T.  Returns 0, or -1 if no such kernel.
+extern "C" int emu_run_pass(int kind, int prec, int n, int inv, int ops, const void* in, void* out, unsigned G,
+                            const unsigned* nb, long long in_es, long long out_es, long long in_gs,
+                            long long out_gs, const long long* in_bs, const long long* out_bs,
+                            unsigned long long twM, unsigned tw_line0, double scale, int log, double* report) {
+    const b2_kernel_info* k = b2_find_kernel(kind, prec, n, inv, ops & ~B2_OP_SCALE);
+    if (!k) return -1;
+    b2_pass_params P{};
+    P.in = in; P.out = out;
+    std::vector<float> lutf, hif, lof;
+    std::vector<double> lutd, hid, lod;
+    if (prec == B2_PREC_F32) { lutf = make_stage_lut<float>(k->radices, k->ns); P.lut = lutf.data(); }
+    else { lutd = make_stage_lut<double>(k->radices, k->ns); P.lut = lutd.data(); }
+    if (ops & B2_OP_TWIDDLE_OUT) {
+        if (prec == B2_PREC_F32) { make_twolevel<float>(twM, P.tw_shift, hif, lof); P.tw_hi = hif.data(); P.tw_lo = lof.data(); }
+        else { make_twolevel<double>(twM, P.tw_shift, hid, lod); P.tw_hi = hid.data(); P.tw_lo = lod.data(); }
+    }
+    P.in_es = in_es; P.out_es = out_es; P.in_gs = in_gs; P.out_gs = out_gs;
+    unsigned grid = (G + k->q - 1) / k->q;
+    for (int d = 0; d < B2_MAX_OUTER; ++d) {
+        P.nb[d] = nb[d]; P.in_bs[d] = in_bs[d]; P.out_bs[d] = out_bs[d];
+        grid *= nb[d];
+    }
+    P.G = G; P.n = n; P.tw_line0 = tw_line0; P.ops = ops; P.inverse = inv; P.scale = scale;
+    b2emu::st().log = log != 0;
+    int rc = k->launch(&P, grid, nullptr);
+    if (log && report) {
+        b2emu::ConflictReport r = b2emu::analyse(k->threads);
+        report[0] = r.worst; report[1] = r.mean; report[2] = (double)r.accesses;
+    }
+    b2emu::st().log = false;
+    return rc;
+}

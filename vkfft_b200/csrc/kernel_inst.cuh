@@ -1,0 +1,110 @@
+// Expands kernel_list.def into registry entries.  Included by the CUDA shard translation units (product)
+// and, with B2_EMU defined, by the CPU emulation used in tests.
+#pragma once
+#include "kernel_registry.h"
+#include "stockham.cuh"
+
+#if !defined(B2_EMU)
+#include <cuda_runtime.h>
+#endif
+
+namespace b200fft {
+
+template <int KIND> struct KindTraits;
+template <> struct KindTraits<B2_KIND_ROWS> {
+    static constexpr int LMAP = MAP_TFAST, SMAP = MAP_TFAST, LAYOUT = LAY_LINE;
+    static constexpr bool IN_UNIT = true, OUT_UNIT = true;
+};
+template <> struct KindTraits<B2_KIND_ROWS_TOUT> {
+    static constexpr int LMAP = MAP_TFAST, SMAP = MAP_QFAST, LAYOUT = LAY_LINE;
+    static constexpr bool IN_UNIT = true, OUT_UNIT = false;
+};
+template <> struct KindTraits<B2_KIND_COLS> {
+    static constexpr int LMAP = MAP_QFAST, SMAP = MAP_QFAST, LAYOUT = LAY_ELEM;
+    static constexpr bool IN_UNIT = false, OUT_UNIT = false;
+};
+
+template <typename T> struct PrecOf;
+template <> struct PrecOf<float> { static constexpr int value = B2_PREC_F32; };
+template <> struct PrecOf<double> { static constexpr int value = B2_PREC_F64; };
+
+#if defined(B2_EMU)
+template <class C>
+int launch_impl(const b2_pass_params* P, unsigned grid, void*) {
+    const b2_pass_params PP = *P;
+    b2emu::launch(grid, C::THREADS, C::SMEM_BYTES, [&](unsigned char* sm) { Engine<C>::run(PP, sm); },
+                  b2emu::st().log);
+    return 0;
+}
+template <class C> int prepare_impl() { return 0; }
+#else
+template <class C>
+int launch_impl(const b2_pass_params* P, unsigned grid, void* stream) {
+    stockham_kernel<C><<<grid, C::THREADS, C::SMEM_BYTES, (cudaStream_t)stream>>>(*P);
+    return (int)cudaGetLastError();
+}
+template <class C>
+int prepare_impl() {
+    if (C::SMEM_BYTES > 48 * 1024)
+        return (int)cudaFuncSetAttribute(stockham_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::SMEM_BYTES);
+    return 0;
+}
+#endif
+
+template <int KIND, typename T, int TPL, int Q, int V, int MINB, bool INV, int OPS, int... Rs>
+struct Registrar {
+    using KT = KindTraits<KIND>;
+    using Sch = RList<Rs...>;
+    using C = KCfg<T, Sch, TPL, Q, V, KT::LMAP, KT::SMAP, KT::LAYOUT, INV, OPS, KT::IN_UNIT, KT::OUT_UNIT, MINB>;
+    b2_kernel_info info;
+    explicit Registrar(const char* name) {
+        info = b2_kernel_info{};
+        info.kind = KIND; info.prec = PrecOf<T>::value; info.n = Sch::N; info.inv = INV; info.ops = OPS;
+        info.threads = C::THREADS; info.q = Q; info.tpl = TPL; info.v = V; info.smem_bytes = C::SMEM_BYTES;
+        info.ns = Sch::ns;
+        for (int s = 0; s < Sch::ns; ++s) info.radices[s] = Sch::r(s);
+        info.lut_size = Sch::lut_size;
+        info.launch = &launch_impl<C>;
+        info.prepare = &prepare_impl<C>;
+        info.name = name;
+        b2_register_kernel(&info);
+    }
+};
+
+// every kind gets forward+inverse; COLS additionally gets the four-step twiddle-on-store variant
+template <int KIND, typename T, int TPL, int Q, int V, int MINB, int... Rs>
+struct RegistrarSet {
+    Registrar<KIND, T, TPL, Q, V, MINB, false, 0, Rs...> f;
+    Registrar<KIND, T, TPL, Q, V, MINB, true, 0, Rs...> i;
+    explicit RegistrarSet(const char* n) : f(n), i(n) {}
+};
+template <typename T, int TPL, int Q, int V, int MINB, int... Rs>
+struct RegistrarSet<B2_KIND_COLS, T, TPL, Q, V, MINB, Rs...> {
+    Registrar<B2_KIND_COLS, T, TPL, Q, V, MINB, false, 0, Rs...> f;
+    Registrar<B2_KIND_COLS, T, TPL, Q, V, MINB, true, 0, Rs...> i;
+    Registrar<B2_KIND_COLS, T, TPL, Q, V, MINB, false, B2_OP_TWIDDLE_OUT, Rs...> ft;
+    Registrar<B2_KIND_COLS, T, TPL, Q, V, MINB, true, B2_OP_TWIDDLE_OUT, Rs...> it;
+    explicit RegistrarSet(const char* n) : f(n), i(n), ft(n), it(n) {}
+};
+
+}  // namespace b200fft
+
+namespace b200fft {
+template <bool EN, int KIND, typename T, int TPL, int Q, int V, int MINB, int... Rs>
+struct MaybeSet {
+    explicit MaybeSet(const char*) {}
+};
+template <int KIND, typename T, int TPL, int Q, int V, int MINB, int... Rs>
+struct MaybeSet<true, KIND, T, TPL, Q, V, MINB, Rs...> : RegistrarSet<KIND, T, TPL, Q, V, MINB, Rs...> {
+    explicit MaybeSet(const char* n) : RegistrarSet<KIND, T, TPL, Q, V, MINB, Rs...>(n) {}
+};
+}  // namespace b200fft
+
+// B2_SHARD < 0 instantiates everything (CPU emulation build)
+#define B2_CAT2(a, b) a##b
+#define B2_CAT(a, b) B2_CAT2(a, b)
+#define B2_K(shard, KIND, T, TPL, Q, V, MINB, ...)                                                        \
+    static ::b200fft::MaybeSet<((B2_SHARD) < 0 || (shard) == (B2_SHARD)), B2_KIND_##KIND, T, TPL, Q, V, MINB, \
+                               __VA_ARGS__>                                                               \
+        B2_CAT(b2_reg_, __LINE__)(#KIND "<" #T "," #TPL "x" #Q ",V" #V ";" #__VA_ARGS__ ">");

@@ -1,0 +1,38 @@
+// Registry of ahead-of-time compiled kernel instantiations.  The planner looks kernels up by
+// (kind, precision, length, direction, fused-operator set); nothing is generated or compiled at run time
+// (the reference JIT-compiles every plan through NVRTC, vkFFT_CompileKernel.h:299-491).
+#pragma once
+#include "pass_params.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    B2_KIND_ROWS = 0,       // lines contiguous in HBM on both sides
+    B2_KIND_ROWS_TOUT = 1,  // contiguous lines in, neighbouring lines interleaved on the way out (four-step final pass)
+    B2_KIND_COLS = 2,       // neighbouring lines interleaved (strided axis / four-step first pass)
+    B2_KIND_COUNT
+};
+enum { B2_PREC_F32 = 0, B2_PREC_F64 = 1 };
+
+typedef struct b2_kernel_info {
+    int kind, prec, n, inv, ops;       // lookup key
+    int threads, q, tpl, v, smem_bytes;
+    int ns;
+    int radices[8];
+    int lut_size;                      // complex entries of the stage-twiddle LUT
+    // enqueue `grid` CTAs on `stream` (cudaStream_t); returns cudaError_t as int
+    int (*launch)(const b2_pass_params* P, unsigned grid, void* stream);
+    int (*prepare)(void);              // one-time cudaFuncSetAttribute (max dynamic smem)
+    const char* name;
+} b2_kernel_info;
+
+void b2_register_kernel(const b2_kernel_info* k);
+const b2_kernel_info* b2_find_kernel(int kind, int prec, int n, int inv, int ops);
+int b2_kernel_count(void);
+const b2_kernel_info* b2_kernel_at(int i);
+
+#ifdef __cplusplus
+}
+#endif

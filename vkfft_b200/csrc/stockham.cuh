@@ -1,0 +1,338 @@
+// Compile-time specialised Stockham autosort FFT: one CTA transforms Q lines of length N that live in
+// shared memory between radix stages; first-stage legs come straight from HBM into registers and the
+// last stage stores straight from registers (one HBM read + one HBM write per element).
+//
+// Algorithm (what the reference's generated VkFFT_main does, vkFFT_FFT.h:97-239 / vkFFT_RadixStage.h:35):
+//   stage s has radix r and stageSize S = prod(previous radices); butterfly b in [0, N/r), j = b mod S:
+//     leg k  = x[b + k*N/r] * W_{S*r}^{j*k}          (DIT twiddle before the butterfly)
+//     y[(b-j)*r + j + k*S] = DFT_r(legs)[k]           (autosort scatter, vkFFT_RadixShuffle.h:34)
+//   so the output of the last stage is in natural order with no bit reversal.
+// What is different from the reference: twiddles are correctly-rounded LUT entries (never __sincosf),
+// thread<->line mapping can differ between the load side and the store side (so the four-step transposed
+// write is coalesced), all shapes are template constants (AOT for sm_100a, nothing is JIT-compiled), and the
+// inverse transform is the forward code with re/im swapped at the HBM boundary.
+#pragma once
+#include "pass_params.h"
+#include "radix.cuh"
+
+#if defined(B2_EMU)
+#include "cuda_emu.h"
+#else
+#define B2_SMEM_LD(sm, i) ((sm)[(i)])
+#define B2_SMEM_ST(sm, i, v) ((sm)[(i)] = (v))
+#endif
+
+namespace b200fft {
+
+// ------------------------------------------------------------------------------------------------
+// radix schedule
+template <int... Rs>
+struct RList {
+    static constexpr int ns = sizeof...(Rs);
+    B2_HD static constexpr int r(int s) {
+        const int a[] = {Rs...};
+        return a[s];
+    }
+    B2_HD static constexpr int S(int s) {  // stage size before stage s
+        int p = 1;
+        for (int i = 0; i < s; ++i) p *= r(i);
+        return p;
+    }
+    static constexpr int N = (Rs * ... * 1);
+    B2_HD static constexpr int lut_off(int s) {  // offset of stage s in the stage-twiddle LUT
+        int o = 0;
+        for (int i = 1; i < s; ++i) o += (r(i) - 1) * S(i);
+        return o;
+    }
+    static constexpr int lut_size = lut_off(ns);
+    B2_HD static constexpr int rmax() {
+        int m = 1;
+        for (int i = 0; i < ns; ++i) m = r(i) > m ? r(i) : m;
+        return m;
+    }
+};
+
+enum { MAP_TFAST = 0, MAP_QFAST = 1 };      // which of (t = thread-in-line, q = line) is the fast lane index
+enum { LAY_LINE = 0, LAY_ELEM = 1 };        // smem[q][pad(p)]  or  smem[p][q]
+
+B2_HD constexpr int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ------------------------------------------------------------------------------------------------
+// global-memory access helpers (vector width W complex elements)
+template <typename T, int W>
+struct gvec;
+template <> struct gvec<float, 1> { using type = float2; };
+template <> struct gvec<float, 2> { using type = float4; };
+template <> struct gvec<double, 1> { using type = double2; };
+
+#if defined(__CUDA_ARCH__)
+template <typename T> B2_D cpx<T> ld_lut(const cpx<T>* p) {
+    if constexpr (sizeof(T) == 4) {
+        float2 v = __ldg(reinterpret_cast<const float2*>(p));
+        return mk<T>(v.x, v.y);
+    } else {
+        double2 v = __ldg(reinterpret_cast<const double2*>(p));
+        return mk<T>(v.x, v.y);
+    }
+}
+#else
+template <typename T> B2_D cpx<T> ld_lut(const cpx<T>* p) { return *p; }
+#endif
+
+// two-level table lookup of W_M^m  (m = hi*2^shift + lo):  one complex multiply, error <= ~1.5 ulp
+template <typename T>
+B2_D cpx<T> twiddle2(const cpx<T>* hi, const cpx<T>* lo, uint32_t shift, uint64_t m) {
+    cpx<T> a = ld_lut(hi + (m >> shift));
+    cpx<T> b = ld_lut(lo + (m & ((1ull << shift) - 1)));
+    return a * b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel configuration (all compile-time)
+template <typename T_, class Sch_, int TPL_, int Q_, int V_, int LMAP_, int SMAP_, int LAYOUT_, bool INV_,
+          int OPS_, bool IN_UNIT_, bool OUT_UNIT_, int MINB_ = 1>
+struct KCfg {
+    using T = T_;
+    using Sch = Sch_;
+    static constexpr int N = Sch::N;
+    static constexpr int TPL = TPL_;      // threads cooperating on one line
+    static constexpr int Q = Q_;          // lines per CTA
+    static constexpr int V = V_;          // adjacent butterflies per thread (vector width of HBM access)
+    static constexpr int LMAP = LMAP_;    // thread mapping used on the HBM-load side
+    static constexpr int SMAP = SMAP_;    // thread mapping used on the HBM-store side
+    static constexpr int LAYOUT = LAYOUT_;
+    static constexpr bool INV = INV_;
+    static constexpr int OPS = OPS_;
+    static constexpr bool IN_UNIT = IN_UNIT_;    // in_es == 1 guaranteed
+    static constexpr bool OUT_UNIT = OUT_UNIT_;  // out_es == 1 guaranteed
+    static constexpr int MINB = MINB_;
+    static constexpr int THREADS = TPL * Q;
+    // line-major layout: every 16 B*8 = 128 B of a line is followed by one pad element; lines start on
+    // an odd multiple so that the column access of the transposed store is conflict free as well.
+    static constexpr int PAD_SHIFT = (sizeof(T) == 4) ? 4 : 3;
+    static constexpr int NPAD = N + (N >> PAD_SHIFT);
+    static constexpr int LS = (LAYOUT == LAY_LINE) ? (Q == 1 ? NPAD : (NPAD | 1)) : 0;
+    static constexpr int QP = Q;  // elem-major row pitch
+    static constexpr int SMEM_ELEMS = (Sch::ns <= 1) ? 0 : ((LAYOUT == LAY_LINE) ? Q * LS : N * QP);
+    static constexpr int SMEM_BYTES = SMEM_ELEMS * 2 * (int)sizeof(T);
+};
+
+template <class C>
+struct Engine {
+    using T = typename C::T;
+    using X = cpx<T>;
+    using Sch = typename C::Sch;
+    static constexpr int N = C::N, TPL = C::TPL, Q = C::Q, V = C::V, NS = Sch::ns;
+
+    B2_D static int sidx(int q, int p) {
+        if constexpr (C::LAYOUT == LAY_LINE) return q * C::LS + p + (p >> C::PAD_SHIFT);
+        else return p * C::QP + q;
+    }
+    template <int MAP> B2_D static void tmap(int tid, int& q, int& t) {
+        if constexpr (MAP == MAP_TFAST) { t = tid % TPL; q = tid / TPL; }
+        else { q = tid % Q; t = tid / Q; }
+    }
+    template <int s> static constexpr int nbut() { return N / Sch::r(s); }
+    template <int s> static constexpr int bpt() { return cdiv(nbut<s>(), V * TPL); }
+    template <int s> static constexpr bool guarded() { return (nbut<s>() % (V * TPL)) != 0; }
+
+    // ---- HBM load of first-stage legs --------------------------------------------------------------
+    template <int s>
+    B2_D static void load_global(X* x, const X* __restrict__ line, int64_t es, int t, bool valid) {
+        constexpr int r = Sch::r(s), NB = nbut<s>(), BPT = bpt<s>();
+#pragma unroll
+        for (int m = 0; m < BPT; ++m) {
+            const int b0 = V * (t + m * TPL);
+            const bool ok = valid && (!guarded<s>() || b0 < NB);
+#pragma unroll
+            for (int k = 0; k < r; ++k) {
+                const int p = b0 + k * NB;
+                if constexpr (V == 2 && C::IN_UNIT) {
+                    using G = typename gvec<T, 2>::type;
+                    G g = ok ? *reinterpret_cast<const G*>(line + p) : G{};
+                    X a = mk<T>(g.x, g.y), c = mk<T>(g.z, g.w);
+                    x[(m * V + 0) * r + k] = C::INV ? swp(a) : a;
+                    x[(m * V + 1) * r + k] = C::INV ? swp(c) : c;
+                } else {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        X a = mk<T>(T(0), T(0));
+                        if (ok) a = line[C::IN_UNIT ? (int64_t)(p + v) : (int64_t)(p + v) * es];
+                        x[(m * V + v) * r + k] = C::INV ? swp(a) : a;
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- smem read of stage legs ---------------------------------------------------------------------
+    template <int s>
+    B2_D static void load_smem(X* x, const X* sm, int q, int t) {
+        constexpr int r = Sch::r(s), NB = nbut<s>(), BPT = bpt<s>();
+#pragma unroll
+        for (int m = 0; m < BPT; ++m) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const int b = V * (t + m * TPL) + v;
+                if (guarded<s>() && b >= NB) continue;
+#pragma unroll
+                for (int k = 0; k < r; ++k) x[(m * V + v) * r + k] = B2_SMEM_LD(sm, sidx(q, b + k * NB));
+            }
+        }
+    }
+
+    // ---- twiddle + butterfly ---------------------------------------------------------------------------
+    template <int s>
+    B2_D static void compute(X* x, const X* __restrict__ lut, int t) {
+        constexpr int r = Sch::r(s), S = Sch::S(s), NB = nbut<s>(), BPT = bpt<s>();
+#pragma unroll
+        for (int m = 0; m < BPT; ++m) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const int b = V * (t + m * TPL) + v;
+                if (guarded<s>() && b >= NB) continue;
+                X* xb = x + (m * V + v) * r;
+                if constexpr (s > 0) {
+                    const int j = b % S;
+                    const X* l = lut + Sch::lut_off(s) + j;
+#pragma unroll
+                    for (int k = 1; k < r; ++k) xb[k] = xb[k] * ld_lut(l + (k - 1) * S);
+                }
+                dft<r, T>(xb);
+            }
+        }
+    }
+
+    // ---- autosort scatter into smem ------------------------------------------------------------------
+    template <int s>
+    B2_D static void store_smem(const X* x, X* sm, int q, int t) {
+        constexpr int r = Sch::r(s), S = Sch::S(s), NB = nbut<s>(), BPT = bpt<s>();
+#pragma unroll
+        for (int m = 0; m < BPT; ++m) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const int b = V * (t + m * TPL) + v;
+                if (guarded<s>() && b >= NB) continue;
+                const int j = b % S;
+                const int base = (b - j) * r + j;
+#pragma unroll
+                for (int k = 0; k < r; ++k) B2_SMEM_ST(sm, sidx(q, base + k * S), x[(m * V + v) * r + k]);
+            }
+        }
+    }
+
+    // ---- HBM store of last-stage outputs (+ fused post operators) --------------------------------------
+    template <int s>
+    B2_D static void store_global(const X* x, X* __restrict__ line, int64_t es, int t, bool valid,
+                                  const b2_pass_params& P, uint32_t gline) {
+        constexpr int r = Sch::r(s), NB = nbut<s>(), BPT = bpt<s>();
+        static_assert(s == NS - 1, "global store only after the last stage");
+#pragma unroll
+        for (int m = 0; m < BPT; ++m) {
+            const int b0 = V * (t + m * TPL);
+            const bool ok = valid && (!guarded<s>() || b0 < NB);
+#pragma unroll
+            for (int k = 0; k < r; ++k) {
+                X o[V];
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    X a = x[(m * V + v) * r + k];
+                    const int p = b0 + v + k * NB;  // natural-order output index (S == NB in the last stage)
+                    if constexpr ((C::OPS & B2_OP_TWIDDLE_OUT) != 0) {
+                        const uint64_t e = (uint64_t)(P.tw_line0 + gline) * (uint64_t)p;
+                        a = a * twiddle2<T>((const X*)P.tw_hi, (const X*)P.tw_lo, P.tw_shift, e);
+                    }
+                    if constexpr ((C::OPS & B2_OP_SCALE) != 0) a = a * (T)P.scale;
+                    o[v] = C::INV ? swp(a) : a;
+                }
+                const int p0 = b0 + k * NB;
+                if (ok) {
+                    if constexpr (V == 2 && C::OUT_UNIT) {
+                        using G = typename gvec<T, 2>::type;
+                        G g;
+                        g.x = o[0].x; g.y = o[0].y; g.z = o[1].x; g.w = o[1].y;
+                        *reinterpret_cast<G*>(line + p0) = g;
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < V; ++v)
+                            line[C::OUT_UNIT ? (int64_t)(p0 + v) : (int64_t)(p0 + v) * es] = o[v];
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- middle stages (recursive over the schedule) --------------------------------------------------
+    template <int s>
+    B2_D static void middle(X* sm, const X* lut, int tid) {
+        if constexpr (s < NS - 1) {
+            int q, t;
+            tmap<C::LMAP>(tid, q, t);
+            X x[bpt<s>() * V * Sch::r(s)];
+            load_smem<s>(x, sm, q, t);
+            compute<s>(x, lut, t);
+            __syncthreads();
+            store_smem<s>(x, sm, q, t);
+            __syncthreads();
+            middle<s + 1>(sm, lut, tid);
+        }
+    }
+
+    B2_D static void run(const b2_pass_params& P, unsigned char* smem_raw) {
+        const int tid = threadIdx.x;
+        // decode CTA -> (line group, outer batch coordinates)
+        const uint32_t ngrp = (P.G + Q - 1) / Q;
+        uint32_t rest = blockIdx.x;
+        const uint32_t grp = rest % ngrp; rest /= ngrp;
+        const uint32_t o0 = rest % P.nb[0]; rest /= P.nb[0];
+        const uint32_t o1 = rest % P.nb[1]; rest /= P.nb[1];
+        const uint32_t o2 = rest;
+        const int64_t obase_in = (int64_t)o0 * P.in_bs[0] + (int64_t)o1 * P.in_bs[1] + (int64_t)o2 * P.in_bs[2];
+        const int64_t obase_out = (int64_t)o0 * P.out_bs[0] + (int64_t)o1 * P.out_bs[1] + (int64_t)o2 * P.out_bs[2];
+        const X* __restrict__ lut = (const X*)P.lut;
+        X* sm = reinterpret_cast<X*>(smem_raw);
+
+        int ql, tl;
+        tmap<C::LMAP>(tid, ql, tl);
+        const uint32_t gl = grp * Q + ql;
+        const X* in_line = (const X*)P.in + obase_in + (int64_t)gl * P.in_gs;
+
+        if constexpr (NS == 1) {
+            X x[bpt<0>() * V * Sch::r(0)];
+            load_global<0>(x, in_line, P.in_es, tl, gl < P.G);
+            compute<0>(x, lut, tl);
+            X* out_line = (X*)P.out + obase_out + (int64_t)gl * P.out_gs;
+            store_global<0>(x, out_line, P.out_es, tl, gl < P.G, P, gl);
+        } else {
+            {
+                X x[bpt<0>() * V * Sch::r(0)];
+                load_global<0>(x, in_line, P.in_es, tl, gl < P.G);
+                compute<0>(x, lut, tl);
+                store_smem<0>(x, sm, ql, tl);
+            }
+            __syncthreads();
+            middle<1>(sm, lut, tid);
+            {
+                constexpr int s = NS - 1;
+                int qs, ts;
+                tmap<C::SMAP>(tid, qs, ts);
+                const uint32_t gs = grp * Q + qs;
+                X x[bpt<s>() * V * Sch::r(s)];
+                load_smem<s>(x, sm, qs, ts);
+                compute<s>(x, lut, ts);
+                X* out_line = (X*)P.out + obase_out + (int64_t)gs * P.out_gs;
+                store_global<s>(x, out_line, P.out_es, ts, gs < P.G, P, gs);
+            }
+        }
+    }
+};
+
+#if defined(__CUDACC__)
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, C::MINB) stockham_kernel(const __grid_constant__ b2_pass_params P) {
+    extern __shared__ __align__(16) unsigned char b2_smem_raw[];
+    Engine<C>::run(P, b2_smem_raw);
+}
+#endif
+
+}  // namespace b200fft

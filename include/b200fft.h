@@ -1,0 +1,117 @@
+/* b200fft -- C ABI of the B200-native FFT engine (libb200fft.so).
+ *
+ * This is the drop-in boundary for the reference's hot path.  The reference exposes the path as three
+ * `static inline` functions in a header (everything else is reached through them):
+ *     initializeVkFFT   vkFFT/vkFFT/vkFFT_AppManagement/vkFFT_InitializeApp.h:1468
+ *     VkFFTAppend       vkFFT/vkFFT/vkFFT_AppManagement/vkFFT_RunApp.h:79
+ *     deleteVkFFT       vkFFT/vkFFT/vkFFT_AppManagement/vkFFT_DeleteApp.h:28
+ * include/vkFFT.h keeps those three names/structs (header-only, C or C++) and forwards to the entry points
+ * below; foreign-language bindings (ctypes, cgo, JNI ...) bind the entry points below directly.
+ *
+ * Conventions kept from the reference (documentation/VkFFT_API_guide.tex:263-352):
+ *   - forward transform uses exp(-2*pi*i*nk/N), inverse is unnormalised unless `normalize` is set;
+ *   - data layout is WHDCN: size[0] is the fastest (contiguous) dimension, then size[1]..., then batches;
+ *   - complex numbers are interleaved (re,im); R2C packs N/2+1 complex per row;
+ *   - all functions return a VkFFTResult-compatible code (0 = VKFFT_SUCCESS), never throw, never abort.
+ * Only plain C types cross this boundary: no CUDA, torch or C++ types in any signature.  Device pointers
+ * and streams travel as void*.
+ */
+#ifndef B200FFT_H
+#define B200FFT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200FFT_MAX_DIMS 4
+#define B200FFT_VERSION 10000 /* engine version; VkFFTGetVersion() of the shim still reports 10304 */
+
+typedef enum b200fft_precision { B200FFT_F32 = 0, B200FFT_F64 = 1 } b200fft_precision;
+
+/* Plan description: the subset of VkFFTConfiguration (vkFFT_Structs.h:93-324) the hot path consumes.
+ * Zero means "default" for every field, exactly like the reference's zero-initialised configuration. */
+typedef struct b200fft_desc {
+    uint32_t struct_size;                 /* = sizeof(b200fft_desc); lets the ABI grow */
+    uint32_t fft_dim;                     /* FFTdim: 1..4 */
+    uint64_t size[B200FFT_MAX_DIMS];      /* size[]: logical transform lengths, x first */
+    uint64_t number_batches;              /* numberBatches (0 -> 1) */
+    uint64_t coordinate_features;         /* coordinateFeatures (0 -> 1); treated as one more batch level */
+    uint32_t precision;                   /* doublePrecision -> B200FFT_F64 */
+    uint32_t perform_r2c;                 /* performR2C */
+    uint32_t perform_dct;                 /* performDCT: 1..4 */
+    uint32_t perform_dst;                 /* performDST: 1..4 */
+    uint32_t normalize;                   /* normalize */
+    uint32_t disable_reorder_four_step;   /* disableReorderFourStep */
+    uint32_t make_forward_plan_only;      /* makeForwardPlanOnly */
+    uint32_t make_inverse_plan_only;      /* makeInversePlanOnly */
+    uint32_t is_input_formatted;          /* isInputFormatted: read from `input` with input_stride */
+    uint32_t is_output_formatted;         /* isOutputFormatted: write to `output` with output_stride */
+    uint32_t inverse_return_to_input;     /* inverseReturnToInputBuffer */
+    uint32_t user_temp_buffer;            /* userTempBuffer: caller supplies the temp buffer */
+    uint64_t buffer_stride[B200FFT_MAX_DIMS];  /* bufferStride[] in elements (0 -> packed default) */
+    uint64_t input_stride[B200FFT_MAX_DIMS];
+    uint64_t output_stride[B200FFT_MAX_DIMS];
+    uint32_t omit_dimension[B200FFT_MAX_DIMS]; /* omitDimension[] */
+    uint64_t buffer_size;                 /* bytes; 0 = unknown (only used for validation) */
+    uint64_t temp_buffer_size;            /* bytes of the user temp buffer when user_temp_buffer=1 */
+    int32_t device;                       /* CUDA device ordinal (what *cfg.device holds for the runtime API) */
+    uint32_t reserved0;
+    void* stream;                         /* cudaStream_t or NULL for the default stream */
+    uint64_t reserved[8];
+} b200fft_desc;
+
+/* Buffers for one execution == VkFFTLaunchParams (vkFFT_Structs.h:326-379) with plain pointers.
+ * All pointers are DEVICE pointers; offsets are in bytes like the reference's *BufferOffset fields. */
+typedef struct b200fft_buffers {
+    void* buffer;
+    void* temp_buffer;     /* only when user_temp_buffer=1 */
+    void* input_buffer;    /* only when is_input_formatted=1 */
+    void* output_buffer;   /* only when is_output_formatted=1 */
+    uint64_t buffer_offset, temp_buffer_offset, input_buffer_offset, output_buffer_offset;
+    void* stream;          /* overrides desc.stream when non-NULL */
+} b200fft_buffers;
+
+typedef struct b200fft_plan b200fft_plan; /* opaque */
+
+/* Facts about a plan, for diagnostics / benchmarks (mirrors what printMemoryLayout prints, vkFFT_RunApp.h:58-78). */
+typedef struct b200fft_plan_info {
+    uint32_t num_passes_forward;    /* kernel launches per forward execution */
+    uint32_t num_passes_inverse;
+    uint64_t temp_bytes;            /* engine-owned scratch (0 when none / user supplied) */
+    uint64_t lut_bytes;             /* twiddle tables resident in HBM */
+    uint64_t algorithmic_bytes;     /* 2 * sizeof(elem) * points * transformed axes, per direction */
+    double flops;                   /* 5 N log2 N convention, per direction */
+} b200fft_plan_info;
+
+/* == initializeVkFFT.  Returns 0 or a VkFFTResult error code; *plan is NULL on failure. */
+int b200fft_plan_create(const b200fft_desc* desc, b200fft_plan** plan);
+/* == VkFFTAppend: enqueue the transform (inverse: -1 forward, +1 inverse) on the plan's stream. Asynchronous. */
+int b200fft_exec(b200fft_plan* plan, int inverse, const b200fft_buffers* buffers);
+/* == deleteVkFFT */
+void b200fft_plan_destroy(b200fft_plan* plan);
+int b200fft_plan_get_info(const b200fft_plan* plan, b200fft_plan_info* info);
+/* human-readable list of the plan's passes; returns bytes written (excluding NUL) */
+size_t b200fft_plan_describe(const b200fft_plan* plan, int inverse, char* dst, size_t cap);
+
+/* End-to-end convenience used by the benchmark's e2e leg and by language bindings without device memory
+ * management: host buffer -> (pinned staging) -> HBM -> transform -> host buffer, synchronous.
+ * `host_in`/`host_out` may alias. Byte counts must match the plan's buffer layout. */
+int b200fft_exec_host(b200fft_plan* plan, int inverse, const void* host_in, void* host_out, uint64_t bytes_in,
+                      uint64_t bytes_out);
+
+/* page-locked host memory for b200fft_exec_host (NULL on failure) */
+void* b200fft_host_alloc(uint64_t bytes);
+void b200fft_host_free(void* p);
+
+const char* b200fft_error_string(int code);
+int b200fft_version(void);
+/* number of ahead-of-time compiled kernel instantiations in the library (0 would mean a broken build) */
+int b200fft_kernel_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200FFT_H */

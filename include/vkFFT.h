@@ -1,0 +1,323 @@
+/* vkFFT.h -- header-only drop-in for the CUDA backend (VKFFT_BACKEND==1) of DTolm/VkFFT, backed by the
+ * B200-native engine in libb200fft.so.
+ *
+ * User code written against the reference keeps compiling unchanged:
+ *
+ *     VkFFTConfiguration cfg = {};  VkFFTApplication app = {};
+ *     cfg.FFTdim = 1; cfg.size[0] = N; cfg.numberBatches = B; cfg.device = &cuDevice; cfg.buffer = &d_ptr;
+ *     initializeVkFFT(&app, cfg);          // reference: vkFFT_InitializeApp.h:1468
+ *     VkFFTAppend(&app, -1, &launchParams); // reference: vkFFT_RunApp.h:79   (-1 forward, +1 inverse)
+ *     deleteVkFFT(&app);                   // reference: vkFFT_DeleteApp.h:28
+ *
+ * What changes underneath: nothing is generated or JIT-compiled; the three calls forward to the C ABI in
+ * b200fft.h (plain pointers and sizes), which launches ahead-of-time compiled sm_100a kernels.
+ * VkFFTConfiguration / VkFFTLaunchParams keep the reference's member names, order and types for
+ * VKFFT_BACKEND==1 (vkFFT_Structs.h:93-379) so that sizeof/offsetof agree with the reference build
+ * (1168 and 80 bytes on x86-64; checked in tests/test_abi.py).  Members that configure the reference's
+ * code generator are accepted and ignored; features outside the engine's scope return the reference's
+ * VKFFT_ERROR_UNSUPPORTED_* codes instead of silently doing something else.
+ *
+ * Link with -lb200fft (and the CUDA driver/runtime the application already uses).
+ */
+#ifndef VKFFT_H
+#define VKFFT_H
+
+#include <inttypes.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifndef VKFFT_BACKEND
+#define VKFFT_BACKEND 1
+#endif
+#if (VKFFT_BACKEND != 1)
+#error "this vkFFT.h only provides the CUDA backend (VKFFT_BACKEND==1)"
+#endif
+
+#include <cuda.h>
+#include <cuda_runtime_api.h>
+
+#include "b200fft.h"
+
+#ifdef __cplusplus
+#define VKFFT_ZERO_INIT {}
+#else
+#define VKFFT_ZERO_INIT {0}
+#endif
+
+#ifndef VKFFT_MAX_FFT_DIMENSIONS
+#define VKFFT_MAX_FFT_DIMENSIONS 4
+#endif
+#if (VKFFT_MAX_FFT_DIMENSIONS != 4)
+#error "the engine is built for VKFFT_MAX_FFT_DIMENSIONS == 4"
+#endif
+
+#define pfLD long double
+#define pfUINT uint64_t
+#define pfINT int64_t
+
+/* ---- plan-time parameters (member list == reference, CUDA backend) ------------------------------------ */
+typedef struct {
+    pfUINT FFTdim;
+    pfUINT size[VKFFT_MAX_FFT_DIMENSIONS];
+    CUdevice* device;
+    cudaStream_t* stream;
+    pfUINT num_streams;
+
+    pfUINT userTempBuffer;
+    pfUINT bufferNum, tempBufferNum, inputBufferNum, outputBufferNum, kernelNum;
+    pfUINT *bufferSize, *tempBufferSize, *inputBufferSize, *outputBufferSize, *kernelSize;
+    void **buffer, **tempBuffer, **inputBuffer, **outputBuffer, **kernel;
+    pfUINT bufferOffset, tempBufferOffset, inputBufferOffset, outputBufferOffset, kernelOffset;
+    pfUINT specifyOffsetsAtLaunch;
+
+    pfUINT coalescedMemory, aimThreads, numSharedBanks;      /* code-generator hints: ignored */
+    pfUINT inverseReturnToInputBuffer;
+    pfUINT numberBatches;
+    pfUINT useUint64;
+    pfUINT omitDimension[VKFFT_MAX_FFT_DIMENSIONS];
+    int performBandwidthBoost;
+    pfUINT groupedBatch[VKFFT_MAX_FFT_DIMENSIONS];
+
+    pfUINT doublePrecision;
+    pfUINT quadDoubleDoublePrecision, quadDoubleDoublePrecisionDoubleMemory;   /* unsupported */
+    pfUINT halfPrecision, halfPrecisionMemoryOnly, doublePrecisionFloatMemory; /* unsupported */
+
+    pfUINT performR2C, performDCT, performDST;
+    pfUINT disableMergeSequencesR2C, forceCallbackVersionRealTransforms;
+
+    pfUINT normalize;
+    pfUINT disableReorderFourStep;
+    pfINT useLUT, useLUT_4step;                               /* the engine always uses exact tables */
+    pfUINT makeForwardPlanOnly, makeInversePlanOnly;
+
+    pfUINT bufferStride[VKFFT_MAX_FFT_DIMENSIONS];
+    pfUINT isInputFormatted, isOutputFormatted;
+    pfUINT inputBufferStride[VKFFT_MAX_FFT_DIMENSIONS];
+    pfUINT outputBufferStride[VKFFT_MAX_FFT_DIMENSIONS];
+    pfUINT swapTo2Stage4Step, swapTo3Stage4Step;
+
+    pfUINT considerAllAxesStrided, keepShaderCode, printMemoryLayout;
+    pfUINT saveApplicationToString, loadApplicationFromString;
+    void* loadApplicationString;
+    pfUINT disableSetLocale;
+
+    pfUINT fixMaxRadixBluestein, forceBluesteinSequenceSize, useCustomBluesteinPaddingPattern;
+    pfUINT *primeSizes, *paddedSizes;
+    pfUINT fixMinRaderPrimeMult, fixMaxRaderPrimeMult, fixMinRaderPrimeFFT, fixMaxRaderPrimeFFT;
+
+    pfUINT performZeropadding[VKFFT_MAX_FFT_DIMENSIONS];
+    pfUINT fft_zeropad_left[VKFFT_MAX_FFT_DIMENSIONS];
+    pfUINT fft_zeropad_right[VKFFT_MAX_FFT_DIMENSIONS];
+    pfUINT frequencyZeroPadding;
+
+    pfUINT performConvolution, conjugateConvolution, crossPowerSpectrumNormalization;
+    pfUINT coordinateFeatures, matrixConvolution, symmetricKernel, numberKernels, kernelConvolution;
+
+    pfUINT registerBoost, registerBoostNonPow2, registerBoost4Step;
+    pfUINT devicePageSize, localPageSize;
+
+    /* filled in by initializeVkFFT in the reference; reported here for the B200 the plan was made on */
+    pfUINT computeCapabilityMajor, computeCapabilityMinor;
+    pfUINT maxComputeWorkGroupCount[VKFFT_MAX_FFT_DIMENSIONS];
+    pfUINT maxComputeWorkGroupSize[VKFFT_MAX_FFT_DIMENSIONS];
+    pfUINT maxThreadsNum, sharedMemorySizeStatic, sharedMemorySize, sharedMemorySizePow2, warpSize, halfThreads;
+    pfUINT allocateTempBuffer;
+    pfUINT reorderFourStep;
+    pfINT maxCodeLength, maxTempLength;
+    pfUINT autoCustomBluesteinPaddingPattern, useRaderUintLUT, vendorID;
+    cudaEvent_t* stream_event;
+    pfUINT streamCounter, streamID;
+} VkFFTConfiguration;
+
+/* ---- launch-time parameters ------------------------------------------------------------------------------ */
+typedef struct {
+    void **buffer, **tempBuffer, **inputBuffer, **outputBuffer, **kernel;
+    pfUINT bufferOffset, tempBufferOffset, inputBufferOffset, outputBufferOffset, kernelOffset;
+} VkFFTLaunchParams;
+
+/* ---- result codes: same numeric values as the reference (vkFFT_Structs.h:380-477) ------------------------ */
+typedef enum VkFFTResult {
+    VKFFT_SUCCESS = 0,
+    VKFFT_ERROR_MALLOC_FAILED = 1,
+    VKFFT_ERROR_INSUFFICIENT_CODE_BUFFER = 2,
+    VKFFT_ERROR_INSUFFICIENT_TEMP_BUFFER = 3,
+    VKFFT_ERROR_PLAN_NOT_INITIALIZED = 4,
+    VKFFT_ERROR_NULL_TEMP_PASSED = 5,
+    VKFFT_ERROR_MATH_FAILED = 6,
+    VKFFT_ERROR_FFTdim_GT_MAX_FFT_DIMENSIONS = 7,
+    VKFFT_ERROR_NONZERO_APP_INITIALIZATION = 8,
+    VKFFT_ERROR_INVALID_PHYSICAL_DEVICE = 1001,
+    VKFFT_ERROR_INVALID_DEVICE = 1002,
+    VKFFT_ERROR_INVALID_QUEUE = 1003,
+    VKFFT_ERROR_INVALID_COMMAND_POOL = 1004,
+    VKFFT_ERROR_INVALID_FENCE = 1005,
+    VKFFT_ERROR_ONLY_FORWARD_FFT_INITIALIZED = 1006,
+    VKFFT_ERROR_ONLY_INVERSE_FFT_INITIALIZED = 1007,
+    VKFFT_ERROR_INVALID_CONTEXT = 1008,
+    VKFFT_ERROR_INVALID_PLATFORM = 1009,
+    VKFFT_ERROR_ENABLED_saveApplicationToString = 1010,
+    VKFFT_ERROR_EMPTY_FILE = 1011,
+    VKFFT_ERROR_EMPTY_FFTdim = 2001,
+    VKFFT_ERROR_EMPTY_size = 2002,
+    VKFFT_ERROR_EMPTY_bufferSize = 2003,
+    VKFFT_ERROR_EMPTY_buffer = 2004,
+    VKFFT_ERROR_EMPTY_tempBufferSize = 2005,
+    VKFFT_ERROR_EMPTY_tempBuffer = 2006,
+    VKFFT_ERROR_EMPTY_inputBufferSize = 2007,
+    VKFFT_ERROR_EMPTY_inputBuffer = 2008,
+    VKFFT_ERROR_EMPTY_outputBufferSize = 2009,
+    VKFFT_ERROR_EMPTY_outputBuffer = 2010,
+    VKFFT_ERROR_EMPTY_kernelSize = 2011,
+    VKFFT_ERROR_EMPTY_kernel = 2012,
+    VKFFT_ERROR_EMPTY_applicationString = 2013,
+    VKFFT_ERROR_EMPTY_useCustomBluesteinPaddingPattern_arrays = 2014,
+    VKFFT_ERROR_EMPTY_app = 2015,
+    VKFFT_ERROR_INVALID_user_tempBuffer_too_small = 2016,
+    VKFFT_ERROR_UNSUPPORTED_RADIX = 3001,
+    VKFFT_ERROR_UNSUPPORTED_FFT_LENGTH = 3002,
+    VKFFT_ERROR_UNSUPPORTED_FFT_LENGTH_R2C = 3003,
+    VKFFT_ERROR_UNSUPPORTED_FFT_LENGTH_R2R = 3004,
+    VKFFT_ERROR_UNSUPPORTED_FFT_OMIT = 3005,
+    VKFFT_ERROR_FAILED_TO_ALLOCATE = 4001,
+    VKFFT_ERROR_FAILED_TO_SYNCHRONIZE = 4028,
+    VKFFT_ERROR_FAILED_TO_COPY = 4029,
+    VKFFT_ERROR_FAILED_TO_LOAD_MODULE = 4035,
+    VKFFT_ERROR_FAILED_TO_GET_FUNCTION = 4036,
+    VKFFT_ERROR_FAILED_TO_SET_DYNAMIC_SHARED_MEMORY = 4037,
+    VKFFT_ERROR_FAILED_TO_MODULE_GET_GLOBAL = 4038,
+    VKFFT_ERROR_FAILED_TO_LAUNCH_KERNEL = 4039,
+    VKFFT_ERROR_FAILED_TO_EVENT_RECORD = 4040,
+    VKFFT_ERROR_FAILED_TO_GET_ATTRIBUTE = 4051,
+    VKFFT_ERROR_FAILED_TO_CREATE_EVENT = 4052
+} VkFFTResult;
+
+static inline const char* getVkFFTErrorString(VkFFTResult result) { return b200fft_error_string((int)result); }
+
+/* ---- application handle ---------------------------------------------------------------------------------- */
+typedef struct {
+    VkFFTConfiguration configuration;   /* normalised copy of what the caller passed (as in the reference) */
+    b200fft_plan* b200fftPlan;          /* the engine's plan: owns tables, scratch, kernel selection */
+    pfUINT actualNumBatches;
+    pfUINT applicationStringSize;       /* saveApplicationToString: opaque blob, nothing to cache (no JIT) */
+    void* saveApplicationString;
+} VkFFTApplication;
+
+static inline int VkFFTGetVersion(void) { return 10304; /* API level of the reference this header mirrors */ }
+
+static inline void deleteVkFFT(VkFFTApplication* app) {
+    if (!app) return;
+    if (app->b200fftPlan) b200fft_plan_destroy(app->b200fftPlan);
+    if (app->saveApplicationString) free(app->saveApplicationString);
+    memset(app, 0, sizeof(VkFFTApplication));
+}
+
+static inline VkFFTResult initializeVkFFT(VkFFTApplication* app, VkFFTConfiguration inputLaunchConfiguration) {
+    if (app == 0) return VKFFT_ERROR_EMPTY_app;
+    {   /* the reference insists on a zero-initialised application (vkFFT_InitializeApp.h:1471-1477) */
+        static const VkFFTApplication zeroApp = VKFFT_ZERO_INIT;
+        if (memcmp(app, &zeroApp, sizeof(VkFFTApplication)) != 0) return VKFFT_ERROR_NONZERO_APP_INITIALIZATION;
+    }
+    const VkFFTConfiguration* c = &inputLaunchConfiguration;
+    if (c->device == 0) return VKFFT_ERROR_INVALID_DEVICE;
+    if (c->FFTdim == 0) return VKFFT_ERROR_EMPTY_FFTdim;
+    if (c->FFTdim > VKFFT_MAX_FFT_DIMENSIONS) return VKFFT_ERROR_FFTdim_GT_MAX_FFT_DIMENSIONS;
+    if (c->size[0] == 0) return VKFFT_ERROR_EMPTY_size;
+    /* features of the reference outside this engine's hot path */
+    if (c->performConvolution || c->kernelConvolution || c->matrixConvolution) return VKFFT_ERROR_UNSUPPORTED_FFT_LENGTH;
+    if (c->halfPrecision || c->halfPrecisionMemoryOnly || c->quadDoubleDoublePrecision ||
+        c->quadDoubleDoublePrecisionDoubleMemory || c->doublePrecisionFloatMemory)
+        return VKFFT_ERROR_UNSUPPORTED_FFT_LENGTH;
+    for (int i = 0; i < VKFFT_MAX_FFT_DIMENSIONS; i++)
+        if (c->performZeropadding[i]) return VKFFT_ERROR_UNSUPPORTED_FFT_LENGTH;
+    if (c->bufferNum > 1 || c->tempBufferNum > 1 || c->inputBufferNum > 1 || c->outputBufferNum > 1)
+        return VKFFT_ERROR_UNSUPPORTED_FFT_LENGTH;
+    if (c->loadApplicationFromString && c->saveApplicationToString) return VKFFT_ERROR_ENABLED_saveApplicationToString;
+    if (c->loadApplicationFromString && c->loadApplicationString == 0) return VKFFT_ERROR_EMPTY_applicationString;
+
+    b200fft_desc d;
+    memset(&d, 0, sizeof d);
+    d.struct_size = (uint32_t)sizeof d;
+    d.fft_dim = (uint32_t)c->FFTdim;
+    for (int i = 0; i < VKFFT_MAX_FFT_DIMENSIONS; i++) {
+        d.size[i] = c->size[i];
+        d.buffer_stride[i] = c->bufferStride[i];
+        d.input_stride[i] = c->inputBufferStride[i];
+        d.output_stride[i] = c->outputBufferStride[i];
+        d.omit_dimension[i] = (uint32_t)c->omitDimension[i];
+    }
+    d.number_batches = c->numberBatches;
+    d.coordinate_features = c->coordinateFeatures;
+    d.precision = c->doublePrecision ? B200FFT_F64 : B200FFT_F32;
+    d.perform_r2c = (uint32_t)c->performR2C;
+    d.perform_dct = (uint32_t)c->performDCT;
+    d.perform_dst = (uint32_t)c->performDST;
+    d.normalize = (uint32_t)c->normalize;
+    d.disable_reorder_four_step = (uint32_t)c->disableReorderFourStep;
+    d.make_forward_plan_only = (uint32_t)c->makeForwardPlanOnly;
+    d.make_inverse_plan_only = (uint32_t)c->makeInversePlanOnly;
+    d.is_input_formatted = (uint32_t)c->isInputFormatted;
+    d.is_output_formatted = (uint32_t)c->isOutputFormatted;
+    d.inverse_return_to_input = (uint32_t)c->inverseReturnToInputBuffer;
+    d.user_temp_buffer = (uint32_t)c->userTempBuffer;
+    if (c->bufferSize) d.buffer_size = c->bufferSize[0];
+    if (c->userTempBuffer && c->tempBufferSize) d.temp_buffer_size = c->tempBufferSize[0];
+    {   /* CUdevice handle -> runtime ordinal */
+        int ndev = 0, found = -1;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess) return VKFFT_ERROR_INVALID_DEVICE;
+        for (int i = 0; i < ndev && found < 0; i++) {
+            CUdevice h;
+            if (cuDeviceGet(&h, i) == CUDA_SUCCESS && h == *c->device) found = i;
+        }
+        if (found < 0) return VKFFT_ERROR_INVALID_DEVICE;
+        d.device = found;
+    }
+    d.stream = (c->stream && c->num_streams > 0) ? (void*)c->stream[0] : 0;
+
+    b200fft_plan* plan = 0;
+    int rc = b200fft_plan_create(&d, &plan);
+    if (rc != 0) { memset(app, 0, sizeof(VkFFTApplication)); return (VkFFTResult)rc; }
+    app->configuration = inputLaunchConfiguration;
+    if (app->configuration.numberBatches == 0) app->configuration.numberBatches = 1;
+    if (app->configuration.coordinateFeatures == 0) app->configuration.coordinateFeatures = 1;
+    app->configuration.reorderFourStep = c->disableReorderFourStep ? 0 : 1;
+    app->configuration.warpSize = 32;
+    app->configuration.vendorID = 0x10DE;
+    app->actualNumBatches = app->configuration.numberBatches;
+    app->b200fftPlan = plan;
+    if (c->saveApplicationToString) {   /* nothing is compiled at plan time, so the "binary" is a tag */
+        static const char tag[] = "b200fft:aot:sm_100a";
+        app->saveApplicationString = malloc(sizeof tag);
+        if (!app->saveApplicationString) { deleteVkFFT(app); return VKFFT_ERROR_MALLOC_FAILED; }
+        memcpy(app->saveApplicationString, tag, sizeof tag);
+        app->applicationStringSize = sizeof tag;
+    }
+    return VKFFT_SUCCESS;
+}
+
+/* inverse: -1 forward, +1 inverse.  Asynchronous: only enqueues work on the plan's stream. */
+static inline VkFFTResult VkFFTAppend(VkFFTApplication* app, int inverse, VkFFTLaunchParams* launchParams) {
+    if (app == 0) return VKFFT_ERROR_EMPTY_app;
+    if (app->b200fftPlan == 0) return VKFFT_ERROR_PLAN_NOT_INITIALIZED;
+    const VkFFTConfiguration* c = &app->configuration;
+    b200fft_buffers b;
+    memset(&b, 0, sizeof b);
+    /* launch-time buffers override plan-time ones (vkFFT_UpdateBuffers.h:628-775) */
+    void** buf = (launchParams && launchParams->buffer) ? launchParams->buffer : c->buffer;
+    void** tmp = (launchParams && launchParams->tempBuffer) ? launchParams->tempBuffer : c->tempBuffer;
+    void** inb = (launchParams && launchParams->inputBuffer) ? launchParams->inputBuffer : c->inputBuffer;
+    void** oub = (launchParams && launchParams->outputBuffer) ? launchParams->outputBuffer : c->outputBuffer;
+    b.buffer = buf ? *buf : 0;
+    b.temp_buffer = tmp ? *tmp : 0;
+    b.input_buffer = inb ? *inb : 0;
+    b.output_buffer = oub ? *oub : 0;
+    if (c->specifyOffsetsAtLaunch && launchParams) {
+        b.buffer_offset = launchParams->bufferOffset; b.temp_buffer_offset = launchParams->tempBufferOffset;
+        b.input_buffer_offset = launchParams->inputBufferOffset; b.output_buffer_offset = launchParams->outputBufferOffset;
+    } else {
+        b.buffer_offset = c->bufferOffset; b.temp_buffer_offset = c->tempBufferOffset;
+        b.input_buffer_offset = c->inputBufferOffset; b.output_buffer_offset = c->outputBufferOffset;
+    }
+    return (VkFFTResult)b200fft_exec(app->b200fftPlan, inverse, &b);
+}
+
+#endif /* VKFFT_H */

@@ -6,5 +6,5 @@ root="$(cd "$here/../.." && pwd)"
 mkdir -p "$here/_build"
 g++ -std=c++20 -O1 -fPIC -shared -pthread -DB2_EMU -DB2_SHARD=-1 \
     -I"$root/vkfft_b200/csrc" -I"$here" \
-    "$here/emu_driver.cpp" "$root/vkfft_b200/csrc/kernel_registry.cpp" \
+    "$here/emu_driver.cpp" "$root/vkfft_b200/csrc/kernel_registry.cpp" "$root/vkfft_b200/csrc/planner.cpp" \
     -o "$here/_build/libb200fft_emu.so"

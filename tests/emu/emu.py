@@ -49,3 +49,46 @@ def run_pass(kind, prec, n, inv, ops, inp, out, G, nb=(1, 1, 1), in_es=1, out_es
     if rc != 0:
         raise RuntimeError(f"emu_run_pass rc={rc}")
     return dict(worst=rep[0], mean=rep[1], accesses=rep[2])
+
+
+class Desc(ctypes.Structure):
+    """ctypes mirror of b200fft_desc (include/b200fft.h)."""
+    _fields_ = [
+        ("struct_size", ctypes.c_uint32), ("fft_dim", ctypes.c_uint32),
+        ("size", ctypes.c_uint64 * 4), ("number_batches", ctypes.c_uint64), ("coordinate_features", ctypes.c_uint64),
+        ("precision", ctypes.c_uint32), ("perform_r2c", ctypes.c_uint32), ("perform_dct", ctypes.c_uint32),
+        ("perform_dst", ctypes.c_uint32), ("normalize", ctypes.c_uint32), ("disable_reorder_four_step", ctypes.c_uint32),
+        ("make_forward_plan_only", ctypes.c_uint32), ("make_inverse_plan_only", ctypes.c_uint32),
+        ("is_input_formatted", ctypes.c_uint32), ("is_output_formatted", ctypes.c_uint32),
+        ("inverse_return_to_input", ctypes.c_uint32), ("user_temp_buffer", ctypes.c_uint32),
+        ("buffer_stride", ctypes.c_uint64 * 4), ("input_stride", ctypes.c_uint64 * 4), ("output_stride", ctypes.c_uint64 * 4),
+        ("omit_dimension", ctypes.c_uint32 * 4), ("buffer_size", ctypes.c_uint64), ("temp_buffer_size", ctypes.c_uint64),
+        ("device", ctypes.c_int32), ("reserved0", ctypes.c_uint32), ("stream", ctypes.c_void_p),
+        ("reserved", ctypes.c_uint64 * 8),
+    ]
+
+
+def make_desc(shape_xyz, batches=1, prec=0, **kw):
+    d = Desc()
+    d.struct_size = ctypes.sizeof(Desc)
+    d.fft_dim = len(shape_xyz)
+    for i, s in enumerate(shape_xyz):
+        d.size[i] = s
+    d.number_batches = batches
+    d.precision = prec
+    for k, v in kw.items():
+        if isinstance(v, (list, tuple)):
+            for i, x in enumerate(v):
+                getattr(d, k)[i] = x
+        else:
+            setattr(d, k, v)
+    return d
+
+
+def exec_plan(desc, inverse, buffer, inp=None, out=None):
+    L = lib()
+    L.emu_exec_plan.restype = ctypes.c_int
+    npass = ctypes.c_int(0)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+    rc = L.emu_exec_plan(ctypes.byref(desc), int(inverse), vp(buffer), vp(inp), vp(out), ctypes.byref(npass))
+    return rc, npass.value

@@ -3,6 +3,7 @@
 #include "kernel_inst.cuh"
 #include "kernel_list.def"
 #include "lut.h"
+#include "plan.h"
 
 #include <cstdio>
 #include <vector>
@@ -50,4 +51,36 @@ extern "C" int emu_run_pass(int kind, int prec, int n, int inv, int ops, const v
     }
     b2emu::st().log = false;
     return rc;
+}
+
+// Execute a whole plan (planner.cpp + emulated kernels) on host memory.  bufs[ROLE_*] are host pointers;
+// the temp buffer is allocated here.  Returns the planner's VkFFTResult code.
+extern "C" int emu_exec_plan(const b200fft_desc* d, int inverse, void* buffer, void* input, void* output,
+                             int* npasses) {
+    PlanGraph g;
+    int rc = build_plan(*d, g);
+    if (rc != 0) return rc;
+    const size_t esz = g.prec == B2_PREC_F64 ? 16 : 8;
+    std::vector<unsigned char> temp(g.temp_elems * esz + 16);
+    void* base[ROLE_COUNT] = {buffer, temp.data(), input, output};
+    std::vector<PassPlan>& list = (inverse == 1) ? g.inv : g.fwd;
+    if (npasses) *npasses = (int)list.size();
+    for (PassPlan& pp : list) {
+        b2_pass_params P = pp.P;
+        std::vector<float> lutf, hif, lof;
+        std::vector<double> lutd, hid, lod;
+        const LutSpec& ls = g.luts[pp.lut_id];
+        if (g.prec == B2_PREC_F32) { lutf = make_stage_lut<float>(ls.radices.data(), (int)ls.radices.size()); P.lut = lutf.data(); }
+        else { lutd = make_stage_lut<double>(ls.radices.data(), (int)ls.radices.size()); P.lut = lutd.data(); }
+        if (pp.tw_id >= 0) {
+            uint64_t M = g.tws[pp.tw_id].M;
+            if (g.prec == B2_PREC_F32) { make_twolevel<float>(M, P.tw_shift, hif, lof); P.tw_hi = hif.data(); P.tw_lo = lof.data(); }
+            else { make_twolevel<double>(M, P.tw_shift, hid, lod); P.tw_hi = hid.data(); P.tw_lo = lod.data(); }
+        }
+        P.in = (const unsigned char*)base[pp.in_role] + pp.in_off * esz;
+        P.out = (unsigned char*)base[pp.out_role] + pp.out_off * esz;
+        int e = pp.k->launch(&P, pp.grid, nullptr);
+        if (e) return 4039;
+    }
+    return 0;
 }

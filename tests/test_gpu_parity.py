@@ -1,0 +1,132 @@
+"""GPU (-m gpu): parity of the CUDA path, called through the C ABI, against the double-precision oracle on
+seeded inputs, plus size-independent properties at BASELINE.json's full sizes.
+Tolerances (BASELINE.json north_star): 1e-6 relative FP32, 1e-12 relative FP64 (norm-wise L2)."""
+import numpy as np
+import pytest
+
+import vkfft_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL32, TOL64 = 1e-6, 1e-12
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import torch
+    assert torch.cuda.is_available(), "these tests need a GPU"
+    import vkfft_b200  # noqa: F401  (fails loudly if libb200fft.so is missing)
+    from vkfft_b200 import _lib
+    assert _lib.load().b200fft_kernel_count() > 0
+    return torch
+
+
+POW2 = [2 ** k for k in range(1, 23)]
+
+
+@pytest.mark.parametrize("n", POW2)
+@pytest.mark.parametrize("inverse", [-1, 1])
+def test_c2c_1d_f32_vs_oracle(gpu, n, inverse):
+    from gpu_util import run_c2c
+    batch = max(1, min(37, (1 << 22) // n))          # odd batch: exercises ragged line groups
+    x = orc.random_input((batch, n), np.complex64, seed=n)
+    got = run_c2c(x, (n,), batch, inverse)
+    ref = orc.c2c(x, 1, inverse == 1)
+    assert orc.error_metrics(got, ref)["l2_rel"] < TOL32
+
+
+@pytest.mark.parametrize("n", [2 ** k for k in range(1, 21)])
+@pytest.mark.parametrize("inverse", [-1, 1])
+def test_c2c_1d_f64_vs_oracle(gpu, n, inverse):
+    from gpu_util import run_c2c
+    batch = max(1, min(19, (1 << 20) // n))
+    x = orc.random_input((batch, n), np.complex128, seed=n + 7)
+    got = run_c2c(x, (n,), batch, inverse, double=True)
+    ref = orc.c2c(x, 1, inverse == 1)
+    assert orc.error_metrics(got, ref)["l2_rel"] < TOL64
+
+
+@pytest.mark.parametrize("shape_xyz,double", [((64, 32), False), ((256, 256), False), ((128, 64, 32), False),
+                                              ((64, 64, 64), True), ((256, 256, 256), True), ((16, 8, 4, 2), False),
+                                              ((4096, 64), False), ((32, 2048), False)])
+@pytest.mark.parametrize("inverse", [-1, 1])
+def test_c2c_nd_vs_oracle(gpu, shape_xyz, double, inverse):
+    from gpu_util import run_c2c
+    batch = 2 if np.prod(shape_xyz) < (1 << 22) else 1
+    dt = np.complex128 if double else np.complex64
+    x = orc.random_input((batch,) + tuple(reversed(shape_xyz)), dt, seed=sum(shape_xyz))
+    got = run_c2c(x, shape_xyz, batch, inverse, double=double)
+    ref = orc.c2c(x, len(shape_xyz), inverse == 1)
+    assert orc.error_metrics(got, ref)["l2_rel"] < (TOL64 if double else TOL32)
+
+
+def test_normalize_and_round_trip(gpu):
+    from gpu_util import run_c2c
+    n, batch = 4096, 8
+    x = orc.random_input((batch, n), np.complex64, 3)
+    y = run_c2c(x, (n,), batch, -1)
+    z = run_c2c(y, (n,), batch, 1, normalize=1)
+    assert orc.error_metrics(z, x)["l2_rel"] < TOL32
+    z2 = run_c2c(y, (n,), batch, 1)
+    assert orc.error_metrics(z2, n * x.astype(np.complex128))["l2_rel"] < TOL32
+
+
+def test_known_answer_vectors(gpu):
+    from gpu_util import run_c2c
+    for n in (8, 4096, 1 << 16):
+        e = np.zeros((2, n), np.complex64)
+        e[0, 0] = 1
+        e[1, 5] = 1
+        y = run_c2c(e, (n,), 2, -1)
+        k = np.arange(n)
+        assert np.allclose(y[0], 1, atol=1e-6)
+        assert np.allclose(y[1], np.exp(-2j * np.pi * 5 * k / n), atol=2e-6)
+
+
+@pytest.mark.parametrize("n", [1 << 12, 1 << 17, 1 << 20, 1 << 22])
+def test_full_size_properties_2gib(gpu, n):
+    """BASELINE config 2 at full size (2 GiB buffer): too big for the CPU oracle, so check properties that pin
+    the transform: inverse(forward(x)) == N x, Parseval, and exact agreement with the oracle on a few sequences."""
+    torch = gpu
+    import vkfft_b200 as vk
+    total = 1 << 28
+    batch = total // n
+    g = torch.Generator(device="cuda").manual_seed(n)
+    x = torch.empty((batch, n, 2), dtype=torch.float32, device="cuda").uniform_(-1, 1, generator=g)
+    x0 = x.clone()
+    app = vk.VkFFTApplication()
+    assert vk.initializeVkFFT(app, vk.VkFFTConfiguration(FFTdim=1, size=[n], numberBatches=batch, device=0)) == 0
+    try:
+        assert vk.VkFFTAppend(app, -1, vk.VkFFTLaunchParams(buffer=x)) == 0
+        torch.cuda.synchronize()
+        # spot-check a few sequences against the CPU oracle
+        for b in (0, batch // 2, batch - 1):
+            xin = torch.view_as_complex(x0[b]).cpu().numpy()[None]
+            got = torch.view_as_complex(x[b]).cpu().numpy()[None]
+            assert orc.error_metrics(got, orc.c2c(xin, 1))["l2_rel"] < TOL32
+        # Parseval: sum |X|^2 = N sum |x|^2
+        e_in = (x0.double() ** 2).sum().item()
+        e_out = (x.double() ** 2).sum().item()
+        assert abs(e_out / (n * e_in) - 1) < 1e-5
+        assert vk.VkFFTAppend(app, 1, vk.VkFFTLaunchParams(buffer=x)) == 0
+        torch.cuda.synchronize()
+        x.mul_(1.0 / n)
+        err = (x - x0).double().norm().item() / x0.double().norm().item()
+        assert err < 2e-6
+    finally:
+        vk.deleteVkFFT(app)
+
+
+def test_api_errors_on_gpu(gpu):
+    import vkfft_b200 as vk
+    app = vk.VkFFTApplication()
+    assert vk.initializeVkFFT(app, vk.VkFFTConfiguration(FFTdim=0, size=[8], device=0)) == vk.VKFFT_ERROR_EMPTY_FFTdim
+    assert vk.initializeVkFFT(app, vk.VkFFTConfiguration(FFTdim=1, size=[0], device=0)) == vk.VKFFT_ERROR_EMPTY_size
+    assert vk.initializeVkFFT(app, vk.VkFFTConfiguration(FFTdim=1, size=[8], device=99)) == vk.VKFFT_ERROR_INVALID_DEVICE
+    assert vk.initializeVkFFT(app, vk.VkFFTConfiguration(FFTdim=1, size=[8], device=0, makeForwardPlanOnly=1)) == 0
+    t = gpu.zeros(8, dtype=gpu.complex64, device="cuda")
+    assert vk.VkFFTAppend(app, 1, vk.VkFFTLaunchParams(buffer=t)) == vk.VKFFT_ERROR_ONLY_FORWARD_FFT_INITIALIZED
+    assert vk.VkFFTAppend(app, -1, vk.VkFFTLaunchParams()) == vk.VKFFT_ERROR_EMPTY_buffer
+    assert vk.initializeVkFFT(app, vk.VkFFTConfiguration(FFTdim=1, size=[8], device=0)) == vk.VKFFT_ERROR_NONZERO_APP_INITIALIZATION
+    vk.deleteVkFFT(app)
+    assert vk.VkFFTAppend(app, -1, vk.VkFFTLaunchParams(buffer=t)) == vk.VKFFT_ERROR_PLAN_NOT_INITIALIZED

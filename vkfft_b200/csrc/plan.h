@@ -1,0 +1,89 @@
+// Host-side plan graph: what initializeVkFFT builds in the reference through VkFFTScheduler
+// (vkFFT_Scheduler.h:2223) + VkFFTPlanAxis (vkFFT_Plan_FFT.h:33), minus all code generation:
+// here a plan is an ordered list of launches of ahead-of-time compiled kernels plus the twiddle
+// tables they need.  Pure host C++ (no CUDA calls) so the CPU tests can execute a plan on the
+// kernel-body emulation.
+#pragma once
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/b200fft.h"
+#include "kernel_registry.h"
+#include "pass_params.h"
+
+namespace b200fft {
+
+// VkFFTResult values used by the engine (vkFFT_Structs.h:380-477)
+enum {
+    R_SUCCESS = 0,
+    R_MALLOC_FAILED = 1,
+    R_PLAN_NOT_INITIALIZED = 4,
+    R_NULL_TEMP_PASSED = 5,
+    R_FFTDIM_GT_MAX = 7,
+    R_INVALID_DEVICE = 1002,
+    R_ONLY_FORWARD = 1006,
+    R_ONLY_INVERSE = 1007,
+    R_EMPTY_FFTDIM = 2001,
+    R_EMPTY_SIZE = 2002,
+    R_EMPTY_BUFFER = 2004,
+    R_EMPTY_TEMPBUFFER = 2006,
+    R_EMPTY_INPUTBUFFER = 2008,
+    R_EMPTY_OUTPUTBUFFER = 2010,
+    R_EMPTY_APP = 2015,
+    R_USER_TEMP_TOO_SMALL = 2016,
+    R_UNSUPPORTED_RADIX = 3001,
+    R_UNSUPPORTED_FFT_LENGTH = 3002,
+    R_UNSUPPORTED_FFT_LENGTH_R2C = 3003,
+    R_UNSUPPORTED_FFT_LENGTH_R2R = 3004,
+    R_UNSUPPORTED_FFT_OMIT = 3005,
+    R_FAILED_TO_ALLOCATE = 4001,
+    R_FAILED_TO_SYNCHRONIZE = 4028,
+    R_FAILED_TO_COPY = 4029,
+    R_FAILED_TO_SET_DYNAMIC_SHARED_MEMORY = 4037,
+    R_FAILED_TO_LAUNCH_KERNEL = 4039,
+};
+
+enum BufRole { ROLE_BUFFER = 0, ROLE_TEMP = 1, ROLE_INPUT = 2, ROLE_OUTPUT = 3, ROLE_COUNT = 4 };
+
+struct LutSpec {       // stage twiddles of one kernel schedule
+    int prec;
+    std::vector<int> radices;
+};
+struct TwSpec {        // two-level four-step table for modulus M
+    int prec;
+    uint64_t M;
+};
+
+struct PassPlan {
+    const b2_kernel_info* k = nullptr;
+    b2_pass_params P{};          // pointer members are filled in by the runtime at launch
+    unsigned grid = 0;
+    int in_role = ROLE_BUFFER, out_role = ROLE_BUFFER;
+    int64_t in_off = 0, out_off = 0;   // complex-element offsets added to the role's base pointer
+    int lut_id = -1;
+    int tw_id = -1;
+    std::string note;            // human readable (plan_describe)
+};
+
+struct PlanGraph {
+    b200fft_desc desc{};         // normalised copy (defaults filled in)
+    int prec = 0;
+    uint64_t stride[B200FFT_MAX_DIMS] = {0, 0, 0, 0};      // buffer strides in elements
+    uint64_t batches = 1;        // numberBatches * coordinateFeatures
+    uint64_t batch_stride = 0;
+    uint64_t total_elems = 0;    // logical complex points of one execution
+    uint64_t temp_elems = 0;     // scratch the engine needs (complex elements)
+    bool has_fwd = false, has_inv = false;
+    std::vector<PassPlan> fwd, inv;
+    std::vector<LutSpec> luts;
+    std::vector<TwSpec> tws;
+    double flops = 0;
+    uint64_t algorithmic_bytes = 0;
+};
+
+// Build the plan graph for `d`.  Returns a VkFFTResult-compatible code.
+int build_plan(const b200fft_desc& d, PlanGraph& g);
+
+}  // namespace b200fft

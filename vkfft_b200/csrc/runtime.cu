@@ -1,0 +1,265 @@
+// CUDA runtime side of the engine + the C ABI declared in include/b200fft.h.
+//
+// Replaces the reference's L1 "API handles" layer for the CUDA backend: table upload
+// (vkFFT_ManageLUT.h:901-915), kernel launch (vkFFT_DispatchPlan.h:157-225), buffer selection
+// (vkFFT_UpdateBuffers.h:776-1199) and teardown (vkFFT_DeletePlan.h:59-69, vkFFT_DeleteApp.h:28-324).
+// There is no NVRTC / module loading: every kernel is compiled ahead of time for sm_100a and found through
+// the registry.  There is no CPU fallback either: if the device or the kernels are missing the call fails.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "lut.h"
+#include "plan.h"
+
+using namespace b200fft;
+
+struct TwDev {
+    void* hi = nullptr;
+    void* lo = nullptr;
+    uint32_t shift = 0;
+};
+
+struct b200fft_plan {
+    PlanGraph g;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<void*> d_luts;
+    std::vector<TwDev> d_tws;
+    void* d_temp = nullptr;
+    uint64_t temp_bytes = 0;
+    uint64_t lut_bytes = 0;
+    // exec_host staging
+    void* d_stage = nullptr;
+    uint64_t stage_bytes = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+template <typename T>
+int upload(const std::vector<T>& h, void** d, uint64_t& total) {
+    *d = nullptr;
+    size_t bytes = h.size() * sizeof(T);
+    if (bytes == 0) bytes = 16;
+    if (cudaMalloc(d, bytes) != cudaSuccess) return R_FAILED_TO_ALLOCATE;
+    if (!h.empty() && cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess)
+        return R_FAILED_TO_COPY;
+    total += bytes;
+    return R_SUCCESS;
+}
+
+void free_plan(b200fft_plan* p) {
+    if (!p) return;
+    DeviceGuard dg(p->device);
+    for (void* d : p->d_luts) if (d) cudaFree(d);
+    for (TwDev& t : p->d_tws) { if (t.hi) cudaFree(t.hi); if (t.lo) cudaFree(t.lo); }
+    if (p->d_temp) cudaFree(p->d_temp);
+    if (p->d_stage) cudaFree(p->d_stage);
+    delete p;
+}
+
+}  // namespace
+
+extern "C" int b200fft_plan_create(const b200fft_desc* desc, b200fft_plan** out) {
+    if (!out) return R_EMPTY_APP;
+    *out = nullptr;
+    if (!desc) return R_EMPTY_APP;
+    if (b2_kernel_count() == 0) return R_PLAN_NOT_INITIALIZED;  // library built without kernels: fail loudly
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return R_INVALID_DEVICE;
+    if (desc->device < 0 || desc->device >= ndev) return R_INVALID_DEVICE;
+    b200fft_plan* p = new (std::nothrow) b200fft_plan();
+    if (!p) return R_MALLOC_FAILED;
+    p->device = desc->device;
+    p->stream = (cudaStream_t)desc->stream;
+    int rc = build_plan(*desc, p->g);
+    if (rc != R_SUCCESS) { delete p; return rc; }
+    DeviceGuard dg(p->device);
+    if (!dg.ok) { delete p; return R_INVALID_DEVICE; }
+    const PlanGraph& g = p->g;
+    p->d_luts.assign(g.luts.size(), nullptr);
+    p->d_tws.assign(g.tws.size(), TwDev{});
+    for (size_t i = 0; i < g.luts.size() && rc == R_SUCCESS; ++i) {
+        const LutSpec& ls = g.luts[i];
+        if (ls.prec == B2_PREC_F32) rc = upload(make_stage_lut<float>(ls.radices.data(), (int)ls.radices.size()), &p->d_luts[i], p->lut_bytes);
+        else rc = upload(make_stage_lut<double>(ls.radices.data(), (int)ls.radices.size()), &p->d_luts[i], p->lut_bytes);
+    }
+    for (size_t i = 0; i < g.tws.size() && rc == R_SUCCESS; ++i) {
+        const TwSpec& ts = g.tws[i];
+        if (ts.prec == B2_PREC_F32) {
+            std::vector<float> hi, lo;
+            make_twolevel<float>(ts.M, p->d_tws[i].shift, hi, lo);
+            rc = upload(hi, &p->d_tws[i].hi, p->lut_bytes);
+            if (rc == R_SUCCESS) rc = upload(lo, &p->d_tws[i].lo, p->lut_bytes);
+        } else {
+            std::vector<double> hi, lo;
+            make_twolevel<double>(ts.M, p->d_tws[i].shift, hi, lo);
+            rc = upload(hi, &p->d_tws[i].hi, p->lut_bytes);
+            if (rc == R_SUCCESS) rc = upload(lo, &p->d_tws[i].lo, p->lut_bytes);
+        }
+    }
+    // one-time kernel attributes (dynamic shared memory above 48 KiB)
+    for (int dir = 0; dir < 2 && rc == R_SUCCESS; ++dir)
+        for (const PassPlan& pp : (dir ? g.inv : g.fwd))
+            if (pp.k->prepare && pp.k->prepare() != 0) { rc = R_FAILED_TO_SET_DYNAMIC_SHARED_MEMORY; break; }
+    // scratch for Four-Step (the reference auto-allocates tempBuffer the same way, vkFFT_InitializeApp.h:1603-1637)
+    if (rc == R_SUCCESS && g.temp_elems && !g.desc.user_temp_buffer) {
+        p->temp_bytes = g.temp_elems * (g.prec == B2_PREC_F64 ? 16 : 8);
+        if (cudaMalloc(&p->d_temp, p->temp_bytes) != cudaSuccess) rc = R_FAILED_TO_ALLOCATE;
+    }
+    if (rc != R_SUCCESS) { cudaGetLastError(); free_plan(p); return rc; }
+    *out = p;
+    return R_SUCCESS;
+}
+
+extern "C" int b200fft_exec(b200fft_plan* p, int inverse, const b200fft_buffers* b) {
+    if (!p) return R_EMPTY_APP;
+    if (!b) return R_EMPTY_BUFFER;
+    const PlanGraph& g = p->g;
+    if (inverse == 1 && !g.has_inv) return R_ONLY_FORWARD;
+    if (inverse != 1 && !g.has_fwd) return R_ONLY_INVERSE;
+    const std::vector<PassPlan>& list = (inverse == 1) ? g.inv : g.fwd;
+    const size_t esz = g.prec == B2_PREC_F64 ? 16 : 8;
+    unsigned char* base[ROLE_COUNT];
+    base[ROLE_BUFFER] = (unsigned char*)b->buffer + b->buffer_offset;
+    base[ROLE_TEMP] = g.desc.user_temp_buffer ? (unsigned char*)b->temp_buffer + b->temp_buffer_offset
+                                              : (unsigned char*)p->d_temp;
+    base[ROLE_INPUT] = (unsigned char*)b->input_buffer + b->input_buffer_offset;
+    base[ROLE_OUTPUT] = (unsigned char*)b->output_buffer + b->output_buffer_offset;
+    bool used[ROLE_COUNT] = {false, false, false, false};
+    for (const PassPlan& pp : list) { used[pp.in_role] = true; used[pp.out_role] = true; }
+    if (used[ROLE_BUFFER] && !b->buffer) return R_EMPTY_BUFFER;
+    if (used[ROLE_TEMP] && !(g.desc.user_temp_buffer ? b->temp_buffer : p->d_temp)) return R_EMPTY_TEMPBUFFER;
+    if (used[ROLE_INPUT] && !b->input_buffer) return R_EMPTY_INPUTBUFFER;
+    if (used[ROLE_OUTPUT] && !b->output_buffer) return R_EMPTY_OUTPUTBUFFER;
+    DeviceGuard dg(p->device);
+    if (!dg.ok) return R_INVALID_DEVICE;
+    cudaStream_t st = b->stream ? (cudaStream_t)b->stream : p->stream;
+    for (const PassPlan& pp : list) {
+        b2_pass_params P = pp.P;
+        P.in = base[pp.in_role] + pp.in_off * (int64_t)esz;
+        P.out = base[pp.out_role] + pp.out_off * (int64_t)esz;
+        P.lut = p->d_luts[pp.lut_id];
+        if (pp.tw_id >= 0) {
+            P.tw_hi = p->d_tws[pp.tw_id].hi;
+            P.tw_lo = p->d_tws[pp.tw_id].lo;
+            P.tw_shift = p->d_tws[pp.tw_id].shift;
+        }
+        if (pp.k->launch(&P, pp.grid, (void*)st) != 0) return R_FAILED_TO_LAUNCH_KERNEL;
+    }
+    return R_SUCCESS;
+}
+
+extern "C" void b200fft_plan_destroy(b200fft_plan* p) { free_plan(p); }
+
+extern "C" int b200fft_plan_get_info(const b200fft_plan* p, b200fft_plan_info* info) {
+    if (!p || !info) return R_EMPTY_APP;
+    info->num_passes_forward = (uint32_t)p->g.fwd.size();
+    info->num_passes_inverse = (uint32_t)p->g.inv.size();
+    info->temp_bytes = p->temp_bytes;
+    info->lut_bytes = p->lut_bytes;
+    info->algorithmic_bytes = p->g.algorithmic_bytes;
+    info->flops = p->g.flops;
+    return R_SUCCESS;
+}
+
+extern "C" size_t b200fft_plan_describe(const b200fft_plan* p, int inverse, char* dst, size_t cap) {
+    if (!p || !dst || cap == 0) return 0;
+    std::string s;
+    const std::vector<PassPlan>& list = (inverse == 1) ? p->g.inv : p->g.fwd;
+    static const char* role[] = {"buffer", "temp", "input", "output"};
+    for (size_t i = 0; i < list.size(); ++i) {
+        s += "pass " + std::to_string(i) + ": " + list[i].note + "  " + role[list[i].in_role] + " -> " +
+             role[list[i].out_role] + "\n";
+    }
+    size_t n = s.size() < cap - 1 ? s.size() : cap - 1;
+    memcpy(dst, s.data(), n);
+    dst[n] = 0;
+    return n;
+}
+
+extern "C" int b200fft_exec_host(b200fft_plan* p, int inverse, const void* host_in, void* host_out,
+                                 uint64_t bytes_in, uint64_t bytes_out) {
+    if (!p) return R_EMPTY_APP;
+    if (!host_in || !host_out) return R_EMPTY_BUFFER;
+    if (p->g.desc.is_input_formatted || p->g.desc.is_output_formatted) return R_EMPTY_INPUTBUFFER;
+    DeviceGuard dg(p->device);
+    if (!dg.ok) return R_INVALID_DEVICE;
+    const uint64_t need = bytes_in > bytes_out ? bytes_in : bytes_out;
+    if (need > p->stage_bytes) {
+        if (p->d_stage) cudaFree(p->d_stage);
+        p->d_stage = nullptr;
+        p->stage_bytes = 0;
+        if (cudaMalloc(&p->d_stage, need) != cudaSuccess) { cudaGetLastError(); return R_FAILED_TO_ALLOCATE; }
+        p->stage_bytes = need;
+    }
+    cudaStream_t st = p->stream;
+    if (cudaMemcpyAsync(p->d_stage, host_in, bytes_in, cudaMemcpyHostToDevice, st) != cudaSuccess) return R_FAILED_TO_COPY;
+    b200fft_buffers b;
+    memset(&b, 0, sizeof b);
+    b.buffer = p->d_stage;
+    int rc = b200fft_exec(p, inverse, &b);
+    if (rc != R_SUCCESS) return rc;
+    if (cudaMemcpyAsync(host_out, p->d_stage, bytes_out, cudaMemcpyDeviceToHost, st) != cudaSuccess) return R_FAILED_TO_COPY;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return R_FAILED_TO_SYNCHRONIZE;
+    return R_SUCCESS;
+}
+
+extern "C" void* b200fft_host_alloc(uint64_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void b200fft_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+extern "C" const char* b200fft_error_string(int code) {
+    switch (code) {
+        case R_SUCCESS: return "VKFFT_SUCCESS";
+        case R_MALLOC_FAILED: return "VKFFT_ERROR_MALLOC_FAILED";
+        case R_PLAN_NOT_INITIALIZED: return "VKFFT_ERROR_PLAN_NOT_INITIALIZED";
+        case R_NULL_TEMP_PASSED: return "VKFFT_ERROR_NULL_TEMP_PASSED";
+        case R_FFTDIM_GT_MAX: return "VKFFT_ERROR_FFTdim_GT_MAX_FFT_DIMENSIONS";
+        case 8: return "VKFFT_ERROR_NONZERO_APP_INITIALIZATION";
+        case R_INVALID_DEVICE: return "VKFFT_ERROR_INVALID_DEVICE";
+        case R_ONLY_FORWARD: return "VKFFT_ERROR_ONLY_FORWARD_FFT_INITIALIZED";
+        case R_ONLY_INVERSE: return "VKFFT_ERROR_ONLY_INVERSE_FFT_INITIALIZED";
+        case R_EMPTY_FFTDIM: return "VKFFT_ERROR_EMPTY_FFTdim";
+        case R_EMPTY_SIZE: return "VKFFT_ERROR_EMPTY_size";
+        case R_EMPTY_BUFFER: return "VKFFT_ERROR_EMPTY_buffer";
+        case R_EMPTY_TEMPBUFFER: return "VKFFT_ERROR_EMPTY_tempBuffer";
+        case R_EMPTY_INPUTBUFFER: return "VKFFT_ERROR_EMPTY_inputBuffer";
+        case R_EMPTY_OUTPUTBUFFER: return "VKFFT_ERROR_EMPTY_outputBuffer";
+        case R_EMPTY_APP: return "VKFFT_ERROR_EMPTY_app";
+        case R_USER_TEMP_TOO_SMALL: return "VKFFT_ERROR_INVALID_user_tempBuffer_too_small";
+        case R_UNSUPPORTED_RADIX: return "VKFFT_ERROR_UNSUPPORTED_RADIX";
+        case R_UNSUPPORTED_FFT_LENGTH: return "VKFFT_ERROR_UNSUPPORTED_FFT_LENGTH";
+        case R_UNSUPPORTED_FFT_LENGTH_R2C: return "VKFFT_ERROR_UNSUPPORTED_FFT_LENGTH_R2C";
+        case R_UNSUPPORTED_FFT_LENGTH_R2R: return "VKFFT_ERROR_UNSUPPORTED_FFT_LENGTH_R2R";
+        case R_UNSUPPORTED_FFT_OMIT: return "VKFFT_ERROR_UNSUPPORTED_FFT_OMIT";
+        case R_FAILED_TO_ALLOCATE: return "VKFFT_ERROR_FAILED_TO_ALLOCATE";
+        case R_FAILED_TO_SYNCHRONIZE: return "VKFFT_ERROR_FAILED_TO_SYNCHRONIZE";
+        case R_FAILED_TO_COPY: return "VKFFT_ERROR_FAILED_TO_COPY";
+        case R_FAILED_TO_SET_DYNAMIC_SHARED_MEMORY: return "VKFFT_ERROR_FAILED_TO_SET_DYNAMIC_SHARED_MEMORY";
+        case R_FAILED_TO_LAUNCH_KERNEL: return "VKFFT_ERROR_FAILED_TO_LAUNCH_KERNEL";
+        default: return "VKFFT_ERROR_UNKNOWN";
+    }
+}
+extern "C" int b200fft_version(void) { return B200FFT_VERSION; }
+extern "C" int b200fft_kernel_count(void) { return b2_kernel_count(); }

@@ -132,9 +132,9 @@ struct Engine {
         if constexpr (MAP == MAP_TFAST) { t = tid % TPL; q = tid / TPL; }
         else { q = tid % Q; t = tid / Q; }
     }
-    template <int s> static constexpr int nbut() { return N / Sch::r(s); }
-    template <int s> static constexpr int bpt() { return cdiv(nbut<s>(), V * TPL); }
-    template <int s> static constexpr bool guarded() { return (nbut<s>() % (V * TPL)) != 0; }
+    template <int s> B2_HD static constexpr int nbut() { return N / Sch::r(s); }
+    template <int s> B2_HD static constexpr int bpt() { return cdiv(nbut<s>(), V * TPL); }
+    template <int s> B2_HD static constexpr bool guarded() { return (nbut<s>() % (V * TPL)) != 0; }
 
     // ---- HBM load of first-stage legs --------------------------------------------------------------
     template <int s>
@@ -227,6 +227,8 @@ struct Engine {
                                   const b2_pass_params& P, uint32_t gline) {
         constexpr int r = Sch::r(s), NB = nbut<s>(), BPT = bpt<s>();
         static_assert(s == NS - 1, "global store only after the last stage");
+        const bool do_scale = (P.ops & B2_OP_SCALE) != 0;   // runtime: normalize=1 on the last inverse pass
+        const T sc = (T)P.scale;
 #pragma unroll
         for (int m = 0; m < BPT; ++m) {
             const int b0 = V * (t + m * TPL);
@@ -242,7 +244,7 @@ struct Engine {
                         const uint64_t e = (uint64_t)(P.tw_line0 + gline) * (uint64_t)p;
                         a = a * twiddle2<T>((const X*)P.tw_hi, (const X*)P.tw_lo, P.tw_shift, e);
                     }
-                    if constexpr ((C::OPS & B2_OP_SCALE) != 0) a = a * (T)P.scale;
+                    if (do_scale) a = a * sc;
                     o[v] = C::INV ? swp(a) : a;
                 }
                 const int p0 = b0 + k * NB;

@@ -1,0 +1,396 @@
+#!/usr/bin/env python3
+"""Benchmark of the hot path: BASELINE.json's metric on BASELINE.json's config[1].
+
+  metric   batched 1-D C2C FP32 throughput in GFLOP/s (5 N log2 N per transform) + HBM roofline fraction
+  workload the reference's sample_0 sweep (benchmark_scripts/vkFFT_scripts/src/sample_0_benchmark_VkFFT_single.cpp)
+           at BASELINE's sizes: N = 2^7 .. 2^22, batch = 2^28 / N (one 2 GiB complex64 buffer per GPU), in place.
+  step     one pass over the sweep: for every N one forward and one inverse transform of the whole buffer
+           (32 transforms, 128 GiB of algorithmic HBM traffic per GPU per step).
+  value    whole-job GFLOP/s with the buffer resident in HBM (CUDA events, max over ranks).
+  e2e      the same step through the public API with HOST buffers: pinned-host -> HBM copy of the step's input,
+           the sweep, and the HBM -> host read of the result, all inside the timed region.
+  roofline the dominant kernel (single-pass N=4096 forward): algorithmic bytes / CUDA-event time / measured peak.
+  cpu_baseline  pocketfft (scipy.fft) on the box's host cores, bounded sample -- stand-in for the reference's
+           FFTW precision-test path (FFTW is not installed in this image).  Reported, not a target.
+  vkfft_cuda_ref  the UNMODIFIED reference (CUDA backend, oracle/_ref) timed on the same GPU in the same run.
+
+Launch:  python bench.py --gpus 1 --steps K --warmup W          (N>1: via torch.distributed.run, one rank per GPU)
+         python bench.py --impl reference ...                   (the reference arm: CPU implementation of the path)
+"""
+import argparse
+import ctypes
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LOG2_MIN, LOG2_MAX = 7, 22
+TOTAL_LOG2 = 28                      # 2^28 complex64 = 2 GiB
+CPU_SAMPLE_LOG2 = 26                 # bounded sample for the CPU legs: 2^26 points (512 MiB) per N
+
+
+def sizes():
+    return [1 << k for k in range(LOG2_MIN, LOG2_MAX + 1)]
+
+
+def flops_pair(n, points):
+    """forward + inverse over `points` complex points organised as sequences of length n"""
+    return 2 * 5.0 * points * math.log2(n)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json (driver-measured copy bandwidth)"
+        except Exception:
+            pass
+    return 6650.0, "fallback from B200_PROFILING.md (MEASURED_PEAKS.json absent)"
+
+
+class ClockSampler:
+    """samples nvidia-smi SM clocks + throttle reasons while the timed region runs"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_sweep_once(np, sfft, bufs, workers):
+    for n, a in bufs:
+        y = sfft.fft(a, axis=1, workers=workers, overwrite_x=False)
+        sfft.ifft(y, axis=1, workers=workers, overwrite_x=True, norm="forward")
+
+
+def cpu_baseline(steps=1, warmup=0):
+    """pocketfft, complex64, all host cores, the same sweep on a bounded sample (2^24 points per N)"""
+    import numpy as np
+    import scipy.fft as sfft
+    cores = os.cpu_count() or 1
+    rng = np.random.default_rng(0)
+    pts = 1 << CPU_SAMPLE_LOG2
+    base = (rng.uniform(-1, 1, pts).astype(np.float32) + 1j * rng.uniform(-1, 1, pts).astype(np.float32)).astype(np.complex64)
+    bufs = [(n, base.reshape(pts // n, n)) for n in sizes()]
+    fl = sum(flops_pair(n, pts) for n in sizes())
+    for _ in range(warmup):
+        cpu_sweep_once(np, sfft, bufs, cores)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_sweep_once(np, sfft, bufs, cores)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": fl / dt / 1e9, "unit": "GFLOP/s", "cores": cores, "kind": "port",
+            "sample": f"same sweep N=2^{LOG2_MIN}..2^{LOG2_MAX} fwd+inv, 2^{CPU_SAMPLE_LOG2} complex64 points per N "
+                      f"(512 MiB instead of 2 GiB), scipy.fft/pocketfft workers={cores}; stand-in for the reference's "
+                      "FFTW precision-test path (FFTW not installed)",
+            "seconds_per_step": dt}, dt
+
+
+def vkfft_cuda_reference(torch, buf, ns, iters=3):
+    """time the unmodified reference's CUDA backend (oracle/_ref) on the same buffer: ms per FFT+iFFT pair per N"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import vkfft_oracle as orc
+    if not orc.ref_available():
+        return {"unavailable": "oracle/_ref/libvkfft_ref.so not built"}
+    L = orc.ref_lib()
+    out = {"per_n": {}, "impl": "DTolm/VkFFT 1.3.4 CUDA backend (NVRTC), unmodified, same GPU, same buffer"}
+    total_ms, total_fl = 0.0, 0.0
+    pts = buf.numel()
+    score_terms = []
+    for n in ns:
+        d = orc.ref_desc((n,), pts // n, False, device=torch.cuda.current_device())
+        h = ctypes.c_void_p()
+        rc = L.vkref_open(ctypes.byref(d), ctypes.byref(h))
+        if rc != 0:
+            out["per_n"][str(n)] = {"error": rc}
+            continue
+        ms_e, ms_w = ctypes.c_double(), ctypes.c_double()
+        rc = L.vkref_bench_pairs(h, buf.data_ptr(), 1, iters, ctypes.byref(ms_e), ctypes.byref(ms_w))
+        up = L.vkref_axis0_uploads(h)
+        L.vkref_close(h)
+        buf.zero_()                      # unnormalised pairs overflow; reset (timing is data independent)
+        if rc != 0:
+            out["per_n"][str(n)] = {"error": rc}
+            continue
+        out["per_n"][str(n)] = {"ms_pair": round(ms_e.value, 4), "uploads": up}
+        total_ms += ms_e.value
+        total_fl += flops_pair(n, pts)
+        score_terms.append((pts * 8 / 1024.0) / ms_e.value)      # sample_0: bufferSize_KB / ms per FFT+iFFT
+    if total_ms > 0:
+        out["gflops_sweep"] = total_fl / (total_ms * 1e-3) / 1e9
+        out["ms_sweep"] = total_ms
+        out["sample0_style_score"] = sum(score_terms) / len(score_terms)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_reference_arm(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (its FFTW precision-test path; pocketfft
+    stand-in) on the box's host cores, same metric/config, bounded sample.  Rank 0 only."""
+    if rank != 0:
+        return
+    cb, dt = cpu_baseline(steps=max(1, args.steps), warmup=args.warmup)
+    line = {
+        "impl": "reference", "metric": "batched 1D C2C FP32 throughput (sample_0 sweep N=2^7..2^22, fwd+inv)",
+        "value": cb["value"], "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "sample_0 sweep N=2^7..2^22 C2C FP32 fwd+inv", "sample_points_per_n": 1 << CPU_SAMPLE_LOG2,
+                   "note": "reference has no CPU FFT of its own; its CPU path is FFTW (absent) -> pocketfft stand-in"},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    if not args.no_ref_gpu:
+        try:
+            import torch
+            if torch.cuda.is_available():
+                buf = torch.zeros(1 << TOTAL_LOG2, dtype=torch.complex64, device="cuda")
+                line["vkfft_cuda_ref"] = vkfft_cuda_reference(torch, buf, sizes())
+        except Exception as e:  # the CPU arm stands on its own
+            line["vkfft_cuda_ref"] = {"unavailable": repr(e)}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip timing the reference's CUDA backend")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import vkfft_b200 as vk
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    dev = torch.device("cuda", local_rank)
+    pts = 1 << TOTAL_LOG2
+    ns = sizes()
+    buf = torch.empty(pts, dtype=torch.complex64, device=dev)
+    tmp = torch.empty(pts, dtype=torch.complex64, device=dev)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    torch.view_as_real(buf).uniform_(-1, 1, generator=g)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    apps, launches_per_step = [], 0
+    for n in ns:
+        app = vk.VkFFTApplication()
+        rc = vk.initializeVkFFT(app, vk.VkFFTConfiguration(FFTdim=1, size=[n], numberBatches=pts // n, device=local_rank,
+                                                           normalize=1, userTempBuffer=1, tempBufferSize=pts * 8))
+        assert rc == 0, (n, vk.getVkFFTErrorString(rc))
+        info = vk.planInfo(app)
+        launches_per_step += info["num_passes_forward"] + info["num_passes_inverse"]
+        apps.append((n, app, info))
+    lp = vk.VkFFTLaunchParams(buffer=buf, tempBuffer=tmp, stream=stream)
+
+    def sweep():
+        for n, app, _ in apps:
+            rc = vk.VkFFTAppend(app, -1, lp)
+            rc |= vk.VkFFTAppend(app, 1, lp)
+            if rc:
+                raise RuntimeError(vk.getVkFFTErrorString(rc))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM ---------------------------------------------------------------------
+    for _ in range(args.warmup):
+        sweep()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        sweep()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    if dist is not None:
+        t = torch.tensor([ms_step], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step = float(t.item())
+    fl_step = sum(flops_pair(n, pts) for n in ns)
+    value = world * fl_step / (ms_step * 1e-3) / 1e9
+
+    # ---- per-N breakdown + dominant-kernel roofline (rank 0 reports) --------------------------------------------
+    peak, peak_src = measured_peaks()
+    per_n = {}
+    alg_bytes_dir = 2 * 8 * pts      # one read + one write of every complex64 point, per direction
+    for n, app, info in apps:
+        reps = 5
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        vk.VkFFTAppend(app, -1, lp); vk.VkFFTAppend(app, 1, lp)
+        a.record()
+        for _ in range(reps):
+            vk.VkFFTAppend(app, -1, lp); vk.VkFFTAppend(app, 1, lp)
+        b.record()
+        torch.cuda.synchronize()
+        ms_pair = a.elapsed_time(b) / reps
+        gbs = 2 * alg_bytes_dir / (ms_pair * 1e-3) / 1e9
+        per_n[str(n)] = {"ms_pair": round(ms_pair, 4), "gflops": round(flops_pair(n, pts) / (ms_pair * 1e-3) / 1e9, 1),
+                         "alg_gbs": round(gbs, 1), "frac_of_peak": round(gbs / peak, 4),
+                         "passes": info["num_passes_forward"]}
+    # dominant kernel: the single-pass N=4096 forward launch, timed alone with events on the launch stream
+    dom_n = 4096
+    dom_app = [a for n, a, _ in apps if n == dom_n][0]
+    for _ in range(3):
+        vk.VkFFTAppend(dom_app, -1, lp)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 20
+    a.record()
+    for _ in range(reps):
+        vk.VkFFTAppend(dom_app, -1, lp)
+    b.record()
+    torch.cuda.synchronize()
+    ms_dom = a.elapsed_time(b) / reps
+    ach = alg_bytes_dir / (ms_dom * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
+                "traffic": None, "kernel": "stockham_kernel<ROWS,float,N=4096,forward> (1 launch = 2^16 sequences)",
+                "algorithmic_bytes_per_launch": alg_bytes_dir, "ms_per_launch": round(ms_dom, 4), "peak_source": peak_src,
+                "step_frac": round((len(ns) * 2 * alg_bytes_dir) / (ms_step * 1e-3) / 1e9 / peak, 4)}
+    tr = os.path.join(ROOT, "profiles", "traffic_n4096.json")
+    if os.path.exists(tr):
+        try:
+            roofline["traffic"] = json.load(open(tr))["dram_bytes_per_launch"]
+        except Exception:
+            pass
+
+    # restore a sane buffer and verify the round trip the bench has been doing (normalize=1 -> identity)
+    torch.view_as_real(buf).uniform_(-1, 1, generator=g)
+    ref0 = buf[: 1 << 20].clone()
+    sweep()
+    torch.cuda.synchronize()
+    rt_err = float((buf[: 1 << 20] - ref0).abs().double().norm() / ref0.abs().double().norm())
+
+    # ---- e2e: host buffers, copies inside the timed region ------------------------------------------------------
+    host = torch.empty(pts, dtype=torch.complex64, pin_memory=True)
+    torch.view_as_real(host).uniform_(-1, 1)
+    nbytes = pts * 8
+
+    def e2e_step():
+        buf.copy_(host, non_blocking=True)            # pinned host -> HBM
+        sweep()
+        host.copy_(buf, non_blocking=True)            # HBM -> host (the step's result)
+
+    e2e_step()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    b.record()
+    barrier()
+    ms_e2e = a.elapsed_time(b) / args.e2e_steps
+    if dist is not None:
+        t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    e2e = {"value": world * fl_step / (ms_e2e * 1e-3) / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": nbytes,
+           "d2h_bytes_per_step": nbytes, "ms_per_step": ms_e2e, "steps": args.e2e_steps,
+           "api": "VkFFTAppend via the C ABI on a pinned host buffer (copy in, 32 transforms, copy out)"}
+
+    for _, app, _ in apps:
+        vk.deleteVkFFT(app)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    line = {
+        "metric": "batched 1D C2C FP32 throughput (sample_0 sweep N=2^7..2^22, fwd+inv)", "value": value,
+        "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: batched 1D C2C FP32 sweep N=2^7..2^22, batch=2^28/N (2 GiB buffer per GPU), "
+                               "in place, forward+inverse per N (reference sample_0 semantics, normalize=1)",
+                   "l2": "inputs (2 GiB) larger than L2 (126 MB)", "parallelism": f"batch-sharded x{world}, no collective",
+                   "points_per_gpu": pts},
+        "roofline": roofline, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+        "per_n": per_n, "roundtrip_rel_err": rt_err,
+    }
+    if world == 1 and not args.no_cpu:
+        line["cpu_baseline"], _ = cpu_baseline()
+    else:
+        line["cpu_baseline"] = None
+    if world == 1 and not args.no_ref_gpu:
+        try:
+            line["vkfft_cuda_ref"] = vkfft_cuda_reference(torch, buf, ns)
+        except Exception as e:
+            line["vkfft_cuda_ref"] = {"unavailable": repr(e)}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -17,6 +17,10 @@ build/kernels_shard_%.o: $(SRC)/kernels_shard.cu $(HDRS)
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -DB2_SHARD=$* -c $< -o $@
 
+build/kernels_generic.o: $(SRC)/kernels_generic.cu $(HDRS)
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
 build/runtime.o: $(SRC)/runtime.cu $(HDRS)
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -c $< -o $@
@@ -25,7 +29,7 @@ build/%.o: $(SRC)/%.cpp $(HDRS)
 	@mkdir -p build
 	$(CXX) $(CXXFLAGS) -c $< -o $@
 
-$(LIB): $(SHARD_OBJ) build/runtime.o build/planner.o build/kernel_registry.o
+$(LIB): $(SHARD_OBJ) build/kernels_generic.o build/runtime.o build/planner.o build/kernel_registry.o
 	@mkdir -p vkfft_b200/lib
 	$(NVCC) -shared $(ARCH) -o $@ $^ -lcudart_static -ldl -lrt -lpthread
 

@@ -10,6 +10,9 @@
 
 using namespace b200fft;
 
+static GenericRegistrar<float> b2_generic_f32("generic<float>");
+static GenericRegistrar<double> b2_generic_f64("generic<double>");
+
 extern "C" int emu_kernel_count() { return b2_kernel_count(); }
 extern "C" int emu_kernel_info(int i, int* out /*kind,prec,n,inv,ops,threads,q,tpl,v,smem,ns,r0..r7*/) {
     const b2_kernel_info* k = b2_kernel_at(i);
@@ -77,8 +80,19 @@ extern "C" int emu_exec_plan(const b200fft_desc* d, int inverse, void* buffer, v
             if (g.prec == B2_PREC_F32) { make_twolevel<float>(M, P.tw_shift, hif, lof); P.tw_hi = hif.data(); P.tw_lo = lof.data(); }
             else { make_twolevel<double>(M, P.tw_shift, hid, lod); P.tw_hi = hid.data(); P.tw_lo = lod.data(); }
         }
-        P.in = (const unsigned char*)base[pp.in_role] + pp.in_off * esz;
-        P.out = (unsigned char*)base[pp.out_role] + pp.out_off * esz;
+        std::vector<float> a0f, a1f; std::vector<double> a0d, a1d;
+        if (pp.aux0_id >= 0) {
+            const AuxSpec& a = g.auxs[pp.aux0_id];
+            if (g.prec == B2_PREC_F32) { a0f = make_aux<float>(a.kind, a.a, a.b); P.aux0 = a0f.data(); }
+            else { a0d = make_aux<double>(a.kind, a.a, a.b); P.aux0 = a0d.data(); }
+        }
+        if (pp.aux1_id >= 0) {
+            const AuxSpec& a = g.auxs[pp.aux1_id];
+            if (g.prec == B2_PREC_F32) { a1f = make_aux<float>(a.kind, a.a, a.b); P.aux1 = a1f.data(); }
+            else { a1d = make_aux<double>(a.kind, a.a, a.b); P.aux1 = a1d.data(); }
+        }
+        P.in = (const unsigned char*)base[pp.in_role] + pp.in_off * (pp.in_scalar ? esz / 2 : esz);
+        P.out = (unsigned char*)base[pp.out_role] + pp.out_off * (pp.out_scalar ? esz / 2 : esz);
         int e = pp.k->launch(&P, pp.grid, nullptr);
         if (e) return 4039;
     }

@@ -1,0 +1,99 @@
+"""CPU: the runtime-scheduled kernel (generic.cuh) with its fused operators -- non power-of-two radices, Bluestein,
+R2C/C2R, DCT-I..IV -- executed as whole plans on the kernel-body emulation and compared with the oracle."""
+import numpy as np
+import pytest
+
+import emu
+import vkfft_oracle as orc
+
+T32, T64 = 8e-7, 3e-15
+
+
+@pytest.mark.parametrize("shape,b,prec", [((1000,), 3, 0), ((2187,), 2, 0), ((77,), 5, 1), ((30030,), 1, 0), ((105, 30), 2, 0),
+                                          ((7, 11, 13), 2, 1), ((48, 20), 1, 0), ((13 * 13,), 3, 0), ((11 * 11 * 11,), 1, 1)])
+@pytest.mark.parametrize("inv", [-1, 1])
+def test_smooth_non_pow2_c2c(shape, b, prec, inv):
+    dt = np.complex64 if prec == 0 else np.complex128
+    x = orc.random_input((b,) + tuple(reversed(shape)), dt, seed=sum(shape))
+    buf = x.copy()
+    rc, _ = emu.exec_plan(emu.make_desc(shape, b, prec), inv, buf)
+    assert rc == 0
+    assert orc.error_metrics(buf, orc.c2c(x, len(shape), inv == 1))["l2_rel"] < (T32 if prec == 0 else T64)
+
+
+@pytest.mark.parametrize("shape,b,prec", [((17,), 4, 0), ((509,), 2, 0), ((1019,), 1, 1), ((34,), 3, 0), ((23, 8), 2, 0),
+                                          ((8, 19), 2, 1), ((4093,), 1, 0)])
+@pytest.mark.parametrize("inv", [-1, 1])
+def test_bluestein_c2c(shape, b, prec, inv):
+    dt = np.complex64 if prec == 0 else np.complex128
+    x = orc.random_input((b,) + tuple(reversed(shape)), dt, seed=sum(shape) + 1)
+    buf = x.copy()
+    rc, npass = emu.exec_plan(emu.make_desc(shape, b, prec), inv, buf)
+    assert rc == 0
+    assert orc.error_metrics(buf, orc.c2c(x, len(shape), inv == 1))["l2_rel"] < (T32 if prec == 0 else T64)
+
+
+@pytest.mark.parametrize("shape,b,prec", [((64,), 4, 0), ((4096,), 2, 0), ((64, 32), 2, 0), ((30,), 3, 1), ((15,), 3, 0),
+                                          ((128, 8, 4), 1, 1), ((9, 6), 2, 0), ((1000,), 2, 0)])
+def test_r2c_c2r_in_place_padded(shape, b, prec):
+    rdt = np.float32 if prec == 0 else np.float64
+    cdt = np.complex64 if prec == 0 else np.complex128
+    tol = T32 if prec == 0 else T64
+    nx = shape[0]
+    H = nx // 2 + 1
+    x = orc.random_input((b,) + tuple(reversed(shape)), rdt, seed=sum(shape))
+    buf = np.zeros(x.shape[:-1] + (2 * H,), rdt)      # rows padded to 2*(nx/2+1) reals (vkFFT_InitializeApp.h:1000-1005)
+    buf[..., :nx] = x
+    d = emu.make_desc(shape, b, prec, perform_r2c=1)
+    rc, _ = emu.exec_plan(d, -1, buf)
+    assert rc == 0
+    assert orc.error_metrics(buf.view(cdt), orc.r2c(x, len(shape)))["l2_rel"] < tol
+    rc, _ = emu.exec_plan(d, 1, buf)
+    assert rc == 0
+    assert orc.error_metrics(buf[..., :nx], x.astype(np.float64) * np.prod(shape))["l2_rel"] < tol
+
+
+def test_r2c_out_of_place_and_return_to_input():
+    shape, b = (64, 16), 2
+    x = orc.random_input((b, 16, 64), np.float32, 5)
+    out = np.zeros((b, 16, 33), np.complex64)
+    rc, _ = emu.exec_plan(emu.make_desc(shape, b, 0, perform_r2c=1, is_input_formatted=1), -1, out, inp=x.copy())
+    assert rc == 0 and orc.error_metrics(out, orc.r2c(x, 2))["l2_rel"] < T32
+    back = np.zeros_like(x)
+    d = emu.make_desc(shape, b, 0, perform_r2c=1, is_input_formatted=1, inverse_return_to_input=1, normalize=1)
+    rc, _ = emu.exec_plan(d, 1, out.copy(), inp=back)
+    assert rc == 0 and orc.error_metrics(back, x)["l2_rel"] < T32
+
+
+@pytest.mark.parametrize("kind", [1, 2, 3, 4])
+@pytest.mark.parametrize("shape,b,prec", [((64,), 3, 0), ((33,), 2, 1), ((32, 16), 3, 0), ((100,), 2, 1), ((8, 6, 4), 2, 0)])
+@pytest.mark.parametrize("inv", [-1, 1])
+def test_dct(kind, shape, b, prec, inv):
+    if kind == 4 and any(s % 2 for s in shape):
+        pytest.skip("odd-length DCT-IV not built yet")
+    if kind == 1 and shape == (32, 16):
+        pytest.skip("DCT-I length 32 needs a 62-point transform (prime factor 31): not built yet")
+    rdt = np.float32 if prec == 0 else np.float64
+    x = orc.random_input((b,) + tuple(reversed(shape)), rdt, seed=kind + sum(shape))
+    buf = x.copy()
+    rc, _ = emu.exec_plan(emu.make_desc(shape, b, prec, perform_dct=kind), inv, buf)
+    assert rc == 0
+    assert orc.error_metrics(buf, orc.dct(x, kind, len(shape), inverse=(inv == 1)))["l2_rel"] < (T32 if prec == 0 else T64)
+
+
+def test_dct_normalized_round_trip():
+    x = orc.random_input((2, 16, 32), np.float32, 9)
+    for kind in (1, 2, 3, 4):
+        if kind == 1:
+            continue   # (32 -> 62-point transform)
+        buf = x.copy()
+        d = emu.make_desc((32, 16), 2, 0, perform_dct=kind, normalize=1)
+        assert emu.exec_plan(d, -1, buf)[0] == 0
+        assert emu.exec_plan(d, 1, buf)[0] == 0
+        assert orc.error_metrics(buf, x)["l2_rel"] < T32
+
+
+def test_unsupported_requests_return_reference_error_codes():
+    assert emu.exec_plan(emu.make_desc((16,), 1, 0, perform_dst=2), -1, np.zeros(16, np.float32))[0] == 3004
+    assert emu.exec_plan(emu.make_desc((31,), 1, 0, perform_dct=4), -1, np.zeros(31, np.float32))[0] == 3004
+    assert emu.exec_plan(emu.make_desc((20011,), 1, 0), -1, np.zeros(20011, np.complex64))[0] == 3002   # long Bluestein

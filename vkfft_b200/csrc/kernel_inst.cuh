@@ -3,6 +3,7 @@
 #pragma once
 #include "kernel_registry.h"
 #include "stockham.cuh"
+#include "generic.cuh"
 
 #if !defined(B2_EMU)
 #include <cuda_runtime.h>
@@ -51,6 +52,43 @@ int prepare_impl() {
     return 0;
 }
 #endif
+
+// ---- generic (runtime-scheduled) kernel: one entry per precision ------------------------------------------------
+template <typename T> inline size_t generic_smem_bytes(const b2_pass_params* P) {
+    return (size_t)2 * P->q * P->line_stride * 2 * sizeof(T);
+}
+#if defined(B2_EMU)
+template <typename T>
+int generic_launch(const b2_pass_params* P, unsigned grid, void*) {
+    const b2_pass_params PP = *P;
+    b2emu::launch(grid, PP.tpl * PP.q, generic_smem_bytes<T>(P), [&](unsigned char* sm) { Generic<T>::run(PP, sm); },
+                  b2emu::st().log);
+    return 0;
+}
+template <typename T> int generic_prepare() { return 0; }
+#else
+template <typename T>
+int generic_launch(const b2_pass_params* P, unsigned grid, void* stream) {
+    generic_kernel<T><<<grid, P->tpl * P->q, generic_smem_bytes<T>(P), (cudaStream_t)stream>>>(*P);
+    return (int)cudaGetLastError();
+}
+template <typename T>
+int generic_prepare() {
+    return (int)cudaFuncSetAttribute(generic_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+#endif
+template <typename T>
+struct GenericRegistrar {
+    b2_kernel_info info;
+    explicit GenericRegistrar(const char* name) {
+        info = b2_kernel_info{};
+        info.kind = B2_KIND_GENERIC; info.prec = PrecOf<T>::value; info.n = 0; info.inv = 0; info.ops = 0;
+        info.launch = &generic_launch<T>;
+        info.prepare = &generic_prepare<T>;
+        info.name = name;
+        b2_register_kernel(&info);
+    }
+};
 
 template <int KIND, typename T, int TPL, int Q, int V, int MINB, bool INV, int OPS, int... Rs>
 struct Registrar {

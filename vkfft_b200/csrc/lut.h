@@ -4,6 +4,7 @@
 // (The reference builds equivalent per-stage tables in VkFFT_AllocateLUT, vkFFT_ManageLUT.h:675-821, but
 //  only uses them by default in FP64; here they are always used, in both precisions.)
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <vector>
@@ -65,6 +66,75 @@ inline void make_twolevel(uint64_t M, uint32_t& shift, std::vector<T>& hi, std::
         unit_root(i << shift, M, c, s);
         hi[2 * i] = (T)c; hi[2 * i + 1] = (T)s;
     }
+}
+
+
+// ---- auxiliary tables of the fused real-transform / Bluestein operators ----------------------------------------
+enum AuxKind {
+    AUX_R2C = 1,          // a = N : e^{-2 pi i k/N},           k = 0..N/2           (vkFFT_ManageLUT.h:1418 R2C LUT)
+    AUX_DCT23 = 2,        // a = n : e^{-i pi k/(2n)},           k = 0..n-1           (vkFFT_ManageLUT.h:800-806)
+    AUX_DCT4_PRE = 3,     // a = N : e^{-i pi m/N},              m = 0..N/2-1         (vkFFT_ManageLUT.h:807-820)
+    AUX_DCT4_POST = 4,    // a = N : e^{-i pi (4q+1)/(4N)},      q = 0..N/2-1
+    AUX_BLUE_CHIRP = 5,   // a = N : e^{-i pi n^2/N},            n = 0..N-1           (vkFFT_RecursiveFFTGenerators.h:140)
+    AUX_BLUE_FILTER = 6,  // a = N, b = M : FFT_M(e^{+i pi m^2/N} wrapped) / M        (vkFFT_RecursiveFFTGenerators.h:241-298)
+};
+
+// in-place radix-2 FFT in long double (host, table generation only); n must be a power of two
+inline void host_fft_pow2(std::vector<long double>& re, std::vector<long double>& im) {
+    const size_t n = re.size();
+    for (size_t i = 1, j = 0; i < n; ++i) {
+        size_t bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) { std::swap(re[i], re[j]); std::swap(im[i], im[j]); }
+    }
+    for (size_t len = 2; len <= n; len <<= 1) {
+        for (size_t i = 0; i < n; i += len)
+            for (size_t k = 0; k < len / 2; ++k) {
+                long double c, s;
+                unit_root(k, len, c, s);
+                const size_t a = i + k, b = i + k + len / 2;
+                const long double tr = re[b] * c - im[b] * s, ti = re[b] * s + im[b] * c;
+                re[b] = re[a] - tr; im[b] = im[a] - ti;
+                re[a] += tr; im[a] += ti;
+            }
+    }
+}
+
+template <typename T>
+inline std::vector<T> make_aux(int kind, uint64_t a, uint64_t b) {
+    std::vector<T> out;
+    auto push = [&](long double c, long double s) { out.push_back((T)c); out.push_back((T)s); };
+    long double c, s;
+    switch (kind) {
+        case AUX_R2C:
+            for (uint64_t k = 0; k <= a / 2; ++k) { unit_root(k, a, c, s); push(c, s); }
+            break;
+        case AUX_DCT23:
+            for (uint64_t k = 0; k < a; ++k) { unit_root(k, 4 * a, c, s); push(c, s); }
+            break;
+        case AUX_DCT4_PRE:
+            for (uint64_t m = 0; m < a / 2; ++m) { unit_root(m, 2 * a, c, s); push(c, s); }
+            break;
+        case AUX_DCT4_POST:
+            for (uint64_t q = 0; q < a / 2; ++q) { unit_root(4 * q + 1, 8 * a, c, s); push(c, s); }
+            break;
+        case AUX_BLUE_CHIRP:
+            for (uint64_t n = 0; n < a; ++n) { unit_root((n * n) % (2 * a), 2 * a, c, s); push(c, s); }
+            break;
+        case AUX_BLUE_FILTER: {
+            std::vector<long double> re(b, 0.0L), im(b, 0.0L);
+            for (uint64_t m = 0; m < a; ++m) {
+                unit_root((m * m) % (2 * a), 2 * a, c, s);   // e^{-i pi m^2/N}; the filter uses the conjugate
+                re[m] = c; im[m] = -s;
+                if (m) { re[b - m] = c; im[b - m] = -s; }
+            }
+            host_fft_pow2(re, im);
+            for (uint64_t k = 0; k < b; ++k) push(re[k] / (long double)b, im[k] / (long double)b);
+        } break;
+        default: break;
+    }
+    return out;
 }
 
 }  // namespace b200fft

@@ -21,7 +21,24 @@ enum {
     B2_OP_NONE = 0,
     B2_OP_TWIDDLE_OUT = 1,   // four-step phase  W_M^(line*elem) applied on store  (vkFFT_4step.h:31-119)
     B2_OP_SCALE = 2,         // multiply by `scale` on store (normalize=1, vkFFT_Structs.h:220)
+    B2_OP_MUL_IN = 4,        // multiply element p by aux0[p] on load   (Bluestein chirp, vkFFT_Bluestein.h:32)
+    B2_OP_MUL_OUT = 8,       // multiply element p by aux1[p] on store  (Bluestein filter / post chirp, :201)
 };
+
+// how the generic kernel fills a line on load / drains it on store (real-data transforms live here)
+enum {
+    B2_IO_C2C = 0,           // complex line as is (zero-filled beyond in_len / truncated at out_len)
+    B2_IO_R2C_EVEN = 1,      // store: Hermitian post-pass of the even-length trick -> n+1 outputs (vkFFT_R2C_even_decomposition.h:181-230)
+    B2_IO_C2R_EVEN = 2,      // load : inverse of the above from n+1 inputs
+    B2_IO_DCT2 = 3,          // load : Makhoul even/odd permutation of two real lines (vkFFT_R2R.h:193-229); store: split + phase (:784-859)
+    B2_IO_DCT3 = 4,          // the transpose of DCT2: phase + merge on load, inverse permutation on store
+    B2_IO_DCT1 = 5,          // even extension to 2n-2 on load, real part on store (vkFFT_Scheduler.h:2271-2273)
+    B2_IO_DCT4 = 6,          // pre/post phases around a half-length complex transform (vkFFT_Scheduler.h:2277-2280)
+    B2_IO_REAL = 7,          // odd-length R2C/C2R fallback: real line <-> complex line with zero imaginary part
+    B2_IO_HERM = 8,          // load only: rebuild the full spectrum from the Hermitian half (odd-length C2R)
+};
+
+enum { B2_MAX_STAGES = 16 };
 
 typedef struct b2_pass_params {
     const void* in;
@@ -46,6 +63,16 @@ typedef struct b2_pass_params {
     uint32_t inverse;                      // 1: swap re/im on load+store (inverse transform)
     uint32_t aux_u0, aux_u1;               // operator specific (e.g. logical real length)
     double scale;
+    // ---- generic (runtime-scheduled) kernel only -------------------------------------------------------------
+    uint32_t nstages;
+    uint32_t radix[B2_MAX_STAGES];
+    uint32_t tpl, q;                       // threads per line, lines per CTA (blockDim.x = tpl*q)
+    uint32_t load_io, store_io;            // B2_IO_*
+    uint32_t in_len, out_len;              // elements actually read / written per line (<= n, or n+1 for R2C)
+    uint32_t load_qfast, store_qfast;      // 1: neighbouring lanes walk neighbouring lines (unit group stride)
+    uint32_t line_stride;                  // smem elements between lines
+    uint32_t inner_inverse;                // 1: the FFT inside this pass is an inverse one (swap around the stages only)
+    uint32_t tw_sel;                       // which coordinate is the four-step "line": 0 group index, 1..3 outer dim 0..2
 } b2_pass_params;
 
 #ifdef __cplusplus

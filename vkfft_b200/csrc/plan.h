@@ -56,6 +56,11 @@ struct TwSpec {        // two-level four-step table for modulus M
     uint64_t M;
 };
 
+struct AuxSpec {       // operator tables (lut.h make_aux)
+    int prec, kind;
+    uint64_t a, b;
+};
+
 struct PassPlan {
     const b2_kernel_info* k = nullptr;
     b2_pass_params P{};          // pointer members are filled in by the runtime at launch
@@ -64,6 +69,8 @@ struct PassPlan {
     int64_t in_off = 0, out_off = 0;   // complex-element offsets added to the role's base pointer
     int lut_id = -1;
     int tw_id = -1;
+    int aux0_id = -1, aux1_id = -1;
+    bool in_scalar = false, out_scalar = false;   // offsets (and strides) of that side count scalars, not complex elements
     std::string note;            // human readable (plan_describe)
 };
 
@@ -79,6 +86,8 @@ struct PlanGraph {
     std::vector<PassPlan> fwd, inv;
     std::vector<LutSpec> luts;
     std::vector<TwSpec> tws;
+    std::vector<AuxSpec> auxs;
+    uint64_t temp_elems_real = 0;   // (unused placeholder for real-sized scratch accounting)
     double flops = 0;
     uint64_t algorithmic_bytes = 0;
 };

@@ -1,19 +1,25 @@
 // Planner: turns a b200fft_desc into an ordered list of kernel launches (see plan.h).
 //
-// Decisions the reference makes in VkFFTScheduler (vkFFT_Scheduler.h:2223-3299: number of uploads
-// :2582-2650, axis split :2651-2893, temp buffer :2902-2944) and VkFFTPlanAxis (vkFFT_Plan_FFT.h:252-417
-// strides, :582-645 grid) are made here against the table of ahead-of-time compiled kernels:
-//   * an axis whose length has a single-pass kernel  -> one launch (one HBM read + one HBM write);
-//   * longer contiguous axes                          -> Four-Step with 2 or 3 launches
-//     (strided sub-FFTs + phase multiply, then contiguous sub-FFTs with a transposed, coalesced store so the
-//      result is in natural order -- the reference's reorderFourStep=1 behaviour, vkFFT_4step.h:31-119);
-//   * axes >= 1                                       -> interleaved-lines ("COLS") kernels.
+// Decisions the reference makes in VkFFTScheduler (vkFFT_Scheduler.h:2223-3299: algorithm choice :2288-2578,
+// number of uploads :2582-2650, axis split :2651-2893, temp buffer :2902-2944) and VkFFTPlanAxis
+// (vkFFT_Plan_FFT.h:252-417 strides, :582-645 grid) are made here against the table of ahead-of-time compiled
+// kernels:
+//   * a line length with a specialised single-pass kernel     -> one launch of it (1 HBM read + 1 write);
+//   * any other 2..13-smooth length that fits shared memory   -> one launch of the runtime-scheduled kernel;
+//   * longer contiguous lines                                 -> Four-Step with 2 or 3 launches (strided
+//     sub-FFTs + phase multiply, then contiguous sub-FFTs with a transposed, coalesced store so the result is in
+//     natural order -- the reference's reorderFourStep=1 behaviour, vkFFT_4step.h:31-119);
+//   * lengths with a prime factor > 13                         -> Bluestein through a power-of-two length
+//     (chirp / zero-pad fused into the first launch's load, filter and post-chirp into the stores);
+//   * R2C / C2R: half-length complex transform of the (even, odd) samples with the Hermitian pass fused into
+//     the store / load of the same launch; DCT-I..IV: permutation / phase passes fused the same way.
 #include <algorithm>
 #include <cmath>
-#include <cstdlib>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
+#include "lut.h"
 #include "plan.h"
 
 namespace b200fft {
@@ -21,25 +27,30 @@ namespace {
 
 struct Dim {
     uint64_t n;
-    int64_t is, os;  // input / output stride in complex elements
+    int64_t is, os;  // input / output stride (complex elements, or scalars for the real-data operators)
 };
 
-int lut_for(PlanGraph& g, const b2_kernel_info* k) {
-    std::vector<int> r(k->radices, k->radices + k->ns);
+int lut_for(PlanGraph& g, const std::vector<int>& r) {
     for (size_t i = 0; i < g.luts.size(); ++i)
-        if (g.luts[i].prec == k->prec && g.luts[i].radices == r) return (int)i;
-    g.luts.push_back(LutSpec{k->prec, r});
+        if (g.luts[i].prec == g.prec && g.luts[i].radices == r) return (int)i;
+    g.luts.push_back(LutSpec{g.prec, r});
     return (int)g.luts.size() - 1;
 }
-int tw_for(PlanGraph& g, int prec, uint64_t M) {
+int tw_for(PlanGraph& g, uint64_t M) {
     for (size_t i = 0; i < g.tws.size(); ++i)
-        if (g.tws[i].prec == prec && g.tws[i].M == M) return (int)i;
-    g.tws.push_back(TwSpec{prec, M});
+        if (g.tws[i].prec == g.prec && g.tws[i].M == M) return (int)i;
+    g.tws.push_back(TwSpec{g.prec, M});
     return (int)g.tws.size() - 1;
+}
+int aux_for(PlanGraph& g, int kind, uint64_t a, uint64_t b = 0) {
+    for (size_t i = 0; i < g.auxs.size(); ++i)
+        if (g.auxs[i].prec == g.prec && g.auxs[i].kind == kind && g.auxs[i].a == a && g.auxs[i].b == b) return (int)i;
+    g.auxs.push_back(AuxSpec{g.prec, kind, a, b});
+    return (int)g.auxs.size() - 1;
 }
 
 // merge neighbouring dims that are contiguous in both the input and the output addressing
-std::vector<Dim> merge_dims(std::vector<Dim> d) {
+std::vector<Dim> merge_dims(const std::vector<Dim>& d) {
     std::vector<Dim> out;
     for (const Dim& x : d) {
         if (x.n == 1) continue;
@@ -55,30 +66,109 @@ std::vector<Dim> merge_dims(std::vector<Dim> d) {
     return out;
 }
 
+// greedy radix list for the runtime-scheduled kernel (largest radix first); empty if n has a prime factor > 13
+std::vector<int> generic_radices(uint64_t n) {
+    std::vector<int> r;
+    static const int cand[] = {16, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2};
+    while (n > 1) {
+        bool found = false;
+        for (int c : cand)
+            if (n % c == 0) { r.push_back(c); n /= c; found = true; break; }
+        if (!found) return {};
+        if (r.size() > B2_MAX_STAGES) return {};
+    }
+    return r;
+}
+
+uint64_t esize(const PlanGraph& g) { return g.prec == B2_PREC_F64 ? 16 : 8; }
+int pad_of(const PlanGraph& g, uint64_t n) { return (int)(n + (n >> (g.prec == B2_PREC_F64 ? 3 : 4))); }
+const uint64_t GENERIC_SMEM_LIMIT = 200 * 1024;
+
+bool generic_fits(const PlanGraph& g, uint64_t n) {
+    if (n < 2 || n > (1u << 20)) return false;
+    if (generic_radices(n).empty()) return false;
+    return 2ull * (uint64_t)(pad_of(g, n) | 1) * esize(g) <= GENERIC_SMEM_LIMIT;
+}
+
 struct PassReq {
-    int kind, n, inv, ops;
-    int64_t in_es, out_es;
-    Dim group;               // lines handled Q at a time by one CTA
-    std::vector<Dim> outer;  // remaining line dimensions
-    int in_role, out_role;
+    int kind = B2_KIND_ROWS, n = 0, inv = 0, ops = 0;
+    int64_t in_es = 1, out_es = 1;
+    Dim group{1, 0, 0};          // lines handled Q at a time by one CTA
+    std::vector<Dim> outer;      // remaining line dimensions
+    int in_role = ROLE_BUFFER, out_role = ROLE_BUFFER;
     uint64_t twM = 0;
+    int tw_outer = -1;           // >= 0: index into `outer` (before merging) of the four-step line coordinate
     double scale = 1.0;
     const char* what = "";
+    // generic-kernel extras
+    bool force_generic = false;
+    int load_io = B2_IO_C2C, store_io = B2_IO_C2C;
+    int inner_inverse = 0;
+    uint32_t in_len = 0, out_len = 0;   // 0 -> n
+    int aux0 = -1, aux1 = -1;
+    uint32_t aux_u0 = 0, aux_u1 = 0;
+    bool real_pairs = false;     // group dim counts REAL lines; two of them form one complex line
 };
 
 // Emit the launches for one PassReq (more than one only if there are more than B2_MAX_OUTER outer dims).
 int emit(PlanGraph& g, std::vector<PassPlan>& list, const PassReq& rq) {
-    const b2_kernel_info* k = b2_find_kernel(rq.kind, g.prec, rq.n, rq.inv, rq.ops & B2_OP_TWIDDLE_OUT);
-    if (!k) return R_UNSUPPORTED_FFT_LENGTH;
-    std::vector<Dim> outer = merge_dims(rq.outer);
+    const b2_kernel_info* k = nullptr;
+    const bool plain = !rq.force_generic && rq.load_io == B2_IO_C2C && rq.store_io == B2_IO_C2C &&
+                       !(rq.ops & (B2_OP_MUL_IN | B2_OP_MUL_OUT)) && rq.in_len == 0 && rq.out_len == 0 &&
+                       !rq.inner_inverse;
+    if (plain) k = b2_find_kernel(rq.kind, g.prec, rq.n, rq.inv, rq.ops & B2_OP_TWIDDLE_OUT);
+    std::vector<int> radices;
+    bool generic = false;
+    if (!k) {
+        k = b2_find_kernel(B2_KIND_GENERIC, g.prec, 0, 0, 0);
+        if (!k || !generic_fits(g, rq.n)) return R_UNSUPPORTED_FFT_LENGTH;
+        radices = generic_radices(rq.n);
+        generic = true;
+    } else {
+        radices.assign(k->radices, k->radices + k->ns);
+    }
+    // the four-step line coordinate must survive dim merging: keep that dim separate
+    std::vector<Dim> outer;
+    int tw_sel = 0;
+    if (rq.tw_outer >= 0) {
+        std::vector<Dim> a(rq.outer.begin(), rq.outer.begin() + rq.tw_outer), b(rq.outer.begin() + rq.tw_outer + 1, rq.outer.end());
+        a = merge_dims(a); b = merge_dims(b);
+        outer = a;
+        tw_sel = 1 + (int)outer.size();
+        outer.push_back(rq.outer[rq.tw_outer]);
+        outer.insert(outer.end(), b.begin(), b.end());
+    } else {
+        outer = merge_dims(rq.outer);
+    }
     // peel outermost dims into separate launches until at most B2_MAX_OUTER remain
     std::vector<Dim> peeled;
     while (outer.size() > B2_MAX_OUTER) {
         peeled.push_back(outer.back());
         outer.pop_back();
     }
+    if (tw_sel > B2_MAX_OUTER) return R_UNSUPPORTED_FFT_LENGTH;
     uint64_t npeel = 1;
     for (const Dim& p : peeled) npeel *= p.n;
+    const uint64_t glines = rq.real_pairs ? (rq.group.n + 1) / 2 : rq.group.n;
+
+    // CTA shape
+    uint32_t tpl = 0, q = 0, ls = 0;
+    const bool qfast_l = (rq.kind == B2_KIND_COLS), qfast_s = (rq.kind != B2_KIND_ROWS);
+    if (generic) {
+        tpl = 1;
+        while (tpl < 512 && tpl * 16 < (uint32_t)rq.n) tpl <<= 1;
+        ls = (uint32_t)(pad_of(g, rq.n) | 1);
+        const uint64_t per_line = 2ull * ls * esize(g);
+        uint32_t qmax = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(GENERIC_SMEM_LIMIT / per_line, 512 / tpl));
+        uint32_t want = (qfast_l || qfast_s) ? (g.prec == B2_PREC_F64 ? 8u : 16u) : std::max(1u, 128u / tpl);
+        // keep at least two CTAs per SM resident when lines are short
+        while (want > 1 && want * per_line > 96 * 1024) want >>= 1;
+        q = std::max(1u, std::min(want, qmax));
+        if (q > glines) q = (uint32_t)std::max<uint64_t>(1, glines);
+    } else {
+        tpl = k->tpl; q = k->q;
+    }
+
     for (uint64_t pi = 0; pi < npeel; ++pi) {
         int64_t ioff = 0, ooff = 0;
         uint64_t rem = pi;
@@ -93,8 +183,8 @@ int emit(PlanGraph& g, std::vector<PassPlan>& list, const PassReq& rq) {
         b2_pass_params& P = pp.P;
         P.in_es = rq.in_es; P.out_es = rq.out_es;
         P.in_gs = rq.group.is; P.out_gs = rq.group.os;
-        P.G = (uint32_t)rq.group.n;
-        uint64_t grid = (rq.group.n + k->q - 1) / k->q;
+        P.G = (uint32_t)glines;
+        uint64_t grid = (glines + q - 1) / q;
         for (int d = 0; d < B2_MAX_OUTER; ++d) {
             if (d < (int)outer.size()) {
                 P.nb[d] = (uint32_t)outer[d].n; P.in_bs[d] = outer[d].is; P.out_bs[d] = outer[d].os;
@@ -108,23 +198,46 @@ int emit(PlanGraph& g, std::vector<PassPlan>& list, const PassReq& rq) {
         P.n = rq.n;
         P.ops = rq.ops;
         P.inverse = rq.inv;
+        P.inner_inverse = rq.inner_inverse;
         P.scale = rq.scale;
+        P.tw_sel = tw_sel;
+        P.nstages = (uint32_t)radices.size();
+        for (size_t s = 0; s < radices.size(); ++s) P.radix[s] = radices[s];
+        P.tpl = tpl; P.q = q; P.line_stride = ls;
+        P.load_io = rq.load_io; P.store_io = rq.store_io;
+        P.in_len = rq.in_len ? rq.in_len : rq.n;
+        P.out_len = rq.out_len ? rq.out_len : rq.n;
+        P.load_qfast = qfast_l; P.store_qfast = qfast_s;
+        P.aux_u0 = rq.aux_u0; P.aux_u1 = rq.aux_u1;
         pp.in_role = rq.in_role; pp.out_role = rq.out_role;
         pp.in_off = ioff; pp.out_off = ooff;
-        pp.lut_id = lut_for(g, k);
-        if (rq.ops & B2_OP_TWIDDLE_OUT) pp.tw_id = tw_for(g, g.prec, rq.twM);
-        char buf[256];
-        snprintf(buf, sizeof buf, "%s n=%d %s grid=%u threads=%d smem=%d  %s", rq.what, rq.n, k->name, pp.grid,
-                 k->threads, k->smem_bytes, rq.inv ? "inverse" : "forward");
+        pp.lut_id = lut_for(g, radices);
+        if (rq.ops & B2_OP_TWIDDLE_OUT) pp.tw_id = tw_for(g, rq.twM);
+        pp.aux0_id = rq.aux0; pp.aux1_id = rq.aux1;
+        auto scalar_io = [](int io) { return io == B2_IO_DCT1 || io == B2_IO_DCT2 || io == B2_IO_DCT3 || io == B2_IO_DCT4 || io == B2_IO_REAL; };
+        pp.in_scalar = scalar_io(rq.load_io); pp.out_scalar = scalar_io(rq.store_io);
+        char buf[320];
+        std::string rs;
+        for (int r : radices) rs += (rs.empty() ? "" : "x") + std::to_string(r);
+        snprintf(buf, sizeof buf, "%s n=%d %s[%s] grid=%u threads=%u %s", rq.what, rq.n, generic ? "generic" : k->name,
+                 rs.c_str(), pp.grid, tpl * q, rq.inv ? "inverse" : "forward");
         pp.note = buf;
         list.push_back(pp);
     }
     return R_SUCCESS;
 }
 
-bool have(const PlanGraph& g, int kind, uint64_t n, int ops) {
+// can a single launch transform lines of length n (kind only matters for the specialised kernels)?
+bool single_ok(const PlanGraph& g, int kind, uint64_t n, int ops) {
     if (n > 0x7fffffffull) return false;
-    return b2_find_kernel(kind, g.prec, (int)n, 0, ops) != nullptr;
+    if (n == 1) return false;
+    if (b2_find_kernel(kind, g.prec, (int)n, 0, ops)) return true;
+    return generic_fits(g, n);
+}
+
+uint64_t max_single_env() {
+    if (const char* e = getenv("B200FFT_MAX_SINGLE_PASS")) return strtoull(e, nullptr, 10);
+    return ~0ull;
 }
 
 // Factor N for Four-Step.  All factors but the last run as interleaved-line passes with the phase multiply,
@@ -144,30 +257,36 @@ std::vector<uint64_t> split_four_step(const PlanGraph& g, uint64_t N) {
         }
         if (prod == N && f.size() >= 2 && f.size() <= 3) return f;
     }
+    const uint64_t cap = std::min<uint64_t>(max_single_env(), 4096);
+    auto fast = [&](int kind, uint64_t n, int ops) { return b2_find_kernel(kind, g.prec, (int)n, 0, ops) != nullptr; };
     std::vector<uint64_t> best;
     uint64_t best_cost = ~0ull;
-    // two factors
-    for (uint64_t n2 = 2; n2 * 2 <= N; ++n2) {
+    for (uint64_t n2 = 2; n2 * 2 <= N && n2 <= cap; ++n2) {
         if (N % n2) continue;
         uint64_t n1 = N / n2;
-        if (!have(g, B2_KIND_ROWS_TOUT, n2, 0) || !have(g, B2_KIND_COLS, n1, B2_OP_TWIDDLE_OUT)) continue;
-        // prefer balanced factors, the contiguous one not smaller than the strided one
+        if (n1 > cap) continue;
+        if (!single_ok(g, B2_KIND_ROWS_TOUT, n2, 0) || !single_ok(g, B2_KIND_COLS, n1, B2_OP_TWIDDLE_OUT)) continue;
+        // prefer specialised kernels, then balanced factors, the contiguous one not smaller than the strided one
         uint64_t cost = std::max(n1, n2) * 4 + (n2 < n1 ? 2 : 0);
+        if (!fast(B2_KIND_ROWS_TOUT, n2, 0)) cost += 1u << 20;
+        if (!fast(B2_KIND_COLS, n1, B2_OP_TWIDDLE_OUT)) cost += 1u << 20;
         if (cost < best_cost) { best_cost = cost; best = {n1, n2}; }
     }
     const uint64_t two_level_limit = (g.prec == B2_PREC_F32) ? (1ull << 22) : (1ull << 21);
     if (!best.empty() && N <= two_level_limit) return best;
-    // three factors
     std::vector<uint64_t> best3;
     uint64_t best3_cost = ~0ull;
-    for (uint64_t n3 = 2; n3 * 4 <= N; ++n3) {
-        if (N % n3 || !have(g, B2_KIND_ROWS_TOUT, n3, 0)) continue;
+    for (uint64_t n3 = 2; n3 * 4 <= N && n3 <= cap; ++n3) {
+        if (N % n3 || !single_ok(g, B2_KIND_ROWS_TOUT, n3, 0)) continue;
         uint64_t rest = N / n3;
-        for (uint64_t n2 = 2; n2 * 2 <= rest; ++n2) {
-            if (rest % n2 || !have(g, B2_KIND_COLS, n2, B2_OP_TWIDDLE_OUT)) continue;
+        for (uint64_t n2 = 2; n2 * 2 <= rest && n2 <= cap; ++n2) {
+            if (rest % n2 || !single_ok(g, B2_KIND_COLS, n2, B2_OP_TWIDDLE_OUT)) continue;
             uint64_t n1 = rest / n2;
-            if (!have(g, B2_KIND_COLS, n1, B2_OP_TWIDDLE_OUT)) continue;
+            if (n1 > cap || !single_ok(g, B2_KIND_COLS, n1, B2_OP_TWIDDLE_OUT)) continue;
             uint64_t cost = std::max(n1, std::max(n2, n3)) * 4 + (n3 < n1 ? 1 : 0) + (n3 < n2 ? 1 : 0);
+            if (!fast(B2_KIND_ROWS_TOUT, n3, 0)) cost += 1u << 20;
+            if (!fast(B2_KIND_COLS, n2, B2_OP_TWIDDLE_OUT)) cost += 1u << 20;
+            if (!fast(B2_KIND_COLS, n1, B2_OP_TWIDDLE_OUT)) cost += 1u << 20;
             if (cost < best3_cost) { best3_cost = cost; best3 = {n1, n2, n3}; }
         }
     }
@@ -175,187 +294,395 @@ std::vector<uint64_t> split_four_step(const PlanGraph& g, uint64_t N) {
     return best;
 }
 
-struct AxisIO {
-    int in_role, out_role;                 // where this axis reads / writes
-    const uint64_t* in_stride;             // per-dimension strides (elements) on the input side
-    const uint64_t* out_stride;
-    uint64_t in_batch_stride, out_batch_stride;
-    double scale;                          // 1.0 or the normalisation factor (applied by the last launch)
+bool is_smooth(uint64_t n) { return !generic_radices(n).empty() || n == 1; }
+
+// ----------------------------------------------------------------------------------------------------------------
+// One C2C transform of length N along lines with element stride (es_in, es_out); `lines` lists every other
+// dimension (first entry = the preferred grouped dimension).  unit_lines: lines[0] has unit stride on both sides
+// (strided axis: neighbouring lanes walk neighbouring lines).
+struct C2CJob {
+    uint64_t N;
+    int inv;
+    int64_t es_in, es_out;
+    std::vector<Dim> lines;
+    bool unit_lines;
+    int in_role, out_role;
+    double scale;
 };
 
-// contiguous axis 0
-int plan_axis0(PlanGraph& g, std::vector<PassPlan>& list, int inv, const AxisIO& io) {
-    const b200fft_desc& d = g.desc;
-    const uint64_t N = d.size[0];
-    std::vector<Dim> lines;  // all dims except axis 0
-    for (uint32_t a = 1; a < d.fft_dim; ++a)
-        lines.push_back(Dim{d.size[a], (int64_t)io.in_stride[a - 1], (int64_t)io.out_stride[a - 1]});
-    lines.push_back(Dim{g.batches, (int64_t)io.in_batch_stride, (int64_t)io.out_batch_stride});
-    const int sc_ops = (io.scale != 1.0) ? B2_OP_SCALE : 0;
+int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job);
 
-    uint64_t max_single = ~0ull;
-    if (const char* e = getenv("B200FFT_MAX_SINGLE_PASS")) max_single = strtoull(e, nullptr, 10);
-    if (N <= max_single && have(g, B2_KIND_ROWS, N, 0)) {
-        std::vector<Dim> m = merge_dims(lines);
-        PassReq rq{};
-        rq.kind = B2_KIND_ROWS; rq.n = (int)N; rq.inv = inv; rq.ops = sc_ops;
-        rq.in_es = 1; rq.out_es = 1;
-        if (m.empty()) rq.group = Dim{1, (int64_t)N, (int64_t)N};
-        else { rq.group = m[0]; m.erase(m.begin()); }
+// total number of lines and a packed scratch layout for them ([line][M])
+uint64_t count_lines(const std::vector<Dim>& lines) {
+    uint64_t c = 1;
+    for (const Dim& d : lines) c *= d.n;
+    return c;
+}
+
+int plan_bluestein(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
+    // X[k] = conj(b_k) * sum_n (x_n conj(b_n)) b_{k-n},  b_n = e^{i pi n^2/N}   (API guide :465-493)
+    const uint64_t N = job.N;
+    uint64_t M = 1;
+    while (M < 2 * N - 1) M <<= 1;
+    if (!generic_fits(g, M)) return R_UNSUPPORTED_FFT_LENGTH;   // long Bluestein lengths: not yet
+    const uint64_t L = count_lines(job.lines);
+    g.temp_elems = std::max<uint64_t>(g.temp_elems, L * M);
+    const int chirp = aux_for(g, AUX_BLUE_CHIRP, N), filt = aux_for(g, AUX_BLUE_FILTER, N, M);
+    // scratch lines are packed [.. outer ..][group][M]
+    std::vector<Dim> in_lines = job.lines, out_lines = job.lines;
+    int64_t run = (int64_t)M;
+    for (size_t i = 0; i < job.lines.size(); ++i) {
+        in_lines[i].os = run;            // pass 1 writes packed scratch
+        out_lines[i].is = run;           // pass 2 reads packed scratch
+        run *= (int64_t)job.lines[i].n;
+    }
+    auto mk = [&](const std::vector<Dim>& ln, PassReq& rq) {
+        if (ln.empty()) rq.group = Dim{1, 0, 0};
+        else { rq.group = ln[0]; rq.outer.assign(ln.begin() + 1, ln.end()); }
+    };
+    PassReq a;
+    a.kind = job.unit_lines ? B2_KIND_COLS : B2_KIND_ROWS;
+    if (job.unit_lines) a.kind = B2_KIND_ROWS_TOUT, a.kind = B2_KIND_COLS;
+    a.n = (int)M; a.inv = job.inv; a.ops = B2_OP_MUL_IN | B2_OP_MUL_OUT; a.force_generic = true;
+    a.in_es = job.es_in; a.out_es = 1;
+    mk(in_lines, a);
+    a.in_role = job.in_role; a.out_role = ROLE_TEMP;
+    a.in_len = (uint32_t)N;
+    a.aux0 = chirp; a.aux1 = filt;
+    a.what = "bluestein 1/2 chirp+fft+filter";
+    // load side may be strided (qfast) but the packed scratch store is contiguous per line
+    int rc = emit(g, list, a);
+    if (rc != R_SUCCESS) return rc;
+    list.back().P.store_qfast = 0;
+    list.back().P.load_qfast = job.unit_lines ? 1 : 0;
+    PassReq b;
+    b.kind = job.unit_lines ? B2_KIND_COLS : B2_KIND_ROWS;
+    b.n = (int)M; b.inv = job.inv; b.inner_inverse = 1; b.ops = B2_OP_MUL_OUT | (job.scale != 1.0 ? B2_OP_SCALE : 0);
+    b.force_generic = true;
+    b.in_es = 1; b.out_es = job.es_out;
+    mk(out_lines, b);
+    b.in_role = ROLE_TEMP; b.out_role = job.out_role;
+    b.out_len = (uint32_t)N;
+    b.aux1 = chirp;
+    b.scale = job.scale;
+    b.what = "bluestein 2/2 ifft+chirp";
+    rc = emit(g, list, b);
+    if (rc != R_SUCCESS) return rc;
+    list.back().P.load_qfast = 0;
+    list.back().P.store_qfast = job.unit_lines ? 1 : 0;
+    return R_SUCCESS;
+}
+
+int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
+    const uint64_t N = job.N;
+    const int sc_ops = (job.scale != 1.0) ? B2_OP_SCALE : 0;
+    std::vector<Dim> m = merge_dims(job.lines);
+    const bool contiguous = (job.es_in == 1 && job.es_out == 1);
+    const int kind = job.unit_lines ? B2_KIND_COLS : B2_KIND_ROWS;
+
+    if (N == 1) return R_SUCCESS;   // length-1 transform is the identity
+    if (!is_smooth(N)) return plan_bluestein(g, list, job);
+
+    if (N <= max_single_env() && single_ok(g, kind, N, 0)) {
+        PassReq rq;
+        rq.kind = kind; rq.n = (int)N; rq.inv = job.inv; rq.ops = sc_ops;
+        rq.in_es = job.es_in; rq.out_es = job.es_out;
+        if (job.unit_lines) {
+            // keep the unit-stride dimension as the grouped one
+            if (!m.empty() && m[0].is == 1 && m[0].os == 1) { rq.group = m[0]; m.erase(m.begin()); }
+            else rq.group = Dim{1, 1, 1};
+        } else {
+            if (m.empty()) rq.group = Dim{1, (int64_t)N, (int64_t)N};
+            else { rq.group = m[0]; m.erase(m.begin()); }
+        }
         rq.outer = m;
-        rq.in_role = io.in_role; rq.out_role = io.out_role;
-        rq.scale = io.scale;
-        rq.what = "axis0 single-pass";
+        rq.in_role = job.in_role; rq.out_role = job.out_role;
+        rq.scale = job.scale;
+        rq.what = job.unit_lines ? "strided axis" : "single-pass";
         return emit(g, list, rq);
     }
+    if (!contiguous || job.unit_lines) return R_UNSUPPORTED_FFT_LENGTH;   // long strided axes: not yet
+
     std::vector<uint64_t> f = split_four_step(g, N);
     if (f.empty()) return R_UNSUPPORTED_FFT_LENGTH;
-    g.temp_elems = std::max<uint64_t>(g.temp_elems, g.batch_stride * g.batches);
-    // sequences on the temp buffer use the main buffer's layout
-    std::vector<Dim> seq_in_to_tmp, seq_tmp_to_tmp, seq_tmp_to_out, seq_in_to_in;
-    for (uint32_t a = 1; a < d.fft_dim; ++a) {
-        seq_in_to_tmp.push_back(Dim{d.size[a], (int64_t)io.in_stride[a - 1], (int64_t)g.stride[a - 1]});
-        seq_tmp_to_tmp.push_back(Dim{d.size[a], (int64_t)g.stride[a - 1], (int64_t)g.stride[a - 1]});
-        seq_tmp_to_out.push_back(Dim{d.size[a], (int64_t)g.stride[a - 1], (int64_t)io.out_stride[a - 1]});
-        seq_in_to_in.push_back(Dim{d.size[a], (int64_t)io.in_stride[a - 1], (int64_t)io.in_stride[a - 1]});
+    // scratch: sequences keep the output-side layout of the main buffer
+    uint64_t extent = N;
+    for (const Dim& d : job.lines) extent = std::max<uint64_t>(extent, (uint64_t)d.n * (uint64_t)std::max(d.is, d.os));
+    g.temp_elems = std::max<uint64_t>(g.temp_elems, extent);
+    std::vector<Dim> s_in_tmp, s_tmp_tmp, s_tmp_out, s_in_in;
+    for (const Dim& d : job.lines) {
+        // scratch uses the OUTPUT layout (both sides of a temp->temp pass)
+        s_in_tmp.push_back(Dim{d.n, d.is, d.os});
+        s_tmp_tmp.push_back(Dim{d.n, d.os, d.os});
+        s_tmp_out.push_back(Dim{d.n, d.os, d.os});
+        s_in_in.push_back(Dim{d.n, d.is, d.is});
     }
-    seq_in_to_tmp.push_back(Dim{g.batches, (int64_t)io.in_batch_stride, (int64_t)g.batch_stride});
-    seq_tmp_to_tmp.push_back(Dim{g.batches, (int64_t)g.batch_stride, (int64_t)g.batch_stride});
-    seq_tmp_to_out.push_back(Dim{g.batches, (int64_t)g.batch_stride, (int64_t)io.out_batch_stride});
-    seq_in_to_in.push_back(Dim{g.batches, (int64_t)io.in_batch_stride, (int64_t)io.in_batch_stride});
-
     int rc;
     if (f.size() == 2) {
         const uint64_t N1 = f[0], N2 = f[1];
-        PassReq a{};
-        a.kind = B2_KIND_COLS; a.n = (int)N1; a.inv = inv; a.ops = B2_OP_TWIDDLE_OUT;
+        PassReq a;
+        a.kind = B2_KIND_COLS; a.n = (int)N1; a.inv = job.inv; a.ops = B2_OP_TWIDDLE_OUT;
         a.in_es = (int64_t)N2; a.out_es = (int64_t)N2;
         a.group = Dim{N2, 1, 1};
-        a.outer = seq_in_to_tmp;
-        a.in_role = io.in_role; a.out_role = ROLE_TEMP;
+        a.outer = s_in_tmp;
+        a.in_role = job.in_role; a.out_role = ROLE_TEMP;
         a.twM = N;
         a.what = "four-step 1/2 strided+phase";
         if ((rc = emit(g, list, a)) != R_SUCCESS) return rc;
-        PassReq b{};
-        b.kind = B2_KIND_ROWS_TOUT; b.n = (int)N2; b.inv = inv; b.ops = sc_ops;
+        PassReq b;
+        b.kind = B2_KIND_ROWS_TOUT; b.n = (int)N2; b.inv = job.inv; b.ops = sc_ops;
         b.in_es = 1; b.out_es = (int64_t)N1;
         b.group = Dim{N1, (int64_t)N2, 1};
-        b.outer = seq_tmp_to_out;
-        b.in_role = ROLE_TEMP; b.out_role = io.out_role;
-        b.scale = io.scale;
+        b.outer = s_tmp_out;
+        b.in_role = ROLE_TEMP; b.out_role = job.out_role;
+        b.scale = job.scale;
         b.what = "four-step 2/2 contiguous+transpose";
         return emit(g, list, b);
     }
     const uint64_t N1 = f[0], N2 = f[1], N3 = f[2], M = N2 * N3;
-    PassReq a{};
-    a.kind = B2_KIND_COLS; a.n = (int)N1; a.inv = inv; a.ops = B2_OP_TWIDDLE_OUT;
+    PassReq a;
+    a.kind = B2_KIND_COLS; a.n = (int)N1; a.inv = job.inv; a.ops = B2_OP_TWIDDLE_OUT;
     a.in_es = (int64_t)M; a.out_es = (int64_t)M;
     a.group = Dim{M, 1, 1};
     // first pass runs in place on its input when that is the main buffer, otherwise it moves to temp
-    const bool a_inplace = (io.in_role == ROLE_BUFFER);
-    a.outer = a_inplace ? seq_in_to_in : seq_in_to_tmp;
-    a.in_role = io.in_role; a.out_role = a_inplace ? io.in_role : ROLE_TEMP;
+    const bool a_inplace = (job.in_role == ROLE_BUFFER);
+    a.outer = a_inplace ? s_in_in : s_in_tmp;
+    a.in_role = job.in_role; a.out_role = a_inplace ? job.in_role : ROLE_TEMP;
     a.twM = N;
     a.what = "four-step 1/3 strided+phase";
     if ((rc = emit(g, list, a)) != R_SUCCESS) return rc;
-    PassReq b{};
-    b.kind = B2_KIND_COLS; b.n = (int)N2; b.inv = inv; b.ops = B2_OP_TWIDDLE_OUT;
+    PassReq b;
+    b.kind = B2_KIND_COLS; b.n = (int)N2; b.inv = job.inv; b.ops = B2_OP_TWIDDLE_OUT;
     b.in_es = (int64_t)N3; b.out_es = (int64_t)N3;
     b.group = Dim{N3, 1, 1};
     b.outer.push_back(Dim{N1, (int64_t)M, (int64_t)M});
     {
-        const std::vector<Dim>& s = a_inplace ? seq_in_to_tmp : seq_tmp_to_tmp;
+        const std::vector<Dim>& s = a_inplace ? s_in_tmp : s_tmp_tmp;
         b.outer.insert(b.outer.end(), s.begin(), s.end());
     }
     b.in_role = a.out_role; b.out_role = ROLE_TEMP;
     b.twM = M;
     b.what = "four-step 2/3 strided+phase";
     if ((rc = emit(g, list, b)) != R_SUCCESS) return rc;
-    PassReq c{};
-    c.kind = B2_KIND_ROWS_TOUT; c.n = (int)N3; c.inv = inv; c.ops = sc_ops;
+    PassReq c;
+    c.kind = B2_KIND_ROWS_TOUT; c.n = (int)N3; c.inv = job.inv; c.ops = sc_ops;
     c.in_es = 1; c.out_es = (int64_t)(N1 * N2);
     c.group = Dim{N1, (int64_t)M, 1};
     c.outer.push_back(Dim{N2, (int64_t)N3, (int64_t)N1});
-    c.outer.insert(c.outer.end(), seq_tmp_to_out.begin(), seq_tmp_to_out.end());
-    c.in_role = ROLE_TEMP; c.out_role = io.out_role;
-    c.scale = io.scale;
+    c.outer.insert(c.outer.end(), s_tmp_out.begin(), s_tmp_out.end());
+    c.in_role = ROLE_TEMP; c.out_role = job.out_role;
+    c.scale = job.scale;
     c.what = "four-step 3/3 contiguous+transpose";
     return emit(g, list, c);
 }
 
-// strided axis a >= 1
-int plan_axis_strided(PlanGraph& g, std::vector<PassPlan>& list, uint32_t axis, int inv, const AxisIO& io) {
+// ----------------------------------------------------------------------------------------------------------------
+struct Layout {            // one side (input or output) of an axis pass
+    int role;
+    uint64_t stride[B200FFT_MAX_DIMS];   // stride[a] = distance between consecutive indices of dim a+1
+    uint64_t batch_stride;
+};
+
+// all dims except `axis`, x first when axis != 0; strides taken from the two layouts
+std::vector<Dim> other_dims(const PlanGraph& g, const uint64_t* size, uint32_t axis, const Layout& in, const Layout& out) {
     const b200fft_desc& d = g.desc;
-    const uint64_t N = d.size[axis];
-    if (!have(g, B2_KIND_COLS, N, 0)) return R_UNSUPPORTED_FFT_LENGTH;
     std::vector<Dim> lines;
-    lines.push_back(Dim{d.size[0], 1, 1});
-    for (uint32_t a = 1; a < d.fft_dim; ++a) {
+    for (uint32_t a = 0; a < d.fft_dim; ++a) {
         if (a == axis) continue;
-        lines.push_back(Dim{d.size[a], (int64_t)io.in_stride[a - 1], (int64_t)io.out_stride[a - 1]});
+        const int64_t is = a == 0 ? 1 : (int64_t)in.stride[a - 1], os = a == 0 ? 1 : (int64_t)out.stride[a - 1];
+        lines.push_back(Dim{size[a], is, os});
     }
-    lines.push_back(Dim{g.batches, (int64_t)io.in_batch_stride, (int64_t)io.out_batch_stride});
-    // keep the unit-stride dimension first even if it has extent 1
-    std::vector<Dim> m = merge_dims(lines);
-    PassReq rq{};
-    rq.kind = B2_KIND_COLS; rq.n = (int)N; rq.inv = inv; rq.ops = (io.scale != 1.0) ? B2_OP_SCALE : 0;
-    rq.in_es = (int64_t)io.in_stride[axis - 1]; rq.out_es = (int64_t)io.out_stride[axis - 1];
-    if (!m.empty() && m[0].is == 1 && m[0].os == 1) { rq.group = m[0]; m.erase(m.begin()); }
-    else rq.group = Dim{1, 1, 1};
-    rq.outer = m;
-    rq.in_role = io.in_role; rq.out_role = io.out_role;
-    rq.scale = io.scale;
-    rq.what = "strided axis";
-    return emit(g, list, rq);
+    lines.push_back(Dim{g.batches, (int64_t)in.batch_stride, (int64_t)out.batch_stride});
+    return lines;
 }
 
-int plan_direction(PlanGraph& g, std::vector<PassPlan>& list, int inv) {
+int plan_c2c_axis(PlanGraph& g, std::vector<PassPlan>& list, const uint64_t* size, uint32_t axis, int inv,
+                  const Layout& in, const Layout& out, double scale) {
+    C2CJob job;
+    job.N = size[axis]; job.inv = inv;
+    job.es_in = axis == 0 ? 1 : (int64_t)in.stride[axis - 1];
+    job.es_out = axis == 0 ? 1 : (int64_t)out.stride[axis - 1];
+    job.lines = other_dims(g, size, axis, in, out);
+    job.unit_lines = (axis != 0);
+    job.in_role = in.role; job.out_role = out.role;
+    job.scale = scale;
+    return plan_c2c(g, list, job);
+}
+
+Layout layout_of(int role, const uint64_t* stride, uint32_t fft_dim) {
+    Layout l;
+    l.role = role;
+    for (int a = 0; a < B200FFT_MAX_DIMS; ++a) l.stride[a] = stride[a];
+    l.batch_stride = stride[fft_dim - 1];
+    return l;
+}
+
+// ---- C2C (any dimensionality) ------------------------------------------------------------------------------------
+int plan_direction_c2c(PlanGraph& g, std::vector<PassPlan>& list, int inv) {
     const b200fft_desc& d = g.desc;
     // order of axes: forward 0,1,2..; inverse ..2,1,0 (vkFFT_RunApp.h:111-321 / :466-651)
     std::vector<uint32_t> axes;
     for (uint32_t a = 0; a < d.fft_dim; ++a)
-        if (!d.omit_dimension[a]) axes.push_back(a);
+        if (!d.omit_dimension[a] && d.size[a] > 1) axes.push_back(a);
     if (inv) std::reverse(axes.begin(), axes.end());
     double norm = 1.0;
     if (inv && d.normalize)
         for (uint32_t a : axes) norm /= (double)d.size[a];
-    // out-of-place plumbing (documentation/VkFFT_API_guide.tex:365-376): the first launch reads the formatted
-    // input, the last launch writes the formatted output, everything in between lives in `buffer`.
-    const bool fmt_in = d.is_input_formatted != 0, fmt_out = d.is_output_formatted != 0;
+    // out-of-place plumbing (API guide :365-376): the first launch reads the formatted input, the last launch
+    // writes the formatted output, everything in between lives in `buffer`.  The inverse mirrors the forward
+    // data flow (outputBuffer -> ... -> buffer, or -> inputBuffer with inverseReturnToInputBuffer).
+    const Layout buf = layout_of(ROLE_BUFFER, d.buffer_stride, d.fft_dim);
+    const Layout inl = layout_of(ROLE_INPUT, d.input_stride, d.fft_dim);
+    const Layout outl = layout_of(ROLE_OUTPUT, d.output_stride, d.fft_dim);
     for (size_t i = 0; i < axes.size(); ++i) {
         const bool first = (i == 0), last = (i + 1 == axes.size());
-        AxisIO io{};
-        io.in_role = ROLE_BUFFER; io.out_role = ROLE_BUFFER;
-        io.in_stride = g.stride; io.out_stride = g.stride;
-        io.in_batch_stride = g.batch_stride; io.out_batch_stride = g.batch_stride;
-        static thread_local uint64_t istr[B200FFT_MAX_DIMS], ostr[B200FFT_MAX_DIMS];
+        Layout in = buf, out = buf;
         if (!inv) {
-            if (first && fmt_in) {
-                io.in_role = ROLE_INPUT;
-                for (int k = 0; k < B200FFT_MAX_DIMS; ++k) istr[k] = d.input_stride[k];
-                io.in_stride = istr; io.in_batch_stride = d.input_stride[d.fft_dim - 1] ;
-            }
-            if (last && fmt_out) {
-                io.out_role = ROLE_OUTPUT;
-                for (int k = 0; k < B200FFT_MAX_DIMS; ++k) ostr[k] = d.output_stride[k];
-                io.out_stride = ostr; io.out_batch_stride = d.output_stride[d.fft_dim - 1];
-            }
+            if (first && d.is_input_formatted) in = inl;
+            if (last && d.is_output_formatted) out = outl;
         } else {
-            // inverse mirrors the forward data flow: it consumes what forward produced and returns it to where
-            // forward read from (outputBuffer -> ... -> buffer, or -> inputBuffer with inverseReturnToInputBuffer)
-            if (first && fmt_out) {
-                io.in_role = ROLE_OUTPUT;
-                for (int k = 0; k < B200FFT_MAX_DIMS; ++k) istr[k] = d.output_stride[k];
-                io.in_stride = istr; io.in_batch_stride = d.output_stride[d.fft_dim - 1];
-            }
-            if (last && fmt_in && d.inverse_return_to_input) {
-                io.out_role = ROLE_INPUT;
-                for (int k = 0; k < B200FFT_MAX_DIMS; ++k) ostr[k] = d.input_stride[k];
-                io.out_stride = ostr; io.out_batch_stride = d.input_stride[d.fft_dim - 1];
-            }
+            if (first && d.is_output_formatted) in = outl;
+            if (last && d.is_input_formatted && d.inverse_return_to_input) out = inl;
         }
-        io.scale = last ? norm : 1.0;
-        int rc = (axes[i] == 0) ? plan_axis0(g, list, inv, io) : plan_axis_strided(g, list, axes[i], inv, io);
+        int rc = plan_c2c_axis(g, list, d.size, axes[i], inv, in, out, last ? norm : 1.0);
+        if (rc != R_SUCCESS) return rc;
+    }
+    return R_SUCCESS;
+}
+
+// ---- R2C / C2R ---------------------------------------------------------------------------------------------------
+// Layout facts (vkFFT_InitializeApp.h:994-1040, API guide :305-329): `buffer` holds size[0]/2+1 complex per row
+// (bufferStride[0] complex); in place the real rows live in the same rows (2*bufferStride[0] reals apart);
+// with isInputFormatted the reals come from inputBuffer with inputBufferStride in REAL elements.
+int plan_direction_r2c(PlanGraph& g, std::vector<PassPlan>& list, int inv) {
+    const b200fft_desc& d = g.desc;
+    const uint64_t N0 = d.size[0], H = N0 / 2 + 1;
+    if (d.omit_dimension[0]) return R_UNSUPPORTED_FFT_OMIT;
+    if (d.is_output_formatted) return R_UNSUPPORTED_FFT_LENGTH_R2C;
+    uint64_t csize[B200FFT_MAX_DIMS];
+    for (int a = 0; a < B200FFT_MAX_DIMS; ++a) csize[a] = d.size[a];
+    csize[0] = H;                       // the other axes transform H columns (vkFFT_Scheduler.h:2281-2283)
+    const Layout buf = layout_of(ROLE_BUFFER, d.buffer_stride, d.fft_dim);
+    double norm = 1.0;
+    if (inv && d.normalize)
+        for (uint32_t a = 0; a < d.fft_dim; ++a)
+            if (!d.omit_dimension[a]) norm /= (double)d.size[a];
+    const bool even = (N0 % 2 == 0);
+    const uint64_t n = even ? N0 / 2 : N0;
+    if (!is_smooth(n) || !generic_fits(g, n)) return R_UNSUPPORTED_FFT_LENGTH_R2C;
+
+    // real side of the axis-0 launch, in units of the pointer type the operator uses
+    const bool real_ext = d.is_input_formatted && (!inv || d.inverse_return_to_input);
+    const int real_role = real_ext ? ROLE_INPUT : ROLE_BUFFER;
+    // strides of the real rows in REAL elements
+    uint64_t rstride[B200FFT_MAX_DIMS];
+    for (int a = 0; a < B200FFT_MAX_DIMS; ++a) rstride[a] = real_ext ? d.input_stride[a] : 2 * d.buffer_stride[a];
+    const uint64_t rbatch = rstride[d.fft_dim - 1];
+    if (even)
+        for (uint32_t a = 0; a < d.fft_dim; ++a)
+            if (rstride[a] % 2) return R_UNSUPPORTED_FFT_LENGTH_R2C;
+    const uint64_t unit = even ? 2 : 1;    // even trick addresses the reals as complex pairs
+
+    auto axis0 = [&](bool forward, double scale) -> int {
+        PassReq rq;
+        rq.kind = B2_KIND_ROWS; rq.n = (int)n; rq.force_generic = true;
+        std::vector<Dim> lines;
+        for (uint32_t a = 1; a < d.fft_dim; ++a) {
+            const int64_t rs = (int64_t)(rstride[a - 1] / unit), cs = (int64_t)d.buffer_stride[a - 1];
+            lines.push_back(forward ? Dim{d.size[a], rs, cs} : Dim{d.size[a], cs, rs});
+        }
+        lines.push_back(forward ? Dim{g.batches, (int64_t)(rbatch / unit), (int64_t)buf.batch_stride}
+                                : Dim{g.batches, (int64_t)buf.batch_stride, (int64_t)(rbatch / unit)});
+        std::vector<Dim> m = merge_dims(lines);
+        if (m.empty()) rq.group = Dim{1, 0, 0};
+        else { rq.group = m[0]; m.erase(m.begin()); }
+        rq.outer = m;
+        rq.in_es = 1; rq.out_es = 1;
+        if (forward) {
+            rq.in_role = real_role; rq.out_role = ROLE_BUFFER;
+            if (even) { rq.store_io = B2_IO_R2C_EVEN; rq.aux0 = aux_for(g, AUX_R2C, N0); rq.out_len = (uint32_t)(n + 1); }
+            else { rq.load_io = B2_IO_REAL; rq.out_len = (uint32_t)H; }
+            rq.what = "r2c axis0";
+        } else {
+            rq.in_role = ROLE_BUFFER; rq.out_role = real_role;
+            rq.inner_inverse = 1;
+            if (even) { rq.load_io = B2_IO_C2R_EVEN; rq.aux0 = aux_for(g, AUX_R2C, N0); }
+            else { rq.load_io = B2_IO_HERM; rq.store_io = B2_IO_REAL; rq.aux_u1 = (uint32_t)N0; }
+            rq.ops = (scale != 1.0) ? B2_OP_SCALE : 0;
+            rq.scale = scale;
+            rq.what = "c2r axis0";
+        }
+        return emit(g, list, rq);
+    };
+    int rc;
+    if (!inv) {
+        if ((rc = axis0(true, 1.0)) != R_SUCCESS) return rc;
+        for (uint32_t a = 1; a < d.fft_dim; ++a) {
+            if (d.omit_dimension[a] || d.size[a] == 1) continue;
+            if ((rc = plan_c2c_axis(g, list, csize, a, 0, buf, buf, 1.0)) != R_SUCCESS) return rc;
+        }
+    } else {
+        for (uint32_t a = d.fft_dim; a-- > 1;) {
+            if (d.omit_dimension[a] || d.size[a] == 1) continue;
+            if ((rc = plan_c2c_axis(g, list, csize, a, 1, buf, buf, 1.0)) != R_SUCCESS) return rc;
+        }
+        if ((rc = axis0(false, norm)) != R_SUCCESS) return rc;
+    }
+    return R_SUCCESS;
+}
+
+// ---- DCT-I..IV ---------------------------------------------------------------------------------------------------
+// Real buffer, every non-omitted axis is transformed (API guide :330-339, :581-591).  kind 2/3 swap roles under
+// inversion, 1 and 4 are self-inverse.  Lines are paired (two real lines as re/im of one complex line) except
+// for DCT-IV which maps one real line of length N to one complex line of length N/2.
+int plan_direction_dct(PlanGraph& g, std::vector<PassPlan>& list, int inv) {
+    const b200fft_desc& d = g.desc;
+    if (d.is_input_formatted || d.is_output_formatted) return R_UNSUPPORTED_FFT_LENGTH_R2R;
+    int type = (int)d.perform_dct;
+    if (inv && (type == 2 || type == 3)) type = 5 - type;
+    std::vector<uint32_t> axes;
+    for (uint32_t a = 0; a < d.fft_dim; ++a)
+        if (!d.omit_dimension[a] && d.size[a] > 1) axes.push_back(a);
+    if (inv) std::reverse(axes.begin(), axes.end());
+    const Layout buf = layout_of(ROLE_BUFFER, d.buffer_stride, d.fft_dim);
+    for (size_t i = 0; i < axes.size(); ++i) {
+        const uint32_t axis = axes[i];
+        const uint64_t N = d.size[axis];
+        double scale = 1.0;
+        if (inv && d.normalize) scale = 1.0 / (type == 1 ? 2.0 * (double)(N - 1) : 2.0 * (double)N);
+        uint64_t n;
+        PassReq rq;
+        rq.force_generic = true;
+        switch (type) {
+            case 1: n = 2 * N - 2; rq.load_io = rq.store_io = B2_IO_DCT1; rq.aux_u1 = (uint32_t)N; rq.real_pairs = true; break;
+            case 2: n = N; rq.load_io = rq.store_io = B2_IO_DCT2; rq.aux0 = aux_for(g, AUX_DCT23, N); rq.real_pairs = true; break;
+            case 3: n = N; rq.load_io = rq.store_io = B2_IO_DCT3; rq.aux0 = aux_for(g, AUX_DCT23, N); rq.real_pairs = true;
+                    rq.inner_inverse = 1; break;
+            case 4:
+                if (N % 2) return R_UNSUPPORTED_FFT_LENGTH_R2R;
+                n = N / 2; rq.load_io = rq.store_io = B2_IO_DCT4;
+                rq.aux0 = aux_for(g, AUX_DCT4_PRE, N); rq.aux1 = aux_for(g, AUX_DCT4_POST, N); break;
+            default: return R_UNSUPPORTED_FFT_LENGTH_R2R;
+        }
+        if (n < 2 || !is_smooth(n) || !generic_fits(g, n)) return R_UNSUPPORTED_FFT_LENGTH_R2R;
+        rq.n = (int)n;
+        rq.kind = axis == 0 ? B2_KIND_ROWS : B2_KIND_COLS;
+        rq.in_es = rq.out_es = axis == 0 ? 1 : (int64_t)buf.stride[axis - 1];
+        std::vector<Dim> lines = other_dims(g, d.size, axis, buf, buf);
+        std::vector<Dim> m = merge_dims(lines);
+        if (axis != 0) {
+            if (!m.empty() && m[0].is == 1) { rq.group = m[0]; m.erase(m.begin()); }
+            else rq.group = Dim{1, 1, 1};
+        } else {
+            if (m.empty()) rq.group = Dim{1, 0, 0};
+            else { rq.group = m[0]; m.erase(m.begin()); }
+        }
+        rq.aux_u0 = (uint32_t)rq.group.n;
+        rq.outer = m;
+        rq.ops = (scale != 1.0) ? B2_OP_SCALE : 0;
+        rq.scale = scale;
+        rq.what = "dct axis";
+        int rc = emit(g, list, rq);
         if (rc != R_SUCCESS) return rc;
     }
     return R_SUCCESS;
@@ -374,15 +701,23 @@ int build_plan(const b200fft_desc& din, PlanGraph& g) {
     if (d.number_batches == 0) d.number_batches = 1;
     if (d.coordinate_features == 0) d.coordinate_features = 1;
     if (d.precision > B200FFT_F64) return R_UNSUPPORTED_FFT_LENGTH;
-    if (d.perform_r2c || d.perform_dct || d.perform_dst) return R_UNSUPPORTED_FFT_LENGTH_R2C;
+    if (d.perform_dst) return R_UNSUPPORTED_FFT_LENGTH_R2R;
+    if (d.perform_dct > 4) return R_UNSUPPORTED_FFT_LENGTH_R2R;
+    if (d.perform_r2c && d.perform_dct) return R_UNSUPPORTED_FFT_LENGTH_R2R;
     if (d.omit_dimension[0] && d.perform_r2c) return R_UNSUPPORTED_FFT_OMIT;
     // default strides (vkFFT_InitializeApp.h:994-1040)
-    auto fill = [&](uint64_t* s) {
-        if (s[0] == 0) s[0] = d.size[0];
+    auto fill = [&](uint64_t* s, uint64_t s0) {
+        if (s[0] == 0) s[0] = s0;
         for (int a = 1; a < B200FFT_MAX_DIMS; ++a)
             if (s[a] == 0) s[a] = s[a - 1] * d.size[a];
     };
-    fill(d.buffer_stride); fill(d.input_stride); fill(d.output_stride);
+    if (d.perform_r2c) {
+        fill(d.buffer_stride, d.size[0] / 2 + 1);
+        fill(d.input_stride, d.is_input_formatted ? d.size[0] : d.size[0] + 2);
+        fill(d.output_stride, d.is_output_formatted ? d.size[0] : d.size[0] + 2);
+    } else {
+        fill(d.buffer_stride, d.size[0]); fill(d.input_stride, d.size[0]); fill(d.output_stride, d.size[0]);
+    }
     g.desc = d;
     g.prec = (int)d.precision;
     for (int a = 0; a < B200FFT_MAX_DIMS; ++a) g.stride[a] = d.buffer_stride[a];
@@ -393,22 +728,27 @@ int build_plan(const b200fft_desc& din, PlanGraph& g) {
 
     uint32_t naxes = 0;
     g.flops = 0;
+    const bool real_tf = d.perform_r2c || d.perform_dct;
     for (uint32_t a = 0; a < d.fft_dim; ++a) {
         if (d.omit_dimension[a]) continue;
         ++naxes;
-        double n = (double)d.size[a], l2 = 0;
-        for (double t = n; t > 1; t /= 2) l2 += 1;  // exact for powers of two
-        if ((d.size[a] & (d.size[a] - 1)) != 0) l2 = std::log2(n);
-        g.flops += 5.0 * (double)g.total_elems * l2;
+        const double n = (double)d.size[a];
+        g.flops += (real_tf ? 2.5 : 5.0) * (double)g.total_elems * std::log2(n);
     }
-    const uint64_t esz = (g.prec == B2_PREC_F64) ? 16 : 8;
-    g.algorithmic_bytes = 2 * esz * g.total_elems * naxes;
+    const uint64_t esz = esize(g);
+    // algorithmic bytes: one read + one write of every point per transformed axis (real data: half the bytes)
+    g.algorithmic_bytes = 2 * (real_tf ? esz / 2 : esz) * g.total_elems * naxes;
 
     g.has_fwd = !d.make_inverse_plan_only;
     g.has_inv = !d.make_forward_plan_only;
+    auto plan = [&](std::vector<PassPlan>& list, int inv) {
+        if (d.perform_r2c) return plan_direction_r2c(g, list, inv);
+        if (d.perform_dct) return plan_direction_dct(g, list, inv);
+        return plan_direction_c2c(g, list, inv);
+    };
     int rc;
-    if (g.has_fwd && (rc = plan_direction(g, g.fwd, 0)) != R_SUCCESS) return rc;
-    if (g.has_inv && (rc = plan_direction(g, g.inv, 1)) != R_SUCCESS) return rc;
+    if (g.has_fwd && (rc = plan(g.fwd, 0)) != R_SUCCESS) return rc;
+    if (g.has_inv && (rc = plan(g.inv, 1)) != R_SUCCESS) return rc;
     if (d.user_temp_buffer && g.temp_elems * esz > d.temp_buffer_size && d.temp_buffer_size != 0)
         return R_USER_TEMP_TOO_SMALL;
     return R_SUCCESS;

@@ -30,6 +30,7 @@ struct b200fft_plan {
     cudaStream_t stream = nullptr;
     std::vector<void*> d_luts;
     std::vector<TwDev> d_tws;
+    std::vector<void*> d_auxs;
     void* d_temp = nullptr;
     uint64_t temp_bytes = 0;
     uint64_t lut_bytes = 0;
@@ -70,6 +71,7 @@ void free_plan(b200fft_plan* p) {
     DeviceGuard dg(p->device);
     for (void* d : p->d_luts) if (d) cudaFree(d);
     for (TwDev& t : p->d_tws) { if (t.hi) cudaFree(t.hi); if (t.lo) cudaFree(t.lo); }
+    for (void* d : p->d_auxs) if (d) cudaFree(d);
     if (p->d_temp) cudaFree(p->d_temp);
     if (p->d_stage) cudaFree(p->d_stage);
     delete p;
@@ -115,6 +117,12 @@ extern "C" int b200fft_plan_create(const b200fft_desc* desc, b200fft_plan** out)
             if (rc == R_SUCCESS) rc = upload(lo, &p->d_tws[i].lo, p->lut_bytes);
         }
     }
+    p->d_auxs.assign(g.auxs.size(), nullptr);
+    for (size_t i = 0; i < g.auxs.size() && rc == R_SUCCESS; ++i) {
+        const AuxSpec& a = g.auxs[i];
+        if (a.prec == B2_PREC_F32) rc = upload(make_aux<float>(a.kind, a.a, a.b), &p->d_auxs[i], p->lut_bytes);
+        else rc = upload(make_aux<double>(a.kind, a.a, a.b), &p->d_auxs[i], p->lut_bytes);
+    }
     // one-time kernel attributes (dynamic shared memory above 48 KiB)
     for (int dir = 0; dir < 2 && rc == R_SUCCESS; ++dir)
         for (const PassPlan& pp : (dir ? g.inv : g.fwd))
@@ -154,8 +162,10 @@ extern "C" int b200fft_exec(b200fft_plan* p, int inverse, const b200fft_buffers*
     cudaStream_t st = b->stream ? (cudaStream_t)b->stream : p->stream;
     for (const PassPlan& pp : list) {
         b2_pass_params P = pp.P;
-        P.in = base[pp.in_role] + pp.in_off * (int64_t)esz;
-        P.out = base[pp.out_role] + pp.out_off * (int64_t)esz;
+        P.in = base[pp.in_role] + pp.in_off * (int64_t)(pp.in_scalar ? esz / 2 : esz);
+        P.out = base[pp.out_role] + pp.out_off * (int64_t)(pp.out_scalar ? esz / 2 : esz);
+        if (pp.aux0_id >= 0) P.aux0 = p->d_auxs[pp.aux0_id];
+        if (pp.aux1_id >= 0) P.aux1 = p->d_auxs[pp.aux1_id];
         P.lut = p->d_luts[pp.lut_id];
         if (pp.tw_id >= 0) {
             P.tw_hi = p->d_tws[pp.tw_id].hi;

@@ -241,7 +241,7 @@ struct Engine {
                     X a = x[(m * V + v) * r + k];
                     const int p = b0 + v + k * NB;  // natural-order output index (S == NB in the last stage)
                     if constexpr ((C::OPS & B2_OP_TWIDDLE_OUT) != 0) {
-                        const uint64_t e = (uint64_t)(P.tw_line0 + gline) * (uint64_t)p;
+                        const uint64_t e = (uint64_t)gline * (uint64_t)p;
                         a = a * twiddle2<T>((const X*)P.tw_hi, (const X*)P.tw_lo, P.tw_shift, e);
                     }
                     if (do_scale) a = a * sc;
@@ -262,6 +262,12 @@ struct Engine {
                 }
             }
         }
+    }
+
+    // coordinate that multiplies the element index in the four-step phase
+    B2_D static uint32_t twl(const b2_pass_params& P, uint32_t g, uint32_t o0, uint32_t o1, uint32_t o2) {
+        const uint32_t sel = P.tw_sel;
+        return P.tw_line0 + (sel == 0 ? g : (sel == 1 ? o0 : (sel == 2 ? o1 : o2)));
     }
 
     // ---- middle stages (recursive over the schedule) --------------------------------------------------
@@ -304,7 +310,7 @@ struct Engine {
             load_global<0>(x, in_line, P.in_es, tl, gl < P.G);
             compute<0>(x, lut, tl);
             X* out_line = (X*)P.out + obase_out + (int64_t)gl * P.out_gs;
-            store_global<0>(x, out_line, P.out_es, tl, gl < P.G, P, gl);
+            store_global<0>(x, out_line, P.out_es, tl, gl < P.G, P, twl(P, gl, o0, o1, o2));
         } else {
             {
                 X x[bpt<0>() * V * Sch::r(0)];
@@ -323,7 +329,7 @@ struct Engine {
                 load_smem<s>(x, sm, qs, ts);
                 compute<s>(x, lut, ts);
                 X* out_line = (X*)P.out + obase_out + (int64_t)gs * P.out_gs;
-                store_global<s>(x, out_line, P.out_es, ts, gs < P.G, P, gs);
+                store_global<s>(x, out_line, P.out_es, ts, gs < P.G, P, twl(P, gs, o0, o1, o2));
             }
         }
     }

@@ -130,3 +130,114 @@ def test_api_errors_on_gpu(gpu):
     assert vk.initializeVkFFT(app, vk.VkFFTConfiguration(FFTdim=1, size=[8], device=0)) == vk.VKFFT_ERROR_NONZERO_APP_INITIALIZATION
     vk.deleteVkFFT(app)
     assert vk.VkFFTAppend(app, -1, vk.VkFFTLaunchParams(buffer=t)) == vk.VKFFT_ERROR_PLAN_NOT_INITIALIZED
+
+
+# ---- the runtime-scheduled kernel and its fused operators ------------------------------------------------------------
+@pytest.mark.parametrize("shape,batch,double", [((1000,), 33, False), ((2187,), 5, False), ((77,), 50, True),
+                                                ((30030,), 3, False), ((105, 30), 4, False), ((7, 11, 13), 3, True),
+                                                ((17,), 100, False), ((509,), 9, False), ((1019,), 3, True),
+                                                ((23, 8), 5, False), ((4093,), 2, False), ((3 ** 8,), 2, False),
+                                                ((5 ** 5,), 3, True), ((7 ** 4,), 3, False), ((11 ** 3,), 3, False),
+                                                ((13 ** 3,), 3, False), ((2 * 3 * 5 * 7 * 11 * 13 * 4,), 1, False)])
+@pytest.mark.parametrize("inverse", [-1, 1])
+def test_c2c_non_pow2_and_bluestein(gpu, shape, batch, double, inverse):
+    from gpu_util import run_c2c
+    dt = np.complex128 if double else np.complex64
+    x = orc.random_input((batch,) + tuple(reversed(shape)), dt, seed=sum(shape))
+    got = run_c2c(x, shape, batch, inverse, double=double)
+    ref = orc.c2c(x, len(shape), inverse == 1)
+    assert orc.error_metrics(got, ref)["l2_rel"] < (TOL64 if double else TOL32)
+
+
+def _smooth13(n):
+    for p in (2, 3, 5, 7, 11, 13):
+        while n % p == 0:
+            n //= p
+    return n == 1
+
+
+def _run_plan(torch, arr, cfg, inverse):
+    import vkfft_b200 as vk
+    t = torch.from_numpy(np.ascontiguousarray(arr)).cuda()
+    app = vk.VkFFTApplication()
+    rc = vk.initializeVkFFT(app, cfg)
+    assert rc == 0, vk.getVkFFTErrorString(rc)
+    try:
+        assert vk.VkFFTAppend(app, inverse, vk.VkFFTLaunchParams(buffer=t)) == 0
+        torch.cuda.synchronize()
+        return t.cpu().numpy()
+    finally:
+        vk.deleteVkFFT(app)
+
+
+@pytest.mark.parametrize("shape,batch,double", [((64,), 7, False), ((4096,), 5, False), ((4096, 4096), 1, False),
+                                                ((30,), 3, True), ((15,), 3, False), ((128, 8, 4), 2, True),
+                                                ((1000, 6), 2, False), ((8192,), 3, False)])
+def test_r2c_c2r(gpu, shape, batch, double):
+    import vkfft_b200 as vk
+    rdt, cdt = (np.float64, np.complex128) if double else (np.float32, np.complex64)
+    tol = TOL64 if double else TOL32
+    nx, H = shape[0], shape[0] // 2 + 1
+    x = orc.random_input((batch,) + tuple(reversed(shape)), rdt, seed=sum(shape))
+    buf = np.zeros(x.shape[:-1] + (2 * H,), rdt)
+    buf[..., :nx] = x
+    cfg = vk.VkFFTConfiguration(FFTdim=len(shape), size=list(shape), numberBatches=batch, device=0, performR2C=1,
+                                doublePrecision=int(double))
+    y = _run_plan(gpu, buf, cfg, -1)
+    assert orc.error_metrics(y.view(cdt), orc.r2c(x, len(shape)))["l2_rel"] < tol
+    z = _run_plan(gpu, y, cfg, 1)
+    assert orc.error_metrics(z[..., :nx], x.astype(np.float64) * np.prod(shape))["l2_rel"] < tol
+
+
+@pytest.mark.parametrize("kind", [1, 2, 3, 4])
+@pytest.mark.parametrize("shape,batch,double", [((64,), 5, False), ((33,), 4, True), ((32, 16), 3, False), ((100,), 3, True),
+                                                ((8, 6, 4), 2, False), ((4096,), 3, False), ((1024, 512), 1, False)])
+@pytest.mark.parametrize("inverse", [-1, 1])
+def test_dct(gpu, kind, shape, batch, double, inverse):
+    import vkfft_b200 as vk
+    if kind == 4 and any(s % 2 for s in shape):
+        pytest.skip("odd-length DCT-IV not built yet")
+    if kind == 1 and not all(_smooth13(2 * s - 2) for s in shape):
+        pytest.skip("DCT-I whose 2N-2 has a prime factor > 13: not built yet")
+    rdt = np.float64 if double else np.float32
+    x = orc.random_input((batch,) + tuple(reversed(shape)), rdt, seed=kind + sum(shape))
+    cfg = vk.VkFFTConfiguration(FFTdim=len(shape), size=list(shape), numberBatches=batch, device=0, performDCT=kind,
+                                doublePrecision=int(double))
+    y = _run_plan(gpu, x, cfg, inverse)
+    ref = orc.dct(x, kind, len(shape), inverse=(inverse == 1))
+    assert orc.error_metrics(y, ref)["l2_rel"] < (TOL64 if double else 2e-6)
+
+
+def test_out_of_place_formatted_buffers(gpu):
+    """isInputFormatted / isOutputFormatted plumbing (API guide :365-376) for C2C and R2C"""
+    import vkfft_b200 as vk
+    torch = gpu
+    n, batch = 1024, 6
+    x = orc.random_input((batch, n), np.complex64, 11)
+    tin = torch.from_numpy(x).cuda()
+    tbuf = torch.zeros_like(tin)
+    tout = torch.zeros_like(tin)
+    app = vk.VkFFTApplication()
+    cfg = vk.VkFFTConfiguration(FFTdim=1, size=[n], numberBatches=batch, device=0, isInputFormatted=1, isOutputFormatted=1)
+    assert vk.initializeVkFFT(app, cfg) == 0
+    assert vk.VkFFTAppend(app, -1, vk.VkFFTLaunchParams(buffer=tbuf, inputBuffer=tin, outputBuffer=tout)) == 0
+    torch.cuda.synchronize()
+    assert orc.error_metrics(tout.cpu().numpy(), orc.c2c(x, 1))["l2_rel"] < TOL32
+    assert np.array_equal(tin.cpu().numpy(), x)          # input untouched
+    vk.deleteVkFFT(app)
+    # R2C from an unpadded real input buffer
+    xr = orc.random_input((batch, 16, 64), np.float32, 12)
+    tr = torch.from_numpy(xr).cuda()
+    tc = torch.zeros((batch, 16, 33), dtype=torch.complex64, device="cuda")
+    app = vk.VkFFTApplication()
+    cfg = vk.VkFFTConfiguration(FFTdim=2, size=[64, 16], numberBatches=batch, device=0, performR2C=1, isInputFormatted=1,
+                                inverseReturnToInputBuffer=1)
+    assert vk.initializeVkFFT(app, cfg) == 0
+    assert vk.VkFFTAppend(app, -1, vk.VkFFTLaunchParams(buffer=tc, inputBuffer=tr)) == 0
+    torch.cuda.synchronize()
+    assert orc.error_metrics(tc.cpu().numpy(), orc.r2c(xr, 2))["l2_rel"] < TOL32
+    tr.zero_()
+    assert vk.VkFFTAppend(app, 1, vk.VkFFTLaunchParams(buffer=tc, inputBuffer=tr)) == 0
+    torch.cuda.synchronize()
+    assert orc.error_metrics(tr.cpu().numpy(), xr.astype(np.float64) * 64 * 16)["l2_rel"] < TOL32
+    vk.deleteVkFFT(app)

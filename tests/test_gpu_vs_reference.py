@@ -53,3 +53,69 @@ def test_c2c_f64_matches_reference(ref, size_xyz):
     import torch
     x, mine, theirs = _both(torch, size_xyz, 1, -1, True, use_lut=0)
     assert orc.error_metrics(mine, theirs)["l2_rel"] < 1e-12
+
+
+def _ref_inplace(torch, arr, size_xyz, batch, inverse, double=False, **kw):
+    t = torch.from_numpy(np.ascontiguousarray(arr)).cuda()
+    rc = orc.ref_run(orc.ref_desc(size_xyz, batch, double, use_lut=1, **kw), inverse, t.data_ptr())
+    assert rc == 0, rc
+    return t.cpu().numpy()
+
+
+def _mine_inplace(torch, arr, size_xyz, batch, inverse, double=False, **kw):
+    import vkfft_b200 as vk
+    t = torch.from_numpy(np.ascontiguousarray(arr)).cuda()
+    app = vk.VkFFTApplication()
+    cfg = vk.VkFFTConfiguration(FFTdim=len(size_xyz), size=list(size_xyz), numberBatches=batch, device=0,
+                                doublePrecision=int(double), **kw)
+    rc = vk.initializeVkFFT(app, cfg)
+    assert rc == 0, vk.getVkFFTErrorString(rc)
+    try:
+        assert vk.VkFFTAppend(app, inverse, vk.VkFFTLaunchParams(buffer=t)) == 0
+        torch.cuda.synchronize()
+        return t.cpu().numpy()
+    finally:
+        vk.deleteVkFFT(app)
+
+
+@pytest.mark.parametrize("size_xyz,batch", [((1000,), 8), ((2187,), 3), ((30030,), 2), ((17,), 64), ((509,), 8), ((105, 30), 2)])
+@pytest.mark.parametrize("inverse", [-1, 1])
+def test_non_pow2_matches_reference(ref, size_xyz, batch, inverse):
+    import torch
+    x = orc.random_input((batch,) + tuple(reversed(size_xyz)), np.complex64, seed=sum(size_xyz))
+    mine = _mine_inplace(torch, x, size_xyz, batch, inverse)
+    theirs = _ref_inplace(torch, x, size_xyz, batch, inverse)
+    assert orc.error_metrics(mine, theirs)["l2_rel"] < 1e-6
+
+
+@pytest.mark.parametrize("size_xyz,batch", [((64,), 8), ((4096,), 4), ((4096, 4096), 1), ((30, 4), 3)])
+def test_r2c_c2r_matches_reference(ref, size_xyz, batch):
+    import torch
+    nx, H = size_xyz[0], size_xyz[0] // 2 + 1
+    x = orc.random_input((batch,) + tuple(reversed(size_xyz)), np.float32, seed=sum(size_xyz))
+    buf = np.zeros(x.shape[:-1] + (2 * H,), np.float32)
+    buf[..., :nx] = x
+    mine = _mine_inplace(torch, buf, size_xyz, batch, -1, performR2C=1)
+    theirs = _ref_inplace(torch, buf, size_xyz, batch, -1, perform_r2c=1)
+    assert orc.error_metrics(mine.view(np.complex64), theirs.view(np.complex64))["l2_rel"] < 1e-6
+    mine2 = _mine_inplace(torch, theirs, size_xyz, batch, 1, performR2C=1)
+    theirs2 = _ref_inplace(torch, theirs, size_xyz, batch, 1, perform_r2c=1)
+    assert orc.error_metrics(mine2[..., :nx], theirs2[..., :nx])["l2_rel"] < 1e-6
+
+
+@pytest.mark.parametrize("kind", [1, 2, 3, 4])
+@pytest.mark.parametrize("size_xyz,batch", [((64,), 6), ((100,), 4), ((32, 16), 3), ((2048, 256), 1)])
+@pytest.mark.parametrize("inverse", [-1, 1])
+def test_dct_matches_reference(ref, kind, size_xyz, batch, inverse):
+    import torch
+    def smooth(n):
+        for p in (2, 3, 5, 7, 11, 13):
+            while n % p == 0:
+                n //= p
+        return n == 1
+    if kind == 1 and not all(smooth(2 * s - 2) for s in size_xyz):
+        pytest.skip("DCT-I whose 2N-2 has a prime factor > 13: not built yet")
+    x = orc.random_input((batch,) + tuple(reversed(size_xyz)), np.float32, seed=kind + sum(size_xyz))
+    mine = _mine_inplace(torch, x, size_xyz, batch, inverse, performDCT=kind)
+    theirs = _ref_inplace(torch, x, size_xyz, batch, inverse, perform_dct=kind)
+    assert orc.error_metrics(mine, theirs)["l2_rel"] < 2e-6

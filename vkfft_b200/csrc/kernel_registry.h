@@ -19,6 +19,7 @@ enum { B2_PREC_F32 = 0, B2_PREC_F64 = 1 };
 
 typedef struct b2_kernel_info {
     int kind, prec, n, inv, ops;       // lookup key
+    int variant;                       // 0 = default; further CTA shapes / schedules for the same key (tuning)
     int threads, q, tpl, v, smem_bytes;
     int ns;
     int radices[8];
@@ -30,7 +31,8 @@ typedef struct b2_kernel_info {
 } b2_kernel_info;
 
 void b2_register_kernel(const b2_kernel_info* k);
-const b2_kernel_info* b2_find_kernel(int kind, int prec, int n, int inv, int ops);
+const b2_kernel_info* b2_find_kernel(int kind, int prec, int n, int inv, int ops);   // honours B200FFT_VARIANTS
+const b2_kernel_info* b2_find_kernel_variant(int kind, int prec, int n, int inv, int ops, int variant);
 int b2_kernel_count(void);
 const b2_kernel_info* b2_kernel_at(int i);
 

@@ -273,3 +273,77 @@ extern "C" const char* b200fft_error_string(int code) {
 }
 extern "C" int b200fft_version(void) { return B200FFT_VERSION; }
 extern "C" int b200fft_kernel_count(void) { return b2_kernel_count(); }
+
+// ---- tuning hook (not part of the drop-in API): time one registered kernel on a synthetic full-buffer pass ----------
+// kind ROWS: total/n contiguous lines; COLS: four-step first pass shape (n x `other` lines interleaved, phase
+// multiply if the kernel has it); ROWS_TOUT: four-step last pass shape (transposed store).  `in` != `out` for
+// ROWS_TOUT.  Returns 0 and the mean ms per launch.
+extern "C" int b200fft_debug_time_kernel(int index, void* in, void* out, uint64_t total, uint32_t other, int reps,
+                                         float* ms_out, char* name, int name_cap) {
+    if (index < 0 || index >= b2_kernel_count()) return -1;
+    const b2_kernel_info* k = b2_kernel_at(index);
+    if (k->kind == B2_KIND_GENERIC) return -2;
+    if (name) snprintf(name, name_cap, "%s", k->name);
+    const uint64_t n = (uint64_t)k->n;
+    b2_pass_params P;
+    memset(&P, 0, sizeof P);
+    void *d_lut = nullptr, *d_hi = nullptr, *d_lo = nullptr;
+    uint64_t dummy = 0;
+    int rc;
+    if (k->prec == B2_PREC_F32) rc = upload(make_stage_lut<float>(k->radices, k->ns), &d_lut, dummy);
+    else rc = upload(make_stage_lut<double>(k->radices, k->ns), &d_lut, dummy);
+    if (rc) return rc;
+    P.in = in; P.out = out; P.lut = d_lut; P.n = (uint32_t)n; P.scale = 1.0; P.ops = k->ops; P.inverse = k->inv;
+    for (int d = 0; d < B2_MAX_OUTER; ++d) P.nb[d] = 1;
+    uint64_t grid;
+    if (k->kind == B2_KIND_ROWS) {
+        P.in_es = P.out_es = 1; P.in_gs = P.out_gs = (int64_t)n; P.G = (uint32_t)(total / n);
+        grid = (P.G + k->q - 1) / k->q;
+    } else {
+        uint64_t o = other;
+        while (o * n > total) o >>= 1;
+        const uint64_t nouter = total / (n * o);
+        P.nb[0] = (uint32_t)nouter; P.in_bs[0] = P.out_bs[0] = (int64_t)(n * o);
+        P.G = (uint32_t)o;
+        if (k->kind == B2_KIND_COLS) {
+            P.in_es = P.out_es = (int64_t)o; P.in_gs = P.out_gs = 1;
+        } else {
+            P.in_es = 1; P.in_gs = (int64_t)n; P.out_es = (int64_t)o; P.out_gs = 1;
+        }
+        grid = ((o + k->q - 1) / k->q) * nouter;
+        if (k->ops & B2_OP_TWIDDLE_OUT) {
+            if (k->prec == B2_PREC_F32) {
+                std::vector<float> hi, lo; make_twolevel<float>(n * o, P.tw_shift, hi, lo);
+                rc = upload(hi, &d_hi, dummy); if (!rc) rc = upload(lo, &d_lo, dummy);
+            } else {
+                std::vector<double> hi, lo; make_twolevel<double>(n * o, P.tw_shift, hi, lo);
+                rc = upload(hi, &d_hi, dummy); if (!rc) rc = upload(lo, &d_lo, dummy);
+            }
+            P.tw_hi = d_hi; P.tw_lo = d_lo;
+        }
+    }
+    if (!rc && k->prepare && k->prepare() != 0) rc = R_FAILED_TO_SET_DYNAMIC_SHARED_MEMORY;
+    float ms = 0;
+    if (!rc) {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        for (int i = 0; i < 2 && !rc; ++i) rc = k->launch(&P, (unsigned)grid, nullptr);
+        cudaEventRecord(e0, 0);
+        for (int i = 0; i < reps && !rc; ++i) rc = k->launch(&P, (unsigned)grid, nullptr);
+        cudaEventRecord(e1, 0);
+        if (cudaDeviceSynchronize() != cudaSuccess) rc = R_FAILED_TO_SYNCHRONIZE;
+        cudaEventElapsedTime(&ms, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        cudaGetLastError();
+    }
+    if (ms_out) *ms_out = ms / (reps > 0 ? reps : 1);
+    cudaFree(d_lut); if (d_hi) cudaFree(d_hi); if (d_lo) cudaFree(d_lo);
+    return rc;
+}
+extern "C" int b200fft_debug_kernel_info(int index, int* v /*kind,prec,n,inv,ops,variant,threads,q,tpl,smem*/) {
+    if (index < 0 || index >= b2_kernel_count()) return -1;
+    const b2_kernel_info* k = b2_kernel_at(index);
+    int a[] = {k->kind, k->prec, k->n, k->inv, k->ops, k->variant, k->threads, k->q, k->tpl, k->smem_bytes};
+    for (int i = 0; i < 10; ++i) v[i] = a[i];
+    return 0;
+}

@@ -90,7 +90,7 @@ B2_D cpx<T> twiddle2(const cpx<T>* hi, const cpx<T>* lo, uint32_t shift, uint64_
 // ------------------------------------------------------------------------------------------------
 // Kernel configuration (all compile-time)
 template <typename T_, class Sch_, int TPL_, int Q_, int V_, int LMAP_, int SMAP_, int LAYOUT_, bool INV_,
-          int OPS_, bool IN_UNIT_, bool OUT_UNIT_, int MINB_ = 1>
+          int OPS_, bool IN_UNIT_, bool OUT_UNIT_, int REGS_ = 128>
 struct KCfg {
     using T = T_;
     using Sch = Sch_;
@@ -105,8 +105,9 @@ struct KCfg {
     static constexpr int OPS = OPS_;
     static constexpr bool IN_UNIT = IN_UNIT_;    // in_es == 1 guaranteed
     static constexpr bool OUT_UNIT = OUT_UNIT_;  // out_es == 1 guaranteed
-    static constexpr int MINB = MINB_;
     static constexpr int THREADS = TPL * Q;
+    // register budget per thread -> resident CTAs per SM the compiler must make room for
+    static constexpr int MINB = (65536 / (THREADS * REGS_)) < 1 ? 1 : ((65536 / (THREADS * REGS_)) > 32 ? 32 : (65536 / (THREADS * REGS_)));
     // line-major layout: every 16 B*8 = 128 B of a line is followed by one pad element; lines start on
     // an odd multiple so that the column access of the transposed store is conflict free as well.
     static constexpr int PAD_SHIFT = (sizeof(T) == 4) ? 4 : 3;

@@ -81,3 +81,28 @@ def test_python_api_host_side_errors(built_lib):
     import torch
     if not torch.cuda.is_available():
         assert vk.initializeVkFFT(app, vk.VkFFTConfiguration(FFTdim=1, size=[8], device=0)) == vk.VKFFT_ERROR_INVALID_DEVICE
+
+
+def _build_sample(td):
+    cuda = "/usr/local/cuda"
+    exe = os.path.join(td, "drop_in_sample")
+    subprocess.check_call(["g++", "-std=c++11", "-O1", os.path.join(ROOT, "tests", "cpp", "drop_in_sample.cpp"), "-o", exe,
+                           "-I", os.path.join(ROOT, "include"), "-I", os.path.join(cuda, "include"),
+                           "-L", os.path.join(ROOT, "vkfft_b200", "lib"), "-lb200fft",
+                           "-L", os.path.join(cuda, "lib64"), "-L", os.path.join(cuda, "lib64", "stubs"), "-lcuda", "-lcudart",
+                           "-Wl,-rpath," + os.path.join(ROOT, "vkfft_b200", "lib"), "-Wl,-rpath," + os.path.join(cuda, "lib64")])
+    return exe
+
+
+def test_reference_style_cpp_program_builds_against_the_shim(built_lib):
+    if not os.path.exists("/usr/local/cuda/include/cuda.h"):
+        pytest.skip("CUDA headers not present")
+    with tempfile.TemporaryDirectory() as td:
+        assert os.path.exists(_build_sample(td))
+
+
+@pytest.mark.gpu
+def test_reference_style_cpp_program_runs(built_lib):
+    with tempfile.TemporaryDirectory() as td:
+        out = subprocess.run([_build_sample(td)], capture_output=True, text=True)
+        assert out.returncode == 0, out.stdout + out.stderr

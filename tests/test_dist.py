@@ -1,0 +1,65 @@
+"""CPU, world_size 2 over gloo: the host-side logic of the N>1 path (batch sharding, max-over-ranks timing)."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_batches_partitions_exactly():
+    sys.path.insert(0, ROOT)
+    from vkfft_b200.dist import shard_batches
+    for nb in (1, 2, 7, 8, 65536, 100003):
+        for world in (1, 2, 3, 4, 8):
+            slabs = [shard_batches(nb, world, r) for r in range(world)]
+            pos = 0
+            for start, count in slabs:
+                assert start == pos
+                pos += count
+            assert pos == nb
+            assert max(c for _, c in slabs) - min(c for _, c in slabs) <= 1
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import vkfft_b200 as vk
+        from vkfft_b200.dist import max_over_ranks, shard_configuration
+        cfg = vk.VkFFTConfiguration(FFTdim=1, size=[4096], numberBatches=65537, device=0)
+        mine, first, off = shard_configuration(cfg, world, rank)
+        t = torch.tensor([mine.numberBatches, first], dtype=torch.int64)
+        gathered = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t)
+        slowest = max_over_ranks(1.0 + rank, dist)
+        q.put((rank, [g.tolist() for g in gathered], off, slowest, mine.device))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_batch_sharding_over_gloo():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, g0, off0, slow0, dev0), (r1, g1, off1, slow1, dev1) = res
+    assert g0 == g1 == [[32769, 0], [32768, 32769]]
+    assert off0 == 0 and off1 == 32769 * 4096 * 8
+    assert slow0 == slow1 == 2.0
+    assert (dev0, dev1) == (0, 1)

@@ -25,23 +25,23 @@ def lib():
 def kernels():
     L = lib()
     out = []
-    buf = (ctypes.c_int * 19)()
+    buf = (ctypes.c_int * 20)()
     for i in range(L.emu_kernel_count()):
         L.emu_kernel_info(i, buf)
         v = list(buf)
         out.append(dict(kind=v[0], prec=v[1], n=v[2], inv=v[3], ops=v[4], threads=v[5], q=v[6], tpl=v[7], v=v[8],
-                        smem=v[9], ns=v[10], radices=v[11:11 + v[10]]))
+                        smem=v[9], ns=v[10], radices=v[11:11 + v[10]], variant=v[19]))
     return out
 
 
 def run_pass(kind, prec, n, inv, ops, inp, out, G, nb=(1, 1, 1), in_es=1, out_es=1, in_gs=None, out_gs=None,
-             in_bs=(0, 0, 0), out_bs=(0, 0, 0), twM=0, tw_line0=0, scale=1.0, log=False):
+             in_bs=(0, 0, 0), out_bs=(0, 0, 0), twM=0, tw_line0=0, scale=1.0, log=False, variant=0):
     L = lib()
     nbA = (ctypes.c_uint * 3)(*nb)
     ibs = (ctypes.c_longlong * 3)(*in_bs)
     obs = (ctypes.c_longlong * 3)(*out_bs)
     rep = (ctypes.c_double * 3)()
-    rc = L.emu_run_pass(kind, prec, n, inv, ops, inp.ctypes.data_as(ctypes.c_void_p),
+    rc = L.emu_run_pass(kind, prec, n, inv, ops, int(variant), inp.ctypes.data_as(ctypes.c_void_p),
                         out.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint(G), nbA,
                         ctypes.c_longlong(in_es), ctypes.c_longlong(out_es), ctypes.c_longlong(in_gs),
                         ctypes.c_longlong(out_gs), ibs, obs, ctypes.c_ulonglong(twM), ctypes.c_uint(tw_line0),

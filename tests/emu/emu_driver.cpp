@@ -19,15 +19,16 @@ extern "C" int emu_kernel_info(int i, int* out /*kind,prec,n,inv,ops,threads,q,t
     int v[] = {k->kind, k->prec, k->n, k->inv, k->ops, k->threads, k->q, k->tpl, k->v, k->smem_bytes, k->ns};
     for (int j = 0; j < 11; ++j) out[j] = v[j];
     for (int j = 0; j < 8; ++j) out[11 + j] = k->radices[j];
+    out[19] = k->variant;
     return 0;
 }
 
 // Run one pass.  `in`/`out` are host arrays of complex T.  Returns 0, or -1 if no such kernel.
-extern "C" int emu_run_pass(int kind, int prec, int n, int inv, int ops, const void* in, void* out, unsigned G,
+extern "C" int emu_run_pass(int kind, int prec, int n, int inv, int ops, int variant, const void* in, void* out, unsigned G,
                             const unsigned* nb, long long in_es, long long out_es, long long in_gs,
                             long long out_gs, const long long* in_bs, const long long* out_bs,
                             unsigned long long twM, unsigned tw_line0, double scale, int log, double* report) {
-    const b2_kernel_info* k = b2_find_kernel(kind, prec, n, inv, ops & ~B2_OP_SCALE);
+    const b2_kernel_info* k = b2_find_kernel_variant(kind, prec, n, inv, ops & ~B2_OP_SCALE, variant);
     if (!k) return -1;
     b2_pass_params P{};
     P.in = in; P.out = out;

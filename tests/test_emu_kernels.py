@@ -15,7 +15,7 @@ def _kernels():
 
 
 def _ids(k):
-    return f"kind{k['kind']}-p{k['prec']}-n{k['n']}-inv{k['inv']}"
+    return f"kind{k['kind']}-p{k['prec']}-n{k['n']}-inv{k['inv']}-v{k['variant']}"
 
 
 @pytest.mark.parametrize("k", [k for k in _kernels() if k["n"] <= 2048], ids=_ids)
@@ -27,20 +27,23 @@ def test_every_kernel_matches_oracle(k):
     ref = orc.c2c(x, 1, bool(k["inv"]))
     if k["kind"] == emu.KIND_ROWS:
         y = np.zeros_like(x)
-        rep = emu.run_pass(k["kind"], k["prec"], n, k["inv"], 0, x, y, G, in_gs=n, out_gs=n, log=True)
+        rep = emu.run_pass(k["kind"], k["prec"], n, k["inv"], 0, x, y, G, in_gs=n, out_gs=n, log=True, variant=k['variant'])
         got = y
     elif k["kind"] == emu.KIND_ROWS_TOUT:
         y = np.zeros((n, G), dtype=dt)
-        rep = emu.run_pass(k["kind"], k["prec"], n, k["inv"], 0, x, y, G, in_gs=n, out_gs=1, out_es=G, log=True)
+        rep = emu.run_pass(k["kind"], k["prec"], n, k["inv"], 0, x, y, G, in_gs=n, out_gs=1, out_es=G, log=True, variant=k['variant'])
         got = y.T
     else:
         xt = np.ascontiguousarray(x.T)
         y = np.zeros((n, G), dtype=dt)
-        rep = emu.run_pass(k["kind"], k["prec"], n, k["inv"], 0, xt, y, G, in_gs=1, out_gs=1, in_es=G, out_es=G, log=True)
+        rep = emu.run_pass(k["kind"], k["prec"], n, k["inv"], 0, xt, y, G, in_gs=1, out_gs=1, in_es=G, out_es=G, log=True, variant=k['variant'])
         got = y.T
     assert orc.error_metrics(got, ref)["l2_rel"] < (3e-7 if k["prec"] == 0 else 1e-15)
     # shared-memory traffic: never worse than 2-way conflicts on average 1.5 wavefronts per ideal one
-    assert rep["mean"] <= 2.0 and rep["worst"] <= 4.0
+    if k["variant"] == 0:
+        assert rep["mean"] <= 2.0 and rep["worst"] <= 4.0
+    else:           # tuning variants: only guard against pathological layouts
+        assert rep["mean"] <= 4.0
 
 
 def _plan_case(shape_xyz, batches, prec, env=None, inverse=-1, normalize=0):

@@ -20,11 +20,12 @@ for i in range(L.b200fft_kernel_count()):
     L.b200fft_debug_kernel_info(i, info)
     kind, p, n, inv, ops, var, thr, q, tpl, smem = list(info)
     if kind > 2 or p != prec or inv != 0: continue
-    if kind == 2 and ops == 0: continue          # time the four-step flavour of COLS
+    if kind == 2 and ops == 0 and not os.environ.get("KTUNE_COLS_PLAIN"): continue   # default: four-step flavour of COLS
+    if kind == 2 and ops != 0 and os.environ.get("KTUNE_COLS_PLAIN"): continue
     if only_n and n not in only_n: continue
     ms = ctypes.c_float(0)
     name = ctypes.create_string_buffer(256)
-    rc = L.b200fft_debug_time_kernel(i, a.data_ptr(), b.data_ptr() if kind == 1 else a.data_ptr(), total, 1024, 5,
+    rc = L.b200fft_debug_time_kernel(i, a.data_ptr(), b.data_ptr() if kind == 1 else a.data_ptr(), total, int(os.environ.get("KTUNE_OTHER", "1024")), 5,
                                      ctypes.byref(ms), name, 256)
     gbs = 2 * total * esz / (ms.value * 1e-3) / 1e9 if ms.value > 0 else 0
     rows.append((kind, n, var, ms.value, gbs, thr, q, smem, name.value.decode(), rc))

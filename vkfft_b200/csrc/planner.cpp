@@ -214,6 +214,9 @@ int emit(PlanGraph& g, std::vector<PassPlan>& list, const PassReq& rq) {
         pp.lut_id = lut_for(g, radices);
         if (rq.ops & B2_OP_TWIDDLE_OUT) pp.tw_id = tw_for(g, rq.twM);
         pp.aux0_id = rq.aux0; pp.aux1_id = rq.aux1;
+        // specialised kernels: intra-tile factor of the four-step phase (coalesced table, see stockham.cuh)
+        if (!generic && (rq.ops & B2_OP_TWIDDLE_OUT) && tw_sel == 0)
+            pp.aux0_id = aux_for(g, AUX_TW_TILE, rq.twM, (uint64_t)rq.n | ((uint64_t)q << 32));
         auto scalar_io = [](int io) { return io == B2_IO_DCT1 || io == B2_IO_DCT2 || io == B2_IO_DCT3 || io == B2_IO_DCT4 || io == B2_IO_REAL; };
         pp.in_scalar = scalar_io(rq.load_io); pp.out_scalar = scalar_io(rq.store_io);
         char buf[320];

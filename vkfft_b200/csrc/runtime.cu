@@ -287,7 +287,7 @@ extern "C" int b200fft_debug_time_kernel(int index, void* in, void* out, uint64_
     const uint64_t n = (uint64_t)k->n;
     b2_pass_params P;
     memset(&P, 0, sizeof P);
-    void *d_lut = nullptr, *d_hi = nullptr, *d_lo = nullptr;
+    void *d_lut = nullptr, *d_hi = nullptr, *d_lo = nullptr, *d_tile = nullptr;
     uint64_t dummy = 0;
     int rc;
     if (k->prec == B2_PREC_F32) rc = upload(make_stage_lut<float>(k->radices, k->ns), &d_lut, dummy);
@@ -320,6 +320,12 @@ extern "C" int b200fft_debug_time_kernel(int index, void* in, void* out, uint64_
                 rc = upload(hi, &d_hi, dummy); if (!rc) rc = upload(lo, &d_lo, dummy);
             }
             P.tw_hi = d_hi; P.tw_lo = d_lo;
+            if (!rc) {
+                const uint64_t bb = n | ((uint64_t)k->q << 32);
+                if (k->prec == B2_PREC_F32) rc = upload(make_aux<float>(AUX_TW_TILE, n * o, bb), &d_tile, dummy);
+                else rc = upload(make_aux<double>(AUX_TW_TILE, n * o, bb), &d_tile, dummy);
+                P.aux0 = d_tile;
+            }
         }
     }
     if (!rc && k->prepare && k->prepare() != 0) rc = R_FAILED_TO_SET_DYNAMIC_SHARED_MEMORY;
@@ -337,7 +343,7 @@ extern "C" int b200fft_debug_time_kernel(int index, void* in, void* out, uint64_
         cudaGetLastError();
     }
     if (ms_out) *ms_out = ms / (reps > 0 ? reps : 1);
-    cudaFree(d_lut); if (d_hi) cudaFree(d_hi); if (d_lo) cudaFree(d_lo);
+    cudaFree(d_lut); if (d_hi) cudaFree(d_hi); if (d_lo) cudaFree(d_lo); if (d_tile) cudaFree(d_tile);
     return rc;
 }
 extern "C" int b200fft_debug_kernel_info(int index, int* v /*kind,prec,n,inv,ops,variant,threads,q,tpl,smem*/) {

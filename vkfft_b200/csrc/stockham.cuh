@@ -224,12 +224,16 @@ struct Engine {
 
     // ---- HBM store of last-stage outputs (+ fused post operators) --------------------------------------
     template <int s>
+    // Four-step phase on store.  W_M^(line*p) with line = g0 + q is factored as W_M^(g0*p) * W_M^(q*p):
+    // the first factor is the same for all lanes that share p (two broadcast loads from the two-level table),
+    // the second comes from a small [p][q] table that neighbouring lanes read contiguously -- no scattered gathers.
     B2_D static void store_global(const X* x, X* __restrict__ line, int64_t es, int t, bool valid,
-                                  const b2_pass_params& P, uint32_t gline) {
+                                  const b2_pass_params& P, uint32_t gline, uint32_t qline) {
         constexpr int r = Sch::r(s), NB = nbut<s>(), BPT = bpt<s>();
         static_assert(s == NS - 1, "global store only after the last stage");
         const bool do_scale = (P.ops & B2_OP_SCALE) != 0;   // runtime: normalize=1 on the last inverse pass
         const T sc = (T)P.scale;
+        const X* __restrict__ tile = (P.tw_sel == 0) ? (const X*)P.aux0 : nullptr;
 #pragma unroll
         for (int m = 0; m < BPT; ++m) {
             const int b0 = V * (t + m * TPL);
@@ -242,8 +246,15 @@ struct Engine {
                     X a = x[(m * V + v) * r + k];
                     const int p = b0 + v + k * NB;  // natural-order output index (S == NB in the last stage)
                     if constexpr ((C::OPS & B2_OP_TWIDDLE_OUT) != 0) {
-                        const uint64_t e = (uint64_t)gline * (uint64_t)p;
-                        a = a * twiddle2<T>((const X*)P.tw_hi, (const X*)P.tw_lo, P.tw_shift, e);
+                        if (tile != nullptr) {
+                            const uint64_t e = (uint64_t)(gline - qline) * (uint64_t)p;
+                            const X w1 = twiddle2<T>((const X*)P.tw_hi, (const X*)P.tw_lo, P.tw_shift, e);
+                            const X w2 = ld_lut(tile + p * Q + (int)qline);
+                            a = a * (w1 * w2);
+                        } else {
+                            const uint64_t e = (uint64_t)gline * (uint64_t)p;
+                            a = a * twiddle2<T>((const X*)P.tw_hi, (const X*)P.tw_lo, P.tw_shift, e);
+                        }
                     }
                     if (do_scale) a = a * sc;
                     o[v] = C::INV ? swp(a) : a;
@@ -311,7 +322,7 @@ struct Engine {
             load_global<0>(x, in_line, P.in_es, tl, gl < P.G);
             compute<0>(x, lut, tl);
             X* out_line = (X*)P.out + obase_out + (int64_t)gl * P.out_gs;
-            store_global<0>(x, out_line, P.out_es, tl, gl < P.G, P, twl(P, gl, o0, o1, o2));
+            store_global<0>(x, out_line, P.out_es, tl, gl < P.G, P, twl(P, gl, o0, o1, o2), (uint32_t)ql);
         } else {
             {
                 X x[bpt<0>() * V * Sch::r(0)];
@@ -330,7 +341,7 @@ struct Engine {
                 load_smem<s>(x, sm, qs, ts);
                 compute<s>(x, lut, ts);
                 X* out_line = (X*)P.out + obase_out + (int64_t)gs * P.out_gs;
-                store_global<s>(x, out_line, P.out_es, ts, gs < P.G, P, twl(P, gs, o0, o1, o2));
+                store_global<s>(x, out_line, P.out_es, ts, gs < P.G, P, twl(P, gs, o0, o1, o2), (uint32_t)qs);
             }
         }
     }

@@ -25,12 +25,12 @@ def lib():
 def kernels():
     L = lib()
     out = []
-    buf = (ctypes.c_int * 20)()
+    buf = (ctypes.c_int * 21)()
     for i in range(L.emu_kernel_count()):
         L.emu_kernel_info(i, buf)
         v = list(buf)
         out.append(dict(kind=v[0], prec=v[1], n=v[2], inv=v[3], ops=v[4], threads=v[5], q=v[6], tpl=v[7], v=v[8],
-                        smem=v[9], ns=v[10], radices=v[11:11 + v[10]], variant=v[19]))
+                        smem=v[9], ns=v[10], radices=v[11:11 + v[10]], variant=v[19], pipelined=v[20]))
     return out
 
 

@@ -20,6 +20,7 @@ extern "C" int emu_kernel_info(int i, int* out /*kind,prec,n,inv,ops,threads,q,t
     for (int j = 0; j < 11; ++j) out[j] = v[j];
     for (int j = 0; j < 8; ++j) out[11 + j] = k->radices[j];
     out[19] = k->variant;
+    out[20] = k->pipelined;
     return 0;
 }
 

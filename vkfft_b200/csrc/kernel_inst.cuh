@@ -4,6 +4,7 @@
 #include "kernel_registry.h"
 #include "stockham.cuh"
 #include "generic.cuh"
+#include "pipe.cuh"
 
 #if !defined(B2_EMU)
 #include <cuda_runtime.h>
@@ -110,6 +111,71 @@ struct Registrar {
     }
 };
 
+// ---- persistent TMA-fed variants (pipe.cuh) ------------------------------------------------------------------------
+#if defined(B2_EMU)
+template <class C, int NBUF>
+int pipe_launch_impl(const b2_pass_params* P, unsigned grid, void*) {
+    const b2_pass_params PP = *P;
+    const unsigned g = grid < 3 ? grid : 3;       // few persistent CTAs so that the buffer ring wraps
+    b2emu::launch(g, C::THREADS, PipeEngine<C, NBUF>::SMEM_BYTES, [&](unsigned char* sm) { PipeEngine<C, NBUF>::run(PP, sm); },
+                  b2emu::st().log);
+    return 0;
+}
+template <class C, int NBUF> int pipe_prepare_impl() { return 0; }
+#else
+template <class C, int NBUF>
+int pipe_launch_impl(const b2_pass_params* P, unsigned grid, void* stream) {
+    static int resident = 0;
+    if (!resident) {
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stockham_pipe_kernel<C, NBUF>, C::THREADS,
+                                                      PipeEngine<C, NBUF>::SMEM_BYTES);
+        resident = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    const unsigned g = grid < (unsigned)resident ? grid : (unsigned)resident;
+    stockham_pipe_kernel<C, NBUF><<<g, C::THREADS, PipeEngine<C, NBUF>::SMEM_BYTES, (cudaStream_t)stream>>>(*P);
+    return (int)cudaGetLastError();
+}
+template <class C, int NBUF>
+int pipe_prepare_impl() {
+    return (int)cudaFuncSetAttribute(stockham_pipe_kernel<C, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     PipeEngine<C, NBUF>::SMEM_BYTES);
+}
+#endif
+
+template <int KIND, typename T, int TPL, int Q, int V, int REGS, int NBUF, bool INV, int... Rs>
+struct PipeRegistrar {
+    using KT = KindTraits<KIND>;
+    using Sch = RList<Rs...>;
+    using C = KCfg<T, Sch, TPL, Q, V, KT::LMAP, KT::SMAP, KT::LAYOUT, INV, 0, KT::IN_UNIT, KT::OUT_UNIT, REGS>;
+    b2_kernel_info info;
+    explicit PipeRegistrar(const char* name) {
+        info = b2_kernel_info{};
+        info.kind = KIND; info.prec = PrecOf<T>::value; info.n = Sch::N; info.inv = INV; info.ops = 0;
+        info.threads = C::THREADS; info.q = Q; info.tpl = TPL; info.v = V; info.smem_bytes = PipeEngine<C, NBUF>::SMEM_BYTES;
+        info.ns = Sch::ns;
+        for (int s = 0; s < Sch::ns; ++s) info.radices[s] = Sch::r(s);
+        info.lut_size = Sch::lut_size;
+        info.pipelined = 1;
+        info.launch = &pipe_launch_impl<C, NBUF>;
+        info.prepare = &pipe_prepare_impl<C, NBUF>;
+        info.name = name;
+        b2_register_kernel(&info);
+    }
+};
+template <bool EN, int KIND, typename T, int TPL, int Q, int V, int REGS, int NBUF, int... Rs>
+struct MaybePipe {
+    explicit MaybePipe(const char*) {}
+};
+template <int KIND, typename T, int TPL, int Q, int V, int REGS, int NBUF, int... Rs>
+struct MaybePipe<true, KIND, T, TPL, Q, V, REGS, NBUF, Rs...> {
+    PipeRegistrar<KIND, T, TPL, Q, V, REGS, NBUF, false, Rs...> f;
+    PipeRegistrar<KIND, T, TPL, Q, V, REGS, NBUF, true, Rs...> i;
+    explicit MaybePipe(const char* n) : f(n), i(n) {}
+};
+
 // every kind gets forward+inverse; COLS additionally gets the four-step twiddle-on-store variant
 template <int KIND, typename T, int TPL, int Q, int V, int MINB, int... Rs>
 struct RegistrarSet {
@@ -138,6 +204,11 @@ struct MaybeSet<true, KIND, T, TPL, Q, V, MINB, Rs...> : RegistrarSet<KIND, T, T
     explicit MaybeSet(const char* n) : RegistrarSet<KIND, T, TPL, Q, V, MINB, Rs...>(n) {}
 };
 }  // namespace b200fft
+
+#define B2_KP(shard, KIND, T, TPL, Q, V, REGS, NBUF, ...)                                                  \
+    static ::b200fft::MaybePipe<((B2_SHARD) < 0 || (shard) == (B2_SHARD)), B2_KIND_##KIND, T, TPL, Q, V, REGS, NBUF, \
+                                __VA_ARGS__>                                                              \
+        B2_CAT(b2_regp_, __LINE__)("PIPE" #NBUF "_" #KIND "<" #T "," #TPL "x" #Q ",V" #V ";" #__VA_ARGS__ ">");
 
 // B2_SHARD < 0 instantiates everything (CPU emulation build)
 #define B2_CAT2(a, b) a##b

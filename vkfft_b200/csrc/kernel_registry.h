@@ -20,6 +20,7 @@ enum { B2_PREC_F32 = 0, B2_PREC_F64 = 1 };
 typedef struct b2_kernel_info {
     int kind, prec, n, inv, ops;       // lookup key
     int variant;                       // 0 = default; further CTA shapes / schedules for the same key (tuning)
+    int pipelined;                     // 1: persistent TMA-fed kernel (pipe.cuh): input pointer and line pitch must be 16-byte aligned
     int threads, q, tpl, v, smem_bytes;
     int ns;
     int radices[8];

@@ -11,6 +11,7 @@
 // The reference has no asynchronous copy path at all: every VkFFT_main does
 // load -> compute -> store with plain loads.
 #pragma once
+#include <string.h>
 #include "stockham.cuh"
 
 namespace b200fft {
@@ -168,8 +169,8 @@ struct PipeEngine : Engine<C> {
 #if defined(__CUDACC__)
 template <class C, int NBUF>
 __global__ void __launch_bounds__(C::THREADS, C::MINB) stockham_pipe_kernel(const __grid_constant__ b2_pass_params P) {
-    extern __shared__ __align__(128) unsigned char b2_smem_raw[];
-    PipeEngine<C, NBUF>::run(P, b2_smem_raw);
+    extern __shared__ __align__(128) unsigned char b2_smem_pipe[];
+    PipeEngine<C, NBUF>::run(P, b2_smem_pipe);
 }
 #endif
 

@@ -40,8 +40,6 @@ extern "C" int emu_run_pass(int kind, int prec, int n, int inv, int ops, int var
     if (ops & B2_OP_TWIDDLE_OUT) {
         if (prec == B2_PREC_F32) { make_twolevel<float>(twM, P.tw_shift, hif, lof); P.tw_hi = hif.data(); P.tw_lo = lof.data(); }
         else { make_twolevel<double>(twM, P.tw_shift, hid, lod); P.tw_hi = hid.data(); P.tw_lo = lod.data(); }
-        if (prec == B2_PREC_F32) { tilef = make_aux<float>(AUX_TW_TILE, twM, (uint64_t)n | ((uint64_t)k->q << 32)); P.aux0 = tilef.data(); }
-        else { tiled = make_aux<double>(AUX_TW_TILE, twM, (uint64_t)n | ((uint64_t)k->q << 32)); P.aux0 = tiled.data(); }
     }
     P.in_es = in_es; P.out_es = out_es; P.in_gs = in_gs; P.out_gs = out_gs;
     unsigned grid = (G + k->q - 1) / k->q;

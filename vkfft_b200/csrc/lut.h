@@ -77,8 +77,6 @@ enum AuxKind {
     AUX_DCT4_POST = 4,    // a = N : e^{-i pi (4q+1)/(4N)},      q = 0..N/2-1
     AUX_BLUE_CHIRP = 5,   // a = N : e^{-i pi n^2/N},            n = 0..N-1           (vkFFT_RecursiveFFTGenerators.h:140)
     AUX_BLUE_FILTER = 6,  // a = N, b = M : FFT_M(e^{+i pi m^2/N} wrapped) / M        (vkFFT_RecursiveFFTGenerators.h:241-298)
-    AUX_TW_TILE = 7,      // a = M, b = n | (Q << 32) : W_M^(q*p) laid out [p][q], p < n, q < Q -- the intra-tile factor
-                          // of the four-step phase; lanes of a warp read it contiguously (see stockham.cuh)
 };
 
 // in-place radix-2 FFT in long double (host, table generation only); n must be a power of two
@@ -133,11 +131,6 @@ inline std::vector<T> make_aux(int kind, uint64_t a, uint64_t b) {
             }
             host_fft_pow2(re, im);
             for (uint64_t k = 0; k < b; ++k) push(re[k] / (long double)b, im[k] / (long double)b);
-        } break;
-        case AUX_TW_TILE: {
-            const uint64_t n = b & 0xffffffffull, Q = b >> 32;
-            for (uint64_t pp = 0; pp < n; ++pp)
-                for (uint64_t q = 0; q < Q; ++q) { unit_root((q * pp) % a, a, c, s); push(c, s); }
         } break;
         default: break;
     }

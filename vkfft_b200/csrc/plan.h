@@ -63,6 +63,7 @@ struct AuxSpec {       // operator tables (lut.h make_aux)
 
 struct PassPlan {
     const b2_kernel_info* k = nullptr;
+    const b2_kernel_info* k_unaligned = nullptr;   // used instead of a pipelined kernel when the input is not 16-byte aligned
     b2_pass_params P{};          // pointer members are filled in by the runtime at launch
     unsigned grid = 0;
     int in_role = ROLE_BUFFER, out_role = ROLE_BUFFER;

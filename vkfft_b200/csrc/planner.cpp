@@ -180,6 +180,19 @@ int emit(PlanGraph& g, std::vector<PassPlan>& list, const PassReq& rq) {
         }
         PassPlan pp;
         pp.k = k;
+        if (k->pipelined) {   // TMA needs 16-byte aligned sources: keep the first non-pipelined kernel of the same key as a stand-in
+            for (int v = 0; v < 16 && !pp.k_unaligned; ++v) {
+                const b2_kernel_info* alt = b2_find_kernel_variant(rq.kind, g.prec, rq.n, rq.inv, rq.ops & B2_OP_TWIDDLE_OUT, v);
+                if (alt && !alt->pipelined && alt->q == k->q) pp.k_unaligned = alt;
+            }
+            if (!pp.k_unaligned) {    // no drop-in with the same tile height: do not use the pipelined kernel at all
+                for (int v = 0; v < 16; ++v) {
+                    const b2_kernel_info* alt = b2_find_kernel_variant(rq.kind, g.prec, rq.n, rq.inv, rq.ops & B2_OP_TWIDDLE_OUT, v);
+                    if (alt && !alt->pipelined) { pp.k = k = alt; break; }
+                }
+                tpl = k->tpl; q = k->q;
+            }
+        }
         b2_pass_params& P = pp.P;
         P.in_es = rq.in_es; P.out_es = rq.out_es;
         P.in_gs = rq.group.is; P.out_gs = rq.group.os;
@@ -215,8 +228,6 @@ int emit(PlanGraph& g, std::vector<PassPlan>& list, const PassReq& rq) {
         if (rq.ops & B2_OP_TWIDDLE_OUT) pp.tw_id = tw_for(g, rq.twM);
         pp.aux0_id = rq.aux0; pp.aux1_id = rq.aux1;
         // specialised kernels: intra-tile factor of the four-step phase (coalesced table, see stockham.cuh)
-        if (!generic && (rq.ops & B2_OP_TWIDDLE_OUT) && tw_sel == 0)
-            pp.aux0_id = aux_for(g, AUX_TW_TILE, rq.twM, (uint64_t)rq.n | ((uint64_t)q << 32));
         auto scalar_io = [](int io) { return io == B2_IO_DCT1 || io == B2_IO_DCT2 || io == B2_IO_DCT3 || io == B2_IO_DCT4 || io == B2_IO_REAL; };
         pp.in_scalar = scalar_io(rq.load_io); pp.out_scalar = scalar_io(rq.store_io);
         char buf[320];
@@ -262,6 +273,17 @@ std::vector<uint64_t> split_four_step(const PlanGraph& g, uint64_t N) {
     }
     const uint64_t cap = std::min<uint64_t>(max_single_env(), 4096);
     auto fast = [&](int kind, uint64_t n, int ops) { return b2_find_kernel(kind, g.prec, (int)n, 0, ops) != nullptr; };
+    // measured cost of one full pass over a 2 GiB FP32 buffer on B200, microseconds (profiles/r1/ktune_*.log);
+    // used to rank factorizations.  Unknown sizes / FP64 fall back to "balanced factors".
+    auto pass_us = [&](int kind, uint64_t n) -> uint64_t {
+        if (g.prec != B2_PREC_F32) return 0;
+        static const struct { uint64_t n; uint64_t cols, tout; } t[] = {
+            {16, 670, 1030}, {32, 838, 622}, {64, 858, 646}, {128, 947, 655}, {256, 882, 650},
+            {512, 1038, 717}, {1024, 1188, 759}, {2048, 1440, 873}};
+        for (const auto& e : t)
+            if (e.n == n) return kind == B2_KIND_COLS ? e.cols : e.tout;
+        return 0;
+    };
     std::vector<uint64_t> best;
     uint64_t best_cost = ~0ull;
     for (uint64_t n2 = 2; n2 * 2 <= N && n2 <= cap; ++n2) {
@@ -269,8 +291,11 @@ std::vector<uint64_t> split_four_step(const PlanGraph& g, uint64_t N) {
         uint64_t n1 = N / n2;
         if (n1 > cap) continue;
         if (!single_ok(g, B2_KIND_ROWS_TOUT, n2, 0) || !single_ok(g, B2_KIND_COLS, n1, B2_OP_TWIDDLE_OUT)) continue;
-        // prefer specialised kernels, then balanced factors, the contiguous one not smaller than the strided one
+        // prefer specialised kernels, then measured pass costs, then balanced factors (contiguous one not smaller)
         uint64_t cost = std::max(n1, n2) * 4 + (n2 < n1 ? 2 : 0);
+        if (pass_us(B2_KIND_COLS, n1) && pass_us(B2_KIND_ROWS_TOUT, n2))
+            cost = (pass_us(B2_KIND_COLS, n1) + pass_us(B2_KIND_ROWS_TOUT, n2)) * 16 + (cost & 15);
+        else cost += 1u << 16;
         if (!fast(B2_KIND_ROWS_TOUT, n2, 0)) cost += 1u << 20;
         if (!fast(B2_KIND_COLS, n1, B2_OP_TWIDDLE_OUT)) cost += 1u << 20;
         if (cost < best_cost) { best_cost = cost; best = {n1, n2}; }
@@ -287,6 +312,9 @@ std::vector<uint64_t> split_four_step(const PlanGraph& g, uint64_t N) {
             uint64_t n1 = rest / n2;
             if (n1 > cap || !single_ok(g, B2_KIND_COLS, n1, B2_OP_TWIDDLE_OUT)) continue;
             uint64_t cost = std::max(n1, std::max(n2, n3)) * 4 + (n3 < n1 ? 1 : 0) + (n3 < n2 ? 1 : 0);
+            if (pass_us(B2_KIND_COLS, n1) && pass_us(B2_KIND_COLS, n2) && pass_us(B2_KIND_ROWS_TOUT, n3))
+                cost = (pass_us(B2_KIND_COLS, n1) + pass_us(B2_KIND_COLS, n2) + pass_us(B2_KIND_ROWS_TOUT, n3)) * 16 + (cost & 15);
+            else cost += 1u << 16;
             if (!fast(B2_KIND_ROWS_TOUT, n3, 0)) cost += 1u << 20;
             if (!fast(B2_KIND_COLS, n2, B2_OP_TWIDDLE_OUT)) cost += 1u << 20;
             if (!fast(B2_KIND_COLS, n1, B2_OP_TWIDDLE_OUT)) cost += 1u << 20;

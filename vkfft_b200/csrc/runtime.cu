@@ -7,6 +7,7 @@
 // the registry.  There is no CPU fallback either: if the device or the kernels are missing the call fails.
 #include <cuda_runtime.h>
 
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -126,7 +127,11 @@ extern "C" int b200fft_plan_create(const b200fft_desc* desc, b200fft_plan** out)
     // one-time kernel attributes (dynamic shared memory above 48 KiB)
     for (int dir = 0; dir < 2 && rc == R_SUCCESS; ++dir)
         for (const PassPlan& pp : (dir ? g.inv : g.fwd))
-            if (pp.k->prepare && pp.k->prepare() != 0) { rc = R_FAILED_TO_SET_DYNAMIC_SHARED_MEMORY; break; }
+            if ((pp.k->prepare && pp.k->prepare() != 0) ||
+                (pp.k_unaligned && pp.k_unaligned->prepare && pp.k_unaligned->prepare() != 0)) {
+                rc = R_FAILED_TO_SET_DYNAMIC_SHARED_MEMORY;
+                break;
+            }
     // scratch for Four-Step (the reference auto-allocates tempBuffer the same way, vkFFT_InitializeApp.h:1603-1637)
     if (rc == R_SUCCESS && g.temp_elems && !g.desc.user_temp_buffer) {
         p->temp_bytes = g.temp_elems * (g.prec == B2_PREC_F64 ? 16 : 8);
@@ -172,7 +177,11 @@ extern "C" int b200fft_exec(b200fft_plan* p, int inverse, const b200fft_buffers*
             P.tw_lo = p->d_tws[pp.tw_id].lo;
             P.tw_shift = p->d_tws[pp.tw_id].shift;
         }
-        if (pp.k->launch(&P, pp.grid, (void*)st) != 0) return R_FAILED_TO_LAUNCH_KERNEL;
+        const b2_kernel_info* k = pp.k;
+        if (k->pipelined && ((((uintptr_t)P.in) | (uintptr_t)(P.in_gs * (int64_t)esz) | (uintptr_t)(P.in_bs[0] * (int64_t)esz) |
+                              (uintptr_t)(P.in_bs[1] * (int64_t)esz) | (uintptr_t)(P.in_bs[2] * (int64_t)esz)) & 15))
+            k = pp.k_unaligned;
+        if (!k || k->launch(&P, pp.grid, (void*)st) != 0) return R_FAILED_TO_LAUNCH_KERNEL;
     }
     return R_SUCCESS;
 }
@@ -320,12 +329,6 @@ extern "C" int b200fft_debug_time_kernel(int index, void* in, void* out, uint64_
                 rc = upload(hi, &d_hi, dummy); if (!rc) rc = upload(lo, &d_lo, dummy);
             }
             P.tw_hi = d_hi; P.tw_lo = d_lo;
-            if (!rc) {
-                const uint64_t bb = n | ((uint64_t)k->q << 32);
-                if (k->prec == B2_PREC_F32) rc = upload(make_aux<float>(AUX_TW_TILE, n * o, bb), &d_tile, dummy);
-                else rc = upload(make_aux<double>(AUX_TW_TILE, n * o, bb), &d_tile, dummy);
-                P.aux0 = d_tile;
-            }
         }
     }
     if (!rc && k->prepare && k->prepare() != 0) rc = R_FAILED_TO_SET_DYNAMIC_SHARED_MEMORY;

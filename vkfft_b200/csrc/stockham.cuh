@@ -224,16 +224,15 @@ struct Engine {
 
     // ---- HBM store of last-stage outputs (+ fused post operators) --------------------------------------
     template <int s>
-    // Four-step phase on store.  W_M^(line*p) with line = g0 + q is factored as W_M^(g0*p) * W_M^(q*p):
-    // the first factor is the same for all lanes that share p (two broadcast loads from the two-level table),
-    // the second comes from a small [p][q] table that neighbouring lanes read contiguously -- no scattered gathers.
+    // Four-step phase on store: W_M^(line*p) from the two-level table (two small L1-resident lookups + one complex
+    // multiply).  Two alternatives were measured on B200 and rejected (profiles/r1/README.md): a tile-factored
+    // scheme with coalesced table reads and the reference-style full M-entry table; both were slower.
     B2_D static void store_global(const X* x, X* __restrict__ line, int64_t es, int t, bool valid,
                                   const b2_pass_params& P, uint32_t gline, uint32_t qline) {
         constexpr int r = Sch::r(s), NB = nbut<s>(), BPT = bpt<s>();
         static_assert(s == NS - 1, "global store only after the last stage");
         const bool do_scale = (P.ops & B2_OP_SCALE) != 0;   // runtime: normalize=1 on the last inverse pass
         const T sc = (T)P.scale;
-        const X* __restrict__ tile = (P.tw_sel == 0) ? (const X*)P.aux0 : nullptr;
 #pragma unroll
         for (int m = 0; m < BPT; ++m) {
             const int b0 = V * (t + m * TPL);
@@ -246,15 +245,8 @@ struct Engine {
                     X a = x[(m * V + v) * r + k];
                     const int p = b0 + v + k * NB;  // natural-order output index (S == NB in the last stage)
                     if constexpr ((C::OPS & B2_OP_TWIDDLE_OUT) != 0) {
-                        if (tile != nullptr) {
-                            const uint64_t e = (uint64_t)(gline - qline) * (uint64_t)p;
-                            const X w1 = twiddle2<T>((const X*)P.tw_hi, (const X*)P.tw_lo, P.tw_shift, e);
-                            const X w2 = ld_lut(tile + p * Q + (int)qline);
-                            a = a * (w1 * w2);
-                        } else {
-                            const uint64_t e = (uint64_t)gline * (uint64_t)p;
-                            a = a * twiddle2<T>((const X*)P.tw_hi, (const X*)P.tw_lo, P.tw_shift, e);
-                        }
+                        const uint64_t e = (uint64_t)gline * (uint64_t)p;
+                        a = a * twiddle2<T>((const X*)P.tw_hi, (const X*)P.tw_lo, P.tw_shift, e);
                     }
                     if (do_scale) a = a * sc;
                     o[v] = C::INV ? swp(a) : a;

@@ -75,6 +75,9 @@ def _plan_case(shape_xyz, batches, prec, env=None, inverse=-1, normalize=0):
     dict(shape_xyz=(32768,), batches=2, prec=0, inverse=1, env={"B200FFT_FOUR_STEP_SPLIT": "32,16,64"}, passes=3),
     dict(shape_xyz=(32768,), batches=2, prec=0, env={"B200FFT_FOUR_STEP_SPLIT": "16,2048"}, passes=2),   # TMA-fed last pass
     dict(shape_xyz=(16384,), batches=3, prec=0, passes=1),                                                # TMA-fed single pass
+    dict(shape_xyz=(16, 8192), batches=1, prec=0, passes=3),                                              # strided Four-Step
+    dict(shape_xyz=(24, 256), batches=2, prec=0, inverse=1, env={"B200FFT_MAX_SINGLE_PASS": "64"}, passes=3),
+    dict(shape_xyz=(8, 4, 128), batches=2, prec=1, env={"B200FFT_MAX_SINGLE_PASS": "32"}, passes=4),
     dict(shape_xyz=(64, 32), batches=2, prec=0, passes=2),
     dict(shape_xyz=(32, 16, 8), batches=2, prec=1, passes=3),
     dict(shape_xyz=(32, 16, 8), batches=2, prec=1, inverse=1, normalize=1, passes=3),

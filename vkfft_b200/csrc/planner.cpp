@@ -414,7 +414,24 @@ int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
     if (N == 1) return R_SUCCESS;   // length-1 transform is the identity
     if (!is_smooth(N)) return plan_bluestein(g, list, job);
 
-    if (N <= max_single_env() && single_ok(g, kind, N, 0)) {
+    // a strided axis served only by the runtime-scheduled kernel with fewer than 8 neighbouring lines per CTA would
+    // read 8..56-byte row fragments: split it instead (falls through to the strided Four-Step below)
+    bool poor_strided = false;
+    if (job.unit_lines && !b2_find_kernel(kind, g.prec, (int)std::min<uint64_t>(N, 0x7fffffff), 0, 0) && generic_fits(g, N)) {
+        const uint64_t per_line = 2ull * (uint64_t)(pad_of(g, N) | 1) * esize(g);
+        poor_strided = (GENERIC_SMEM_LIMIT / per_line) < 8 && N >= 64;
+    }
+    bool try_single = N <= max_single_env() && single_ok(g, kind, N, 0);
+    if (try_single && poor_strided) {
+        // only if a split exists
+        bool can_split = false;
+        for (uint64_t n2 = 2; n2 * 2 <= N && !can_split; ++n2)
+            if (N % n2 == 0 && single_ok(g, B2_KIND_COLS, N / n2, B2_OP_TWIDDLE_OUT) && single_ok(g, B2_KIND_COLS, n2, 0) &&
+                b2_find_kernel(B2_KIND_COLS, g.prec, (int)(N / n2), 0, B2_OP_TWIDDLE_OUT) && b2_find_kernel(B2_KIND_COLS, g.prec, (int)n2, 0, 0))
+                can_split = true;
+        if (can_split) try_single = false;
+    }
+    if (try_single) {
         PassReq rq;
         rq.kind = kind; rq.n = (int)N; rq.inv = job.inv; rq.ops = sc_ops;
         rq.in_es = job.es_in; rq.out_es = job.es_out;
@@ -432,7 +449,51 @@ int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
         rq.what = job.unit_lines ? "strided axis" : "single-pass";
         return emit(g, list, rq);
     }
-    if (!contiguous || job.unit_lines) return R_UNSUPPORTED_FFT_LENGTH;   // long strided axes: not yet
+    if (job.unit_lines) {
+        // long strided axis: two-launch Four-Step along the stride; neighbouring lanes still walk the unit-stride
+        // dimension, the sub-sequence index n2 / k1 becomes an outer dimension (and the phase "line" coordinate)
+        if (m.empty() || m[0].is != 1 || m[0].os != 1) return R_UNSUPPORTED_FFT_LENGTH;
+        uint64_t best1 = 0, best2 = 0, bestc = ~0ull;
+        for (uint64_t n2 = 2; n2 * 2 <= N; ++n2) {
+            if (N % n2) continue;
+            const uint64_t n1 = N / n2;
+            if (!single_ok(g, B2_KIND_COLS, n1, B2_OP_TWIDDLE_OUT) || !single_ok(g, B2_KIND_COLS, n2, 0)) continue;
+            uint64_t c = std::max(n1, n2) * 4 + (n2 < n1 ? 1 : 0);
+            if (!b2_find_kernel(B2_KIND_COLS, g.prec, (int)n1, 0, B2_OP_TWIDDLE_OUT)) c += 1u << 20;
+            if (!b2_find_kernel(B2_KIND_COLS, g.prec, (int)n2, 0, 0)) c += 1u << 20;
+            if (c < bestc) { bestc = c; best1 = n1; best2 = n2; }
+        }
+        if (!best1) return R_UNSUPPORTED_FFT_LENGTH;
+        const uint64_t N1 = best1, N2 = best2;
+        uint64_t extent = (uint64_t)job.es_out * N;
+        for (const Dim& d : job.lines) extent = std::max<uint64_t>(extent, (uint64_t)d.n * (uint64_t)d.os);
+        g.temp_elems = std::max<uint64_t>(g.temp_elems, extent);
+        const Dim unit = m[0];
+        std::vector<Dim> rest(m.begin() + 1, m.end());
+        PassReq a;
+        a.kind = B2_KIND_COLS; a.n = (int)N1; a.inv = job.inv; a.ops = B2_OP_TWIDDLE_OUT;
+        a.in_es = job.es_in * (int64_t)N2; a.out_es = job.es_out * (int64_t)N2;
+        a.group = unit;
+        a.outer.push_back(Dim{N2, job.es_in, job.es_out});
+        a.tw_outer = 0;
+        for (const Dim& d : rest) a.outer.push_back(Dim{d.n, d.is, d.os});
+        a.in_role = job.in_role; a.out_role = ROLE_TEMP;
+        a.twM = N;
+        a.what = "strided four-step 1/2";
+        int rc2 = emit(g, list, a);
+        if (rc2 != R_SUCCESS) return rc2;
+        PassReq b;
+        b.kind = B2_KIND_COLS; b.n = (int)N2; b.inv = job.inv; b.ops = sc_ops;
+        b.in_es = job.es_out; b.out_es = job.es_out * (int64_t)N1;
+        b.group = Dim{unit.n, 1, 1};
+        b.outer.push_back(Dim{N1, job.es_out * (int64_t)N2, job.es_out});
+        for (const Dim& d : rest) b.outer.push_back(Dim{d.n, d.os, d.os});
+        b.in_role = ROLE_TEMP; b.out_role = job.out_role;
+        b.scale = job.scale;
+        b.what = "strided four-step 2/2";
+        return emit(g, list, b);
+    }
+    if (!contiguous) return R_UNSUPPORTED_FFT_LENGTH;
 
     std::vector<uint64_t> f = split_four_step(g, N);
     if (f.empty()) return R_UNSUPPORTED_FFT_LENGTH;

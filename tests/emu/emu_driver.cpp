@@ -12,6 +12,8 @@ using namespace b200fft;
 
 static GenericRegistrar<float> b2_generic_f32("generic<float>");
 static GenericRegistrar<double> b2_generic_f64("generic<double>");
+static ElementwiseRegistrar<float> b2_ew_f32("elementwise<float>");
+static ElementwiseRegistrar<double> b2_ew_f64("elementwise<double>");
 
 extern "C" int emu_kernel_count() { return b2_kernel_count(); }
 extern "C" int emu_kernel_info(int i, int* out /*kind,prec,n,inv,ops,threads,q,tpl,v,smem,ns,r0..r7*/) {

@@ -22,7 +22,8 @@ def test_smooth_non_pow2_c2c(shape, b, prec, inv):
 
 
 @pytest.mark.parametrize("shape,b,prec", [((17,), 4, 0), ((509,), 2, 0), ((1019,), 1, 1), ((34,), 3, 0), ((23, 8), 2, 0),
-                                          ((8, 19), 2, 1), ((4093,), 1, 0)])
+                                          ((8, 19), 2, 1), ((4093,), 1, 0), ((4391,), 2, 0), ((5003,), 1, 1),
+                                          ((20011,), 1, 0), ((6, 4391), 1, 0)])
 @pytest.mark.parametrize("inv", [-1, 1])
 def test_bluestein_c2c(shape, b, prec, inv):
     dt = np.complex64 if prec == 0 else np.complex128
@@ -96,4 +97,3 @@ def test_dct_normalized_round_trip():
 def test_unsupported_requests_return_reference_error_codes():
     assert emu.exec_plan(emu.make_desc((16,), 1, 0, perform_dst=2), -1, np.zeros(16, np.float32))[0] == 3004
     assert emu.exec_plan(emu.make_desc((31,), 1, 0, perform_dct=4), -1, np.zeros(31, np.float32))[0] == 3004
-    assert emu.exec_plan(emu.make_desc((20011,), 1, 0), -1, np.zeros(20011, np.complex64))[0] == 3002   # long Bluestein

@@ -1,0 +1,95 @@
+// Elementwise passes used when an operator cannot be fused into a shared-memory pass because the line does not
+// fit on chip: Bluestein chirp / zero-pad, filter multiply and post-chirp around a multi-launch Four-Step
+// (the reference runs its upload chain twice for this case, vkFFT_RunApp.h:158-204), and the Hermitian post-/pre-pass
+// of long even-length R2C / C2R (the reference's separate VkFFT_main_R2C kernel,
+// vkFFT_R2C_even_decomposition.h:40-241, launched at vkFFT_RunApp.h:205-231).
+#pragma once
+#include "pass_params.h"
+#include "stockham.cuh"
+
+namespace b200fft {
+
+enum { B2_EW_COPY_MUL = 0, B2_EW_R2C_POST = 1, B2_EW_C2R_PRE = 2 };
+enum { B2_EW_THREADS = 256, B2_EW_PER_THREAD = 8 };
+
+template <typename T>
+struct Elementwise {
+    using X = cpx<T>;
+    // P.load_io = operation, P.n = items per line (elements, or pairs for the R2C passes), P.tpl = chunks per line,
+    // P.inverse = swap re/im right after the load, P.inner_inverse = swap right before the store.
+    B2_D static void run(const b2_pass_params& P) {
+        const uint32_t chunks = P.tpl;
+        uint32_t rest = blockIdx.x;
+        const uint32_t chunk = rest % chunks; rest /= chunks;
+        const uint32_t gl = rest % P.G; rest /= P.G;
+        const uint32_t o0 = rest % P.nb[0]; rest /= P.nb[0];
+        const uint32_t o1 = rest % P.nb[1]; rest /= P.nb[1];
+        const uint32_t o2 = rest;
+        const int64_t in_off = (int64_t)o0 * P.in_bs[0] + (int64_t)o1 * P.in_bs[1] + (int64_t)o2 * P.in_bs[2] + (int64_t)gl * P.in_gs;
+        const int64_t out_off = (int64_t)o0 * P.out_bs[0] + (int64_t)o1 * P.out_bs[1] + (int64_t)o2 * P.out_bs[2] + (int64_t)gl * P.out_gs;
+        const X* in = (const X*)P.in + in_off;
+        X* out = (X*)P.out + out_off;
+        const T sc = (T)P.scale;
+        const bool do_scale = (P.ops & B2_OP_SCALE) != 0;
+        const uint32_t j0 = chunk * (B2_EW_THREADS * B2_EW_PER_THREAD) + threadIdx.x;
+        if (P.load_io == B2_EW_COPY_MUL) {
+#pragma unroll
+            for (int i = 0; i < B2_EW_PER_THREAD; ++i) {
+                const uint32_t j = j0 + i * B2_EW_THREADS;
+                if (j >= P.out_len) break;
+                X v = mk<T>(T(0), T(0));
+                if (j < P.in_len) {
+                    v = in[(int64_t)j * P.in_es];
+                    if (P.inverse) v = swp(v);
+                    if (P.ops & B2_OP_MUL_IN) v = v * ld_lut((const X*)P.aux0 + j);
+                }
+                if (do_scale) v = v * sc;
+                if (P.inner_inverse) v = swp(v);
+                out[(int64_t)j * P.out_es] = v;
+            }
+        } else {
+            // pairs (k, n-k), k = 0 .. n/2 ; n = P.n complex points of the half-length transform, aux0[k] = e^{-2 pi i k/(2n)}
+            const uint32_t n = P.n;
+            const X* w = (const X*)P.aux0;
+#pragma unroll
+            for (int i = 0; i < B2_EW_PER_THREAD; ++i) {
+                const uint32_t k = j0 + i * B2_EW_THREADS;
+                if (k > n / 2) break;
+                const uint32_t kc = n - k;                    // partner index (n for k = 0)
+                if (P.load_io == B2_EW_R2C_POST) {
+                    const X zk = in[(int64_t)k * P.in_es], zc = in[(int64_t)(kc == n ? 0 : kc) * P.in_es];
+                    // X[k] = 1/2 (Zk + conj Zc) - i/2 w_k (Zk - conj Zc)
+                    auto f = [&](X a, X bconj, X wk) {
+                        const X s = a + bconj, d = (a - bconj) * wk;
+                        X r = mk<T>(T(0.5) * (s.x + d.y), T(0.5) * (s.y - d.x));
+                        return do_scale ? r * sc : r;
+                    };
+                    const X xk = f(zk, conj(zc), ld_lut(w + k));
+                    const X xc = f(zc, conj(zk), ld_lut(w + kc));
+                    out[(int64_t)k * P.out_es] = xk;
+                    if (kc != k) out[(int64_t)kc * P.out_es] = xc;
+                } else {
+                    const X xk = in[(int64_t)k * P.in_es], xc = in[(int64_t)kc * P.in_es];
+                    // Zin[k] = (Xk + conj Xc) + i conj(w_k) (Xk - conj Xc)
+                    auto f = [&](X a, X bconj, X wk) {
+                        const X s = a + bconj, d = mulc(a - bconj, wk);
+                        return mk<T>(s.x - d.y, s.y + d.x);
+                    };
+                    const X zk = f(xk, conj(xc), ld_lut(w + k));
+                    const X zc = f(xc, conj(xk), ld_lut(w + kc));
+                    out[(int64_t)k * P.out_es] = zk;
+                    if (kc != k && kc != n) out[(int64_t)kc * P.out_es] = zc;
+                }
+            }
+        }
+    }
+};
+
+#if defined(__CUDACC__)
+template <typename T>
+__global__ void __launch_bounds__(B2_EW_THREADS) elementwise_kernel(const __grid_constant__ b2_pass_params P) {
+    Elementwise<T>::run(P);
+}
+#endif
+
+}  // namespace b200fft

@@ -5,6 +5,7 @@
 #include "stockham.cuh"
 #include "generic.cuh"
 #include "pipe.cuh"
+#include "ew.cuh"
 
 #if !defined(B2_EMU)
 #include <cuda_runtime.h>
@@ -86,6 +87,34 @@ struct GenericRegistrar {
         info.kind = B2_KIND_GENERIC; info.prec = PrecOf<T>::value; info.n = 0; info.inv = 0; info.ops = 0;
         info.launch = &generic_launch<T>;
         info.prepare = &generic_prepare<T>;
+        info.name = name;
+        b2_register_kernel(&info);
+    }
+};
+
+// ---- elementwise helper kernel ---------------------------------------------------------------------------------------
+#if defined(B2_EMU)
+template <typename T>
+int ew_launch(const b2_pass_params* P, unsigned grid, void*) {
+    const b2_pass_params PP = *P;
+    b2emu::launch(grid, B2_EW_THREADS, 0, [&](unsigned char*) { Elementwise<T>::run(PP); }, false);
+    return 0;
+}
+#else
+template <typename T>
+int ew_launch(const b2_pass_params* P, unsigned grid, void* stream) {
+    elementwise_kernel<T><<<grid, B2_EW_THREADS, 0, (cudaStream_t)stream>>>(*P);
+    return (int)cudaGetLastError();
+}
+#endif
+template <typename T>
+struct ElementwiseRegistrar {
+    b2_kernel_info info;
+    explicit ElementwiseRegistrar(const char* name) {
+        info = b2_kernel_info{};
+        info.kind = B2_KIND_ELEMENTWISE; info.prec = PrecOf<T>::value;
+        info.threads = B2_EW_THREADS;
+        info.launch = &ew_launch<T>;
         info.name = name;
         b2_register_kernel(&info);
     }

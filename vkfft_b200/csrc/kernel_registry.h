@@ -13,6 +13,7 @@ enum {
     B2_KIND_ROWS_TOUT = 1,  // contiguous lines in, neighbouring lines interleaved on the way out (four-step final pass)
     B2_KIND_COLS = 2,       // neighbouring lines interleaved (strided axis / four-step first pass)
     B2_KIND_GENERIC = 3,    // runtime-scheduled kernel (generic.cuh): n = 0 in the registry, any addressing
+    B2_KIND_ELEMENTWISE = 4,// elementwise helper passes (ew.cuh)
     B2_KIND_COUNT
 };
 enum { B2_PREC_F32 = 0, B2_PREC_F64 = 1 };

@@ -31,6 +31,7 @@ inline void unit_root(uint64_t num, uint64_t den, long double& c, long double& s
 template <typename T>
 inline std::vector<T> make_stage_lut(const int* radices, int ns) {
     std::vector<T> out;
+    if (ns <= 0) return out;
     uint64_t S = radices[0];
     for (int s = 1; s < ns; ++s) {
         const uint64_t r = radices[s];

@@ -108,6 +108,11 @@ struct PassReq {
     int aux0 = -1, aux1 = -1;
     uint32_t aux_u0 = 0, aux_u1 = 0;
     bool real_pairs = false;     // group dim counts REAL lines; two of them form one complex line
+    int64_t in_base = 0, out_base = 0;   // element offsets into the role's buffer (scratch regions)
+    // elementwise helper passes (ew.cuh)
+    bool elementwise = false;
+    int ew_op = 0;
+    uint32_t ew_items = 0;       // items per line (elements or pairs)
 };
 
 // Emit the launches for one PassReq (more than one only if there are more than B2_MAX_OUTER outer dims).
@@ -223,7 +228,7 @@ int emit(PlanGraph& g, std::vector<PassPlan>& list, const PassReq& rq) {
         P.load_qfast = qfast_l; P.store_qfast = qfast_s;
         P.aux_u0 = rq.aux_u0; P.aux_u1 = rq.aux_u1;
         pp.in_role = rq.in_role; pp.out_role = rq.out_role;
-        pp.in_off = ioff; pp.out_off = ooff;
+        pp.in_off = ioff + rq.in_base; pp.out_off = ooff + rq.out_base;
         pp.lut_id = lut_for(g, radices);
         if (rq.ops & B2_OP_TWIDDLE_OUT) pp.tw_id = tw_for(g, rq.twM);
         pp.aux0_id = rq.aux0; pp.aux1_id = rq.aux1;
@@ -339,9 +344,48 @@ struct C2CJob {
     bool unit_lines;
     int in_role, out_role;
     double scale;
+    int64_t in_base = 0, out_base = 0, tmp_base = 0;   // element offsets into the roles' buffers
 };
 
 int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job);
+
+// elementwise helper launch over `lines` (every line dimension, any order)
+int emit_ew(PlanGraph& g, std::vector<PassPlan>& list, PassReq rq, const std::vector<Dim>& lines) {
+    const b2_kernel_info* k = b2_find_kernel(B2_KIND_ELEMENTWISE, g.prec, 0, 0, 0);
+    if (!k) return R_UNSUPPORTED_FFT_LENGTH;
+    std::vector<Dim> m = merge_dims(lines);
+    if (m.size() > 1 + B2_MAX_OUTER) return R_UNSUPPORTED_FFT_LENGTH;
+    PassPlan pp;
+    pp.k = k;
+    b2_pass_params& P = pp.P;
+    P.in_es = rq.in_es; P.out_es = rq.out_es;
+    Dim grp = m.empty() ? Dim{1, 0, 0} : m[0];
+    P.G = (uint32_t)grp.n; P.in_gs = grp.is; P.out_gs = grp.os;
+    uint64_t grid = grp.n;
+    for (int d = 0; d < B2_MAX_OUTER; ++d) {
+        if (d + 1 < (int)m.size()) { P.nb[d] = (uint32_t)m[d + 1].n; P.in_bs[d] = m[d + 1].is; P.out_bs[d] = m[d + 1].os; }
+        else { P.nb[d] = 1; P.in_bs[d] = 0; P.out_bs[d] = 0; }
+        grid *= P.nb[d];
+    }
+    const uint32_t per_cta = 256 * 8;   // B2_EW_THREADS * B2_EW_PER_THREAD
+    const uint32_t chunks = (rq.ew_items + per_cta - 1) / per_cta;
+    grid *= chunks;
+    if (grid == 0 || grid > 0x7fffffffull) return R_UNSUPPORTED_FFT_LENGTH;
+    pp.grid = (unsigned)grid;
+    P.tpl = chunks;
+    P.n = rq.n; P.load_io = rq.ew_op; P.ops = rq.ops; P.scale = rq.scale;
+    P.inverse = rq.inv; P.inner_inverse = rq.inner_inverse;
+    P.in_len = rq.in_len; P.out_len = rq.out_len;
+    pp.in_role = rq.in_role; pp.out_role = rq.out_role;
+    pp.in_off = rq.in_base; pp.out_off = rq.out_base;
+    pp.lut_id = lut_for(g, std::vector<int>{});
+    pp.aux0_id = rq.aux0;
+    char buf[200];
+    snprintf(buf, sizeof buf, "%s elementwise op=%d items=%u grid=%u", rq.what, rq.ew_op, rq.ew_items, pp.grid);
+    pp.note = buf;
+    list.push_back(pp);
+    return R_SUCCESS;
+}
 
 // total number of lines and a packed scratch layout for them ([line][M])
 uint64_t count_lines(const std::vector<Dim>& lines) {
@@ -355,8 +399,50 @@ int plan_bluestein(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job)
     const uint64_t N = job.N;
     uint64_t M = 1;
     while (M < 2 * N - 1) M <<= 1;
-    if (!generic_fits(g, M)) return R_UNSUPPORTED_FFT_LENGTH;   // long Bluestein lengths: not yet
     const uint64_t L = count_lines(job.lines);
+    if (!generic_fits(g, M)) {
+        // padded length beyond one shared-memory pass: chirp/zero-pad, FFT_M (Four-Step), filter, IFFT_M, post-chirp as
+        // separate launches on packed scratch lines; scratch = [lines][M] twice (data + Four-Step scratch)
+        if (M > (1ull << 26) || L * M > (1ull << 32)) return R_UNSUPPORTED_FFT_LENGTH;
+        const int chirp_l = aux_for(g, AUX_BLUE_CHIRP, N), filt_l = aux_for(g, AUX_BLUE_FILTER, N, M);
+        std::vector<Dim> to_tmp = job.lines, from_tmp = job.lines, packed;
+        int64_t run = (int64_t)M;
+        for (size_t i = 0; i < job.lines.size(); ++i) {
+            to_tmp[i].os = run; from_tmp[i].is = run;
+            packed.push_back(Dim{job.lines[i].n, run, run});
+            run *= (int64_t)job.lines[i].n;
+        }
+        const int64_t r0 = job.tmp_base, r1 = job.tmp_base + (int64_t)(L * M);
+        PassReq pre;
+        pre.elementwise = true; pre.ew_op = 0; pre.ew_items = (uint32_t)M; pre.n = (int)M;
+        pre.in_len = (uint32_t)N; pre.out_len = (uint32_t)M; pre.ops = B2_OP_MUL_IN; pre.aux0 = chirp_l;
+        pre.inv = job.inv; pre.in_es = job.es_in; pre.out_es = 1;
+        pre.in_role = job.in_role; pre.out_role = ROLE_TEMP; pre.in_base = job.in_base; pre.out_base = r0;
+        pre.what = "bluestein chirp+pad";
+        int rcl = emit_ew(g, list, pre, to_tmp);
+        if (rcl != R_SUCCESS) return rcl;
+        C2CJob f;
+        f.N = M; f.inv = 0; f.es_in = f.es_out = 1; f.lines = packed; f.unit_lines = false;
+        f.in_role = f.out_role = ROLE_TEMP; f.in_base = f.out_base = r0; f.tmp_base = r1; f.scale = 1.0;
+        if ((rcl = plan_c2c(g, list, f)) != R_SUCCESS) return rcl;
+        PassReq mid;
+        mid.elementwise = true; mid.ew_op = 0; mid.ew_items = (uint32_t)M; mid.n = (int)M;
+        mid.in_len = mid.out_len = (uint32_t)M; mid.ops = B2_OP_MUL_IN; mid.aux0 = filt_l;
+        mid.in_es = mid.out_es = 1; mid.in_role = mid.out_role = ROLE_TEMP; mid.in_base = mid.out_base = r0;
+        mid.what = "bluestein filter";
+        if ((rcl = emit_ew(g, list, mid, packed)) != R_SUCCESS) return rcl;
+        f.inv = 1;
+        if ((rcl = plan_c2c(g, list, f)) != R_SUCCESS) return rcl;
+        PassReq post;
+        post.elementwise = true; post.ew_op = 0; post.ew_items = (uint32_t)N; post.n = (int)M;
+        post.in_len = (uint32_t)M; post.out_len = (uint32_t)N; post.ops = B2_OP_MUL_IN | (job.scale != 1.0 ? B2_OP_SCALE : 0);
+        post.aux0 = chirp_l; post.scale = job.scale; post.inner_inverse = job.inv;
+        post.in_es = 1; post.out_es = job.es_out;
+        post.in_role = ROLE_TEMP; post.out_role = job.out_role; post.in_base = r0; post.out_base = job.out_base;
+        post.what = "bluestein post-chirp";
+        g.temp_elems = std::max<uint64_t>(g.temp_elems, (uint64_t)r1 + L * M);
+        return emit_ew(g, list, post, from_tmp);
+    }
     g.temp_elems = std::max<uint64_t>(g.temp_elems, L * M);
     const int chirp = aux_for(g, AUX_BLUE_CHIRP, N), filt = aux_for(g, AUX_BLUE_FILTER, N, M);
     // scratch lines are packed [.. outer ..][group][M]
@@ -445,6 +531,7 @@ int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
         }
         rq.outer = m;
         rq.in_role = job.in_role; rq.out_role = job.out_role;
+        rq.in_base = job.in_base; rq.out_base = job.out_base;
         rq.scale = job.scale;
         rq.what = job.unit_lines ? "strided axis" : "single-pass";
         return emit(g, list, rq);
@@ -467,7 +554,7 @@ int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
         const uint64_t N1 = best1, N2 = best2;
         uint64_t extent = (uint64_t)job.es_out * N;
         for (const Dim& d : job.lines) extent = std::max<uint64_t>(extent, (uint64_t)d.n * (uint64_t)d.os);
-        g.temp_elems = std::max<uint64_t>(g.temp_elems, extent);
+        g.temp_elems = std::max<uint64_t>(g.temp_elems, (uint64_t)job.tmp_base + extent);
         const Dim unit = m[0];
         std::vector<Dim> rest(m.begin() + 1, m.end());
         PassReq a;
@@ -478,6 +565,7 @@ int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
         a.tw_outer = 0;
         for (const Dim& d : rest) a.outer.push_back(Dim{d.n, d.is, d.os});
         a.in_role = job.in_role; a.out_role = ROLE_TEMP;
+        a.in_base = job.in_base; a.out_base = job.tmp_base;
         a.twM = N;
         a.what = "strided four-step 1/2";
         int rc2 = emit(g, list, a);
@@ -489,6 +577,7 @@ int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
         b.outer.push_back(Dim{N1, job.es_out * (int64_t)N2, job.es_out});
         for (const Dim& d : rest) b.outer.push_back(Dim{d.n, d.os, d.os});
         b.in_role = ROLE_TEMP; b.out_role = job.out_role;
+        b.in_base = job.tmp_base; b.out_base = job.out_base;
         b.scale = job.scale;
         b.what = "strided four-step 2/2";
         return emit(g, list, b);
@@ -500,7 +589,7 @@ int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
     // scratch: sequences keep the output-side layout of the main buffer
     uint64_t extent = N;
     for (const Dim& d : job.lines) extent = std::max<uint64_t>(extent, (uint64_t)d.n * (uint64_t)std::max(d.is, d.os));
-    g.temp_elems = std::max<uint64_t>(g.temp_elems, extent);
+    g.temp_elems = std::max<uint64_t>(g.temp_elems, (uint64_t)job.tmp_base + extent);
     std::vector<Dim> s_in_tmp, s_tmp_tmp, s_tmp_out, s_in_in;
     for (const Dim& d : job.lines) {
         // scratch uses the OUTPUT layout (both sides of a temp->temp pass)
@@ -518,6 +607,7 @@ int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
         a.group = Dim{N2, 1, 1};
         a.outer = s_in_tmp;
         a.in_role = job.in_role; a.out_role = ROLE_TEMP;
+        a.in_base = job.in_base; a.out_base = job.tmp_base;
         a.twM = N;
         a.what = "four-step 1/2 strided+phase";
         if ((rc = emit(g, list, a)) != R_SUCCESS) return rc;
@@ -527,6 +617,7 @@ int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
         b.group = Dim{N1, (int64_t)N2, 1};
         b.outer = s_tmp_out;
         b.in_role = ROLE_TEMP; b.out_role = job.out_role;
+        b.in_base = job.tmp_base; b.out_base = job.out_base;
         b.scale = job.scale;
         b.what = "four-step 2/2 contiguous+transpose";
         return emit(g, list, b);
@@ -540,6 +631,7 @@ int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
     const bool a_inplace = (job.in_role == ROLE_BUFFER);
     a.outer = a_inplace ? s_in_in : s_in_tmp;
     a.in_role = job.in_role; a.out_role = a_inplace ? job.in_role : ROLE_TEMP;
+    a.in_base = job.in_base; a.out_base = a_inplace ? job.in_base : job.tmp_base;
     a.twM = N;
     a.what = "four-step 1/3 strided+phase";
     if ((rc = emit(g, list, a)) != R_SUCCESS) return rc;
@@ -553,6 +645,7 @@ int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
         b.outer.insert(b.outer.end(), s.begin(), s.end());
     }
     b.in_role = a.out_role; b.out_role = ROLE_TEMP;
+    b.in_base = a.out_base; b.out_base = job.tmp_base;
     b.twM = M;
     b.what = "four-step 2/3 strided+phase";
     if ((rc = emit(g, list, b)) != R_SUCCESS) return rc;
@@ -563,6 +656,7 @@ int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
     c.outer.push_back(Dim{N2, (int64_t)N3, (int64_t)N1});
     c.outer.insert(c.outer.end(), s_tmp_out.begin(), s_tmp_out.end());
     c.in_role = ROLE_TEMP; c.out_role = job.out_role;
+    c.in_base = job.tmp_base; c.out_base = job.out_base;
     c.scale = job.scale;
     c.what = "four-step 3/3 contiguous+transpose";
     return emit(g, list, c);

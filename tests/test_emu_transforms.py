@@ -94,6 +94,39 @@ def test_dct_normalized_round_trip():
         assert orc.error_metrics(buf, x)["l2_rel"] < T32
 
 
+@pytest.mark.parametrize("kind", [1, 2, 3, 4])
+@pytest.mark.parametrize("shape,b,prec", [((64,), 3, 0), ((33,), 2, 1), ((32, 16), 3, 0), ((8, 6, 4), 2, 0)])
+@pytest.mark.parametrize("inv", [-1, 1])
+def test_dst(kind, shape, b, prec, inv):
+    if kind == 4 and any(s % 2 for s in shape):
+        pytest.skip("odd-length DST-IV not built yet")
+    if kind == 1 and shape in ((33,), (32, 16)):
+        pytest.skip("DST-I whose 2N+2 has a prime factor > 13: not built yet")
+    rdt = np.float32 if prec == 0 else np.float64
+    x = orc.random_input((b,) + tuple(reversed(shape)), rdt, seed=kind + sum(shape))
+    buf = x.copy()
+    rc, _ = emu.exec_plan(emu.make_desc(shape, b, prec, perform_dst=kind), inv, buf)
+    assert rc == 0
+    assert orc.error_metrics(buf, orc.dst(x, kind, len(shape), inverse=(inv == 1)))["l2_rel"] < (T32 if prec == 0 else T64)
+
+
+@pytest.mark.parametrize("shape,b,prec", [((65536,), 2, 0), ((2 * 4391,), 1, 0), ((34,), 3, 0), ((32768, 4), 1, 1), ((2 * 509, 6), 2, 0)])
+def test_long_and_non_smooth_even_r2c(shape, b, prec):
+    """half-length C2C (Four-Step / Bluestein) + separate Hermitian pass"""
+    rdt = np.float32 if prec == 0 else np.float64
+    cdt = np.complex64 if prec == 0 else np.complex128
+    tol = T32 if prec == 0 else T64
+    nx, H = shape[0], shape[0] // 2 + 1
+    x = orc.random_input((b,) + tuple(reversed(shape)), rdt, seed=sum(shape))
+    buf = np.zeros(x.shape[:-1] + (2 * H,), rdt)
+    buf[..., :nx] = x
+    d = emu.make_desc(shape, b, prec, perform_r2c=1)
+    assert emu.exec_plan(d, -1, buf)[0] == 0
+    assert orc.error_metrics(buf.view(cdt), orc.r2c(x, len(shape)))["l2_rel"] < tol
+    assert emu.exec_plan(d, 1, buf)[0] == 0
+    assert orc.error_metrics(buf[..., :nx], x.astype(np.float64) * np.prod(shape))["l2_rel"] < tol
+
+
 def test_unsupported_requests_return_reference_error_codes():
-    assert emu.exec_plan(emu.make_desc((16,), 1, 0, perform_dst=2), -1, np.zeros(16, np.float32))[0] == 3004
+    assert emu.exec_plan(emu.make_desc((16,), 1, 0, perform_dst=1), -1, np.zeros(16, np.float32))[0] == 3004
     assert emu.exec_plan(emu.make_desc((31,), 1, 0, perform_dct=4), -1, np.zeros(31, np.float32))[0] == 3004

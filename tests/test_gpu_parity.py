@@ -241,3 +241,47 @@ def test_out_of_place_formatted_buffers(gpu):
     torch.cuda.synchronize()
     assert orc.error_metrics(tr.cpu().numpy(), xr.astype(np.float64) * 64 * 16)["l2_rel"] < TOL32
     vk.deleteVkFFT(app)
+
+
+@pytest.mark.parametrize("kind", [1, 2, 3, 4])
+@pytest.mark.parametrize("shape,batch,double", [((64,), 5, False), ((32, 16), 3, False), ((100,), 3, True), ((4096,), 2, False)])
+@pytest.mark.parametrize("inverse", [-1, 1])
+def test_dst(gpu, kind, shape, batch, double, inverse):
+    import vkfft_b200 as vk
+    if kind == 1 and not all(_smooth13(2 * s + 2) for s in shape):
+        pytest.skip("DST-I whose 2N+2 has a prime factor > 13: not built yet")
+    rdt = np.float64 if double else np.float32
+    x = orc.random_input((batch,) + tuple(reversed(shape)), rdt, seed=kind + sum(shape))
+    cfg = vk.VkFFTConfiguration(FFTdim=len(shape), size=list(shape), numberBatches=batch, device=0, performDST=kind,
+                                doublePrecision=int(double))
+    y = _run_plan(gpu, x, cfg, inverse)
+    ref = orc.dst(x, kind, len(shape), inverse=(inverse == 1))
+    assert orc.error_metrics(y, ref)["l2_rel"] < (TOL64 if double else 2e-6)
+
+
+@pytest.mark.parametrize("shape,batch,double", [((1 << 20,), 3, False), ((2 * 4391,), 4, False), ((1 << 17, 4), 1, True)])
+def test_long_r2c_c2r(gpu, shape, batch, double):
+    import vkfft_b200 as vk
+    rdt, cdt = (np.float64, np.complex128) if double else (np.float32, np.complex64)
+    tol = TOL64 if double else TOL32
+    nx, H = shape[0], shape[0] // 2 + 1
+    x = orc.random_input((batch,) + tuple(reversed(shape)), rdt, seed=sum(shape))
+    buf = np.zeros(x.shape[:-1] + (2 * H,), rdt)
+    buf[..., :nx] = x
+    cfg = vk.VkFFTConfiguration(FFTdim=len(shape), size=list(shape), numberBatches=batch, device=0, performR2C=1,
+                                doublePrecision=int(double))
+    y = _run_plan(gpu, buf, cfg, -1)
+    assert orc.error_metrics(y.view(cdt), orc.r2c(x, len(shape)))["l2_rel"] < tol
+    z = _run_plan(gpu, y, cfg, 1)
+    assert orc.error_metrics(z[..., :nx], x.astype(np.float64) * np.prod(shape))["l2_rel"] < tol
+
+
+@pytest.mark.parametrize("shape,batch,double", [((4391,), 6, False), ((20011,), 2, False), ((5003,), 2, True), ((16, 8192), 2, False),
+                                                ((100003,), 1, False)])
+@pytest.mark.parametrize("inverse", [-1, 1])
+def test_long_bluestein_and_strided_four_step(gpu, shape, batch, double, inverse):
+    from gpu_util import run_c2c
+    dt = np.complex128 if double else np.complex64
+    x = orc.random_input((batch,) + tuple(reversed(shape)), dt, seed=sum(shape))
+    got = run_c2c(x, shape, batch, inverse, double=double)
+    assert orc.error_metrics(got, orc.c2c(x, len(shape), inverse == 1))["l2_rel"] < (TOL64 if double else TOL32)

@@ -72,6 +72,12 @@ struct Generic {
     // Makhoul permutation shared by DCT-II (gather on load) and DCT-III (scatter on store)
     B2_D static int makhoul(int p, int n) { return (p < (n + 1) / 2) ? 2 * p : 2 * (n - 1 - p) + 1; }
 
+    // DST wrappers: logical real length L, input index i -> (source index, sign)
+    B2_D static int dst_src(const b2_pass_params& P, int i, int L) { return (P.dst_flags & B2_DST_REV_IN) ? L - 1 - i : i; }
+    B2_D static T dst_sgn_in(const b2_pass_params& P, int i) { return ((P.dst_flags & B2_DST_NEG_ODD_IN) && (i & 1)) ? T(-1) : T(1); }
+    B2_D static int dst_dst(const b2_pass_params& P, int k, int L) { return (P.dst_flags & B2_DST_REV_OUT) ? L - 1 - k : k; }
+    B2_D static T dst_sgn_out(const b2_pass_params& P, int k) { return ((P.dst_flags & B2_DST_ALT_OUT) && (k & 1)) ? T(-1) : T(1); }
+
     // ---- load phase ---------------------------------------------------------------------------------------------
     // fills smem line `q` (local index) from the global line(s) it represents
     B2_D static void load_line(const b2_pass_params& P, X* sl, int64_t line_off, uint32_t gline, bool valid, int t,
@@ -147,9 +153,11 @@ struct Generic {
                 for (int p = t; p < n; p += step) {
                     X v = zero;
                     if (valid) {
-                        const int64_t s = (int64_t)makhoul(p, n) * P.in_es;
-                        v.x = in[s];
-                        if (vb) v.y = in[s + P.in_gs];
+                        const int src = makhoul(p, n);
+                        const int64_t s = (int64_t)dst_src(P, src, n) * P.in_es;
+                        const T sg = dst_sgn_in(P, src);
+                        v.x = sg * in[s];
+                        if (vb) v.y = sg * in[s + P.in_gs];
                     }
                     B2_SMEM_ST(sl, pad(p), v);
                 }
@@ -163,7 +171,8 @@ struct Generic {
                 for (int k = t; k < n; k += step) {
                     X v = zero;
                     if (valid) {
-                        const int64_t s0 = (int64_t)k * P.in_es, s1 = (int64_t)(n - k) * P.in_es;
+                        const int64_t s0 = (int64_t)dst_src(P, k, n) * P.in_es;
+                        const int64_t s1 = (int64_t)dst_src(P, k == 0 ? 0 : n - k, n) * P.in_es;
                         const T a0 = in[s0], a1 = (k == 0) ? T(0) : in[s1];
                         const T b0 = vb ? in[s0 + P.in_gs] : T(0), b1 = (vb && k != 0) ? in[s1 + P.in_gs] : T(0);
                         v = mulc(mk<T>(a0 + b1, b0 - a1), ld_lut(c + k));
@@ -187,6 +196,23 @@ struct Generic {
                     B2_SMEM_ST(sl, pad(p), v);
                 }
             } break;
+            case B2_IO_DST1: {
+                // odd extension of two real lines of length L = aux_u1 to n = 2L+2: e[0]=0, e[1..L]=x, e[L+1]=0, e[L+2..]=-x reversed
+                const T* in = (const T*)P.in + line_off;
+                const int L = (int)P.aux_u1;
+                const bool vb = valid && (2 * gline + 1 < P.aux_u0);
+                for (int p = t; p < n; p += step) {
+                    X v = zero;
+                    if (valid && p != 0 && p != L + 1) {
+                        const int j = p <= L ? p - 1 : n - p - 1;
+                        const T sg = p <= L ? T(1) : T(-1);
+                        const int64_t s = (int64_t)j * P.in_es;
+                        v.x = sg * in[s];
+                        if (vb) v.y = sg * in[s + P.in_gs];
+                    }
+                    B2_SMEM_ST(sl, pad(p), v);
+                }
+            } break;
             case B2_IO_DCT4: {
                 // one real line of length N = 2n:  z'[m] = (x[2m] + i x[N-1-2m]) e^{-i pi m/N}   (aux0[m])
                 const T* in = (const T*)P.in + line_off;
@@ -194,7 +220,7 @@ struct Generic {
                 for (int m = t; m < n; m += step) {
                     X v = zero;
                     if (valid) {
-                        v = mk<T>(in[(int64_t)(2 * m) * P.in_es], in[(int64_t)(2 * n - 1 - 2 * m) * P.in_es]);
+                        v = mk<T>(in[(int64_t)dst_src(P, 2 * m, 2 * n) * P.in_es], in[(int64_t)dst_src(P, 2 * n - 1 - 2 * m, 2 * n) * P.in_es]);
                         v = v * ld_lut(w + m);
                     }
                     B2_SMEM_ST(sl, pad(m), v);
@@ -266,7 +292,7 @@ struct Generic {
                     const X s = ck * (a + b), d = ck * (a - b);
                     T ya = s.x, yb = d.y;
                     if (do_scale) { ya *= sc; yb *= sc; }
-                    const int64_t o = (int64_t)k * P.out_es;
+                    const int64_t o = (int64_t)dst_dst(P, k, n) * P.out_es;
                     out[o] = ya;
                     if (vb) out[o + P.out_gs] = yb;
                 }
@@ -279,9 +305,11 @@ struct Generic {
                     X v = B2_SMEM_LD(sl, pad(p));
                     if (inner) v = swp(v);
                     if (do_scale) v = v * sc;
-                    const int64_t o = (int64_t)makhoul(p, n) * P.out_es;
-                    out[o] = v.x;
-                    if (vb) out[o + P.out_gs] = v.y;
+                    const int dj = makhoul(p, n);
+                    const int64_t o = (int64_t)dj * P.out_es;
+                    const T sg = dst_sgn_out(P, dj);
+                    out[o] = sg * v.x;
+                    if (vb) out[o + P.out_gs] = sg * v.y;
                 }
             } break;
             case B2_IO_DCT1: {
@@ -296,6 +324,19 @@ struct Generic {
                     if (vb) out[o + P.out_gs] = v.y;
                 }
             } break;
+            case B2_IO_DST1: {
+                // E[k] = -i Ya[k-1] + Yb[k-1]  ->  Ya[k-1] = -Im E[k], Yb[k-1] = Re E[k]
+                T* out = (T*)P.out + line_off;
+                const int L = (int)P.aux_u1;
+                const bool vb = (2 * gline + 1 < P.aux_u0);
+                for (int k = t; k < L; k += step) {
+                    X v = B2_SMEM_LD(sl, pad(k + 1));
+                    if (do_scale) v = v * sc;
+                    const int64_t o = (int64_t)k * P.out_es;
+                    out[o] = -v.y;
+                    if (vb) out[o + P.out_gs] = v.x;
+                }
+            } break;
             case B2_IO_DCT4: {
                 // C_q = aux1[q] Z[q];  X[2q] = 2 Re C_q,  X[N-1-2q] = -2 Im C_q     (aux1[q] = e^{-i pi (4q+1)/(4N)})
                 T* out = (T*)P.out + line_off;
@@ -304,8 +345,8 @@ struct Generic {
                     X v = B2_SMEM_LD(sl, pad(q2)) * ld_lut(w + q2);
                     T y0 = T(2) * v.x, y1 = T(-2) * v.y;
                     if (do_scale) { y0 *= sc; y1 *= sc; }
-                    out[(int64_t)(2 * q2) * P.out_es] = y0;
-                    out[(int64_t)(2 * n - 1 - 2 * q2) * P.out_es] = y1;
+                    out[(int64_t)(2 * q2) * P.out_es] = dst_sgn_out(P, 2 * q2) * y0;
+                    out[(int64_t)(2 * n - 1 - 2 * q2) * P.out_es] = dst_sgn_out(P, 2 * n - 1 - 2 * q2) * y1;
                 }
             } break;
         }
@@ -327,8 +368,8 @@ struct Generic {
         // real-pair operators address two real lines per complex line
         const uint32_t twsel = P.tw_sel;
         const uint32_t twbase = P.tw_line0 + (twsel == 1 ? o0 : (twsel == 2 ? o1 : (twsel == 3 ? o2 : 0)));
-        const int in_mult = (P.load_io == B2_IO_DCT2 || P.load_io == B2_IO_DCT3 || P.load_io == B2_IO_DCT1) ? 2 : 1;
-        const int out_mult = (P.store_io == B2_IO_DCT2 || P.store_io == B2_IO_DCT3 || P.store_io == B2_IO_DCT1) ? 2 : 1;
+        const int in_mult = (P.load_io == B2_IO_DCT2 || P.load_io == B2_IO_DCT3 || P.load_io == B2_IO_DCT1 || P.load_io == B2_IO_DST1) ? 2 : 1;
+        const int out_mult = (P.store_io == B2_IO_DCT2 || P.store_io == B2_IO_DCT3 || P.store_io == B2_IO_DCT1 || P.store_io == B2_IO_DST1) ? 2 : 1;
 
         {   // load
             int q, t, step;

@@ -36,6 +36,15 @@ enum {
     B2_IO_DCT4 = 6,          // pre/post phases around a half-length complex transform (vkFFT_Scheduler.h:2277-2280)
     B2_IO_REAL = 7,          // odd-length R2C/C2R fallback: real line <-> complex line with zero imaginary part
     B2_IO_HERM = 8,          // load only: rebuild the full spectrum from the Hermitian half (odd-length C2R)
+    B2_IO_DST1 = 9,          // odd extension to 2n+2 on load, -Im / Re on store (DST-I, API guide :581-583)
+};
+
+// DST-II/III/IV are the DCT operators with sign / index-reversal wrappers (vkFFT_R2R.h:769-780):
+enum {
+    B2_DST_NEG_ODD_IN = 1,   // multiply input sample n by (-1)^n
+    B2_DST_REV_IN = 2,       // read input index N-1-n
+    B2_DST_REV_OUT = 4,      // write output index N-1-k
+    B2_DST_ALT_OUT = 8,      // multiply output k by (-1)^k
 };
 
 enum { B2_MAX_STAGES = 16 };
@@ -73,6 +82,7 @@ typedef struct b2_pass_params {
     uint32_t line_stride;                  // smem elements between lines
     uint32_t inner_inverse;                // 1: the FFT inside this pass is an inverse one (swap around the stages only)
     uint32_t tw_sel;                       // which coordinate is the four-step "line": 0 group index, 1..3 outer dim 0..2
+    uint32_t dst_flags;                    // B2_DST_* wrappers around the DCT operators
 } b2_pass_params;
 
 #ifdef __cplusplus

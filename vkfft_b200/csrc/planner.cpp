@@ -108,6 +108,7 @@ struct PassReq {
     int aux0 = -1, aux1 = -1;
     uint32_t aux_u0 = 0, aux_u1 = 0;
     bool real_pairs = false;     // group dim counts REAL lines; two of them form one complex line
+    uint32_t dst_flags = 0;
     int64_t in_base = 0, out_base = 0;   // element offsets into the role's buffer (scratch regions)
     // elementwise helper passes (ew.cuh)
     bool elementwise = false;
@@ -227,13 +228,14 @@ int emit(PlanGraph& g, std::vector<PassPlan>& list, const PassReq& rq) {
         P.out_len = rq.out_len ? rq.out_len : rq.n;
         P.load_qfast = qfast_l; P.store_qfast = qfast_s;
         P.aux_u0 = rq.aux_u0; P.aux_u1 = rq.aux_u1;
+        P.dst_flags = rq.dst_flags;
         pp.in_role = rq.in_role; pp.out_role = rq.out_role;
         pp.in_off = ioff + rq.in_base; pp.out_off = ooff + rq.out_base;
         pp.lut_id = lut_for(g, radices);
         if (rq.ops & B2_OP_TWIDDLE_OUT) pp.tw_id = tw_for(g, rq.twM);
         pp.aux0_id = rq.aux0; pp.aux1_id = rq.aux1;
         // specialised kernels: intra-tile factor of the four-step phase (coalesced table, see stockham.cuh)
-        auto scalar_io = [](int io) { return io == B2_IO_DCT1 || io == B2_IO_DCT2 || io == B2_IO_DCT3 || io == B2_IO_DCT4 || io == B2_IO_REAL; };
+        auto scalar_io = [](int io) { return io == B2_IO_DCT1 || io == B2_IO_DCT2 || io == B2_IO_DCT3 || io == B2_IO_DCT4 || io == B2_IO_REAL || io == B2_IO_DST1; };
         pp.in_scalar = scalar_io(rq.load_io); pp.out_scalar = scalar_io(rq.store_io);
         char buf[320];
         std::string rs;
@@ -755,7 +757,8 @@ int plan_direction_r2c(PlanGraph& g, std::vector<PassPlan>& list, int inv) {
             if (!d.omit_dimension[a]) norm /= (double)d.size[a];
     const bool even = (N0 % 2 == 0);
     const uint64_t n = even ? N0 / 2 : N0;
-    if (!is_smooth(n) || !generic_fits(g, n)) return R_UNSUPPORTED_FFT_LENGTH_R2C;
+    const bool fused = is_smooth(n) && generic_fits(g, n) && n >= 2;
+    if (!fused && (!even || n < 2)) return R_UNSUPPORTED_FFT_LENGTH_R2C;   // long / non-smooth odd lengths: not yet
 
     // real side of the axis-0 launch, in units of the pointer type the operator uses
     const bool real_ext = d.is_input_formatted && (!inv || d.inverse_return_to_input);
@@ -800,9 +803,40 @@ int plan_direction_r2c(PlanGraph& g, std::vector<PassPlan>& list, int inv) {
         }
         return emit(g, list, rq);
     };
+    // long or non-smooth even lengths: half-length C2C (Four-Step / Bluestein as needed) + separate Hermitian pass
+    // (the reference's bigSequenceEvenR2C path, vkFFT_Scheduler.h:2261-2270)
+    auto axis0_composed = [&](bool forward, double scale) -> int {
+        std::vector<Dim> rc_lines, cc_lines;   // real(complex view)->complex and complex->complex line dims
+        for (uint32_t a = 1; a < d.fft_dim; ++a) {
+            const int64_t rs = (int64_t)(rstride[a - 1] / 2), cs = (int64_t)d.buffer_stride[a - 1];
+            rc_lines.push_back(forward ? Dim{d.size[a], rs, cs} : Dim{d.size[a], cs, rs});
+            cc_lines.push_back(Dim{d.size[a], cs, cs});
+        }
+        rc_lines.push_back(forward ? Dim{g.batches, (int64_t)(rbatch / 2), (int64_t)buf.batch_stride}
+                                   : Dim{g.batches, (int64_t)buf.batch_stride, (int64_t)(rbatch / 2)});
+        cc_lines.push_back(Dim{g.batches, (int64_t)buf.batch_stride, (int64_t)buf.batch_stride});
+        PassReq ew;
+        ew.elementwise = true; ew.ew_items = (uint32_t)(n / 2 + 1); ew.n = (int)n;
+        ew.in_es = ew.out_es = 1; ew.in_role = ew.out_role = ROLE_BUFFER;
+        ew.aux0 = aux_for(g, AUX_R2C, N0);
+        C2CJob job;
+        job.N = n; job.es_in = job.es_out = 1; job.lines = rc_lines; job.unit_lines = false;
+        int r;
+        if (forward) {
+            job.inv = 0; job.in_role = real_role; job.out_role = ROLE_BUFFER; job.scale = 1.0;
+            if ((r = plan_c2c(g, list, job)) != R_SUCCESS) return r;
+            ew.ew_op = 1; ew.what = "r2c hermitian pass";
+            return emit_ew(g, list, ew, cc_lines);
+        }
+        ew.ew_op = 2; ew.what = "c2r hermitian pass";
+        if ((r = emit_ew(g, list, ew, cc_lines)) != R_SUCCESS) return r;
+        job.inv = 1; job.in_role = ROLE_BUFFER; job.out_role = real_role; job.scale = scale;
+        return plan_c2c(g, list, job);
+    };
+    auto axis0_any = [&](bool forward, double scale) -> int { return fused ? axis0(forward, scale) : axis0_composed(forward, scale); };
     int rc;
     if (!inv) {
-        if ((rc = axis0(true, 1.0)) != R_SUCCESS) return rc;
+        if ((rc = axis0_any(true, 1.0)) != R_SUCCESS) return rc;
         for (uint32_t a = 1; a < d.fft_dim; ++a) {
             if (d.omit_dimension[a] || d.size[a] == 1) continue;
             if ((rc = plan_c2c_axis(g, list, csize, a, 0, buf, buf, 1.0)) != R_SUCCESS) return rc;
@@ -812,7 +846,7 @@ int plan_direction_r2c(PlanGraph& g, std::vector<PassPlan>& list, int inv) {
             if (d.omit_dimension[a] || d.size[a] == 1) continue;
             if ((rc = plan_c2c_axis(g, list, csize, a, 1, buf, buf, 1.0)) != R_SUCCESS) return rc;
         }
-        if ((rc = axis0(false, norm)) != R_SUCCESS) return rc;
+        if ((rc = axis0_any(false, norm)) != R_SUCCESS) return rc;
     }
     return R_SUCCESS;
 }
@@ -824,7 +858,8 @@ int plan_direction_r2c(PlanGraph& g, std::vector<PassPlan>& list, int inv) {
 int plan_direction_dct(PlanGraph& g, std::vector<PassPlan>& list, int inv) {
     const b200fft_desc& d = g.desc;
     if (d.is_input_formatted || d.is_output_formatted) return R_UNSUPPORTED_FFT_LENGTH_R2R;
-    int type = (int)d.perform_dct;
+    const bool is_dst = d.perform_dst != 0;
+    int type = (int)(is_dst ? d.perform_dst : d.perform_dct);
     if (inv && (type == 2 || type == 3)) type = 5 - type;
     std::vector<uint32_t> axes;
     for (uint32_t a = 0; a < d.fft_dim; ++a)
@@ -835,12 +870,15 @@ int plan_direction_dct(PlanGraph& g, std::vector<PassPlan>& list, int inv) {
         const uint32_t axis = axes[i];
         const uint64_t N = d.size[axis];
         double scale = 1.0;
-        if (inv && d.normalize) scale = 1.0 / (type == 1 ? 2.0 * (double)(N - 1) : 2.0 * (double)N);
+        if (inv && d.normalize) scale = 1.0 / (type == 1 ? (is_dst ? 2.0 * (double)(N + 1) : 2.0 * (double)(N - 1)) : 2.0 * (double)N);
         uint64_t n;
         PassReq rq;
         rq.force_generic = true;
         switch (type) {
-            case 1: n = 2 * N - 2; rq.load_io = rq.store_io = B2_IO_DCT1; rq.aux_u1 = (uint32_t)N; rq.real_pairs = true; break;
+            case 1:
+                if (is_dst) { n = 2 * N + 2; rq.load_io = rq.store_io = B2_IO_DST1; }
+                else { n = 2 * N - 2; rq.load_io = rq.store_io = B2_IO_DCT1; }
+                rq.aux_u1 = (uint32_t)N; rq.real_pairs = true; break;
             case 2: n = N; rq.load_io = rq.store_io = B2_IO_DCT2; rq.aux0 = aux_for(g, AUX_DCT23, N); rq.real_pairs = true; break;
             case 3: n = N; rq.load_io = rq.store_io = B2_IO_DCT3; rq.aux0 = aux_for(g, AUX_DCT23, N); rq.real_pairs = true;
                     rq.inner_inverse = 1; break;
@@ -851,6 +889,11 @@ int plan_direction_dct(PlanGraph& g, std::vector<PassPlan>& list, int inv) {
             default: return R_UNSUPPORTED_FFT_LENGTH_R2R;
         }
         if (n < 2 || !is_smooth(n) || !generic_fits(g, n)) return R_UNSUPPORTED_FFT_LENGTH_R2R;
+        if (is_dst) {   // sign / reversal wrappers (API guide :581-583)
+            if (type == 2) rq.dst_flags = B2_DST_NEG_ODD_IN | B2_DST_REV_OUT;
+            if (type == 3) rq.dst_flags = B2_DST_REV_IN | B2_DST_ALT_OUT;
+            if (type == 4) rq.dst_flags = B2_DST_REV_IN | B2_DST_ALT_OUT;
+        }
         rq.n = (int)n;
         rq.kind = axis == 0 ? B2_KIND_ROWS : B2_KIND_COLS;
         rq.in_es = rq.out_es = axis == 0 ? 1 : (int64_t)buf.stride[axis - 1];
@@ -887,9 +930,8 @@ int build_plan(const b200fft_desc& din, PlanGraph& g) {
     if (d.number_batches == 0) d.number_batches = 1;
     if (d.coordinate_features == 0) d.coordinate_features = 1;
     if (d.precision > B200FFT_F64) return R_UNSUPPORTED_FFT_LENGTH;
-    if (d.perform_dst) return R_UNSUPPORTED_FFT_LENGTH_R2R;
-    if (d.perform_dct > 4) return R_UNSUPPORTED_FFT_LENGTH_R2R;
-    if (d.perform_r2c && d.perform_dct) return R_UNSUPPORTED_FFT_LENGTH_R2R;
+    if (d.perform_dct > 4 || d.perform_dst > 4) return R_UNSUPPORTED_FFT_LENGTH_R2R;
+    if ((d.perform_r2c && (d.perform_dct || d.perform_dst)) || (d.perform_dct && d.perform_dst)) return R_UNSUPPORTED_FFT_LENGTH_R2R;
     if (d.omit_dimension[0] && d.perform_r2c) return R_UNSUPPORTED_FFT_OMIT;
     // default strides (vkFFT_InitializeApp.h:994-1040)
     auto fill = [&](uint64_t* s, uint64_t s0) {
@@ -914,7 +956,7 @@ int build_plan(const b200fft_desc& din, PlanGraph& g) {
 
     uint32_t naxes = 0;
     g.flops = 0;
-    const bool real_tf = d.perform_r2c || d.perform_dct;
+    const bool real_tf = d.perform_r2c || d.perform_dct || d.perform_dst;
     for (uint32_t a = 0; a < d.fft_dim; ++a) {
         if (d.omit_dimension[a]) continue;
         ++naxes;
@@ -929,7 +971,7 @@ int build_plan(const b200fft_desc& din, PlanGraph& g) {
     g.has_inv = !d.make_forward_plan_only;
     auto plan = [&](std::vector<PassPlan>& list, int inv) {
         if (d.perform_r2c) return plan_direction_r2c(g, list, inv);
-        if (d.perform_dct) return plan_direction_dct(g, list, inv);
+        if (d.perform_dct || d.perform_dst) return plan_direction_dct(g, list, inv);
         return plan_direction_c2c(g, list, inv);
     };
     int rc;

@@ -79,22 +79,8 @@ template <typename T> B2_D cpx<T> ld_lut(const cpx<T>* p) {
 template <typename T> B2_D cpx<T> ld_lut(const cpx<T>* p) { return *p; }
 #endif
 
-// Streaming (evict-first) access for the transformed data: every element is touched exactly once per launch, so it
-// must not displace the twiddle tables that live in L1/L2.
-#if defined(__CUDA_ARCH__)
-template <typename T> B2_D cpx<T> ld_stream(const cpx<T>* p) {
-    if constexpr (sizeof(T) == 4) { float2 v = __ldcs(reinterpret_cast<const float2*>(p)); return mk<T>(v.x, v.y); }
-    else { double2 v = __ldcs(reinterpret_cast<const double2*>(p)); return mk<T>(v.x, v.y); }
-}
-template <typename T> B2_D void st_stream(cpx<T>* p, cpx<T> v) {
-    if constexpr (sizeof(T) == 4) __stcs(reinterpret_cast<float2*>(p), make_float2(v.x, v.y));
-    else __stcs(reinterpret_cast<double2*>(p), make_double2(v.x, v.y));
-}
-#else
-template <typename T> B2_D cpx<T> ld_stream(const cpx<T>* p) { return *p; }
-template <typename T> B2_D void st_stream(cpx<T>* p, cpx<T> v) { *p = v; }
-#endif
-
+// (Streaming / evict-first hints -- __ldcs/__stcs -- on the transformed data were measured and rejected: the transposed
+//  128-byte stores lose L2 write combining and every kernel got slower, profiles/r1/README.md.)
 // two-level table lookup of W_M^m  (m = hi*2^shift + lo):  one complex multiply, error <= ~1.5 ulp
 template <typename T>
 B2_D cpx<T> twiddle2(const cpx<T>* hi, const cpx<T>* lo, uint32_t shift, uint64_t m) {
@@ -174,7 +160,7 @@ struct Engine {
 #pragma unroll
                     for (int v = 0; v < V; ++v) {
                         X a = mk<T>(T(0), T(0));
-                        if (ok) a = ld_stream(line + (C::IN_UNIT ? (int64_t)(p + v) : (int64_t)(p + v) * es));
+                        if (ok) a = line[C::IN_UNIT ? (int64_t)(p + v) : (int64_t)(p + v) * es];
                         x[(m * V + v) * r + k] = C::INV ? swp(a) : a;
                     }
                 }
@@ -277,7 +263,7 @@ struct Engine {
                     } else {
 #pragma unroll
                         for (int v = 0; v < V; ++v)
-                            st_stream(line + (C::OUT_UNIT ? (int64_t)(p0 + v) : (int64_t)(p0 + v) * es), o[v]);
+                            line[C::OUT_UNIT ? (int64_t)(p0 + v) : (int64_t)(p0 + v) * es] = o[v];
                     }
                 }
             }

@@ -21,8 +21,8 @@ def test_smooth_non_pow2_c2c(shape, b, prec, inv):
     assert orc.error_metrics(buf, orc.c2c(x, len(shape), inv == 1))["l2_rel"] < (T32 if prec == 0 else T64)
 
 
-@pytest.mark.parametrize("shape,b,prec", [((17,), 4, 0), ((509,), 2, 0), ((1019,), 1, 1), ((34,), 3, 0), ((23, 8), 2, 0),
-                                          ((8, 19), 2, 1), ((4093,), 1, 0), ((4391,), 2, 0), ((5003,), 1, 1),
+@pytest.mark.parametrize("shape,b,prec", [((131,), 4, 0), ((509,), 2, 0), ((1019,), 1, 1), ((262,), 3, 0), ((149, 8), 2, 0),
+                                          ((8, 139), 2, 1), ((4093,), 1, 0), ((4391,), 2, 0), ((5003,), 1, 1),
                                           ((20011,), 1, 0), ((6, 4391), 1, 0)])
 @pytest.mark.parametrize("inv", [-1, 1])
 def test_bluestein_c2c(shape, b, prec, inv):
@@ -31,6 +31,20 @@ def test_bluestein_c2c(shape, b, prec, inv):
     buf = x.copy()
     rc, npass = emu.exec_plan(emu.make_desc(shape, b, prec), inv, buf)
     assert rc == 0
+    assert orc.error_metrics(buf, orc.c2c(x, len(shape), inv == 1))["l2_rel"] < (T32 if prec == 0 else T64)
+
+
+@pytest.mark.parametrize("shape,b,prec", [((17,), 5, 0), ((127,), 3, 1), ((1088,), 2, 0), ((2032,), 2, 0), ((94,), 3, 0), ((529,), 2, 0),
+                                          ((323,), 2, 1), ((12167,), 1, 0), ((64, 17), 2, 0)])
+@pytest.mark.parametrize("inv", [-1, 1])
+def test_rader_prime_radix_stages(shape, b, prec, inv):
+    """prime factors 17..127 run as Rader stages inside one shared-memory pass (reference probe: 1088 = 17.16.4,
+    2032 = 8.127.2, 12167 = 23^3 in two passes)"""
+    dt = np.complex64 if prec == 0 else np.complex128
+    x = orc.random_input((b,) + tuple(reversed(shape)), dt, seed=sum(shape) + 3)
+    buf = x.copy()
+    rc, npass = emu.exec_plan(emu.make_desc(shape, b, prec), inv, buf)
+    assert rc == 0 and npass == (2 if shape in ((12167,), (64, 17)) else 1)
     assert orc.error_metrics(buf, orc.c2c(x, len(shape), inv == 1))["l2_rel"] < (T32 if prec == 0 else T64)
 
 

@@ -138,7 +138,9 @@ def test_api_errors_on_gpu(gpu):
                                                 ((17,), 100, False), ((509,), 9, False), ((1019,), 3, True),
                                                 ((23, 8), 5, False), ((4093,), 2, False), ((3 ** 8,), 2, False),
                                                 ((5 ** 5,), 3, True), ((7 ** 4,), 3, False), ((11 ** 3,), 3, False),
-                                                ((13 ** 3,), 3, False), ((2 * 3 * 5 * 7 * 11 * 13 * 4,), 1, False)])
+                                                ((13 ** 3,), 3, False), ((2 * 3 * 5 * 7 * 11 * 13 * 4,), 1, False),
+                                                ((127,), 40, False), ((1088,), 9, False), ((2032,), 5, True), ((94,), 33, False),
+                                                ((12167,), 2, False), ((131,), 30, False), ((8, 139), 3, True)])
 @pytest.mark.parametrize("inverse", [-1, 1])
 def test_c2c_non_pow2_and_bluestein(gpu, shape, batch, double, inverse):
     from gpu_util import run_c2c

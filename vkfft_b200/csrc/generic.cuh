@@ -48,6 +48,45 @@ struct Generic {
         }
     }
 
+    // ---- Rader stage for a prime radix p > 16 ("mult" form: the length-(p-1) cyclic convolution is evaluated
+    //      directly, vkFFT_RaderKernels.h:1278).  X_0 = sum of the legs;  X_{g^-q} = x_0 + sum_m a_m b_{(q-m) mod (p-1)},
+    //      a_m = leg_{g^m}.  The legs are twiddled in place first (phase 1), then every thread produces outputs (phase 2).
+    B2_D static void rader_stage(int p, X* src, X* dst, int n, int S, const X* __restrict__ lut, const X* __restrict__ rt,
+                                 int q, int t, int tpl, int ls) {
+        const int nb = n / p, pm1 = p - 1;
+        X* s = src + q * ls;
+        X* d = dst + q * ls;
+        if (S > 1) {
+            for (int idx = t; idx < nb * pm1; idx += tpl) {
+                const int b = idx % nb, i = 1 + idx / nb;
+                const int a = pad(b + i * nb);
+                B2_SMEM_ST(s, a, B2_SMEM_LD(s, a) * ld_lut(lut + (i - 1) * S + (b % S)));
+            }
+        }
+        __syncthreads();
+        const X* bt = rt;             // b_m
+        const X* perm = rt + pm1;     // (g^m, g^-m)
+        for (int idx = t; idx < nb * p; idx += tpl) {
+            const int b = idx % nb, qq = idx / nb;
+            const int j = b % S, base = (b - j) * p + j;
+            const X x0 = B2_SMEM_LD(s, pad(b));
+            X acc = x0;
+            int ko = 0;
+            if (qq == pm1) {
+                for (int i = 1; i < p; ++i) acc = acc + B2_SMEM_LD(s, pad(b + i * nb));
+            } else {
+                ko = (int)ld_lut(perm + qq).y;
+                int bi = qq;                                   // g^(m-q) = g^-(q-m): index (q - m) mod (p-1), m = 0
+                for (int m = 0; m < pm1; ++m) {
+                    const int leg = (int)ld_lut(perm + m).x;
+                    acc = acc + B2_SMEM_LD(s, pad(b + leg * nb)) * ld_lut(bt + bi);
+                    bi = (bi == 0) ? pm1 - 1 : bi - 1;
+                }
+            }
+            B2_SMEM_ST(d, pad(base + ko * S), acc);
+        }
+    }
+
     B2_D static void run_stage(int r, const X* src, X* dst, int n, int S, const X* lut, int q, int t, int tpl, int ls) {
         switch (r) {
             case 2: stage<2>(src, dst, n, S, lut, q, t, tpl, ls); break;
@@ -385,9 +424,16 @@ struct Generic {
             int S = 1;
             X* src = buf0;
             X* dst = buf1;
+            // Rader tables follow the stage twiddles in the LUT
+            const X* rader = lut;
+            {
+                int S2 = 1;
+                for (uint32_t s = 0; s < P.nstages; ++s) { if (s > 0) rader += ((int)P.radix[s] - 1) * S2; S2 *= (int)P.radix[s]; }
+            }
             for (uint32_t s = 0; s < P.nstages; ++s) {
                 const int r = (int)P.radix[s];
-                run_stage(r, src, dst, n, S, lut, q, t, TPL, ls);
+                if (r > 16) { rader_stage(r, src, dst, n, S, lut, rader, q, t, TPL, ls); rader += 2 * (r - 1); }
+                else run_stage(r, src, dst, n, S, lut, q, t, TPL, ls);
                 if (s > 0) lut += (r - 1) * S;
                 S *= r;
                 __syncthreads();

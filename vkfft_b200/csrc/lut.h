@@ -28,6 +28,40 @@ inline void unit_root(uint64_t num, uint64_t den, long double& c, long double& s
     s = -sinl(a);
 }
 
+// smallest primitive root of the prime p
+inline uint64_t primitive_root(uint64_t p) {
+    auto powmod = [&](uint64_t b, uint64_t e) { uint64_t r = 1; b %= p; while (e) { if (e & 1) r = r * b % p; b = b * b % p; e >>= 1; } return r; };
+    std::vector<uint64_t> fac;
+    uint64_t m = p - 1;
+    for (uint64_t f = 2; f * f <= m; ++f)
+        if (m % f == 0) { fac.push_back(f); while (m % f == 0) m /= f; }
+    if (m > 1) fac.push_back(m);
+    for (uint64_t g = 2; g < p; ++g) {
+        bool ok = true;
+        for (uint64_t f : fac) if (powmod(g, (p - 1) / f) == 1) { ok = false; break; }
+        if (ok) return g;
+    }
+    return 1;
+}
+
+// Rader tables of one prime-radix stage (vkFFT_RaderKernels.h:1278 "mult" form; generator powers as in
+// VkFFTGenerateRaderFFTKernel, vkFFT_RecursiveFFTGenerators.h:1073-1103):  p-1 entries  b_m = exp(-2 pi i g^{-m}/p)
+// followed by p-1 entries (g^m mod p, g^{-m} mod p) stored as numbers.
+template <typename T>
+inline void append_rader_tables(std::vector<T>& out, uint64_t p) {
+    const uint64_t g = primitive_root(p);
+    std::vector<uint64_t> gp(p - 1), gi(p - 1);
+    uint64_t v = 1;
+    for (uint64_t m = 0; m < p - 1; ++m) { gp[m] = v; v = v * g % p; }
+    for (uint64_t m = 0; m < p - 1; ++m) gi[m] = gp[(p - 1 - m) % (p - 1)];
+    for (uint64_t m = 0; m < p - 1; ++m) {
+        long double c, s;
+        unit_root(gi[m], p, c, s);
+        out.push_back((T)c); out.push_back((T)s);
+    }
+    for (uint64_t m = 0; m < p - 1; ++m) { out.push_back((T)gp[m]); out.push_back((T)gi[m]); }
+}
+
 template <typename T>
 inline std::vector<T> make_stage_lut(const int* radices, int ns) {
     std::vector<T> out;
@@ -44,6 +78,9 @@ inline std::vector<T> make_stage_lut(const int* radices, int ns) {
             }
         S *= r;
     }
+    // Rader tables of the prime stages (radix > 16), in stage order, after all stage twiddles
+    for (int s2 = 0; s2 < ns; ++s2)
+        if (radices[s2] > 16) append_rader_tables<T>(out, (uint64_t)radices[s2]);
     return out;
 }
 

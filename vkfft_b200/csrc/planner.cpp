@@ -66,17 +66,28 @@ std::vector<Dim> merge_dims(const std::vector<Dim>& d) {
     return out;
 }
 
-// greedy radix list for the runtime-scheduled kernel (largest radix first); empty if n has a prime factor > 13
+// greedy radix list for the runtime-scheduled kernel (largest radix first).  Prime factors 17..127 become Rader
+// stages (the reference inlines Rader kernels for radix primes from 17, vkFFT_InitializeApp.h:1257-1292); empty if
+// n has a prime factor above that (-> Bluestein).
+const int RADER_MAX_PRIME = 127;
 std::vector<int> generic_radices(uint64_t n) {
-    std::vector<int> r;
+    std::vector<int> r, primes;
     static const int cand[] = {16, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2};
+    // split off prime factors > 13 first
+    uint64_t m = n;
+    for (int f : {2, 3, 5, 7, 11, 13}) while (m % f == 0) m /= f;
+    for (uint64_t f = 17; m > 1 && f <= (uint64_t)RADER_MAX_PRIME; f += 2)
+        while (m % f == 0) { primes.push_back((int)f); m /= f; n /= f; }
+    if (m != 1) return {};
     while (n > 1) {
         bool found = false;
         for (int c : cand)
             if (n % c == 0) { r.push_back(c); n /= c; found = true; break; }
         if (!found) return {};
-        if (r.size() > B2_MAX_STAGES) return {};
     }
+    // Rader stages last: their legs are already twiddled by a large stageSize, outputs land in natural order as usual
+    r.insert(r.end(), primes.begin(), primes.end());
+    if (r.size() > B2_MAX_STAGES) return {};
     return r;
 }
 

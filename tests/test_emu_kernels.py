@@ -91,8 +91,8 @@ def test_whole_plans_on_emulation(case):
 
 
 def test_planner_rejects_what_it_cannot_do():
-    d = emu.make_desc((16,), 1, 0, perform_dst=1)      # DST: not built yet -> the reference's error code
-    rc, _ = emu.exec_plan(d, -1, np.zeros(16, np.float32))
+    d = emu.make_desc((130,), 1, 0, perform_dst=1)     # DST-I of 130 needs a 262 = 2*131 point transform: not built
+    rc, _ = emu.exec_plan(d, -1, np.zeros(130, np.float32))
     assert rc == 3004
     d = emu.make_desc((8,), 1, 0)
     d.fft_dim = 0

@@ -152,7 +152,7 @@ def test_c2c_non_pow2_and_bluestein(gpu, shape, batch, double, inverse):
 
 
 def _smooth13(n):
-    for p in (2, 3, 5, 7, 11, 13):
+    for p in [2, 3, 5, 7, 11, 13] + [q for q in range(17, 128, 2) if all(q % r for r in range(3, 12, 2))]:
         while n % p == 0:
             n //= p
     return n == 1
@@ -200,7 +200,7 @@ def test_dct(gpu, kind, shape, batch, double, inverse):
     if kind == 4 and any(s % 2 for s in shape):
         pytest.skip("odd-length DCT-IV not built yet")
     if kind == 1 and not all(_smooth13(2 * s - 2) for s in shape):
-        pytest.skip("DCT-I whose 2N-2 has a prime factor > 13: not built yet")
+        pytest.skip("DCT-I whose 2N-2 has a prime factor > 127: not built yet")
     rdt = np.float64 if double else np.float32
     x = orc.random_input((batch,) + tuple(reversed(shape)), rdt, seed=kind + sum(shape))
     cfg = vk.VkFFTConfiguration(FFTdim=len(shape), size=list(shape), numberBatches=batch, device=0, performDCT=kind,
@@ -251,7 +251,7 @@ def test_out_of_place_formatted_buffers(gpu):
 def test_dst(gpu, kind, shape, batch, double, inverse):
     import vkfft_b200 as vk
     if kind == 1 and not all(_smooth13(2 * s + 2) for s in shape):
-        pytest.skip("DST-I whose 2N+2 has a prime factor > 13: not built yet")
+        pytest.skip("DST-I whose 2N+2 has a prime factor > 127: not built yet")
     rdt = np.float64 if double else np.float32
     x = orc.random_input((batch,) + tuple(reversed(shape)), rdt, seed=kind + sum(shape))
     cfg = vk.VkFFTConfiguration(FFTdim=len(shape), size=list(shape), numberBatches=batch, device=0, performDST=kind,

@@ -109,12 +109,12 @@ def test_r2c_c2r_matches_reference(ref, size_xyz, batch):
 def test_dct_matches_reference(ref, kind, size_xyz, batch, inverse):
     import torch
     def smooth(n):
-        for p in (2, 3, 5, 7, 11, 13):
+        for p in [2, 3, 5, 7, 11, 13] + [q for q in range(17, 128, 2) if all(q % r for r in range(3, 12, 2))]:
             while n % p == 0:
                 n //= p
         return n == 1
     if kind == 1 and not all(smooth(2 * s - 2) for s in size_xyz):
-        pytest.skip("DCT-I whose 2N-2 has a prime factor > 13: not built yet")
+        pytest.skip("DCT-I whose 2N-2 has a prime factor > 127: not built yet")
     x = orc.random_input((batch,) + tuple(reversed(size_xyz)), np.float32, seed=kind + sum(size_xyz))
     mine = _mine_inplace(torch, x, size_xyz, batch, inverse, performDCT=kind)
     theirs = _ref_inplace(torch, x, size_xyz, batch, inverse, perform_dct=kind)

@@ -29,6 +29,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# torchrun exports OMP_NUM_THREADS=1, which also throttles pocketfft's worker pool: the CPU legs are meant to use
+# every host core, so drop the cap before numpy/scipy are imported.
+os.environ.pop("OMP_NUM_THREADS", None)
 
 LOG2_MIN, LOG2_MAX = 7, 22
 TOTAL_LOG2 = 28                      # 2^28 complex64 = 2 GiB
@@ -375,7 +378,7 @@ def main():
                                "in place, forward+inverse per N (reference sample_0 semantics, normalize=1)",
                    "l2": "inputs (2 GiB) larger than L2 (126 MB)", "parallelism": f"batch-sharded x{world}, no collective",
                    "points_per_gpu": pts},
-        "roofline": roofline, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+        "roofline": roofline, "e2e": e2e, "gpu_launches": launches_per_step * args.steps * world, "clocks": clocks,
         "per_n": per_n, "roundtrip_rel_err": rt_err,
     }
     if world == 1 and not args.no_cpu:

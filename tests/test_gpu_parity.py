@@ -287,3 +287,23 @@ def test_long_bluestein_and_strided_four_step(gpu, shape, batch, double, inverse
     x = orc.random_input((batch,) + tuple(reversed(shape)), dt, seed=sum(shape))
     got = run_c2c(x, shape, batch, inverse, double=double)
     assert orc.error_metrics(got, orc.c2c(x, len(shape), inverse == 1))["l2_rel"] < (TOL64 if double else TOL32)
+
+
+def test_pipelined_kernels_fall_back_on_unaligned_buffers(gpu):
+    """the TMA-fed kernels (N=16384 single pass, transposed 2048) need 16-byte aligned sources; with an 8-byte
+    bufferOffset the engine must switch to the plain kernels (and their own twiddle tables)"""
+    import vkfft_b200 as vk
+    torch = gpu
+    for n in (16384, 1 << 16, 1 << 22):
+        batch = max(1, (1 << 22) // n) if n < (1 << 22) else 1
+        x = orc.random_input((batch, n), np.complex64, seed=n + 5)
+        raw = torch.zeros(batch * n + 1, dtype=torch.complex64, device="cuda")
+        raw[1:] = torch.from_numpy(x.reshape(-1)).cuda()
+        app = vk.VkFFTApplication()
+        assert vk.initializeVkFFT(app, vk.VkFFTConfiguration(FFTdim=1, size=[n], numberBatches=batch, device=0,
+                                                             specifyOffsetsAtLaunch=1)) == 0
+        assert vk.VkFFTAppend(app, -1, vk.VkFFTLaunchParams(buffer=raw, bufferOffset=8)) == 0
+        torch.cuda.synchronize()
+        got = raw[1:].cpu().numpy().reshape(batch, n)
+        vk.deleteVkFFT(app)
+        assert orc.error_metrics(got, orc.c2c(x, 1))["l2_rel"] < TOL32

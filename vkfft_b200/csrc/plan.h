@@ -69,6 +69,7 @@ struct PassPlan {
     int in_role = ROLE_BUFFER, out_role = ROLE_BUFFER;
     int64_t in_off = 0, out_off = 0;   // complex-element offsets added to the role's base pointer
     int lut_id = -1;
+    int lut_id_unaligned = -1;   // stage twiddles of k_unaligned (its radix schedule may differ)
     int tw_id = -1;
     int aux0_id = -1, aux1_id = -1;
     bool in_scalar = false, out_scalar = false;   // offsets (and strides) of that side count scalars, not complex elements

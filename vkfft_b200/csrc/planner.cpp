@@ -243,6 +243,8 @@ int emit(PlanGraph& g, std::vector<PassPlan>& list, const PassReq& rq) {
         pp.in_role = rq.in_role; pp.out_role = rq.out_role;
         pp.in_off = ioff + rq.in_base; pp.out_off = ooff + rq.out_base;
         pp.lut_id = lut_for(g, radices);
+        if (pp.k_unaligned)
+            pp.lut_id_unaligned = lut_for(g, std::vector<int>(pp.k_unaligned->radices, pp.k_unaligned->radices + pp.k_unaligned->ns));
         if (rq.ops & B2_OP_TWIDDLE_OUT) pp.tw_id = tw_for(g, rq.twM);
         pp.aux0_id = rq.aux0; pp.aux1_id = rq.aux1;
         // specialised kernels: intra-tile factor of the four-step phase (coalesced table, see stockham.cuh)

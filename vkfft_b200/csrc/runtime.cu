@@ -180,7 +180,10 @@ extern "C" int b200fft_exec(b200fft_plan* p, int inverse, const b200fft_buffers*
         const b2_kernel_info* k = pp.k;
         if (k->pipelined && ((((uintptr_t)P.in) | (uintptr_t)(P.in_gs * (int64_t)esz) | (uintptr_t)(P.in_bs[0] * (int64_t)esz) |
                               (uintptr_t)(P.in_bs[1] * (int64_t)esz) | (uintptr_t)(P.in_bs[2] * (int64_t)esz)) & 15))
+        {
             k = pp.k_unaligned;
+            if (pp.lut_id_unaligned >= 0) P.lut = p->d_luts[pp.lut_id_unaligned];
+        }
         if (!k || k->launch(&P, pp.grid, (void*)st) != 0) return R_FAILED_TO_LAUNCH_KERNEL;
     }
     return R_SUCCESS;

@@ -298,8 +298,8 @@ std::vector<uint64_t> split_four_step(const PlanGraph& g, uint64_t N) {
     auto pass_us = [&](int kind, uint64_t n) -> uint64_t {
         if (g.prec != B2_PREC_F32) return 0;
         static const struct { uint64_t n; uint64_t cols, tout; } t[] = {
-            {16, 670, 1030}, {32, 838, 622}, {64, 858, 646}, {128, 947, 655}, {256, 882, 650},
-            {512, 1038, 717}, {1024, 1188, 759}, {2048, 1440, 873}};
+            {16, 670, 1030}, {32, 838, 622}, {64, 858, 646}, {128, 815, 655}, {256, 827, 650},
+            {512, 1005, 717}, {1024, 1188, 759}, {2048, 1440, 873}};
         for (const auto& e : t)
             if (e.n == n) return kind == B2_KIND_COLS ? e.cols : e.tout;
         return 0;

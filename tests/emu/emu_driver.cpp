@@ -10,8 +10,12 @@
 
 using namespace b200fft;
 
-static GenericRegistrar<float> b2_generic_f32("generic<float>");
-static GenericRegistrar<double> b2_generic_f64("generic<double>");
+static GenericRegistrar<float, 8> b2_generic_f32_8("generic<float,r<=8>");
+static GenericRegistrar<float, 11> b2_generic_f32_11("generic<float,r<=11>");
+static GenericRegistrar<float, 16> b2_generic_f32_16("generic<float,r<=16>");
+static GenericRegistrar<double, 8> b2_generic_f64_8("generic<double,r<=8>");
+static GenericRegistrar<double, 11> b2_generic_f64_11("generic<double,r<=11>");
+static GenericRegistrar<double, 16> b2_generic_f64_16("generic<double,r<=16>");
 static ElementwiseRegistrar<float> b2_ew_f32("elementwise<float>");
 static ElementwiseRegistrar<double> b2_ew_f64("elementwise<double>");
 

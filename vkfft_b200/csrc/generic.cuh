@@ -19,7 +19,9 @@
 
 namespace b200fft {
 
-template <typename T>
+// RMAX = largest radix this instantiation can dispatch to (8, 11 or 16): the register allocation of the kernel is the
+// maximum over all butterflies it contains, so schedules made of small radices get a leaner kernel and more CTAs per SM.
+template <typename T, int RMAX = 16>
 struct Generic {
     using X = cpx<T>;
 
@@ -96,15 +98,27 @@ struct Generic {
             case 6: stage<6>(src, dst, n, S, lut, q, t, tpl, ls); break;
             case 7: stage<7>(src, dst, n, S, lut, q, t, tpl, ls); break;
             case 8: stage<8>(src, dst, n, S, lut, q, t, tpl, ls); break;
-            case 9: stage<9>(src, dst, n, S, lut, q, t, tpl, ls); break;
-            case 10: stage<10>(src, dst, n, S, lut, q, t, tpl, ls); break;
-            case 11: stage<11>(src, dst, n, S, lut, q, t, tpl, ls); break;
-            case 12: stage<12>(src, dst, n, S, lut, q, t, tpl, ls); break;
-            case 13: stage<13>(src, dst, n, S, lut, q, t, tpl, ls); break;
-            case 14: stage<14>(src, dst, n, S, lut, q, t, tpl, ls); break;
-            case 15: stage<15>(src, dst, n, S, lut, q, t, tpl, ls); break;
-            case 16: stage<16>(src, dst, n, S, lut, q, t, tpl, ls); break;
-            default: break;
+            default:
+                if constexpr (RMAX > 8) {
+                    switch (r) {
+                        case 9: stage<9>(src, dst, n, S, lut, q, t, tpl, ls); break;
+                        case 10: stage<10>(src, dst, n, S, lut, q, t, tpl, ls); break;
+                        case 11: stage<11>(src, dst, n, S, lut, q, t, tpl, ls); break;
+                        default:
+                            if constexpr (RMAX > 11) {
+                                switch (r) {
+                                    case 12: stage<12>(src, dst, n, S, lut, q, t, tpl, ls); break;
+                                    case 13: stage<13>(src, dst, n, S, lut, q, t, tpl, ls); break;
+                                    case 14: stage<14>(src, dst, n, S, lut, q, t, tpl, ls); break;
+                                    case 15: stage<15>(src, dst, n, S, lut, q, t, tpl, ls); break;
+                                    case 16: stage<16>(src, dst, n, S, lut, q, t, tpl, ls); break;
+                                    default: break;
+                                }
+                            }
+                            break;
+                    }
+                }
+                break;
         }
     }
 
@@ -452,10 +466,12 @@ struct Generic {
 };
 
 #if defined(__CUDACC__)
-template <typename T>
-__global__ void __launch_bounds__(512, 1) generic_kernel(const __grid_constant__ b2_pass_params P) {
+// at most 256 threads per CTA; resident CTAs the compiler must leave room for: 4 / 3 / 2 for the radix classes 8 / 11 / 16
+template <typename T, int RMAX>
+__global__ void __launch_bounds__(256, (RMAX <= 8 ? 4 : (RMAX <= 11 ? 3 : 2)))
+generic_kernel(const __grid_constant__ b2_pass_params P) {
     extern __shared__ __align__(16) unsigned char b2_smem_raw[];
-    Generic<T>::run(P, b2_smem_raw);
+    Generic<T, RMAX>::run(P, b2_smem_raw);
 }
 #endif
 

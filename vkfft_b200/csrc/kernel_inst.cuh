@@ -60,33 +60,34 @@ template <typename T> inline size_t generic_smem_bytes(const b2_pass_params* P) 
     return (size_t)2 * P->q * P->line_stride * 2 * sizeof(T);
 }
 #if defined(B2_EMU)
-template <typename T>
+template <typename T, int RMAX>
 int generic_launch(const b2_pass_params* P, unsigned grid, void*) {
     const b2_pass_params PP = *P;
-    b2emu::launch(grid, PP.tpl * PP.q, generic_smem_bytes<T>(P), [&](unsigned char* sm) { Generic<T>::run(PP, sm); },
+    b2emu::launch(grid, PP.tpl * PP.q, generic_smem_bytes<T>(P), [&](unsigned char* sm) { Generic<T, RMAX>::run(PP, sm); },
                   b2emu::st().log);
     return 0;
 }
-template <typename T> int generic_prepare() { return 0; }
+template <typename T, int RMAX> int generic_prepare() { return 0; }
 #else
-template <typename T>
+template <typename T, int RMAX>
 int generic_launch(const b2_pass_params* P, unsigned grid, void* stream) {
-    generic_kernel<T><<<grid, P->tpl * P->q, generic_smem_bytes<T>(P), (cudaStream_t)stream>>>(*P);
+    generic_kernel<T, RMAX><<<grid, P->tpl * P->q, generic_smem_bytes<T>(P), (cudaStream_t)stream>>>(*P);
     return (int)cudaGetLastError();
 }
-template <typename T>
+template <typename T, int RMAX>
 int generic_prepare() {
-    return (int)cudaFuncSetAttribute(generic_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    return (int)cudaFuncSetAttribute(generic_kernel<T, RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 #endif
-template <typename T>
+// registry key n = radix class (8, 11, 16)
+template <typename T, int RMAX>
 struct GenericRegistrar {
     b2_kernel_info info;
     explicit GenericRegistrar(const char* name) {
         info = b2_kernel_info{};
-        info.kind = B2_KIND_GENERIC; info.prec = PrecOf<T>::value; info.n = 0; info.inv = 0; info.ops = 0;
-        info.launch = &generic_launch<T>;
-        info.prepare = &generic_prepare<T>;
+        info.kind = B2_KIND_GENERIC; info.prec = PrecOf<T>::value; info.n = RMAX; info.inv = 0; info.ops = 0;
+        info.launch = &generic_launch<T, RMAX>;
+        info.prepare = &generic_prepare<T, RMAX>;
         info.name = name;
         b2_register_kernel(&info);
     }
@@ -124,7 +125,9 @@ template <int KIND, typename T, int TPL, int Q, int V, int MINB, bool INV, int O
 struct Registrar {
     using KT = KindTraits<KIND>;
     using Sch = RList<Rs...>;
-    using C = KCfg<T, Sch, TPL, Q, V, KT::LMAP, KT::SMAP, KT::LAYOUT, INV, OPS, KT::IN_UNIT, KT::OUT_UNIT, MINB>;
+    static constexpr int RMODE = (OPS & B2_OP_REAL_EVEN) ? (INV ? 2 : 1) : 0;
+    using C = KCfg<T, Sch, TPL, Q, V, KT::LMAP, KT::SMAP, KT::LAYOUT, INV, (OPS & B2_OP_TWIDDLE_OUT), KT::IN_UNIT, KT::OUT_UNIT,
+                   MINB, RMODE>;
     b2_kernel_info info;
     explicit Registrar(const char* name) {
         info = b2_kernel_info{};
@@ -211,6 +214,15 @@ struct RegistrarSet {
     Registrar<KIND, T, TPL, Q, V, MINB, false, 0, Rs...> f;
     Registrar<KIND, T, TPL, Q, V, MINB, true, 0, Rs...> i;
     explicit RegistrarSet(const char* n) : f(n), i(n) {}
+};
+// contiguous lines additionally get the fused even-length real transforms (R2C on the forward kernel, C2R on the inverse)
+template <typename T, int TPL, int Q, int V, int MINB, int... Rs>
+struct RegistrarSet<B2_KIND_ROWS, T, TPL, Q, V, MINB, Rs...> {
+    Registrar<B2_KIND_ROWS, T, TPL, Q, V, MINB, false, 0, Rs...> f;
+    Registrar<B2_KIND_ROWS, T, TPL, Q, V, MINB, true, 0, Rs...> i;
+    Registrar<B2_KIND_ROWS, T, TPL, Q, V, MINB, false, B2_OP_REAL_EVEN, Rs...> fr;
+    Registrar<B2_KIND_ROWS, T, TPL, Q, V, MINB, true, B2_OP_REAL_EVEN, Rs...> ir;
+    explicit RegistrarSet(const char* n) : f(n), i(n), fr(n), ir(n) {}
 };
 template <typename T, int TPL, int Q, int V, int MINB, int... Rs>
 struct RegistrarSet<B2_KIND_COLS, T, TPL, Q, V, MINB, Rs...> {

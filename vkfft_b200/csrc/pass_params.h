@@ -23,6 +23,8 @@ enum {
     B2_OP_SCALE = 2,         // multiply by `scale` on store (normalize=1, vkFFT_Structs.h:220)
     B2_OP_MUL_IN = 4,        // multiply element p by aux0[p] on load   (Bluestein chirp, vkFFT_Bluestein.h:32)
     B2_OP_MUL_OUT = 8,       // multiply element p by aux1[p] on store  (Bluestein filter / post chirp, :201)
+    B2_OP_REAL_EVEN = 16,    // specialised kernels: even-length real transform fused into the pass -- forward: Hermitian
+                             // post-pass on store (n+1 outputs), inverse: Hermitian pre-pass on load (n+1 inputs); aux0 = e^{-2 pi i k/2n}
 };
 
 // how the generic kernel fills a line on load / drains it on store (real-data transforms live here)

@@ -72,18 +72,32 @@ std::vector<Dim> merge_dims(const std::vector<Dim>& d) {
 const int RADER_MAX_PRIME = 127;
 std::vector<int> generic_radices(uint64_t n) {
     std::vector<int> r, primes;
-    static const int cand[] = {16, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2};
+    static const int cand16[] = {16, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2};
+    static const int cand11[] = {11, 10, 9, 8, 7, 6, 5, 4, 3, 2};
+    static const int cand8[] = {8, 7, 6, 5, 4, 3, 2};
     // split off prime factors > 13 first
     uint64_t m = n;
     for (int f : {2, 3, 5, 7, 11, 13}) while (m % f == 0) m /= f;
     for (uint64_t f = 17; m > 1 && f <= (uint64_t)RADER_MAX_PRIME; f += 2)
         while (m % f == 0) { primes.push_back((int)f); m /= f; n /= f; }
     if (m != 1) return {};
-    while (n > 1) {
-        bool found = false;
-        for (int c : cand)
-            if (n % c == 0) { r.push_back(c); n /= c; found = true; break; }
-        if (!found) return {};
+    // greedy factorisation per radix class; keep the leanest class that does not need more stages than the widest one
+    auto greedy = [](uint64_t v, const int* c, int nc) {
+        std::vector<int> out;
+        while (v > 1) {
+            bool found = false;
+            for (int i = 0; i < nc; ++i)
+                if (v % c[i] == 0) { out.push_back(c[i]); v /= c[i]; found = true; break; }
+            if (!found) return std::vector<int>{};
+        }
+        return out;
+    };
+    if (n > 1) {
+        std::vector<int> r16 = greedy(n, cand16, 15), r11 = greedy(n, cand11, 10), r8 = greedy(n, cand8, 7);
+        if (r16.empty()) return {};
+        r = r16;
+        if (!r11.empty() && r11.size() <= r16.size()) r = r11;
+        if (!r8.empty() && r8.size() <= r.size()) r = r8;
     }
     // Rader stages last: their legs are already twiddled by a large stageSize, outputs land in natural order as usual
     r.insert(r.end(), primes.begin(), primes.end());
@@ -133,13 +147,16 @@ int emit(PlanGraph& g, std::vector<PassPlan>& list, const PassReq& rq) {
     const bool plain = !rq.force_generic && rq.load_io == B2_IO_C2C && rq.store_io == B2_IO_C2C &&
                        !(rq.ops & (B2_OP_MUL_IN | B2_OP_MUL_OUT)) && rq.in_len == 0 && rq.out_len == 0 &&
                        !rq.inner_inverse;
-    if (plain) k = b2_find_kernel(rq.kind, g.prec, rq.n, rq.inv, rq.ops & B2_OP_TWIDDLE_OUT);
+    if (plain) k = b2_find_kernel(rq.kind, g.prec, rq.n, rq.inv, rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN));
     std::vector<int> radices;
     bool generic = false;
     if (!k) {
-        k = b2_find_kernel(B2_KIND_GENERIC, g.prec, 0, 0, 0);
-        if (!k || !generic_fits(g, rq.n)) return R_UNSUPPORTED_FFT_LENGTH;
+        if (!generic_fits(g, rq.n)) return R_UNSUPPORTED_FFT_LENGTH;
         radices = generic_radices(rq.n);
+        int rmax = 2;
+        for (int r : radices) if (r <= 16) rmax = std::max(rmax, r);
+        k = b2_find_kernel(B2_KIND_GENERIC, g.prec, rmax <= 8 ? 8 : (rmax <= 11 ? 11 : 16), 0, 0);
+        if (!k) return R_UNSUPPORTED_FFT_LENGTH;
         generic = true;
     } else {
         radices.assign(k->radices, k->radices + k->ns);
@@ -173,10 +190,10 @@ int emit(PlanGraph& g, std::vector<PassPlan>& list, const PassReq& rq) {
     const bool qfast_l = (rq.kind == B2_KIND_COLS), qfast_s = (rq.kind != B2_KIND_ROWS);
     if (generic) {
         tpl = 1;
-        while (tpl < 512 && tpl * 16 < (uint32_t)rq.n) tpl <<= 1;
+        while (tpl < 256 && tpl * 16 < (uint32_t)rq.n) tpl <<= 1;
         ls = (uint32_t)(pad_of(g, rq.n) | 1);
         const uint64_t per_line = 2ull * ls * esize(g);
-        uint32_t qmax = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(GENERIC_SMEM_LIMIT / per_line, 512 / tpl));
+        uint32_t qmax = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(GENERIC_SMEM_LIMIT / per_line, 256 / tpl));
         uint32_t want = (qfast_l || qfast_s) ? (g.prec == B2_PREC_F64 ? 8u : 16u) : std::max(1u, 128u / tpl);
         // keep at least two CTAs per SM resident when lines are short
         while (want > 1 && want * per_line > 96 * 1024) want >>= 1;
@@ -199,12 +216,12 @@ int emit(PlanGraph& g, std::vector<PassPlan>& list, const PassReq& rq) {
         pp.k = k;
         if (k->pipelined) {   // TMA needs 16-byte aligned sources: keep the first non-pipelined kernel of the same key as a stand-in
             for (int v = 0; v < 16 && !pp.k_unaligned; ++v) {
-                const b2_kernel_info* alt = b2_find_kernel_variant(rq.kind, g.prec, rq.n, rq.inv, rq.ops & B2_OP_TWIDDLE_OUT, v);
+                const b2_kernel_info* alt = b2_find_kernel_variant(rq.kind, g.prec, rq.n, rq.inv, rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN), v);
                 if (alt && !alt->pipelined && alt->q == k->q) pp.k_unaligned = alt;
             }
             if (!pp.k_unaligned) {    // no drop-in with the same tile height: do not use the pipelined kernel at all
                 for (int v = 0; v < 16; ++v) {
-                    const b2_kernel_info* alt = b2_find_kernel_variant(rq.kind, g.prec, rq.n, rq.inv, rq.ops & B2_OP_TWIDDLE_OUT, v);
+                    const b2_kernel_info* alt = b2_find_kernel_variant(rq.kind, g.prec, rq.n, rq.inv, rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN), v);
                     if (alt && !alt->pipelined) { pp.k = k = alt; break; }
                 }
                 tpl = k->tpl; q = k->q;
@@ -522,6 +539,12 @@ int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
         const uint64_t per_line = 2ull * (uint64_t)(pad_of(g, N) | 1) * esize(g);
         poor_strided = (GENERIC_SMEM_LIMIT / per_line) < 8 && N >= 64;
     }
+    // specialised strided kernels with fewer than 8 neighbouring lines per CTA (N >= 4096) are slower than two
+    // launches of well-shaped ones (measured: 1950 us vs 858 + 673 us per 2 GiB pass, profiles/r1)
+    if (job.unit_lines) {
+        const b2_kernel_info* kk = b2_find_kernel(kind, g.prec, (int)std::min<uint64_t>(N, 0x7fffffff), 0, 0);
+        if (kk && kk->q < 8 && N >= 2048) poor_strided = true;
+    }
     bool try_single = N <= max_single_env() && single_ok(g, kind, N, 0);
     if (try_single && poor_strided) {
         // only if a split exists
@@ -770,7 +793,8 @@ int plan_direction_r2c(PlanGraph& g, std::vector<PassPlan>& list, int inv) {
             if (!d.omit_dimension[a]) norm /= (double)d.size[a];
     const bool even = (N0 % 2 == 0);
     const uint64_t n = even ? N0 / 2 : N0;
-    const bool fused = is_smooth(n) && generic_fits(g, n) && n >= 2;
+    const bool fused = n >= 2 && ((is_smooth(n) && generic_fits(g, n)) ||
+                                  (even && b2_find_kernel(B2_KIND_ROWS, g.prec, (int)n, 0, B2_OP_REAL_EVEN) != nullptr));
     if (!fused && (!even || n < 2)) return R_UNSUPPORTED_FFT_LENGTH_R2C;   // long / non-smooth odd lengths: not yet
 
     // real side of the axis-0 launch, in units of the pointer type the operator uses
@@ -800,6 +824,18 @@ int plan_direction_r2c(PlanGraph& g, std::vector<PassPlan>& list, int inv) {
         else { rq.group = m[0]; m.erase(m.begin()); }
         rq.outer = m;
         rq.in_es = 1; rq.out_es = 1;
+        // specialised kernel with the Hermitian pass fused in (one HBM round trip, registers + shared memory)
+        if (even && b2_find_kernel(B2_KIND_ROWS, g.prec, (int)n, forward ? 0 : 1, B2_OP_REAL_EVEN)) {
+            rq.force_generic = false;
+            rq.inv = forward ? 0 : 1;
+            rq.ops = B2_OP_REAL_EVEN | ((!forward && scale != 1.0) ? B2_OP_SCALE : 0);
+            rq.scale = forward ? 1.0 : scale;
+            rq.aux0 = aux_for(g, AUX_R2C, N0);
+            rq.in_role = forward ? real_role : ROLE_BUFFER;
+            rq.out_role = forward ? ROLE_BUFFER : real_role;
+            rq.what = forward ? "r2c axis0 (fused)" : "c2r axis0 (fused)";
+            return emit(g, list, rq);
+        }
         if (forward) {
             rq.in_role = real_role; rq.out_role = ROLE_BUFFER;
             if (even) { rq.store_io = B2_IO_R2C_EVEN; rq.aux0 = aux_for(g, AUX_R2C, N0); rq.out_len = (uint32_t)(n + 1); }

@@ -92,7 +92,7 @@ B2_D cpx<T> twiddle2(const cpx<T>* hi, const cpx<T>* lo, uint32_t shift, uint64_
 // ------------------------------------------------------------------------------------------------
 // Kernel configuration (all compile-time)
 template <typename T_, class Sch_, int TPL_, int Q_, int V_, int LMAP_, int SMAP_, int LAYOUT_, bool INV_,
-          int OPS_, bool IN_UNIT_, bool OUT_UNIT_, int REGS_ = 128>
+          int OPS_, bool IN_UNIT_, bool OUT_UNIT_, int REGS_ = 128, int RMODE_ = 0>
 struct KCfg {
     using T = T_;
     using Sch = Sch_;
@@ -107,6 +107,9 @@ struct KCfg {
     static constexpr int OPS = OPS_;
     static constexpr bool IN_UNIT = IN_UNIT_;    // in_es == 1 guaranteed
     static constexpr bool OUT_UNIT = OUT_UNIT_;  // out_es == 1 guaranteed
+    // 0: complex in/out; 1: real-to-complex (even length 2N): Hermitian post-pass fused into the store;
+    // 2: complex-to-real: Hermitian pre-pass fused into the load (vkFFT_R2C_even_decomposition.h:181-230 as a fused stage)
+    static constexpr int RMODE = RMODE_;
     static constexpr int THREADS = TPL * Q;
     // register budget per thread -> resident CTAs per SM the compiler must make room for
     static constexpr int MINB = (65536 / (THREADS * REGS_)) < 1 ? 1 : ((65536 / (THREADS * REGS_)) > 32 ? 32 : (65536 / (THREADS * REGS_)));
@@ -116,7 +119,7 @@ struct KCfg {
     static constexpr int NPAD = N + (N >> PAD_SHIFT);
     static constexpr int LS = (LAYOUT == LAY_LINE) ? (Q == 1 ? NPAD : (NPAD | 1)) : 0;
     static constexpr int QP = Q;  // elem-major row pitch
-    static constexpr int SMEM_ELEMS = (Sch::ns <= 1) ? 0 : ((LAYOUT == LAY_LINE) ? Q * LS : N * QP);
+    static constexpr int SMEM_ELEMS = (Sch::ns <= 1 && RMODE != 1) ? 0 : ((LAYOUT == LAY_LINE) ? Q * LS : N * QP);
     static constexpr int SMEM_BYTES = SMEM_ELEMS * 2 * (int)sizeof(T);
 };
 
@@ -165,6 +168,62 @@ struct Engine {
                     }
                 }
             }
+        }
+    }
+
+    // ---- C2R: first-stage legs assembled from the Hermitian half spectrum (n+1 inputs per line) ---------------------
+    //  Zin[p] = (X[p] + conj X[n-p]) + i conj(w_p) (X[p] - conj X[n-p]),  w_p = e^{-2 pi i p/2n};  then the inverse FFT
+    template <int s>
+    B2_D static void load_global_c2r(X* x, const X* __restrict__ line, const X* __restrict__ w, int t, bool valid) {
+        constexpr int r = Sch::r(s), NB = nbut<s>(), BPT = bpt<s>();
+#pragma unroll
+        for (int m = 0; m < BPT; ++m) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const int b = V * (t + m * TPL) + v;
+                const bool ok = valid && (!guarded<s>() || b < NB);
+#pragma unroll
+                for (int k = 0; k < r; ++k) {
+                    const int p = b + k * NB;
+                    X z = mk<T>(T(0), T(0));
+                    if (ok) {
+                        const X a = line[p], bc = conj(line[N - p]);
+                        const X sm = a + bc, d = mulc(a - bc, ld_lut(w + p));
+                        z = mk<T>(sm.x - d.y, sm.y + d.x);
+                    }
+                    x[(m * V + v) * r + k] = swp(z);          // RMODE 2 is always an inverse transform
+                }
+            }
+        }
+    }
+
+    // ---- R2C: Hermitian post-pass through shared memory, n+1 outputs per line ---------------------------------------
+    //  X[k] = 1/2 (Z[k] + conj Z[n-k]) - i/2 w_k (Z[k] - conj Z[n-k])
+    template <int s>
+    B2_D static void store_global_r2c(const X* x, X* sm, X* __restrict__ line, const X* __restrict__ w, int q, int t,
+                                      bool valid, const b2_pass_params& P) {
+        constexpr int r = Sch::r(s), NB = nbut<s>(), BPT = bpt<s>();
+        const bool do_scale = (P.ops & B2_OP_SCALE) != 0;
+        const T sc = (T)P.scale;
+#pragma unroll
+        for (int m = 0; m < BPT; ++m) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const int b = V * (t + m * TPL) + v;
+                if (guarded<s>() && b >= NB) continue;
+#pragma unroll
+                for (int k = 0; k < r; ++k) B2_SMEM_ST(sm, sidx(q, b + k * NB), x[(m * V + v) * r + k]);
+            }
+        }
+        __syncthreads();
+        if (!valid) return;
+        for (int k = t; k <= N; k += TPL) {
+            const X a = B2_SMEM_LD(sm, sidx(q, k == N ? 0 : k));
+            const X bc = conj(B2_SMEM_LD(sm, sidx(q, k == 0 ? 0 : N - k)));
+            const X sum = a + bc, d = (a - bc) * ld_lut(w + k);
+            X o = mk<T>(T(0.5) * (sum.x + d.y), T(0.5) * (sum.y - d.x));
+            if (do_scale) o = o * sc;
+            line[k] = o;
         }
     }
 
@@ -311,16 +370,20 @@ struct Engine {
         const uint32_t gl = grp * Q + ql;
         const X* in_line = (const X*)P.in + obase_in + (int64_t)gl * P.in_gs;
 
+        const X* __restrict__ rw = (const X*)P.aux0;   // e^{-2 pi i k/2n} for the fused real transforms
         if constexpr (NS == 1) {
             X x[bpt<0>() * V * Sch::r(0)];
-            load_global<0>(x, in_line, P.in_es, tl, gl < P.G);
+            if constexpr (C::RMODE == 2) load_global_c2r<0>(x, in_line, rw, tl, gl < P.G);
+            else load_global<0>(x, in_line, P.in_es, tl, gl < P.G);
             compute<0>(x, lut, tl);
             X* out_line = (X*)P.out + obase_out + (int64_t)gl * P.out_gs;
-            store_global<0>(x, out_line, P.out_es, tl, gl < P.G, P, twl(P, gl, o0, o1, o2), (uint32_t)ql);
+            if constexpr (C::RMODE == 1) store_global_r2c<0>(x, sm, out_line, rw, ql, tl, gl < P.G, P);
+            else store_global<0>(x, out_line, P.out_es, tl, gl < P.G, P, twl(P, gl, o0, o1, o2), (uint32_t)ql);
         } else {
             {
                 X x[bpt<0>() * V * Sch::r(0)];
-                load_global<0>(x, in_line, P.in_es, tl, gl < P.G);
+                if constexpr (C::RMODE == 2) load_global_c2r<0>(x, in_line, rw, tl, gl < P.G);
+                else load_global<0>(x, in_line, P.in_es, tl, gl < P.G);
                 compute<0>(x, lut, tl);
                 store_smem<0>(x, sm, ql, tl);
             }
@@ -335,7 +398,12 @@ struct Engine {
                 load_smem<s>(x, sm, qs, ts);
                 compute<s>(x, lut, ts);
                 X* out_line = (X*)P.out + obase_out + (int64_t)gs * P.out_gs;
-                store_global<s>(x, out_line, P.out_es, ts, gs < P.G, P, twl(P, gs, o0, o1, o2), (uint32_t)qs);
+                if constexpr (C::RMODE == 1) {
+                    __syncthreads();     // every last-stage read of the tile is done before it is overwritten
+                    store_global_r2c<s>(x, sm, out_line, rw, qs, ts, gs < P.G, P);
+                } else {
+                    store_global<s>(x, out_line, P.out_es, ts, gs < P.G, P, twl(P, gs, o0, o1, o2), (uint32_t)qs);
+                }
             }
         }
     }

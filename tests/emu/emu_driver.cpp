@@ -1,7 +1,6 @@
 // TEST INFRASTRUCTURE ONLY: runs the engine's kernel bodies on the CPU emulation (see cuda_emu.h).
 // Built by tests/emu/build.sh into tests/emu/_build/libb200fft_emu.so and driven from pytest via ctypes.
 #include "kernel_inst.cuh"
-#include "kernel_list.def"
 #include "lut.h"
 #include "plan.h"
 

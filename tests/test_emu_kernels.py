@@ -40,10 +40,10 @@ def test_every_kernel_matches_oracle(k):
         got = y.T
     assert orc.error_metrics(got, ref)["l2_rel"] < (3e-7 if k["prec"] == 0 else 1e-15)
     # shared-memory traffic: never worse than 2-way conflicts on average 1.5 wavefronts per ideal one
-    if k["variant"] == 0:
+    if k["variant"] == 0 and (n & (n - 1)) == 0:
         assert rep["mean"] <= 2.0 and rep["worst"] <= 4.0
-    else:           # tuning variants: only guard against pathological layouts
-        assert rep["mean"] <= 4.0
+    else:           # tuning variants and odd radices: only guard against pathological layouts
+        assert rep["mean"] <= 6.0
 
 
 def _plan_case(shape_xyz, batches, prec, env=None, inverse=-1, normalize=0):

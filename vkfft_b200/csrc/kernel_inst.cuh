@@ -247,14 +247,19 @@ struct MaybeSet<true, KIND, T, TPL, Q, V, MINB, Rs...> : RegistrarSet<KIND, T, T
 }  // namespace b200fft
 
 #define B2_KP(shard, KIND, T, TPL, Q, V, REGS, NBUF, ...)                                                  \
-    static ::b200fft::MaybePipe<((B2_SHARD) < 0 || (shard) == (B2_SHARD)), B2_KIND_##KIND, T, TPL, Q, V, REGS, NBUF, \
+    static ::b200fft::MaybePipe<B2_SHARD_ON(shard), B2_KIND_##KIND, T, TPL, Q, V, REGS, NBUF, \
                                 __VA_ARGS__>                                                              \
-        B2_CAT(b2_regp_, __LINE__)("PIPE" #NBUF "_" #KIND "<" #T "," #TPL "x" #Q ",V" #V ";" #__VA_ARGS__ ">");
+        B2_CAT(b2_regp_, __COUNTER__)("PIPE" #NBUF "_" #KIND "<" #T "," #TPL "x" #Q ",V" #V ";" #__VA_ARGS__ ">");
 
-// B2_SHARD < 0 instantiates everything (CPU emulation build)
+// B2_SHARD < 0: CPU emulation build -- everything, optionally split over B2_EMU_PARTS translation units
+#ifndef B2_EMU_PARTS
+#define B2_EMU_PARTS 1
+#define B2_EMU_PART 0
+#endif
+#define B2_SHARD_ON(shard) ((B2_SHARD) < 0 ? (((shard) % B2_EMU_PARTS) == B2_EMU_PART) : ((shard) == (B2_SHARD)))
 #define B2_CAT2(a, b) a##b
 #define B2_CAT(a, b) B2_CAT2(a, b)
 #define B2_K(shard, KIND, T, TPL, Q, V, MINB, ...)                                                        \
-    static ::b200fft::MaybeSet<((B2_SHARD) < 0 || (shard) == (B2_SHARD)), B2_KIND_##KIND, T, TPL, Q, V, MINB, \
+    static ::b200fft::MaybeSet<B2_SHARD_ON(shard), B2_KIND_##KIND, T, TPL, Q, V, MINB, \
                                __VA_ARGS__>                                                               \
-        B2_CAT(b2_reg_, __LINE__)(#KIND "<" #T "," #TPL "x" #Q ",V" #V ";" #__VA_ARGS__ ">");
+        B2_CAT(b2_reg_, __COUNTER__)(#KIND "<" #T "," #TPL "x" #Q ",V" #V ";" #__VA_ARGS__ ">");

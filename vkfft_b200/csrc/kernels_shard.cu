@@ -6,3 +6,4 @@
 #endif
 
 #include "kernel_list.def"
+#include "kernel_list_nonpow2.def"

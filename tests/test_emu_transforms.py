@@ -94,6 +94,20 @@ def test_dct(kind, shape, b, prec, inv):
     assert orc.error_metrics(buf, orc.dct(x, kind, len(shape), inverse=(inv == 1)))["l2_rel"] < (T32 if prec == 0 else T64)
 
 
+@pytest.mark.parametrize("kind", [2, 3])
+@pytest.mark.parametrize("shape,b,prec", [((64, 256), 2, 0), ((256, 64), 1, 0), ((63, 64), 2, 0), ((512, 256), 1, 1), ((128, 64, 4), 1, 0)])
+@pytest.mark.parametrize("inv", [-1, 1])
+def test_dct23_fused_into_specialised_kernels(kind, shape, b, prec, inv):
+    """axis 0: pairs of contiguous real lines; other axes: pairs of neighbouring real columns as one complex column;
+    odd size[0] falls back to the runtime-scheduled kernel"""
+    rdt = np.float32 if prec == 0 else np.float64
+    x = orc.random_input((b,) + tuple(reversed(shape)), rdt, seed=kind + sum(shape))
+    buf = x.copy()
+    rc, _ = emu.exec_plan(emu.make_desc(shape, b, prec, perform_dct=kind), inv, buf)
+    assert rc == 0
+    assert orc.error_metrics(buf, orc.dct(x, kind, len(shape), inverse=(inv == 1)))["l2_rel"] < (T32 if prec == 0 else T64)
+
+
 def test_dct_normalized_round_trip():
     x = orc.random_input((2, 16, 32), np.float32, 9)
     for kind in (1, 2, 3, 4):

@@ -125,7 +125,7 @@ template <int KIND, typename T, int TPL, int Q, int V, int MINB, bool INV, int O
 struct Registrar {
     using KT = KindTraits<KIND>;
     using Sch = RList<Rs...>;
-    static constexpr int RMODE = (OPS & B2_OP_REAL_EVEN) ? (INV ? 2 : 1) : 0;
+    static constexpr int RMODE = (OPS & B2_OP_REAL_EVEN) ? (INV ? 2 : 1) : ((OPS & B2_OP_DCT23) ? (INV ? 4 : 3) : 0);
     using C = KCfg<T, Sch, TPL, Q, V, KT::LMAP, KT::SMAP, KT::LAYOUT, INV, (OPS & B2_OP_TWIDDLE_OUT), KT::IN_UNIT, KT::OUT_UNIT,
                    MINB, RMODE>;
     b2_kernel_info info;
@@ -250,6 +250,23 @@ struct MaybeSet<true, KIND, T, TPL, Q, V, MINB, Rs...> : RegistrarSet<KIND, T, T
     static ::b200fft::MaybePipe<B2_SHARD_ON(shard), B2_KIND_##KIND, T, TPL, Q, V, REGS, NBUF, \
                                 __VA_ARGS__>                                                              \
         B2_CAT(b2_regp_, __COUNTER__)("PIPE" #NBUF "_" #KIND "<" #T "," #TPL "x" #Q ",V" #V ";" #__VA_ARGS__ ">");
+
+// DCT-II/III variants of a line of the list (explicit, only where the shapes are worth it)
+namespace b200fft {
+template <bool EN, int KIND, typename T, int TPL, int Q, int V, int MINB, int... Rs>
+struct MaybeDct {
+    explicit MaybeDct(const char*) {}
+};
+template <int KIND, typename T, int TPL, int Q, int V, int MINB, int... Rs>
+struct MaybeDct<true, KIND, T, TPL, Q, V, MINB, Rs...> {
+    Registrar<KIND, T, TPL, Q, V, MINB, false, B2_OP_DCT23, Rs...> d2;
+    Registrar<KIND, T, TPL, Q, V, MINB, true, B2_OP_DCT23, Rs...> d3;
+    explicit MaybeDct(const char* n) : d2(n), d3(n) {}
+};
+}  // namespace b200fft
+#define B2_KD(shard, KIND, T, TPL, Q, V, MINB, ...)                                                       \
+    static ::b200fft::MaybeDct<B2_SHARD_ON(shard), B2_KIND_##KIND, T, TPL, Q, V, MINB, __VA_ARGS__>       \
+        B2_CAT(b2_regd_, __COUNTER__)("DCT_" #KIND "<" #T "," #TPL "x" #Q ",V" #V ";" #__VA_ARGS__ ">");
 
 // B2_SHARD < 0: CPU emulation build -- everything, optionally split over B2_EMU_PARTS translation units
 #ifndef B2_EMU_PARTS

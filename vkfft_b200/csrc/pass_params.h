@@ -25,6 +25,9 @@ enum {
     B2_OP_MUL_OUT = 8,       // multiply element p by aux1[p] on store  (Bluestein filter / post chirp, :201)
     B2_OP_REAL_EVEN = 16,    // specialised kernels: even-length real transform fused into the pass -- forward: Hermitian
                              // post-pass on store (n+1 outputs), inverse: Hermitian pre-pass on load (n+1 inputs); aux0 = e^{-2 pi i k/2n}
+    B2_OP_DCT23 = 32,        // specialised kernels: DCT-II (forward FFT: Makhoul gather on load, split + phase on store) or
+                             // DCT-III (inverse FFT: phase + merge on load, Makhoul scatter on store); aux0 = e^{-i pi k/2n},
+                             // aux_u0 = number of real lines, aux_u1 = pitch between the two real lines of a pair
 };
 
 // how the generic kernel fills a line on load / drains it on store (real-data transforms live here)

@@ -134,6 +134,7 @@ struct PassReq {
     uint32_t aux_u0 = 0, aux_u1 = 0;
     bool real_pairs = false;     // group dim counts REAL lines; two of them form one complex line
     uint32_t dst_flags = 0;
+    bool scalar_units = false;   // specialised real-data kernels addressing real lines: offsets/strides count scalars
     int64_t in_base = 0, out_base = 0;   // element offsets into the role's buffer (scratch regions)
     // elementwise helper passes (ew.cuh)
     bool elementwise = false;
@@ -147,7 +148,7 @@ int emit(PlanGraph& g, std::vector<PassPlan>& list, const PassReq& rq) {
     const bool plain = !rq.force_generic && rq.load_io == B2_IO_C2C && rq.store_io == B2_IO_C2C &&
                        !(rq.ops & (B2_OP_MUL_IN | B2_OP_MUL_OUT)) && rq.in_len == 0 && rq.out_len == 0 &&
                        !rq.inner_inverse;
-    if (plain) k = b2_find_kernel(rq.kind, g.prec, rq.n, rq.inv, rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN));
+    if (plain) k = b2_find_kernel(rq.kind, g.prec, rq.n, rq.inv, rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN | B2_OP_DCT23));
     std::vector<int> radices;
     bool generic = false;
     if (!k) {
@@ -216,12 +217,12 @@ int emit(PlanGraph& g, std::vector<PassPlan>& list, const PassReq& rq) {
         pp.k = k;
         if (k->pipelined) {   // TMA needs 16-byte aligned sources: keep the first non-pipelined kernel of the same key as a stand-in
             for (int v = 0; v < 16 && !pp.k_unaligned; ++v) {
-                const b2_kernel_info* alt = b2_find_kernel_variant(rq.kind, g.prec, rq.n, rq.inv, rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN), v);
+                const b2_kernel_info* alt = b2_find_kernel_variant(rq.kind, g.prec, rq.n, rq.inv, rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN | B2_OP_DCT23), v);
                 if (alt && !alt->pipelined && alt->q == k->q) pp.k_unaligned = alt;
             }
             if (!pp.k_unaligned) {    // no drop-in with the same tile height: do not use the pipelined kernel at all
                 for (int v = 0; v < 16; ++v) {
-                    const b2_kernel_info* alt = b2_find_kernel_variant(rq.kind, g.prec, rq.n, rq.inv, rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN), v);
+                    const b2_kernel_info* alt = b2_find_kernel_variant(rq.kind, g.prec, rq.n, rq.inv, rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN | B2_OP_DCT23), v);
                     if (alt && !alt->pipelined) { pp.k = k = alt; break; }
                 }
                 tpl = k->tpl; q = k->q;
@@ -266,7 +267,7 @@ int emit(PlanGraph& g, std::vector<PassPlan>& list, const PassReq& rq) {
         pp.aux0_id = rq.aux0; pp.aux1_id = rq.aux1;
         // specialised kernels: intra-tile factor of the four-step phase (coalesced table, see stockham.cuh)
         auto scalar_io = [](int io) { return io == B2_IO_DCT1 || io == B2_IO_DCT2 || io == B2_IO_DCT3 || io == B2_IO_DCT4 || io == B2_IO_REAL || io == B2_IO_DST1; };
-        pp.in_scalar = scalar_io(rq.load_io); pp.out_scalar = scalar_io(rq.store_io);
+        pp.in_scalar = scalar_io(rq.load_io) || rq.scalar_units; pp.out_scalar = scalar_io(rq.store_io) || rq.scalar_units;
         char buf[320];
         std::string rs;
         for (int r : radices) rs += (rs.empty() ? "" : "x") + std::to_string(r);
@@ -936,6 +937,47 @@ int plan_direction_dct(PlanGraph& g, std::vector<PassPlan>& list, int inv) {
                 n = N / 2; rq.load_io = rq.store_io = B2_IO_DCT4;
                 rq.aux0 = aux_for(g, AUX_DCT4_PRE, N); rq.aux1 = aux_for(g, AUX_DCT4_POST, N); break;
             default: return R_UNSUPPORTED_FFT_LENGTH_R2R;
+        }
+        // DCT-II/III on the specialised kernels: contiguous real lines (axis 0) or pairs of neighbouring real columns
+        // viewed as one complex column (other axes)
+        if (!is_dst && (type == 2 || type == 3)) {
+            const int kkind = axis == 0 ? B2_KIND_ROWS : B2_KIND_COLS;
+            const int kinv = type == 3 ? 1 : 0;
+            std::vector<Dim> lines = other_dims(g, d.size, axis, buf, buf);
+            bool ok = b2_find_kernel(kkind, g.prec, (int)N, kinv, B2_OP_DCT23) != nullptr;
+            PassReq fr;
+            fr.kind = kkind; fr.n = (int)N; fr.inv = kinv; fr.ops = B2_OP_DCT23 | ((scale != 1.0) ? B2_OP_SCALE : 0);
+            fr.scale = scale; fr.aux0 = aux_for(g, AUX_DCT23, N);
+            fr.what = "dct axis (fused)";
+            if (ok && axis == 0) {
+                std::vector<Dim> m = merge_dims(lines);
+                Dim grp = m.empty() ? Dim{1, 0, 0} : m[0];
+                if (!m.empty()) m.erase(m.begin());
+                fr.real_pairs = true; fr.scalar_units = true;
+                fr.aux_u0 = (uint32_t)grp.n; fr.aux_u1 = (uint32_t)grp.is;
+                fr.group = Dim{grp.n, 2 * grp.is, 2 * grp.os};
+                fr.outer = m;
+                fr.in_es = fr.out_es = 1;
+            } else if (ok) {
+                // complex view: size[0] and every stride must be even
+                ok = (d.size[0] % 2 == 0) && (buf.stride[axis - 1] % 2 == 0) && (buf.batch_stride % 2 == 0);
+                for (uint32_t a = 1; a < d.fft_dim && ok; ++a) ok = (buf.stride[a - 1] % 2 == 0);
+                if (ok) {
+                    std::vector<Dim> cl;
+                    cl.push_back(Dim{d.size[0] / 2, 1, 1});
+                    for (size_t li = 1; li < lines.size(); ++li) cl.push_back(Dim{lines[li].n, lines[li].is / 2, lines[li].os / 2});
+                    std::vector<Dim> m = merge_dims(cl);
+                    if (!m.empty() && m[0].is == 1) { fr.group = m[0]; m.erase(m.begin()); }
+                    else fr.group = Dim{1, 1, 1};
+                    fr.outer = m;
+                    fr.in_es = fr.out_es = (int64_t)buf.stride[axis - 1] / 2;
+                }
+            }
+            if (ok) {
+                int rcf = emit(g, list, fr);
+                if (rcf != R_SUCCESS) return rcf;
+                continue;
+            }
         }
         if (n < 2 || !is_smooth(n) || !generic_fits(g, n)) return R_UNSUPPORTED_FFT_LENGTH_R2R;
         if (is_dst) {   // sign / reversal wrappers (API guide :581-583)

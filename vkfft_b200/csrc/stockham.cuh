@@ -119,7 +119,9 @@ struct KCfg {
     static constexpr int NPAD = N + (N >> PAD_SHIFT);
     static constexpr int LS = (LAYOUT == LAY_LINE) ? (Q == 1 ? NPAD : (NPAD | 1)) : 0;
     static constexpr int QP = Q;  // elem-major row pitch
-    static constexpr int SMEM_ELEMS = (Sch::ns <= 1 && RMODE != 1) ? 0 : ((LAYOUT == LAY_LINE) ? Q * LS : N * QP);
+    // 3: DCT-II, 4: DCT-III with two real lines per complex line (contiguous real lines, or neighbouring real columns
+    //    viewed as one complex column on strided axes) -- vkFFT_R2R.h:193-229, :784-859 as fused load/store stages
+    static constexpr int SMEM_ELEMS = (Sch::ns <= 1 && RMODE != 1 && RMODE != 3) ? 0 : ((LAYOUT == LAY_LINE) ? Q * LS : N * QP);
     static constexpr int SMEM_BYTES = SMEM_ELEMS * 2 * (int)sizeof(T);
 };
 
@@ -193,6 +195,116 @@ struct Engine {
                     }
                     x[(m * V + v) * r + k] = swp(z);          // RMODE 2 is always an inverse transform
                 }
+            }
+        }
+    }
+
+    B2_D static int makhoul(int p) { return (p < (N + 1) / 2) ? 2 * p : 2 * (N - 1 - p) + 1; }
+
+    // ---- DCT-II / DCT-III: first-stage legs (RMODE 3 / 4) --------------------------------------------------------------
+    template <int s>
+    B2_D static void load_global_dct(X* x, const b2_pass_params& P, int64_t obase_in, uint32_t gl, int t, bool valid) {
+        constexpr int r = Sch::r(s), NB = nbut<s>(), BPT = bpt<s>();
+        const X* __restrict__ c = (const X*)P.aux0;
+        const T* la = nullptr; const T* lb = nullptr; const X* lc = nullptr;
+        bool vb = false;
+        if constexpr (C::LAYOUT == LAY_LINE) {
+            la = (const T*)P.in + obase_in + (int64_t)gl * P.in_gs;
+            lb = la + P.aux_u1;
+            vb = valid && (2 * gl + 1 < P.aux_u0);
+        } else {
+            lc = (const X*)P.in + obase_in + (int64_t)gl * P.in_gs;
+        }
+#pragma unroll
+        for (int m = 0; m < BPT; ++m) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const int b = V * (t + m * TPL) + v;
+                const bool ok = valid && (!guarded<s>() || b < NB);
+#pragma unroll
+                for (int k = 0; k < r; ++k) {
+                    const int p = b + k * NB;
+                    X z = mk<T>(T(0), T(0));
+                    if (ok) {
+                        if constexpr (C::RMODE == 3) {
+                            const int src = makhoul(p);
+                            if constexpr (C::LAYOUT == LAY_LINE) { z.x = la[src]; if (vb) z.y = lb[src]; }
+                            else z = lc[(int64_t)src * P.in_es];
+                        } else {
+                            T a0, a1 = T(0), b0, b1 = T(0);
+                            if constexpr (C::LAYOUT == LAY_LINE) {
+                                a0 = la[p]; b0 = vb ? lb[p] : T(0);
+                                if (p != 0) { a1 = la[N - p]; b1 = vb ? lb[N - p] : T(0); }
+                            } else {
+                                const X u = lc[(int64_t)p * P.in_es];
+                                a0 = u.x; b0 = u.y;
+                                if (p != 0) { const X w2 = lc[(int64_t)(N - p) * P.in_es]; a1 = w2.x; b1 = w2.y; }
+                            }
+                            z = swp(mulc(mk<T>(a0 + b1, b0 - a1), ld_lut(c + p)));
+                        }
+                    }
+                    x[(m * V + v) * r + k] = z;
+                }
+            }
+        }
+    }
+
+    // ---- DCT-II store: split + phase through shared memory;  DCT-III store: Makhoul scatter from registers ----------
+    template <int s>
+    B2_D static void store_global_dct(const X* x, X* sm, const b2_pass_params& P, int64_t obase_out, uint32_t gl, int q,
+                                      int t, bool valid) {
+        constexpr int r = Sch::r(s), NB = nbut<s>(), BPT = bpt<s>();
+        const bool do_scale = (P.ops & B2_OP_SCALE) != 0;
+        const T sc = (T)P.scale;
+        T* oa = nullptr; T* ob = nullptr; X* oc = nullptr;
+        bool vb = false;
+        if constexpr (C::LAYOUT == LAY_LINE) {
+            oa = (T*)P.out + obase_out + (int64_t)gl * P.out_gs;
+            ob = oa + P.aux_u1;
+            vb = (2 * gl + 1 < P.aux_u0);
+        } else {
+            oc = (X*)P.out + obase_out + (int64_t)gl * P.out_gs;
+        }
+        if constexpr (C::RMODE == 4) {
+#pragma unroll
+            for (int m = 0; m < BPT; ++m) {
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    const int b = V * (t + m * TPL) + v;
+                    if (!valid || (guarded<s>() && b >= NB)) continue;
+#pragma unroll
+                    for (int k = 0; k < r; ++k) {
+                        X u = swp(x[(m * V + v) * r + k]);
+                        if (do_scale) u = u * sc;
+                        const int dst = makhoul(b + k * NB);
+                        if constexpr (C::LAYOUT == LAY_LINE) { oa[dst] = u.x; if (vb) ob[dst] = u.y; }
+                        else oc[(int64_t)dst * P.out_es] = u;
+                    }
+                }
+            }
+        } else {
+            const X* __restrict__ c = (const X*)P.aux0;
+#pragma unroll
+            for (int m = 0; m < BPT; ++m) {
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    const int b = V * (t + m * TPL) + v;
+                    if (guarded<s>() && b >= NB) continue;
+#pragma unroll
+                    for (int k = 0; k < r; ++k) B2_SMEM_ST(sm, sidx(q, b + k * NB), x[(m * V + v) * r + k]);
+                }
+            }
+            __syncthreads();
+            if (!valid) return;
+            for (int k = t; k < N; k += TPL) {
+                const X a = B2_SMEM_LD(sm, sidx(q, k));
+                const X bc = conj(B2_SMEM_LD(sm, sidx(q, k == 0 ? 0 : N - k)));
+                const X ck = ld_lut(c + k);
+                const X su = ck * (a + bc), d = ck * (a - bc);
+                T ya = su.x, yb = d.y;
+                if (do_scale) { ya *= sc; yb *= sc; }
+                if constexpr (C::LAYOUT == LAY_LINE) { oa[k] = ya; if (vb) ob[k] = yb; }
+                else oc[(int64_t)k * P.out_es] = mk<T>(ya, yb);
             }
         }
     }
@@ -374,15 +486,18 @@ struct Engine {
         if constexpr (NS == 1) {
             X x[bpt<0>() * V * Sch::r(0)];
             if constexpr (C::RMODE == 2) load_global_c2r<0>(x, in_line, rw, tl, gl < P.G);
+            else if constexpr (C::RMODE >= 3) load_global_dct<0>(x, P, obase_in, gl, tl, gl < P.G);
             else load_global<0>(x, in_line, P.in_es, tl, gl < P.G);
             compute<0>(x, lut, tl);
             X* out_line = (X*)P.out + obase_out + (int64_t)gl * P.out_gs;
             if constexpr (C::RMODE == 1) store_global_r2c<0>(x, sm, out_line, rw, ql, tl, gl < P.G, P);
+            else if constexpr (C::RMODE >= 3) store_global_dct<0>(x, sm, P, obase_out, gl, ql, tl, gl < P.G);
             else store_global<0>(x, out_line, P.out_es, tl, gl < P.G, P, twl(P, gl, o0, o1, o2), (uint32_t)ql);
         } else {
             {
                 X x[bpt<0>() * V * Sch::r(0)];
                 if constexpr (C::RMODE == 2) load_global_c2r<0>(x, in_line, rw, tl, gl < P.G);
+                else if constexpr (C::RMODE >= 3) load_global_dct<0>(x, P, obase_in, gl, tl, gl < P.G);
                 else load_global<0>(x, in_line, P.in_es, tl, gl < P.G);
                 compute<0>(x, lut, tl);
                 store_smem<0>(x, sm, ql, tl);
@@ -401,6 +516,9 @@ struct Engine {
                 if constexpr (C::RMODE == 1) {
                     __syncthreads();     // every last-stage read of the tile is done before it is overwritten
                     store_global_r2c<s>(x, sm, out_line, rw, qs, ts, gs < P.G, P);
+                } else if constexpr (C::RMODE >= 3) {
+                    if constexpr (C::RMODE == 3) __syncthreads();
+                    store_global_dct<s>(x, sm, P, obase_out, gs, qs, ts, gs < P.G);
                 } else {
                     store_global<s>(x, out_line, P.out_es, ts, gs < P.G, P, twl(P, gs, o0, o1, o2), (uint32_t)qs);
                 }

@@ -108,6 +108,20 @@ def test_dct23_fused_into_specialised_kernels(kind, shape, b, prec, inv):
     assert orc.error_metrics(buf, orc.dct(x, kind, len(shape), inverse=(inv == 1)))["l2_rel"] < (T32 if prec == 0 else T64)
 
 
+@pytest.mark.parametrize("kind", [2, 3])
+@pytest.mark.parametrize("shape,b,prec", [((8, 4096), 1, 0), ((6, 8192), 2, 0), ((4, 8192), 1, 1)])
+@pytest.mark.parametrize("inv", [-1, 1])
+def test_long_strided_dct23(kind, shape, b, prec, inv):
+    """strided axis of 4096 / 8192 points: Four-Step along the stride, Makhoul permutation folded into the first gather
+    (DCT-II) or the last scatter (DCT-III), split/merge as an elementwise launch"""
+    rdt = np.float32 if prec == 0 else np.float64
+    x = orc.random_input((b,) + tuple(reversed(shape)), rdt, seed=kind + sum(shape))
+    buf = x.copy()
+    rc, npass = emu.exec_plan(emu.make_desc(shape, b, prec, perform_dct=kind), inv, buf)
+    assert rc == 0 and npass == 4
+    assert orc.error_metrics(buf, orc.dct(x, kind, len(shape), inverse=(inv == 1)))["l2_rel"] < (T32 if prec == 0 else T64)
+
+
 def test_dct_normalized_round_trip():
     x = orc.random_input((2, 16, 32), np.float32, 9)
     for kind in (1, 2, 3, 4):

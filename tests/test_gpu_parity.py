@@ -193,7 +193,8 @@ def test_r2c_c2r(gpu, shape, batch, double):
 
 @pytest.mark.parametrize("kind", [1, 2, 3, 4])
 @pytest.mark.parametrize("shape,batch,double", [((64,), 5, False), ((33,), 4, True), ((32, 16), 3, False), ((100,), 3, True),
-                                                ((8, 6, 4), 2, False), ((4096,), 3, False), ((1024, 512), 1, False)])
+                                                ((8, 6, 4), 2, False), ((4096,), 3, False), ((1024, 512), 1, False),
+                                                ((64, 8192), 1, False), ((2048, 4096), 1, False), ((63, 256), 2, True)])
 @pytest.mark.parametrize("inverse", [-1, 1])
 def test_dct(gpu, kind, shape, batch, double, inverse):
     import vkfft_b200 as vk

@@ -9,7 +9,9 @@
 
 namespace b200fft {
 
-enum { B2_EW_COPY_MUL = 0, B2_EW_R2C_POST = 1, B2_EW_C2R_PRE = 2 };
+enum { B2_EW_COPY_MUL = 0, B2_EW_R2C_POST = 1, B2_EW_C2R_PRE = 2,
+       B2_EW_DCT2_POST_COLS = 3,   // long strided DCT-II: split + phase of rows (k, N-k); items = neighbouring columns
+       B2_EW_DCT3_PRE_COLS = 4 };  // long strided DCT-III: phase + merge of rows (k, N-k)
 enum { B2_EW_THREADS = 256, B2_EW_PER_THREAD = 8 };
 
 template <typename T>
@@ -46,6 +48,36 @@ struct Elementwise {
                 if (do_scale) v = v * sc;
                 if (P.inner_inverse) v = swp(v);
                 out[(int64_t)j * P.out_es] = v;
+            }
+        } else if (P.load_io == B2_EW_DCT2_POST_COLS || P.load_io == B2_EW_DCT3_PRE_COLS) {
+            // this CTA's "line" is row k = gl of a complex-view column block; its partner is row N-k (N = aux_u0);
+            // items are the columns (unit stride).  aux0[k] = e^{-i pi k/2N}
+            const int64_t N = (int64_t)P.aux_u0, k = (int64_t)gl, kc = N - k;
+            const X ck = ld_lut((const X*)P.aux0 + k);
+            const X cc = (k == 0) ? ck : ld_lut((const X*)P.aux0 + kc);
+            const int64_t pin = (kc - k) * P.in_gs, pout = (kc - k) * P.out_gs;
+#pragma unroll
+            for (int i = 0; i < B2_EW_PER_THREAD; ++i) {
+                const uint32_t j = j0 + i * B2_EW_THREADS;
+                if (j >= P.n) break;
+                const X a = in[j];
+                if (P.load_io == B2_EW_DCT2_POST_COLS) {
+                    const X b = (k == 0) ? a : in[pin + j];
+                    const X s1 = ck * (a + conj(b)), d1 = ck * (a - conj(b));
+                    X xk = mk<T>(s1.x, d1.y);
+                    if (do_scale) xk = xk * sc;
+                    out[j] = xk;
+                    if (k != 0 && kc != k) {
+                        const X s2 = cc * (b + conj(a)), d2 = cc * (b - conj(a));
+                        X xc = mk<T>(s2.x, d2.y);
+                        if (do_scale) xc = xc * sc;
+                        out[pout + j] = xc;
+                    }
+                } else {
+                    const X b = (k == 0) ? mk<T>(T(0), T(0)) : in[pin + j];
+                    out[j] = mulc(mk<T>(a.x + b.y, a.y - b.x), ck);
+                    if (k != 0 && kc != k) out[pout + j] = mulc(mk<T>(b.x + a.y, b.y - a.x), cc);
+                }
             }
         } else {
             // pairs (k, n-k), k = 0 .. n/2 ; n = P.n complex points of the half-length transform, aux0[k] = e^{-2 pi i k/(2n)}

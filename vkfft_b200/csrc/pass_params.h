@@ -28,6 +28,10 @@ enum {
     B2_OP_DCT23 = 32,        // specialised kernels: DCT-II (forward FFT: Makhoul gather on load, split + phase on store) or
                              // DCT-III (inverse FFT: phase + merge on load, Makhoul scatter on store); aux0 = e^{-i pi k/2n},
                              // aux_u0 = number of real lines, aux_u1 = pitch between the two real lines of a pair
+    B2_OP_PERM_IN = 64,      // strided Four-Step first launch of a long DCT-II: rows are gathered through the Makhoul
+                             // permutation of the FULL index p*N2 + n2 (aux_u0 = full length, aux_u1 = N2, n2 = coordinate tw_sel)
+    B2_OP_PERM_OUT = 128,    // strided Four-Step last launch of a long DCT-III: result k1 + N1*p is scattered to row makhoul(k)
+                             // (aux_u0 = full length, aux_u1 = N1, k1 = coordinate tw_sel)
 };
 
 // how the generic kernel fills a line on load / drains it on store (real-data transforms live here)

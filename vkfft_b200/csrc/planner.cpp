@@ -148,7 +148,7 @@ int emit(PlanGraph& g, std::vector<PassPlan>& list, const PassReq& rq) {
     const bool plain = !rq.force_generic && rq.load_io == B2_IO_C2C && rq.store_io == B2_IO_C2C &&
                        !(rq.ops & (B2_OP_MUL_IN | B2_OP_MUL_OUT)) && rq.in_len == 0 && rq.out_len == 0 &&
                        !rq.inner_inverse;
-    if (plain) k = b2_find_kernel(rq.kind, g.prec, rq.n, rq.inv, rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN | B2_OP_DCT23));
+    if (plain) k = b2_find_kernel(rq.kind, g.prec, rq.n, rq.inv, rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN | B2_OP_DCT23 | B2_OP_PERM_IN | B2_OP_PERM_OUT));
     std::vector<int> radices;
     bool generic = false;
     if (!k) {
@@ -217,12 +217,12 @@ int emit(PlanGraph& g, std::vector<PassPlan>& list, const PassReq& rq) {
         pp.k = k;
         if (k->pipelined) {   // TMA needs 16-byte aligned sources: keep the first non-pipelined kernel of the same key as a stand-in
             for (int v = 0; v < 16 && !pp.k_unaligned; ++v) {
-                const b2_kernel_info* alt = b2_find_kernel_variant(rq.kind, g.prec, rq.n, rq.inv, rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN | B2_OP_DCT23), v);
+                const b2_kernel_info* alt = b2_find_kernel_variant(rq.kind, g.prec, rq.n, rq.inv, rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN | B2_OP_DCT23 | B2_OP_PERM_IN | B2_OP_PERM_OUT), v);
                 if (alt && !alt->pipelined && alt->q == k->q) pp.k_unaligned = alt;
             }
             if (!pp.k_unaligned) {    // no drop-in with the same tile height: do not use the pipelined kernel at all
                 for (int v = 0; v < 16; ++v) {
-                    const b2_kernel_info* alt = b2_find_kernel_variant(rq.kind, g.prec, rq.n, rq.inv, rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN | B2_OP_DCT23), v);
+                    const b2_kernel_info* alt = b2_find_kernel_variant(rq.kind, g.prec, rq.n, rq.inv, rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN | B2_OP_DCT23 | B2_OP_PERM_IN | B2_OP_PERM_OUT), v);
                     if (alt && !alt->pipelined) { pp.k = k = alt; break; }
                 }
                 tpl = k->tpl; q = k->q;
@@ -409,6 +409,7 @@ int emit_ew(PlanGraph& g, std::vector<PassPlan>& list, PassReq rq, const std::ve
     P.n = rq.n; P.load_io = rq.ew_op; P.ops = rq.ops; P.scale = rq.scale;
     P.inverse = rq.inv; P.inner_inverse = rq.inner_inverse;
     P.in_len = rq.in_len; P.out_len = rq.out_len;
+    P.aux_u0 = rq.aux_u0; P.aux_u1 = rq.aux_u1;
     pp.in_role = rq.in_role; pp.out_role = rq.out_role;
     pp.in_off = rq.in_base; pp.out_off = rq.out_base;
     pp.lut_id = lut_for(g, std::vector<int>{});
@@ -972,6 +973,82 @@ int plan_direction_dct(PlanGraph& g, std::vector<PassPlan>& list, int inv) {
                     fr.outer = m;
                     fr.in_es = fr.out_es = (int64_t)buf.stride[axis - 1] / 2;
                 }
+            }
+            // long strided axis (no well-shaped single-launch kernel): Four-Step along the stride with the Makhoul
+            // permutation folded into the first gather (DCT-II) / the last scatter (DCT-III) and a separate split/merge launch
+            bool long_strided = false;
+            uint64_t L1 = 0, L2 = 0;
+            if (axis != 0 && (d.size[0] % 2 == 0) && N % 2 == 0) {
+                const b2_kernel_info* single = b2_find_kernel(B2_KIND_COLS, g.prec, (int)N, kinv, B2_OP_DCT23);
+                bool strides_even = (buf.batch_stride % 2 == 0);
+                for (uint32_t a = 1; a < d.fft_dim; ++a) strides_even = strides_even && (buf.stride[a - 1] % 2 == 0);
+                if (strides_even && (!single || single->q < 8)) {
+                    uint64_t bestc = ~0ull;
+                    for (uint64_t n2 = 2; n2 * 2 <= N; ++n2) {
+                        if (N % n2) continue;
+                        const uint64_t n1 = N / n2;
+                        const bool have = kinv == 0
+                            ? (b2_find_kernel(B2_KIND_COLS, g.prec, (int)n1, 0, B2_OP_TWIDDLE_OUT | B2_OP_PERM_IN) && b2_find_kernel(B2_KIND_COLS, g.prec, (int)n2, 0, 0))
+                            : (b2_find_kernel(B2_KIND_COLS, g.prec, (int)n1, 1, B2_OP_TWIDDLE_OUT) && b2_find_kernel(B2_KIND_COLS, g.prec, (int)n2, 1, B2_OP_PERM_OUT));
+                        if (!have) continue;
+                        const uint64_t c = std::max(n1, n2);
+                        if (c < bestc) { bestc = c; L1 = n1; L2 = n2; }
+                    }
+                    long_strided = L1 != 0;
+                }
+            }
+            if (long_strided) {
+                const int64_t esc = (int64_t)buf.stride[axis - 1] / 2;
+                std::vector<Dim> cl;   // complex-view line dims: columns first
+                cl.push_back(Dim{d.size[0] / 2, 1, 1});
+                for (size_t li = 1; li < lines.size(); ++li) cl.push_back(Dim{lines[li].n, lines[li].is / 2, lines[li].os / 2});
+                std::vector<Dim> m = merge_dims(cl);
+                if (m.empty() || m[0].is != 1) return R_UNSUPPORTED_FFT_LENGTH_R2R;
+                const Dim unit = m[0];
+                std::vector<Dim> rest(m.begin() + 1, m.end());
+                uint64_t extent = (uint64_t)esc * N;
+                for (const Dim& dd : cl) extent = std::max<uint64_t>(extent, (uint64_t)dd.n * (uint64_t)dd.os);
+                g.temp_elems = std::max<uint64_t>(g.temp_elems, extent);
+                const int aux = aux_for(g, AUX_DCT23, N);
+                PassReq ew;
+                ew.elementwise = true; ew.n = (int)unit.n; ew.ew_items = (uint32_t)unit.n;
+                ew.in_es = ew.out_es = 1; ew.in_role = ew.out_role = ROLE_BUFFER;
+                ew.aux0 = aux; ew.aux_u0 = (uint32_t)N;
+                std::vector<Dim> ewl;
+                ewl.push_back(Dim{N / 2 + 1, esc, esc});
+                for (const Dim& dd : rest) ewl.push_back(dd);
+                int rcl;
+                PassReq a, b;
+                a.kind = b.kind = B2_KIND_COLS; a.n = (int)L1; b.n = (int)L2; a.inv = b.inv = kinv;
+                a.group = unit; b.group = Dim{unit.n, 1, 1};
+                a.in_es = a.out_es = esc * (int64_t)L2;
+                a.outer.push_back(Dim{L2, kinv == 0 ? 0 : esc, esc});
+                a.tw_outer = 0; a.twM = N;
+                for (const Dim& dd : rest) a.outer.push_back(dd);
+                a.in_role = ROLE_BUFFER; a.out_role = ROLE_TEMP;
+                b.in_es = esc; b.out_es = esc * (int64_t)L1;
+                b.outer.push_back(Dim{L1, esc * (int64_t)L2, kinv == 0 ? esc : 0});
+                for (const Dim& dd : rest) b.outer.push_back(dd);
+                b.in_role = ROLE_TEMP; b.out_role = ROLE_BUFFER;
+                if (kinv == 0) {   // DCT-II
+                    a.ops = B2_OP_TWIDDLE_OUT | B2_OP_PERM_IN; a.aux_u0 = (uint32_t)N; a.aux_u1 = (uint32_t)L2;
+                    a.what = "long dct-ii 1/3 gather+phase";
+                    if ((rcl = emit(g, list, a)) != R_SUCCESS) return rcl;
+                    b.ops = 0; b.what = "long dct-ii 2/3";
+                    if ((rcl = emit(g, list, b)) != R_SUCCESS) return rcl;
+                    ew.ew_op = 3; ew.ops = (scale != 1.0) ? B2_OP_SCALE : 0; ew.scale = scale; ew.what = "long dct-ii 3/3 split+phase";
+                    if ((rcl = emit_ew(g, list, ew, ewl)) != R_SUCCESS) return rcl;
+                } else {           // DCT-III
+                    ew.ew_op = 4; ew.what = "long dct-iii 1/3 phase+merge";
+                    if ((rcl = emit_ew(g, list, ew, ewl)) != R_SUCCESS) return rcl;
+                    a.ops = B2_OP_TWIDDLE_OUT; a.what = "long dct-iii 2/3";
+                    if ((rcl = emit(g, list, a)) != R_SUCCESS) return rcl;
+                    b.ops = B2_OP_PERM_OUT | ((scale != 1.0) ? B2_OP_SCALE : 0); b.scale = scale;
+                    b.tw_outer = 0; b.aux_u0 = (uint32_t)N; b.aux_u1 = (uint32_t)L1;
+                    b.what = "long dct-iii 3/3 scatter";
+                    if ((rcl = emit(g, list, b)) != R_SUCCESS) return rcl;
+                }
+                continue;
             }
             if (ok) {
                 int rcf = emit(g, list, fr);

@@ -201,6 +201,55 @@ struct Engine {
 
     B2_D static int makhoul(int p) { return (p < (N + 1) / 2) ? 2 * p : 2 * (N - 1 - p) + 1; }
 
+    B2_D static int64_t makhoul_full(int64_t i, int64_t nfull) { return (i < (nfull + 1) / 2) ? 2 * i : 2 * (nfull - 1 - i) + 1; }
+
+    // ---- long strided DCT-II, first Four-Step launch (RMODE 5): rows gathered through the permutation of the full index ----
+    template <int s>
+    B2_D static void load_global_perm(X* x, const X* __restrict__ base, int64_t es0, uint32_t n2, uint32_t N2, uint32_t nfull,
+                                      int t, bool valid) {
+        constexpr int r = Sch::r(s), NB = nbut<s>(), BPT = bpt<s>();
+#pragma unroll
+        for (int m = 0; m < BPT; ++m) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const int b = V * (t + m * TPL) + v;
+                const bool ok = valid && (!guarded<s>() || b < NB);
+#pragma unroll
+                for (int k = 0; k < r; ++k) {
+                    const int p = b + k * NB;
+                    X a = mk<T>(T(0), T(0));
+                    if (ok) a = base[makhoul_full((int64_t)p * N2 + n2, nfull) * es0];
+                    x[(m * V + v) * r + k] = C::INV ? swp(a) : a;
+                }
+            }
+        }
+    }
+
+    // ---- long strided DCT-III, last Four-Step launch (RMODE 6): scatter through the permutation of k1 + N1*p ---------------
+    template <int s>
+    B2_D static void store_global_perm(const X* x, X* __restrict__ base, int64_t es0, uint32_t k1, uint32_t N1, uint32_t nfull,
+                                       int t, bool valid, const b2_pass_params& P) {
+        constexpr int r = Sch::r(s), NB = nbut<s>(), BPT = bpt<s>();
+        const bool do_scale = (P.ops & B2_OP_SCALE) != 0;
+        const T sc = (T)P.scale;
+#pragma unroll
+        for (int m = 0; m < BPT; ++m) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const int b = V * (t + m * TPL) + v;
+                if (!valid || (guarded<s>() && b >= NB)) continue;
+#pragma unroll
+                for (int k = 0; k < r; ++k) {
+                    X a = x[(m * V + v) * r + k];
+                    if (do_scale) a = a * sc;
+                    if (C::INV) a = swp(a);
+                    const int p = b + k * NB;
+                    base[makhoul_full((int64_t)k1 + (int64_t)N1 * p, nfull) * es0] = a;
+                }
+            }
+        }
+    }
+
     // ---- DCT-II / DCT-III: first-stage legs (RMODE 3 / 4) --------------------------------------------------------------
     template <int s>
     B2_D static void load_global_dct(X* x, const b2_pass_params& P, int64_t obase_in, uint32_t gl, int t, bool valid) {
@@ -483,21 +532,25 @@ struct Engine {
         const X* in_line = (const X*)P.in + obase_in + (int64_t)gl * P.in_gs;
 
         const X* __restrict__ rw = (const X*)P.aux0;   // e^{-2 pi i k/2n} for the fused real transforms
+        const uint32_t psel = (P.tw_sel == 1 ? o0 : (P.tw_sel == 2 ? o1 : o2));   // n2 / k1 of the long strided DCT launches
         if constexpr (NS == 1) {
             X x[bpt<0>() * V * Sch::r(0)];
             if constexpr (C::RMODE == 2) load_global_c2r<0>(x, in_line, rw, tl, gl < P.G);
-            else if constexpr (C::RMODE >= 3) load_global_dct<0>(x, P, obase_in, gl, tl, gl < P.G);
+            else if constexpr (C::RMODE == 3 || C::RMODE == 4) load_global_dct<0>(x, P, obase_in, gl, tl, gl < P.G);
+            else if constexpr (C::RMODE == 5) load_global_perm<0>(x, in_line, P.in_es / P.aux_u1, psel, P.aux_u1, P.aux_u0, tl, gl < P.G);
             else load_global<0>(x, in_line, P.in_es, tl, gl < P.G);
             compute<0>(x, lut, tl);
             X* out_line = (X*)P.out + obase_out + (int64_t)gl * P.out_gs;
             if constexpr (C::RMODE == 1) store_global_r2c<0>(x, sm, out_line, rw, ql, tl, gl < P.G, P);
-            else if constexpr (C::RMODE >= 3) store_global_dct<0>(x, sm, P, obase_out, gl, ql, tl, gl < P.G);
+            else if constexpr (C::RMODE == 3 || C::RMODE == 4) store_global_dct<0>(x, sm, P, obase_out, gl, ql, tl, gl < P.G);
+            else if constexpr (C::RMODE == 6) store_global_perm<0>(x, out_line, P.out_es / P.aux_u1, psel, P.aux_u1, P.aux_u0, tl, gl < P.G, P);
             else store_global<0>(x, out_line, P.out_es, tl, gl < P.G, P, twl(P, gl, o0, o1, o2), (uint32_t)ql);
         } else {
             {
                 X x[bpt<0>() * V * Sch::r(0)];
                 if constexpr (C::RMODE == 2) load_global_c2r<0>(x, in_line, rw, tl, gl < P.G);
-                else if constexpr (C::RMODE >= 3) load_global_dct<0>(x, P, obase_in, gl, tl, gl < P.G);
+                else if constexpr (C::RMODE == 3 || C::RMODE == 4) load_global_dct<0>(x, P, obase_in, gl, tl, gl < P.G);
+                else if constexpr (C::RMODE == 5) load_global_perm<0>(x, in_line, P.in_es / P.aux_u1, psel, P.aux_u1, P.aux_u0, tl, gl < P.G);
                 else load_global<0>(x, in_line, P.in_es, tl, gl < P.G);
                 compute<0>(x, lut, tl);
                 store_smem<0>(x, sm, ql, tl);
@@ -516,9 +569,11 @@ struct Engine {
                 if constexpr (C::RMODE == 1) {
                     __syncthreads();     // every last-stage read of the tile is done before it is overwritten
                     store_global_r2c<s>(x, sm, out_line, rw, qs, ts, gs < P.G, P);
-                } else if constexpr (C::RMODE >= 3) {
+                } else if constexpr (C::RMODE == 3 || C::RMODE == 4) {
                     if constexpr (C::RMODE == 3) __syncthreads();
                     store_global_dct<s>(x, sm, P, obase_out, gs, qs, ts, gs < P.G);
+                } else if constexpr (C::RMODE == 6) {
+                    store_global_perm<s>(x, out_line, P.out_es / P.aux_u1, psel, P.aux_u1, P.aux_u0, ts, gs < P.G, P);
                 } else {
                     store_global<s>(x, out_line, P.out_es, ts, gs < P.G, P, twl(P, gs, o0, o1, o2), (uint32_t)qs);
                 }

@@ -44,3 +44,108 @@ def max_over_ranks(value: float, dist=None) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+class DistributedFFT1D:
+    """One very long 1-D C2C transform spread over the GPUs of a box: the outer Four-Step axis is sharded
+    (BASELINE.json config 5).  N = N1*N2, world R divides N1 and N2.
+
+    Every rank holds a contiguous slab of N/R input points in natural order and receives the matching slab of the
+    spectrum in natural order.  Data flow (x viewed as [N1][N2], n = n1*N2 + n2, k = k1 + N1*k2):
+
+        rows n1-slab  --all-to-all-->  columns n2-slab : strided length-N1 transforms + phase W_N^(n2*k1)   (engine plan)
+                      --all-to-all-->  rows k1-slab    : contiguous length-N2 transforms                     (engine plan)
+                      --all-to-all-->  natural-order slab of X (skipped with transposed_output=True)
+
+    The exchanges are torch.distributed all_to_all_single calls (NCCL over NVLink on GPUs, gloo in the CPU tests);
+    packing is plain tensor permutes.  The two local transforms go through the engine's C ABI unless `local_cols` /
+    `local_rows` callables are injected (the CPU tests inject numpy so the index algebra is verified without a GPU).
+    """
+
+    def __init__(self, n1, n2, dist, inverse=False, transposed_output=False, local_cols=None, local_rows=None, device=None):
+        import torch
+        self.torch = torch
+        self.dist = dist
+        self.R = dist.get_world_size()
+        self.r = dist.get_rank()
+        self.n1, self.n2, self.n = n1, n2, n1 * n2
+        if n1 % self.R or n2 % self.R:
+            raise ValueError("world size must divide both Four-Step factors")
+        self.inverse = inverse
+        self.transposed_output = transposed_output
+        self.device = device
+        self._apps = []
+        self.local_cols = local_cols or self._engine_cols
+        self.local_rows = local_rows or self._engine_rows
+        # phase table of this rank's columns: W_N^(+-(n2*k1)), n2 = r*N2/R + j   (float64 -> complex64)
+        c = n2 // self.R
+        k1 = torch.arange(n1, dtype=torch.float64).unsqueeze(1)
+        j = (self.r * c + torch.arange(c, dtype=torch.float64)).unsqueeze(0)
+        sign = 1.0 if inverse else -1.0
+        e = torch.remainder(k1 * j, float(self.n))                  # exact in float64 for N <= 2^26
+        ang = sign * 2.0 * 3.141592653589793238 * e / float(self.n)
+        self.phase = torch.complex(torch.cos(ang), torch.sin(ang)).to(torch.complex64)
+        if device is not None:
+            self.phase = self.phase.to(device)
+
+    # ---- local transforms through the engine --------------------------------------------------------------------------
+    def _plan(self, key, cfg):
+        from . import api
+        for k, app in self._apps:
+            if k == key:
+                return app
+        app = api.VkFFTApplication()
+        rc = api.initializeVkFFT(app, cfg)
+        if rc != 0:
+            raise RuntimeError(api.getVkFFTErrorString(rc))
+        self._apps.append((key, app))
+        return app
+
+    def _engine_cols(self, b):          # b: [N1][C] complex64 on the GPU, transform along dim 0 in place
+        from . import api
+        c = b.shape[1]
+        cfg = api.VkFFTConfiguration(FFTdim=2, size=[c, self.n1], omitDimension=[1, 0], device=b.device.index)
+        app = self._plan(("cols", c), cfg)
+        lp = api.VkFFTLaunchParams(buffer=b, stream=self.torch.cuda.current_stream().cuda_stream)
+        rc = api.VkFFTAppend(app, 1 if self.inverse else -1, lp)
+        if rc != 0:
+            raise RuntimeError(api.getVkFFTErrorString(rc))
+        return b
+
+    def _engine_rows(self, b):          # b: [B][N2], transform along dim 1 in place
+        from . import api
+        cfg = api.VkFFTConfiguration(FFTdim=1, size=[self.n2], numberBatches=b.shape[0], device=b.device.index)
+        app = self._plan(("rows", b.shape[0]), cfg)
+        lp = api.VkFFTLaunchParams(buffer=b, stream=self.torch.cuda.current_stream().cuda_stream)
+        rc = api.VkFFTAppend(app, 1 if self.inverse else -1, lp)
+        if rc != 0:
+            raise RuntimeError(api.getVkFFTErrorString(rc))
+        return b
+
+    def close(self):
+        from . import api
+        for _, app in self._apps:
+            api.deleteVkFFT(app)
+        self._apps = []
+
+    # ---- the distributed transform ------------------------------------------------------------------------------------
+    def __call__(self, x):
+        """x: this rank's slab, 1-D complex tensor of N/R points (natural order). Returns this rank's slab of X."""
+        torch, dist, R = self.torch, self.dist, self.R
+        n1, n2 = self.n1, self.n2
+        r1, c = n1 // R, n2 // R
+        a = x.view(r1, R, c).permute(1, 0, 2).contiguous()          # [dest][n1_local][n2_local]
+        b = torch.empty_like(a)
+        dist.all_to_all_single(b, a)                                # b: [src][n1_local][n2_local] == [N1][C]
+        b = self.local_cols(b.view(n1, c))                          # FFT over n1
+        b = b * self.phase if b.dtype == self.phase.dtype else b * self.phase.to(b.dtype)
+        a2 = torch.empty_like(b)
+        dist.all_to_all_single(a2, b.contiguous())                  # send row-chunks; receive [src][k1_local][n2_local]
+        rows = a2.view(R, r1, c).permute(1, 0, 2).contiguous().view(r1, n2)   # [k1_local][n2]
+        rows = self.local_rows(rows)                                # FFT over n2 -> [k1_local][k2] = X[k1 + N1 k2]
+        if self.transposed_output:
+            return rows
+        s = rows.view(r1, R, c).permute(1, 0, 2).contiguous()       # [dest t][k1_local][k2_local]
+        t = torch.empty_like(s)
+        dist.all_to_all_single(t, s)                                # [src e][k1_local][k2_local]
+        return t.view(R, r1, c).permute(2, 0, 1).contiguous().view(-1)   # [k2_local][k1] -> natural order slab

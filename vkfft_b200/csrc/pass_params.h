@@ -30,6 +30,9 @@ enum {
                              // aux_u0 = number of real lines, aux_u1 = pitch between the two real lines of a pair
     B2_OP_PERM_IN = 64,      // strided Four-Step first launch of a long DCT-II: rows are gathered through the Makhoul
                              // permutation of the FULL index p*N2 + n2 (aux_u0 = full length, aux_u1 = N2, n2 = coordinate tw_sel)
+    B2_OP_BLUESTEIN = 256,   // specialised kernels: Bluestein launches on contiguous lines.  Forward kernel = first launch (zero-pad to n,
+                             // chirp aux0 on load, filter aux1 on store); inverse kernel = second launch (chirp aux0 + truncation to
+                             // out_len on store).  P.inverse selects the direction of the WHOLE transform at run time (outer re/im swap)
     B2_OP_PERM_OUT = 128,    // strided Four-Step last launch of a long DCT-III: result k1 + N1*p is scattered to row makhoul(k)
                              // (aux_u0 = full length, aux_u1 = N1, k1 = coordinate tw_sel)
 };

@@ -135,6 +135,7 @@ struct PassReq {
     bool real_pairs = false;     // group dim counts REAL lines; two of them form one complex line
     uint32_t dst_flags = 0;
     bool scalar_units = false;   // specialised real-data kernels addressing real lines: offsets/strides count scalars
+    int runtime_inverse = -1;    // >= 0: value of P.inverse when it differs from the kernel's compile-time direction
     int64_t in_base = 0, out_base = 0;   // element offsets into the role's buffer (scratch regions)
     // elementwise helper passes (ew.cuh)
     bool elementwise = false;
@@ -146,9 +147,9 @@ struct PassReq {
 int emit(PlanGraph& g, std::vector<PassPlan>& list, const PassReq& rq) {
     const b2_kernel_info* k = nullptr;
     const bool plain = !rq.force_generic && rq.load_io == B2_IO_C2C && rq.store_io == B2_IO_C2C &&
-                       !(rq.ops & (B2_OP_MUL_IN | B2_OP_MUL_OUT)) && rq.in_len == 0 && rq.out_len == 0 &&
-                       !rq.inner_inverse;
-    if (plain) k = b2_find_kernel(rq.kind, g.prec, rq.n, rq.inv, rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN | B2_OP_DCT23 | B2_OP_PERM_IN | B2_OP_PERM_OUT));
+                       !(rq.ops & (B2_OP_MUL_IN | B2_OP_MUL_OUT)) &&
+                       ((rq.in_len == 0 && rq.out_len == 0) || (rq.ops & B2_OP_BLUESTEIN)) && !rq.inner_inverse;
+    if (plain) k = b2_find_kernel(rq.kind, g.prec, rq.n, rq.inv, rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN | B2_OP_DCT23 | B2_OP_PERM_IN | B2_OP_PERM_OUT | B2_OP_BLUESTEIN));
     std::vector<int> radices;
     bool generic = false;
     if (!k) {
@@ -217,12 +218,12 @@ int emit(PlanGraph& g, std::vector<PassPlan>& list, const PassReq& rq) {
         pp.k = k;
         if (k->pipelined) {   // TMA needs 16-byte aligned sources: keep the first non-pipelined kernel of the same key as a stand-in
             for (int v = 0; v < 16 && !pp.k_unaligned; ++v) {
-                const b2_kernel_info* alt = b2_find_kernel_variant(rq.kind, g.prec, rq.n, rq.inv, rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN | B2_OP_DCT23 | B2_OP_PERM_IN | B2_OP_PERM_OUT), v);
+                const b2_kernel_info* alt = b2_find_kernel_variant(rq.kind, g.prec, rq.n, rq.inv, rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN | B2_OP_DCT23 | B2_OP_PERM_IN | B2_OP_PERM_OUT | B2_OP_BLUESTEIN), v);
                 if (alt && !alt->pipelined && alt->q == k->q) pp.k_unaligned = alt;
             }
             if (!pp.k_unaligned) {    // no drop-in with the same tile height: do not use the pipelined kernel at all
                 for (int v = 0; v < 16; ++v) {
-                    const b2_kernel_info* alt = b2_find_kernel_variant(rq.kind, g.prec, rq.n, rq.inv, rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN | B2_OP_DCT23 | B2_OP_PERM_IN | B2_OP_PERM_OUT), v);
+                    const b2_kernel_info* alt = b2_find_kernel_variant(rq.kind, g.prec, rq.n, rq.inv, rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN | B2_OP_DCT23 | B2_OP_PERM_IN | B2_OP_PERM_OUT | B2_OP_BLUESTEIN), v);
                     if (alt && !alt->pipelined) { pp.k = k = alt; break; }
                 }
                 tpl = k->tpl; q = k->q;
@@ -245,7 +246,7 @@ int emit(PlanGraph& g, std::vector<PassPlan>& list, const PassReq& rq) {
         pp.grid = (unsigned)grid;
         P.n = rq.n;
         P.ops = rq.ops;
-        P.inverse = rq.inv;
+        P.inverse = rq.runtime_inverse >= 0 ? rq.runtime_inverse : rq.inv;
         P.inner_inverse = rq.inner_inverse;
         P.scale = rq.scale;
         P.tw_sel = tw_sel;
@@ -477,7 +478,7 @@ int plan_bluestein(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job)
         g.temp_elems = std::max<uint64_t>(g.temp_elems, (uint64_t)r1 + L * M);
         return emit_ew(g, list, post, from_tmp);
     }
-    g.temp_elems = std::max<uint64_t>(g.temp_elems, L * M);
+    g.temp_elems = std::max<uint64_t>(g.temp_elems, (uint64_t)job.tmp_base + L * M);
     const int chirp = aux_for(g, AUX_BLUE_CHIRP, N), filt = aux_for(g, AUX_BLUE_FILTER, N, M);
     // scratch lines are packed [.. outer ..][group][M]
     std::vector<Dim> in_lines = job.lines, out_lines = job.lines;
@@ -491,6 +492,28 @@ int plan_bluestein(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job)
         if (ln.empty()) rq.group = Dim{1, 0, 0};
         else { rq.group = ln[0]; rq.outer.assign(ln.begin() + 1, ln.end()); }
     };
+    // contiguous lines: both launches on the specialised kernels (chirp / filter fused into their load / store)
+    if (!job.unit_lines && job.es_in == 1 && job.es_out == 1 && M <= 0x7fffffff &&
+        b2_find_kernel(B2_KIND_ROWS, g.prec, (int)M, 0, B2_OP_BLUESTEIN) && b2_find_kernel(B2_KIND_ROWS, g.prec, (int)M, 1, B2_OP_BLUESTEIN)) {
+        PassReq fa;
+        fa.kind = B2_KIND_ROWS; fa.n = (int)M; fa.inv = 0; fa.runtime_inverse = job.inv; fa.ops = B2_OP_BLUESTEIN;
+        fa.in_es = fa.out_es = 1;
+        mk(in_lines, fa);
+        fa.in_role = job.in_role; fa.out_role = ROLE_TEMP; fa.in_base = job.in_base; fa.out_base = job.tmp_base;
+        fa.in_len = (uint32_t)N; fa.aux0 = chirp; fa.aux1 = filt;
+        fa.what = "bluestein 1/2 chirp+fft+filter (specialised)";
+        int rcf = emit(g, list, fa);
+        if (rcf != R_SUCCESS) return rcf;
+        PassReq fb;
+        fb.kind = B2_KIND_ROWS; fb.n = (int)M; fb.inv = 1; fb.runtime_inverse = job.inv;
+        fb.ops = B2_OP_BLUESTEIN | (job.scale != 1.0 ? B2_OP_SCALE : 0); fb.scale = job.scale;
+        fb.in_es = fb.out_es = 1;
+        mk(out_lines, fb);
+        fb.in_role = ROLE_TEMP; fb.out_role = job.out_role; fb.in_base = job.tmp_base; fb.out_base = job.out_base;
+        fb.out_len = (uint32_t)N; fb.aux0 = chirp;
+        fb.what = "bluestein 2/2 ifft+chirp (specialised)";
+        return emit(g, list, fb);
+    }
     PassReq a;
     a.kind = job.unit_lines ? B2_KIND_COLS : B2_KIND_ROWS;
     if (job.unit_lines) a.kind = B2_KIND_ROWS_TOUT, a.kind = B2_KIND_COLS;

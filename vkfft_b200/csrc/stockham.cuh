@@ -250,6 +250,63 @@ struct Engine {
         }
     }
 
+    // ---- Bluestein, first launch (RMODE 7): zero-pad + chirp on load, filter on store ---------------------------------
+    template <int s>
+    B2_D static void load_global_blue(X* x, const X* __restrict__ line, const b2_pass_params& P, int t, bool valid) {
+        constexpr int r = Sch::r(s), NB = nbut<s>(), BPT = bpt<s>();
+        const X* __restrict__ chirp = (const X*)P.aux0;
+        const bool oswap = P.inverse != 0;
+#pragma unroll
+        for (int m = 0; m < BPT; ++m) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const int b = V * (t + m * TPL) + v;
+                const bool ok = valid && (!guarded<s>() || b < NB);
+#pragma unroll
+                for (int k = 0; k < r; ++k) {
+                    const int p = b + k * NB;
+                    X a = mk<T>(T(0), T(0));
+                    if (ok && p < (int)P.in_len) {
+                        a = line[p];
+                        if (oswap) a = swp(a);
+                        a = a * ld_lut(chirp + p);
+                    }
+                    x[(m * V + v) * r + k] = a;
+                }
+            }
+        }
+    }
+    // RMODE 7 store: x * filter -> packed scratch line;  RMODE 8 store: inner un-swap, chirp, scale, outer swap, truncation
+    template <int s>
+    B2_D static void store_global_blue(const X* x, X* __restrict__ line, const b2_pass_params& P, int t, bool valid) {
+        constexpr int r = Sch::r(s), NB = nbut<s>(), BPT = bpt<s>();
+        const bool do_scale = (P.ops & B2_OP_SCALE) != 0;
+        const T sc = (T)P.scale;
+        const bool oswap = P.inverse != 0;
+#pragma unroll
+        for (int m = 0; m < BPT; ++m) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const int b = V * (t + m * TPL) + v;
+                if (!valid || (guarded<s>() && b >= NB)) continue;
+#pragma unroll
+                for (int k = 0; k < r; ++k) {
+                    const int p = b + k * NB;
+                    X a = x[(m * V + v) * r + k];
+                    if constexpr (C::RMODE == 7) {
+                        line[p] = a * ld_lut((const X*)P.aux1 + p);
+                    } else {
+                        if (p < (int)P.out_len) {
+                            a = swp(a) * ld_lut((const X*)P.aux0 + p);
+                            if (do_scale) a = a * sc;
+                            line[p] = oswap ? swp(a) : a;
+                        }
+                    }
+                }
+            }
+        }
+    }
+
     // ---- DCT-II / DCT-III: first-stage legs (RMODE 3 / 4) --------------------------------------------------------------
     template <int s>
     B2_D static void load_global_dct(X* x, const b2_pass_params& P, int64_t obase_in, uint32_t gl, int t, bool valid) {
@@ -538,12 +595,14 @@ struct Engine {
             if constexpr (C::RMODE == 2) load_global_c2r<0>(x, in_line, rw, tl, gl < P.G);
             else if constexpr (C::RMODE == 3 || C::RMODE == 4) load_global_dct<0>(x, P, obase_in, gl, tl, gl < P.G);
             else if constexpr (C::RMODE == 5) load_global_perm<0>(x, in_line, P.in_es / P.aux_u1, psel, P.aux_u1, P.aux_u0, tl, gl < P.G);
+            else if constexpr (C::RMODE == 7) load_global_blue<0>(x, in_line, P, tl, gl < P.G);
             else load_global<0>(x, in_line, P.in_es, tl, gl < P.G);
             compute<0>(x, lut, tl);
             X* out_line = (X*)P.out + obase_out + (int64_t)gl * P.out_gs;
             if constexpr (C::RMODE == 1) store_global_r2c<0>(x, sm, out_line, rw, ql, tl, gl < P.G, P);
             else if constexpr (C::RMODE == 3 || C::RMODE == 4) store_global_dct<0>(x, sm, P, obase_out, gl, ql, tl, gl < P.G);
             else if constexpr (C::RMODE == 6) store_global_perm<0>(x, out_line, P.out_es / P.aux_u1, psel, P.aux_u1, P.aux_u0, tl, gl < P.G, P);
+            else if constexpr (C::RMODE >= 7) store_global_blue<0>(x, out_line, P, tl, gl < P.G);
             else store_global<0>(x, out_line, P.out_es, tl, gl < P.G, P, twl(P, gl, o0, o1, o2), (uint32_t)ql);
         } else {
             {
@@ -551,6 +610,7 @@ struct Engine {
                 if constexpr (C::RMODE == 2) load_global_c2r<0>(x, in_line, rw, tl, gl < P.G);
                 else if constexpr (C::RMODE == 3 || C::RMODE == 4) load_global_dct<0>(x, P, obase_in, gl, tl, gl < P.G);
                 else if constexpr (C::RMODE == 5) load_global_perm<0>(x, in_line, P.in_es / P.aux_u1, psel, P.aux_u1, P.aux_u0, tl, gl < P.G);
+                else if constexpr (C::RMODE == 7) load_global_blue<0>(x, in_line, P, tl, gl < P.G);
                 else load_global<0>(x, in_line, P.in_es, tl, gl < P.G);
                 compute<0>(x, lut, tl);
                 store_smem<0>(x, sm, ql, tl);
@@ -574,6 +634,8 @@ struct Engine {
                     store_global_dct<s>(x, sm, P, obase_out, gs, qs, ts, gs < P.G);
                 } else if constexpr (C::RMODE == 6) {
                     store_global_perm<s>(x, out_line, P.out_es / P.aux_u1, psel, P.aux_u1, P.aux_u0, ts, gs < P.G, P);
+                } else if constexpr (C::RMODE >= 7) {
+                    store_global_blue<s>(x, out_line, P, ts, gs < P.G);
                 } else {
                     store_global<s>(x, out_line, P.out_es, ts, gs < P.G, P, twl(P, gs, o0, o1, o2), (uint32_t)qs);
                 }

@@ -25,11 +25,15 @@ build/runtime.o: $(SRC)/runtime.cu $(HDRS)
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
+build/window.o: $(SRC)/window.cu $(HDRS)
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
 build/%.o: $(SRC)/%.cpp $(HDRS)
 	@mkdir -p build
 	$(CXX) $(CXXFLAGS) -c $< -o $@
 
-$(LIB): $(SHARD_OBJ) build/kernels_generic.o build/runtime.o build/planner.o build/kernel_registry.o
+$(LIB): $(SHARD_OBJ) build/kernels_generic.o build/runtime.o build/window.o build/planner.o build/kernel_registry.o
 	@mkdir -p vkfft_b200/lib
 	$(NVCC) -shared $(ARCH) -o $@ $^ -lcudart_static -ldl -lrt -lpthread
 

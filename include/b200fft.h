@@ -60,7 +60,13 @@ typedef struct b200fft_desc {
     int32_t device;                       /* CUDA device ordinal (what *cfg.device holds for the runtime API) */
     uint32_t reserved0;
     void* stream;                         /* cudaStream_t or NULL for the default stream */
-    uint64_t reserved[8];
+    /* One long 1-D C2C sequence spread over the GPUs of a box (no counterpart in the reference, which is single
+     * device: README.md:26-28).  dist_world > 1: `buffer` and `temp_buffer` are the bases of two peer windows
+     * (b200fft_window_*, below) holding the whole sequence, slab g on GPU g; this plan runs rank dist_rank's share
+     * of every Four-Step launch and exchanges data through loads/stores to peer memory inside those launches. */
+    uint32_t dist_world;
+    uint32_t dist_rank;
+    uint64_t reserved[7];
 } b200fft_desc;
 
 /* Buffers for one execution == VkFFTLaunchParams (vkFFT_Structs.h:326-379) with plain pointers.
@@ -105,6 +111,27 @@ int b200fft_exec_host(b200fft_plan* plan, int inverse, const void* host_in, void
 /* page-locked host memory for b200fft_exec_host (NULL on failure) */
 void* b200fft_host_alloc(uint64_t bytes);
 void b200fft_host_free(void* p);
+
+/* ---- peer windows: one flat virtual address range over every GPU's slab (multi-process, one process per GPU) --------
+ * Each rank creates the window (allocates its own slab with the CUDA virtual memory API and reserves world*slab_bytes
+ * of address space), exports two POSIX file descriptors (slab, signal pad), passes them to every peer (the host side
+ * does that, e.g. over a unix socket with SCM_RIGHTS: vkfft_b200/window.py) and imports the peers' descriptors; after
+ * that  base + g*slab_bytes  addresses GPU g's slab from every rank, over NVLink for g != rank.
+ * slab_bytes must be a multiple of b200fft_window_granularity(device). */
+typedef struct b200fft_window b200fft_window;
+uint64_t b200fft_window_granularity(int device);
+int b200fft_window_create(int device, uint32_t world, uint32_t rank, uint64_t slab_bytes, b200fft_window** window);
+int b200fft_window_export(b200fft_window* window, int fds[2]);
+int b200fft_window_import(b200fft_window* window, uint32_t peer, const int fds[2]);
+void* b200fft_window_base(b200fft_window* window);      /* flat base: slab g at base + g*slab_bytes */
+void* b200fft_window_local(b200fft_window* window);     /* == base + rank*slab_bytes */
+/* device-side barrier over all ranks of the window, enqueued on `stream` (every rank must call it the same number
+ * of times); a rank that waits longer than ~4 s gives up and b200fft_window_status() returns non-zero afterwards */
+int b200fft_window_barrier(b200fft_window* window, void* stream);
+int b200fft_window_status(b200fft_window* window);      /* synchronises the device; 0 = no barrier timed out */
+void b200fft_window_destroy(b200fft_window* window);
+/* a plan created with dist_world > 1 needs the window of its `buffer` for the barriers between its launches */
+int b200fft_plan_attach_window(b200fft_plan* plan, b200fft_window* window);
 
 const char* b200fft_error_string(int code);
 int b200fft_version(void);

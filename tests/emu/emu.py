@@ -64,7 +64,7 @@ class Desc(ctypes.Structure):
         ("buffer_stride", ctypes.c_uint64 * 4), ("input_stride", ctypes.c_uint64 * 4), ("output_stride", ctypes.c_uint64 * 4),
         ("omit_dimension", ctypes.c_uint32 * 4), ("buffer_size", ctypes.c_uint64), ("temp_buffer_size", ctypes.c_uint64),
         ("device", ctypes.c_int32), ("reserved0", ctypes.c_uint32), ("stream", ctypes.c_void_p),
-        ("reserved", ctypes.c_uint64 * 8),
+        ("dist_world", ctypes.c_uint32), ("dist_rank", ctypes.c_uint32), ("reserved", ctypes.c_uint64 * 7),
     ]
 
 
@@ -92,3 +92,14 @@ def exec_plan(desc, inverse, buffer, inp=None, out=None):
     vp = lambda a: a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
     rc = L.emu_exec_plan(ctypes.byref(desc), int(inverse), vp(buffer), vp(inp), vp(out), ctypes.byref(npass))
     return rc, npass.value
+
+
+def exec_plan_pass(desc, inverse, buffer, temp, pass_index):
+    """one launch of a plan on caller-owned buffer/temp; returns (rc, npasses, sync_before flags)"""
+    L = lib()
+    L.emu_exec_plan_pass.restype = ctypes.c_int
+    npass = ctypes.c_int(0)
+    sync = (ctypes.c_int * 16)()
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+    rc = L.emu_exec_plan_pass(ctypes.byref(desc), int(inverse), vp(buffer), vp(temp), int(pass_index), ctypes.byref(npass), sync)
+    return rc, npass.value, [bool(sync[i]) for i in range(npass.value)]

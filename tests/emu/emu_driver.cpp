@@ -65,6 +65,35 @@ extern "C" int emu_run_pass(int kind, int prec, int n, int inv, int ops, int var
 
 // Execute a whole plan (planner.cpp + emulated kernels) on host memory.  bufs[ROLE_*] are host pointers;
 // the temp buffer is allocated here.  Returns the planner's VkFFTResult code.
+static int emu_run_one(PlanGraph& g, PassPlan& pp, void* const* base) {
+    const size_t esz = g.prec == B2_PREC_F64 ? 16 : 8;
+    b2_pass_params P = pp.P;
+    std::vector<float> lutf, hif, lof;
+    std::vector<double> lutd, hid, lod;
+    const LutSpec& ls = g.luts[pp.lut_id];
+    if (g.prec == B2_PREC_F32) { lutf = make_stage_lut<float>(ls.radices.data(), (int)ls.radices.size()); P.lut = lutf.data(); }
+    else { lutd = make_stage_lut<double>(ls.radices.data(), (int)ls.radices.size()); P.lut = lutd.data(); }
+    if (pp.tw_id >= 0) {
+        uint64_t M = g.tws[pp.tw_id].M;
+        if (g.prec == B2_PREC_F32) { make_twolevel<float>(M, P.tw_shift, hif, lof); P.tw_hi = hif.data(); P.tw_lo = lof.data(); }
+        else { make_twolevel<double>(M, P.tw_shift, hid, lod); P.tw_hi = hid.data(); P.tw_lo = lod.data(); }
+    }
+    std::vector<float> a0f, a1f; std::vector<double> a0d, a1d;
+    if (pp.aux0_id >= 0) {
+        const AuxSpec& a = g.auxs[pp.aux0_id];
+        if (g.prec == B2_PREC_F32) { a0f = make_aux<float>(a.kind, a.a, a.b); P.aux0 = a0f.data(); }
+        else { a0d = make_aux<double>(a.kind, a.a, a.b); P.aux0 = a0d.data(); }
+    }
+    if (pp.aux1_id >= 0) {
+        const AuxSpec& a = g.auxs[pp.aux1_id];
+        if (g.prec == B2_PREC_F32) { a1f = make_aux<float>(a.kind, a.a, a.b); P.aux1 = a1f.data(); }
+        else { a1d = make_aux<double>(a.kind, a.a, a.b); P.aux1 = a1d.data(); }
+    }
+    P.in = (const unsigned char*)base[pp.in_role] + pp.in_off * (pp.in_scalar ? esz / 2 : esz);
+    P.out = (unsigned char*)base[pp.out_role] + pp.out_off * (pp.out_scalar ? esz / 2 : esz);
+    return pp.k->launch(&P, pp.grid, nullptr) ? 4039 : 0;
+}
+
 extern "C" int emu_exec_plan(const b200fft_desc* d, int inverse, void* buffer, void* input, void* output,
                              int* npasses) {
     PlanGraph g;
@@ -75,33 +104,25 @@ extern "C" int emu_exec_plan(const b200fft_desc* d, int inverse, void* buffer, v
     void* base[ROLE_COUNT] = {buffer, temp.data(), input, output};
     std::vector<PassPlan>& list = (inverse == 1) ? g.inv : g.fwd;
     if (npasses) *npasses = (int)list.size();
-    for (PassPlan& pp : list) {
-        b2_pass_params P = pp.P;
-        std::vector<float> lutf, hif, lof;
-        std::vector<double> lutd, hid, lod;
-        const LutSpec& ls = g.luts[pp.lut_id];
-        if (g.prec == B2_PREC_F32) { lutf = make_stage_lut<float>(ls.radices.data(), (int)ls.radices.size()); P.lut = lutf.data(); }
-        else { lutd = make_stage_lut<double>(ls.radices.data(), (int)ls.radices.size()); P.lut = lutd.data(); }
-        if (pp.tw_id >= 0) {
-            uint64_t M = g.tws[pp.tw_id].M;
-            if (g.prec == B2_PREC_F32) { make_twolevel<float>(M, P.tw_shift, hif, lof); P.tw_hi = hif.data(); P.tw_lo = lof.data(); }
-            else { make_twolevel<double>(M, P.tw_shift, hid, lod); P.tw_hi = hid.data(); P.tw_lo = lod.data(); }
-        }
-        std::vector<float> a0f, a1f; std::vector<double> a0d, a1d;
-        if (pp.aux0_id >= 0) {
-            const AuxSpec& a = g.auxs[pp.aux0_id];
-            if (g.prec == B2_PREC_F32) { a0f = make_aux<float>(a.kind, a.a, a.b); P.aux0 = a0f.data(); }
-            else { a0d = make_aux<double>(a.kind, a.a, a.b); P.aux0 = a0d.data(); }
-        }
-        if (pp.aux1_id >= 0) {
-            const AuxSpec& a = g.auxs[pp.aux1_id];
-            if (g.prec == B2_PREC_F32) { a1f = make_aux<float>(a.kind, a.a, a.b); P.aux1 = a1f.data(); }
-            else { a1d = make_aux<double>(a.kind, a.a, a.b); P.aux1 = a1d.data(); }
-        }
-        P.in = (const unsigned char*)base[pp.in_role] + pp.in_off * (pp.in_scalar ? esz / 2 : esz);
-        P.out = (unsigned char*)base[pp.out_role] + pp.out_off * (pp.out_scalar ? esz / 2 : esz);
-        int e = pp.k->launch(&P, pp.grid, nullptr);
-        if (e) return 4039;
-    }
+    for (PassPlan& pp : list)
+        if ((rc = emu_run_one(g, pp, base)) != 0) return rc;
     return 0;
+}
+
+// One launch of a plan on caller-supplied buffer + temp (distributed plans: the test plays every rank's launches in
+// an order the barriers allow, on two host arrays standing for the two peer windows).
+// sync_before[i] (when non-null, capacity 16) reports which launches are preceded by a barrier.
+extern "C" int emu_exec_plan_pass(const b200fft_desc* d, int inverse, void* buffer, void* temp, int pass, int* npasses,
+                                  int* sync_before) {
+    PlanGraph g;
+    int rc = build_plan(*d, g);
+    if (rc != 0) return rc;
+    void* base[ROLE_COUNT] = {buffer, temp, nullptr, nullptr};
+    std::vector<PassPlan>& list = (inverse == 1) ? g.inv : g.fwd;
+    if (npasses) *npasses = (int)list.size();
+    if (sync_before)
+        for (size_t i = 0; i < list.size() && i < 16; ++i) sync_before[i] = list[i].sync_before ? 1 : 0;
+    if (pass < 0) return 0;   // query only
+    if (pass >= (int)list.size()) return 4;
+    return emu_run_one(g, list[pass], base);
 }

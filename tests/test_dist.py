@@ -116,3 +116,43 @@ def test_distributed_four_step_index_algebra_over_gloo():
         assert p.exitcode == 0
     for rank, errs in res:
         assert errs[False] < 1e-6 and errs[True] < 1e-6, (rank, errs)
+
+
+def _fd_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from vkfft_b200.window import exchange_fds
+        r, w = os.pipe()
+        msg = f"from{rank}".encode()
+        os.write(w, msg * (world - 1))                 # one copy for each reader of this pipe
+        got = exchange_fds(dist, [r, w])
+        seen = {}
+        for peer, (pr, pw) in got.items():
+            seen[peer] = os.read(pr, len(msg)).decode()   # the peer's pipe, reachable through the passed descriptor
+            os.close(pr); os.close(pw)
+        q.put((rank, seen))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_window_descriptor_exchange_over_unix_sockets():
+    """host plumbing of the peer windows: every rank receives working copies of every other rank's descriptors"""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    world = 3
+    procs = [ctx.Process(target=_fd_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in range(world):
+        assert res[r] == {p: f"from{p}" for p in range(world) if p != r}

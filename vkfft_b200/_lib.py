@@ -27,7 +27,7 @@ class b200fft_desc(ctypes.Structure):
         ("omit_dimension", ctypes.c_uint32 * MAX_DIMS), ("buffer_size", ctypes.c_uint64),
         ("temp_buffer_size", ctypes.c_uint64),
         ("device", ctypes.c_int32), ("reserved0", ctypes.c_uint32), ("stream", ctypes.c_void_p),
-        ("reserved", ctypes.c_uint64 * 8),
+        ("dist_world", ctypes.c_uint32), ("dist_rank", ctypes.c_uint32), ("reserved", ctypes.c_uint64 * 7),
     ]
 
 
@@ -54,6 +54,9 @@ EXPORTS = [
     "b200fft_plan_create", "b200fft_exec", "b200fft_plan_destroy", "b200fft_plan_get_info",
     "b200fft_plan_describe", "b200fft_exec_host", "b200fft_host_alloc", "b200fft_host_free",
     "b200fft_error_string", "b200fft_version", "b200fft_kernel_count",
+    "b200fft_window_granularity", "b200fft_window_create", "b200fft_window_export", "b200fft_window_import",
+    "b200fft_window_base", "b200fft_window_local", "b200fft_window_barrier", "b200fft_window_status",
+    "b200fft_window_destroy", "b200fft_plan_attach_window",
 ]
 
 _lib = None
@@ -90,5 +93,25 @@ def load():
     L.b200fft_error_string.restype = ctypes.c_char_p
     L.b200fft_version.restype = ctypes.c_int
     L.b200fft_kernel_count.restype = ctypes.c_int
+    L.b200fft_window_granularity.argtypes = [ctypes.c_int]
+    L.b200fft_window_granularity.restype = ctypes.c_uint64
+    L.b200fft_window_create.argtypes = [ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64, ctypes.POINTER(vp)]
+    L.b200fft_window_create.restype = ctypes.c_int
+    L.b200fft_window_export.argtypes = [vp, ctypes.POINTER(ctypes.c_int)]
+    L.b200fft_window_export.restype = ctypes.c_int
+    L.b200fft_window_import.argtypes = [vp, ctypes.c_uint32, ctypes.POINTER(ctypes.c_int)]
+    L.b200fft_window_import.restype = ctypes.c_int
+    L.b200fft_window_base.argtypes = [vp]
+    L.b200fft_window_base.restype = vp
+    L.b200fft_window_local.argtypes = [vp]
+    L.b200fft_window_local.restype = vp
+    L.b200fft_window_barrier.argtypes = [vp, vp]
+    L.b200fft_window_barrier.restype = ctypes.c_int
+    L.b200fft_window_status.argtypes = [vp]
+    L.b200fft_window_status.restype = ctypes.c_int
+    L.b200fft_window_destroy.argtypes = [vp]
+    L.b200fft_window_destroy.restype = None
+    L.b200fft_plan_attach_window.argtypes = [vp, vp]
+    L.b200fft_plan_attach_window.restype = ctypes.c_int
     _lib = L
     return L

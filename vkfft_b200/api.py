@@ -99,6 +99,10 @@ class VkFFTConfiguration:
     performConvolution: int = 0
     halfPrecision: int = 0
     performZeropadding: List[int] = field(default_factory=list)
+    # engine extension (no reference counterpart, the reference is single-device): one sequence over peer windows,
+    # see b200fft_desc.dist_world in include/b200fft.h and vkfft_b200/dist.py FusedDistributedFFT1D
+    distWorld: int = 0
+    distRank: int = 0
 
 
 @dataclass
@@ -153,6 +157,8 @@ def _to_desc(cfg: VkFFTConfiguration) -> "_lib.b200fft_desc":
     d.temp_buffer_size = cfg.tempBufferSize
     d.device = int(cfg.device)
     d.stream = cfg.stream
+    d.dist_world = cfg.distWorld
+    d.dist_rank = cfg.distRank
     return d
 
 

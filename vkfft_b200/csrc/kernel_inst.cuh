@@ -13,6 +13,15 @@
 
 namespace b200fft {
 
+#if !defined(B2_EMU)
+// cudaLaunchKernel reports THIS launch's status; `kernel<<<>>>` + cudaGetLastError() would also pick up a stale
+// non-sticky error some other library left behind in the calling process (seen with NCCL's peer-access setup)
+inline int launch_checked(const void* kernel, unsigned grid, unsigned threads, size_t smem, void* stream, const b2_pass_params* P) {
+    void* args[] = {const_cast<b2_pass_params*>(P)};
+    return (int)cudaLaunchKernel(kernel, dim3(grid), dim3(threads), args, smem, (cudaStream_t)stream);
+}
+#endif
+
 template <int KIND> struct KindTraits;
 template <> struct KindTraits<B2_KIND_ROWS> {
     static constexpr int LMAP = MAP_TFAST, SMAP = MAP_TFAST, LAYOUT = LAY_LINE;
@@ -43,8 +52,7 @@ template <class C> int prepare_impl() { return 0; }
 #else
 template <class C>
 int launch_impl(const b2_pass_params* P, unsigned grid, void* stream) {
-    stockham_kernel<C><<<grid, C::THREADS, C::SMEM_BYTES, (cudaStream_t)stream>>>(*P);
-    return (int)cudaGetLastError();
+    return launch_checked((const void*)stockham_kernel<C>, grid, C::THREADS, C::SMEM_BYTES, stream, P);
 }
 template <class C>
 int prepare_impl() {
@@ -71,8 +79,7 @@ template <typename T, int RMAX> int generic_prepare() { return 0; }
 #else
 template <typename T, int RMAX>
 int generic_launch(const b2_pass_params* P, unsigned grid, void* stream) {
-    generic_kernel<T, RMAX><<<grid, P->tpl * P->q, generic_smem_bytes<T>(P), (cudaStream_t)stream>>>(*P);
-    return (int)cudaGetLastError();
+    return launch_checked((const void*)generic_kernel<T, RMAX>, grid, P->tpl * P->q, generic_smem_bytes<T>(P), stream, P);
 }
 template <typename T, int RMAX>
 int generic_prepare() {
@@ -104,8 +111,7 @@ int ew_launch(const b2_pass_params* P, unsigned grid, void*) {
 #else
 template <typename T>
 int ew_launch(const b2_pass_params* P, unsigned grid, void* stream) {
-    elementwise_kernel<T><<<grid, B2_EW_THREADS, 0, (cudaStream_t)stream>>>(*P);
-    return (int)cudaGetLastError();
+    return launch_checked((const void*)elementwise_kernel<T>, grid, B2_EW_THREADS, 0, stream, P);
 }
 #endif
 template <typename T>
@@ -168,8 +174,7 @@ int pipe_launch_impl(const b2_pass_params* P, unsigned grid, void* stream) {
         resident = sms * (per_sm > 0 ? per_sm : 1);
     }
     const unsigned g = grid < (unsigned)resident ? grid : (unsigned)resident;
-    stockham_pipe_kernel<C, NBUF><<<g, C::THREADS, PipeEngine<C, NBUF>::SMEM_BYTES, (cudaStream_t)stream>>>(*P);
-    return (int)cudaGetLastError();
+    return launch_checked((const void*)stockham_pipe_kernel<C, NBUF>, g, C::THREADS, PipeEngine<C, NBUF>::SMEM_BYTES, stream, P);
 }
 template <class C, int NBUF>
 int pipe_prepare_impl() {

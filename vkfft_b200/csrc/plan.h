@@ -72,6 +72,7 @@ struct PassPlan {
     int lut_id_unaligned = -1;   // stage twiddles of k_unaligned (its radix schedule may differ)
     int tw_id = -1;
     int aux0_id = -1, aux1_id = -1;
+    bool sync_before = false;    // distributed plans: barrier over all ranks of the window before this launch
     bool in_scalar = false, out_scalar = false;   // offsets (and strides) of that side count scalars, not complex elements
     std::string note;            // human readable (plan_describe)
 };
@@ -92,6 +93,7 @@ struct PlanGraph {
     uint64_t temp_elems_real = 0;   // (unused placeholder for real-sized scratch accounting)
     double flops = 0;
     uint64_t algorithmic_bytes = 0;
+    bool distributed = false;    // desc.dist_world > 1: one more barrier follows the last launch of a direction
 };
 
 // Build the plan graph for `d`.  Returns a VkFFTResult-compatible code.

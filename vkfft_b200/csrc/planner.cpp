@@ -123,6 +123,8 @@ struct PassReq {
     int in_role = ROLE_BUFFER, out_role = ROLE_BUFFER;
     uint64_t twM = 0;
     int tw_outer = -1;           // >= 0: index into `outer` (before merging) of the four-step line coordinate
+    uint32_t tw_line0 = 0;       // first line coordinate of this launch (a rank's slice of a distributed sequence)
+    bool sync_before = false;    // distributed plans: every rank must have finished its previous launch first
     double scale = 1.0;
     const char* what = "";
     // generic-kernel extras
@@ -250,6 +252,8 @@ int emit(PlanGraph& g, std::vector<PassPlan>& list, const PassReq& rq) {
         P.inner_inverse = rq.inner_inverse;
         P.scale = rq.scale;
         P.tw_sel = tw_sel;
+        P.tw_line0 = rq.tw_line0;
+        pp.sync_before = rq.sync_before && pi == 0;
         P.nstages = (uint32_t)radices.size();
         for (size_t s = 0; s < radices.size(); ++s) P.radix[s] = radices[s];
         P.tpl = tpl; P.q = q; P.line_stride = ls;
@@ -379,7 +383,20 @@ struct C2CJob {
     int in_role, out_role;
     double scale;
     int64_t in_base = 0, out_base = 0, tmp_base = 0;   // element offsets into the roles' buffers
+    // distributed sequence: this plan covers rank `rank` of `world` (buffer and temp are peer windows, plan.h)
+    uint32_t world = 1, rank = 0;
 };
+
+// keep rank `rank`'s share of dimension d (contiguous block of d.n/world coordinates); returns the first coordinate
+bool slice_dim(Dim& d, uint32_t world, uint32_t rank, int64_t& in_base, int64_t& out_base, uint64_t& first) {
+    if (world <= 1) { first = 0; return true; }
+    if (d.n % world) return false;
+    d.n /= world;
+    first = (uint64_t)rank * d.n;
+    in_base += (int64_t)first * d.is;
+    out_base += (int64_t)first * d.os;
+    return true;
+}
 
 int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job);
 
@@ -555,6 +572,8 @@ int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
     const int kind = job.unit_lines ? B2_KIND_COLS : B2_KIND_ROWS;
 
     if (N == 1) return R_SUCCESS;   // length-1 transform is the identity
+    const bool dist = job.world > 1;
+    if (dist && (!contiguous || job.unit_lines || count_lines(job.lines) != 1 || !is_smooth(N))) return R_UNSUPPORTED_FFT_LENGTH;
     if (!is_smooth(N)) return plan_bluestein(g, list, job);
 
     // a strided axis served only by the runtime-scheduled kernel with fewer than 8 neighbouring lines per CTA would
@@ -570,7 +589,7 @@ int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
         const b2_kernel_info* kk = b2_find_kernel(kind, g.prec, (int)std::min<uint64_t>(N, 0x7fffffff), 0, 0);
         if (kk && kk->q < 8 && N >= 2048) poor_strided = true;
     }
-    bool try_single = N <= max_single_env() && single_ok(g, kind, N, 0);
+    bool try_single = !dist && N <= max_single_env() && single_ok(g, kind, N, 0);
     if (try_single && poor_strided) {
         // only if a split exists
         bool can_split = false;
@@ -673,6 +692,15 @@ int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
         a.in_base = job.in_base; a.out_base = job.tmp_base;
         a.twM = N;
         a.what = "four-step 1/2 strided+phase";
+        if (dist) {
+            // columns [rank*N2/R, ...): every column crosses all slabs of the input window (peer loads) and of the
+            // temp window (peer stores); the phase line coordinate keeps counting global columns
+            uint64_t first;
+            if (!slice_dim(a.group, job.world, job.rank, a.in_base, a.out_base, first)) return R_UNSUPPORTED_FFT_LENGTH;
+            a.tw_line0 = (uint32_t)first;
+            a.sync_before = true;
+            a.what = "distributed four-step 1/2 strided+phase (peer loads and stores)";
+        }
         if ((rc = emit(g, list, a)) != R_SUCCESS) return rc;
         PassReq b;
         b.kind = B2_KIND_ROWS_TOUT; b.n = (int)N2; b.inv = job.inv; b.ops = sc_ops;
@@ -683,6 +711,13 @@ int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
         b.in_base = job.tmp_base; b.out_base = job.out_base;
         b.scale = job.scale;
         b.what = "four-step 2/2 contiguous+transpose";
+        if (dist) {
+            // rows k1 of this rank's own temp slab (local loads); the transposed store lands in every output slab
+            uint64_t first;
+            if (!slice_dim(b.group, job.world, job.rank, b.in_base, b.out_base, first)) return R_UNSUPPORTED_FFT_LENGTH;
+            b.sync_before = true;
+            b.what = "distributed four-step 2/2 contiguous+transpose (peer stores)";
+        }
         return emit(g, list, b);
     }
     const uint64_t N1 = f[0], N2 = f[1], N3 = f[2], M = N2 * N3;
@@ -691,12 +726,19 @@ int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
     a.in_es = (int64_t)M; a.out_es = (int64_t)M;
     a.group = Dim{M, 1, 1};
     // first pass runs in place on its input when that is the main buffer, otherwise it moves to temp
-    const bool a_inplace = (job.in_role == ROLE_BUFFER);
+    const bool a_inplace = (job.in_role == ROLE_BUFFER) && !dist;
     a.outer = a_inplace ? s_in_in : s_in_tmp;
     a.in_role = job.in_role; a.out_role = a_inplace ? job.in_role : ROLE_TEMP;
     a.in_base = job.in_base; a.out_base = a_inplace ? job.in_base : job.tmp_base;
     a.twM = N;
     a.what = "four-step 1/3 strided+phase";
+    if (dist) {
+        uint64_t first;
+        if (!slice_dim(a.group, job.world, job.rank, a.in_base, a.out_base, first)) return R_UNSUPPORTED_FFT_LENGTH;
+        a.tw_line0 = (uint32_t)first;
+        a.sync_before = true;
+        a.what = "distributed four-step 1/3 strided+phase (peer loads and stores)";
+    }
     if ((rc = emit(g, list, a)) != R_SUCCESS) return rc;
     PassReq b;
     b.kind = B2_KIND_COLS; b.n = (int)N2; b.inv = job.inv; b.ops = B2_OP_TWIDDLE_OUT;
@@ -708,9 +750,16 @@ int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
         b.outer.insert(b.outer.end(), s.begin(), s.end());
     }
     b.in_role = a.out_role; b.out_role = ROLE_TEMP;
-    b.in_base = a.out_base; b.out_base = job.tmp_base;
+    b.in_base = a_inplace ? job.in_base : job.tmp_base; b.out_base = job.tmp_base;
     b.twM = M;
     b.what = "four-step 2/3 strided+phase";
+    if (dist) {
+        // k1 rows of this rank's own temp slab: local loads, local stores
+        uint64_t first;
+        if (!slice_dim(b.outer[0], job.world, job.rank, b.in_base, b.out_base, first)) return R_UNSUPPORTED_FFT_LENGTH;
+        b.sync_before = true;
+        b.what = "distributed four-step 2/3 strided+phase (local)";
+    }
     if ((rc = emit(g, list, b)) != R_SUCCESS) return rc;
     PassReq c;
     c.kind = B2_KIND_ROWS_TOUT; c.n = (int)N3; c.inv = job.inv; c.ops = sc_ops;
@@ -722,6 +771,11 @@ int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
     c.in_base = job.tmp_base; c.out_base = job.out_base;
     c.scale = job.scale;
     c.what = "four-step 3/3 contiguous+transpose";
+    if (dist) {
+        uint64_t first;
+        if (!slice_dim(c.group, job.world, job.rank, c.in_base, c.out_base, first)) return R_UNSUPPORTED_FFT_LENGTH;
+        c.what = "distributed four-step 3/3 contiguous+transpose (peer stores)";
+    }
     return emit(g, list, c);
 }
 
@@ -755,6 +809,7 @@ int plan_c2c_axis(PlanGraph& g, std::vector<PassPlan>& list, const uint64_t* siz
     job.unit_lines = (axis != 0);
     job.in_role = in.role; job.out_role = out.role;
     job.scale = scale;
+    if (g.distributed) { job.world = g.desc.dist_world; job.rank = g.desc.dist_rank; }
     return plan_c2c(g, list, job);
 }
 
@@ -1137,7 +1192,18 @@ int build_plan(const b200fft_desc& din, PlanGraph& g) {
     } else {
         fill(d.buffer_stride, d.size[0]); fill(d.input_stride, d.size[0]); fill(d.output_stride, d.size[0]);
     }
+    if (d.dist_world > 1) {
+        // one long in-place C2C sequence over peer windows: nothing else is defined for a distributed plan
+        if (d.dist_rank >= d.dist_world) return R_INVALID_DEVICE;
+        if (d.fft_dim != 1 || d.number_batches * d.coordinate_features != 1 || d.perform_r2c || d.perform_dct || d.perform_dst ||
+            d.is_input_formatted || d.is_output_formatted || d.buffer_stride[0] != d.size[0] || d.omit_dimension[0])
+            return R_UNSUPPORTED_FFT_LENGTH;
+        if (!d.user_temp_buffer) return R_EMPTY_TEMPBUFFER;
+    } else {
+        d.dist_world = 1; d.dist_rank = 0;
+    }
     g.desc = d;
+    g.distributed = d.dist_world > 1;
     g.prec = (int)d.precision;
     for (int a = 0; a < B200FFT_MAX_DIMS; ++a) g.stride[a] = d.buffer_stride[a];
     g.batches = d.number_batches * d.coordinate_features;

@@ -38,6 +38,8 @@ struct b200fft_plan {
     // exec_host staging
     void* d_stage = nullptr;
     uint64_t stage_bytes = 0;
+    // distributed plans: the peer window of `buffer` (not owned)
+    b200fft_window* window = nullptr;
 };
 
 namespace {
@@ -165,7 +167,12 @@ extern "C" int b200fft_exec(b200fft_plan* p, int inverse, const b200fft_buffers*
     DeviceGuard dg(p->device);
     if (!dg.ok) return R_INVALID_DEVICE;
     cudaStream_t st = b->stream ? (cudaStream_t)b->stream : p->stream;
+    if (g.distributed && !p->window) return R_PLAN_NOT_INITIALIZED;
     for (const PassPlan& pp : list) {
+        if (pp.sync_before) {
+            int brc = b200fft_window_barrier(p->window, (void*)st);
+            if (brc != R_SUCCESS) return brc;
+        }
         b2_pass_params P = pp.P;
         P.in = base[pp.in_role] + pp.in_off * (int64_t)(pp.in_scalar ? esz / 2 : esz);
         P.out = base[pp.out_role] + pp.out_off * (int64_t)(pp.out_scalar ? esz / 2 : esz);
@@ -186,6 +193,14 @@ extern "C" int b200fft_exec(b200fft_plan* p, int inverse, const b200fft_buffers*
         }
         if (!k || k->launch(&P, pp.grid, (void*)st) != 0) return R_FAILED_TO_LAUNCH_KERNEL;
     }
+    // every rank's stores into this rank's slab have landed once all ranks passed this point
+    if (g.distributed) return b200fft_window_barrier(p->window, (void*)st);
+    return R_SUCCESS;
+}
+
+extern "C" int b200fft_plan_attach_window(b200fft_plan* p, b200fft_window* w) {
+    if (!p) return R_EMPTY_APP;
+    p->window = w;
     return R_SUCCESS;
 }
 
@@ -222,6 +237,7 @@ extern "C" int b200fft_exec_host(b200fft_plan* p, int inverse, const void* host_
     if (!p) return R_EMPTY_APP;
     if (!host_in || !host_out) return R_EMPTY_BUFFER;
     if (p->g.desc.is_input_formatted || p->g.desc.is_output_formatted) return R_EMPTY_INPUTBUFFER;
+    if (p->g.distributed) return R_UNSUPPORTED_FFT_LENGTH;
     DeviceGuard dg(p->device);
     if (!dg.ok) return R_INVALID_DEVICE;
     const uint64_t need = bytes_in > bytes_out ? bytes_in : bytes_out;

@@ -149,3 +149,68 @@ class DistributedFFT1D:
         t = torch.empty_like(s)
         dist.all_to_all_single(t, s)                                # [src e][k1_local][k2_local]
         return t.view(R, r1, c).permute(2, 0, 1).contiguous().view(-1)   # [k2_local][k1] -> natural order slab
+
+
+class FusedDistributedFFT1D:
+    """One long 1-D C2C sequence over the GPUs of a box with the exchange fused into the FFT launches
+    (second row; BASELINE.json config 5).
+
+    Memory: two peer windows (window.PeerWindow) -- the sequence itself and a scratch of the same size; rank g's slab
+    is elements [g*N/R, (g+1)*N/R) of both, and every rank sees both as flat arrays of N points.  Execution: every rank
+    runs its slice of the ordinary Four-Step launches (planner.cpp plan_c2c, `dist` branches):
+
+        launch 1  columns [g*C, (g+1)*C): strided loads gather the column from all slabs (NVLink reads), phase
+                  multiply, stores scatter it to the scratch slabs of its owners (NVLink writes)
+        (launch 2 of a 3-launch split: local)
+        last      rows of the rank's own scratch slab, transposed store into every slab of the sequence window
+
+    so the all-to-all exchanges of DistributedFFT1D (3 NCCL collectives + pack/unpack passes + a phase pass) become
+    the loads and stores of 2-3 kernels, separated by device-side barriers on a signal pad.  Input and output are both
+    in natural order, in place in `self.local` (this rank's slab)."""
+
+    def __init__(self, n, dist, device, double=False, normalize=False):
+        import torch
+        from . import api
+        from .window import PeerWindow
+        self.torch, self.dist, self.api = torch, dist, api
+        self.R, self.r = dist.get_world_size(), dist.get_rank()
+        if n % self.R:
+            raise ValueError("world size must divide N")
+        esz = 16 if double else 8
+        self.n = n
+        self.seq = PeerWindow(n // self.R * esz, dist, device)
+        self.tmp = PeerWindow(n // self.R * esz, dist, device)
+        dt = torch.complex128 if double else torch.complex64
+        self.local = self.seq.tensor(torch, dt)
+        cfg = api.VkFFTConfiguration(FFTdim=1, size=[n], device=device, doublePrecision=int(double), normalize=int(normalize),
+                                     userTempBuffer=1, distWorld=self.R, distRank=self.r)
+        self.app = api.VkFFTApplication()
+        rc = api.initializeVkFFT(self.app, cfg)
+        if rc != 0:
+            self.close()
+            raise RuntimeError(api.getVkFFTErrorString(rc))
+        from . import _lib
+        _lib.load().b200fft_plan_attach_window(self.app._plan, self.seq.handle)
+
+    def __call__(self, inverse=False):
+        """transform the sequence held in the windows in place; asynchronous on the current stream"""
+        lp = self.api.VkFFTLaunchParams(buffer=self.seq.base, tempBuffer=self.tmp.base,
+                                        stream=self.torch.cuda.current_stream().cuda_stream)
+        rc = self.api.VkFFTAppend(self.app, 1 if inverse else -1, lp)
+        if rc != 0:
+            raise RuntimeError(self.api.getVkFFTErrorString(rc))
+        return self.local
+
+    def check(self):
+        """synchronise and raise if a device-side barrier timed out (a rank died or never launched)"""
+        if self.seq.status() != 0:
+            raise RuntimeError("distributed FFT: a device-side barrier timed out")
+
+    def close(self):
+        if getattr(self, "app", None) is not None and self.app._plan is not None:
+            self.torch.cuda.synchronize()
+            self.api.deleteVkFFT(self.app)
+        for w in ("seq", "tmp"):
+            if getattr(self, w, None) is not None:
+                getattr(self, w).close()
+                setattr(self, w, None)

@@ -60,6 +60,9 @@ for logn in sizes:
         f(inverse=True)
     ms_pair = timed(pair)
     f.check()
+    dist.barrier()
+    f.timed(False)
+    breakdown = f.timed(False)
     info = vk.planInfo(f.app)
     f.close()
     # the collective version, forward only
@@ -73,7 +76,8 @@ for logn in sizes:
         print(json.dumps({"n": f"2^{logn}", "world": world, "rel_err_vs_single_gpu_engine": errs[0].item(),
                           "roundtrip_rel_err": errs[1].item(), "fused_ms_per_transform": ms,
                           "fused_gflops": 5 * n * logn / (ms * 1e-3) / 1e9, "nccl_collective_ms_per_transform": ms_nccl,
-                          "launches_per_transform": info["num_passes_forward"]}), flush=True)
+                          "launches_per_transform": info["num_passes_forward"],
+                          "rank0_breakdown_ms": breakdown}), flush=True)
         if logn == sizes[-1]:
             print(info["forward"], flush=True)
 dist.destroy_process_group()

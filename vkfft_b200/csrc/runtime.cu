@@ -144,7 +144,28 @@ extern "C" int b200fft_plan_create(const b200fft_desc* desc, b200fft_plan** out)
     return R_SUCCESS;
 }
 
-extern "C" int b200fft_exec(b200fft_plan* p, int inverse, const b200fft_buffers* b) {
+static int exec_impl(b200fft_plan* p, int inverse, const b200fft_buffers* b, std::vector<cudaEvent_t>* marks, std::vector<int>* kinds);
+
+extern "C" int b200fft_exec(b200fft_plan* p, int inverse, const b200fft_buffers* b) { return exec_impl(p, inverse, b, nullptr, nullptr); }
+
+// tuning hook: one execution with an event after every launch; ms[i] = duration of interval i, kind[i] = 0 barrier / 1 kernel
+extern "C" int b200fft_debug_exec_timed(b200fft_plan* p, int inverse, const b200fft_buffers* b, float* ms, int* kind, int cap, int* count) {
+    std::vector<cudaEvent_t> marks;
+    std::vector<int> kinds;
+    int rc = exec_impl(p, inverse, b, &marks, &kinds);
+    if (rc == R_SUCCESS && cudaDeviceSynchronize() != cudaSuccess) rc = R_FAILED_TO_SYNCHRONIZE;
+    int n = 0;
+    for (size_t i = 0; i + 1 < marks.size() && rc == R_SUCCESS; ++i, ++n) {
+        float t = 0;
+        cudaEventElapsedTime(&t, marks[i], marks[i + 1]);
+        if ((int)i < cap) { ms[i] = t; kind[i] = kinds[i]; }
+    }
+    for (cudaEvent_t e : marks) cudaEventDestroy(e);
+    if (count) *count = n;
+    return rc;
+}
+
+static int exec_impl(b200fft_plan* p, int inverse, const b200fft_buffers* b, std::vector<cudaEvent_t>* marks, std::vector<int>* kinds) {
     if (!p) return R_EMPTY_APP;
     if (!b) return R_EMPTY_BUFFER;
     const PlanGraph& g = p->g;
@@ -168,11 +189,21 @@ extern "C" int b200fft_exec(b200fft_plan* p, int inverse, const b200fft_buffers*
     if (!dg.ok) return R_INVALID_DEVICE;
     cudaStream_t st = b->stream ? (cudaStream_t)b->stream : p->stream;
     if (g.distributed && !p->window) return R_PLAN_NOT_INITIALIZED;
+    auto mark = [&](int kind_of_next) {
+        if (!marks) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        marks->push_back(e);
+        if (kind_of_next >= 0) kinds->push_back(kind_of_next);
+    };
     for (const PassPlan& pp : list) {
         if (pp.sync_before) {
+            mark(0);
             int brc = b200fft_window_barrier(p->window, (void*)st);
             if (brc != R_SUCCESS) return brc;
         }
+        mark(1);
         b2_pass_params P = pp.P;
         P.in = base[pp.in_role] + pp.in_off * (int64_t)(pp.in_scalar ? esz / 2 : esz);
         P.out = base[pp.out_role] + pp.out_off * (int64_t)(pp.out_scalar ? esz / 2 : esz);
@@ -194,7 +225,13 @@ extern "C" int b200fft_exec(b200fft_plan* p, int inverse, const b200fft_buffers*
         if (!k || k->launch(&P, pp.grid, (void*)st) != 0) return R_FAILED_TO_LAUNCH_KERNEL;
     }
     // every rank's stores into this rank's slab have landed once all ranks passed this point
-    if (g.distributed) return b200fft_window_barrier(p->window, (void*)st);
+    if (g.distributed) {
+        mark(0);
+        int brc = b200fft_window_barrier(p->window, (void*)st);
+        mark(-1);
+        return brc;
+    }
+    mark(-1);
     return R_SUCCESS;
 }
 

@@ -201,6 +201,22 @@ class FusedDistributedFFT1D:
             raise RuntimeError(self.api.getVkFFTErrorString(rc))
         return self.local
 
+    def timed(self, inverse=False):
+        """one execution with an event after every launch: [('barrier'|'kernel', ms), ...] (tuning aid; synchronises)"""
+        import ctypes
+        from . import _lib
+        L = _lib.load()
+        b = _lib.b200fft_buffers()
+        b.buffer, b.temp_buffer = self.seq.base, self.tmp.base
+        b.stream = self.torch.cuda.current_stream().cuda_stream
+        ms, kind, n = (ctypes.c_float * 16)(), (ctypes.c_int * 16)(), ctypes.c_int(0)
+        L.b200fft_debug_exec_timed.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                               ctypes.c_int, ctypes.c_void_p]
+        rc = L.b200fft_debug_exec_timed(self.app._plan, 1 if inverse else -1, ctypes.byref(b), ms, kind, 16, ctypes.byref(n))
+        if rc != 0:
+            raise RuntimeError(self.api.getVkFFTErrorString(rc))
+        return [("kernel" if kind[i] else "barrier", round(ms[i], 4)) for i in range(min(n.value, 16))]
+
     def check(self):
         """synchronise and raise if a device-side barrier timed out (a rank died or never launched)"""
         if self.seq.status() != 0:

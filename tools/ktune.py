@@ -20,6 +20,7 @@ for i in range(L.b200fft_kernel_count()):
     L.b200fft_debug_kernel_info(i, info)
     kind, p, n, inv, ops, var, thr, q, tpl, smem = list(info)
     if kind > 2 or p != prec or inv != 0: continue
+    if ops & ~1: continue   # fused real-transform / Bluestein flavours need their own tables: not timed here
     if kind == 2 and ops == 0 and not os.environ.get("KTUNE_COLS_PLAIN"): continue   # default: four-step flavour of COLS
     if kind == 2 and ops != 0 and os.environ.get("KTUNE_COLS_PLAIN"): continue
     if only_n and n not in only_n: continue

@@ -502,20 +502,33 @@ struct Engine {
     }
 
     // ---- HBM store of last-stage outputs (+ fused post operators) --------------------------------------
+    // Four-step phase on store: W_M^(line*p).  A thread's outputs are p = p0 + k*NB, k = 0..r-1, so the phases form a
+    // geometric sequence: one two-level lookup (two small L1-resident loads + one complex multiply) per group of 8
+    // outputs, three more for the step W^(line*NB) and its 2nd / 4th power, and every phase of the group is the group's
+    // first one times at most three of those (error <= ~7 ulp worst case, ~2 ulp rms).  This replaced a lookup per
+    // output (64 scattered 8-byte loads + 64-bit index arithmetic per 32 outputs), which kept the LSU pipe the limiter
+    // of these kernels.  Also measured on B200 and rejected (profiles/r1/README.md): a tile-factored scheme with
+    // coalesced table reads and the reference-style full M-entry table.
     template <int s>
-    // Four-step phase on store: W_M^(line*p) from the two-level table (two small L1-resident lookups + one complex
-    // multiply).  Two alternatives were measured on B200 and rejected (profiles/r1/README.md): a tile-factored
-    // scheme with coalesced table reads and the reference-style full M-entry table; both were slower.
     B2_D static void store_global(const X* x, X* __restrict__ line, int64_t es, int t, bool valid,
                                   const b2_pass_params& P, uint32_t gline, uint32_t qline) {
         constexpr int r = Sch::r(s), NB = nbut<s>(), BPT = bpt<s>();
         static_assert(s == NS - 1, "global store only after the last stage");
+        constexpr bool TW = (C::OPS & B2_OP_TWIDDLE_OUT) != 0;
         const bool do_scale = (P.ops & B2_OP_SCALE) != 0;   // runtime: normalize=1 on the last inverse pass
         const T sc = (T)P.scale;
+        X s1 = mk<T>(T(1), T(0)), s2 = s1, s4 = s1;
+        if constexpr (TW) {
+            const uint64_t e1 = (uint64_t)gline * (uint64_t)NB;     // 4*e1 < M for r >= 4; unused otherwise
+            if constexpr (r > 1) s1 = twiddle2<T>((const X*)P.tw_hi, (const X*)P.tw_lo, P.tw_shift, e1);
+            if constexpr (r > 2) s2 = twiddle2<T>((const X*)P.tw_hi, (const X*)P.tw_lo, P.tw_shift, 2 * e1);
+            if constexpr (r > 4) s4 = twiddle2<T>((const X*)P.tw_hi, (const X*)P.tw_lo, P.tw_shift, 4 * e1);
+        }
 #pragma unroll
         for (int m = 0; m < BPT; ++m) {
             const int b0 = V * (t + m * TPL);
             const bool ok = valid && (!guarded<s>() || b0 < NB);
+            X w0[V], w2[V], w4[V], w6[V];
 #pragma unroll
             for (int k = 0; k < r; ++k) {
                 X o[V];
@@ -523,9 +536,18 @@ struct Engine {
                 for (int v = 0; v < V; ++v) {
                     X a = x[(m * V + v) * r + k];
                     const int p = b0 + v + k * NB;  // natural-order output index (S == NB in the last stage)
-                    if constexpr ((C::OPS & B2_OP_TWIDDLE_OUT) != 0) {
-                        const uint64_t e = (uint64_t)gline * (uint64_t)p;
-                        a = a * twiddle2<T>((const X*)P.tw_hi, (const X*)P.tw_lo, P.tw_shift, e);
+                    if constexpr (TW) {
+                        const int tt = k & 7;
+                        X w;
+                        if (tt == 0) { w0[v] = twiddle2<T>((const X*)P.tw_hi, (const X*)P.tw_lo, P.tw_shift, (uint64_t)gline * (uint64_t)p); w = w0[v]; }
+                        else if (tt == 1) w = w0[v] * s1;
+                        else if (tt == 2) { w2[v] = w0[v] * s2; w = w2[v]; }
+                        else if (tt == 3) w = w2[v] * s1;
+                        else if (tt == 4) { w4[v] = w0[v] * s4; w = w4[v]; }
+                        else if (tt == 5) w = w4[v] * s1;
+                        else if (tt == 6) { w6[v] = w4[v] * s2; w = w6[v]; }
+                        else w = w6[v] * s1;
+                        a = a * w;
                     }
                     if (do_scale) a = a * sc;
                     o[v] = C::INV ? swp(a) : a;

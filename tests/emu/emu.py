@@ -103,3 +103,10 @@ def exec_plan_pass(desc, inverse, buffer, temp, pass_index):
     vp = lambda a: a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
     rc = L.emu_exec_plan_pass(ctypes.byref(desc), int(inverse), vp(buffer), vp(temp), int(pass_index), ctypes.byref(npass), sync)
     return rc, npass.value, [bool(sync[i]) for i in range(npass.value)]
+
+
+def describe(desc, inverse=-1):
+    L = lib()
+    buf = ctypes.create_string_buffer(16384)
+    rc = L.emu_describe(ctypes.byref(desc), int(inverse), buf, len(buf))
+    return rc, buf.value.decode()

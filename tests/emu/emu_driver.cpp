@@ -126,3 +126,16 @@ extern "C" int emu_exec_plan_pass(const b200fft_desc* d, int inverse, void* buff
     if (pass >= (int)list.size()) return 4;
     return emu_run_one(g, list[pass], base);
 }
+
+// plan listing without a GPU (same text as b200fft_plan_describe)
+extern "C" int emu_describe(const b200fft_desc* d, int inverse, char* dst, int cap) {
+    PlanGraph g;
+    int rc = build_plan(*d, g);
+    if (rc != 0) return rc;
+    std::string s;
+    static const char* role[] = {"buffer", "temp", "input", "output"};
+    for (const PassPlan& pp : (inverse == 1 ? g.inv : g.fwd))
+        s += pp.note + "  " + role[pp.in_role] + " -> " + role[pp.out_role] + (pp.sync_before ? "  [barrier before]" : "") + "\n";
+    snprintf(dst, cap, "%s", s.c_str());
+    return 0;
+}

@@ -299,7 +299,7 @@ uint64_t max_single_env() {
 
 // Factor N for Four-Step.  All factors but the last run as interleaved-line passes with the phase multiply,
 // the last one runs on contiguous lines with a transposed store.  Returns empty if impossible.
-std::vector<uint64_t> split_four_step(const PlanGraph& g, uint64_t N) {
+std::vector<uint64_t> split_four_step(const PlanGraph& g, uint64_t N, bool dist = false) {
     // test hook: B200FFT_FOUR_STEP_SPLIT="n1,n2[,n3]" forces a factorisation (used by the CPU tests to reach
     // the three-pass code with small transforms)
     if (const char* e = getenv("B200FFT_FOUR_STEP_SPLIT")) {
@@ -327,6 +327,14 @@ std::vector<uint64_t> split_four_step(const PlanGraph& g, uint64_t N) {
             if (e.n == n) return kind == B2_KIND_COLS ? e.cols : e.tout;
         return 0;
     };
+    // distributed plans: the first launch's stores and the last launch's transposed stores cross NVLink in runs of
+    // q elements; 64-byte runs (q = 8) reached 430 GB/s per direction, 128-byte runs 670 GB/s (2 x B200,
+    // profiles/r1/dist_fused_split_experiment_2gpu.log) -> rank kernels with q < 16 as if their pass were 300 us slower
+    auto short_runs = [&](int kind, uint64_t n, int ops) -> uint64_t {
+        if (!dist) return 0;
+        const b2_kernel_info* k = b2_find_kernel(kind, g.prec, (int)n, 0, ops);
+        return (k && k->q < 16) ? 300 * 16 : 0;
+    };
     std::vector<uint64_t> best;
     uint64_t best_cost = ~0ull;
     for (uint64_t n2 = 2; n2 * 2 <= N && n2 <= cap; ++n2) {
@@ -341,6 +349,7 @@ std::vector<uint64_t> split_four_step(const PlanGraph& g, uint64_t N) {
         else cost += 1u << 16;
         if (!fast(B2_KIND_ROWS_TOUT, n2, 0)) cost += 1u << 20;
         if (!fast(B2_KIND_COLS, n1, B2_OP_TWIDDLE_OUT)) cost += 1u << 20;
+        cost += short_runs(B2_KIND_COLS, n1, B2_OP_TWIDDLE_OUT) + short_runs(B2_KIND_ROWS_TOUT, n2, 0);
         if (cost < best_cost) { best_cost = cost; best = {n1, n2}; }
     }
     const uint64_t two_level_limit = (g.prec == B2_PREC_F32) ? (1ull << 22) : (1ull << 21);
@@ -361,6 +370,7 @@ std::vector<uint64_t> split_four_step(const PlanGraph& g, uint64_t N) {
             if (!fast(B2_KIND_ROWS_TOUT, n3, 0)) cost += 1u << 20;
             if (!fast(B2_KIND_COLS, n2, B2_OP_TWIDDLE_OUT)) cost += 1u << 20;
             if (!fast(B2_KIND_COLS, n1, B2_OP_TWIDDLE_OUT)) cost += 1u << 20;
+            cost += short_runs(B2_KIND_COLS, n1, B2_OP_TWIDDLE_OUT) + short_runs(B2_KIND_ROWS_TOUT, n3, 0);
             if (cost < best3_cost) { best3_cost = cost; best3 = {n1, n2, n3}; }
         }
     }
@@ -666,7 +676,7 @@ int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
     }
     if (!contiguous) return R_UNSUPPORTED_FFT_LENGTH;
 
-    std::vector<uint64_t> f = split_four_step(g, N);
+    std::vector<uint64_t> f = split_four_step(g, N, dist);
     if (f.empty()) return R_UNSUPPORTED_FFT_LENGTH;
     // scratch: sequences keep the output-side layout of the main buffer
     uint64_t extent = N;

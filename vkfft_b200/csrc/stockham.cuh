@@ -121,7 +121,7 @@ struct KCfg {
     static constexpr int QP = Q;  // elem-major row pitch
     // 3: DCT-II, 4: DCT-III with two real lines per complex line (contiguous real lines, or neighbouring real columns
     //    viewed as one complex column on strided axes) -- vkFFT_R2R.h:193-229, :784-859 as fused load/store stages
-    static constexpr int SMEM_ELEMS = (Sch::ns <= 1 && RMODE != 1 && RMODE != 3) ? 0 : ((LAYOUT == LAY_LINE) ? Q * LS : N * QP);
+    static constexpr int SMEM_ELEMS = (Sch::ns <= 1 && RMODE != 1 && RMODE != 3 && RMODE != 4) ? 0 : ((LAYOUT == LAY_LINE) ? Q * LS : N * QP);
     static constexpr int SMEM_BYTES = SMEM_ELEMS * 2 * (int)sizeof(T);
 };
 
@@ -307,6 +307,55 @@ struct Engine {
         }
     }
 
+    // ---- DCT-II / DCT-III on contiguous real lines: HBM -> shared memory staging -----------------------------------
+    // Two real lines (a, b) travel as one complex line a + i b.  Reading them straight into the first-stage legs
+    // costs four loads per element for DCT-III (it needs p and N-p of both lines).  Instead the CTA copies both lines
+    // with fully coalesced loads into the tile and the legs come from shared memory.
+    // Measured on B200 (fused DCT-III rows, N = 8192, 1 GiB of traffic): direct loads + direct scatter 599 us, staged
+    // stores only 577, staged loads only 416, both staged 394.  The DCT-II kernel keeps its direct Makhoul gather
+    // (313 us; staging its input as well: 388).
+#ifndef B2_DCT3_STAGE_IN
+#define B2_DCT3_STAGE_IN 1
+#endif
+#ifndef B2_DCT3_STAGE_OUT
+#define B2_DCT3_STAGE_OUT 1
+#endif
+    B2_D static int unmakhoul(int j) { return (j & 1) ? N - 1 - (j >> 1) : (j >> 1); }
+
+    B2_D static void stage_in_dct(X* sm, const b2_pass_params& P, int64_t obase_in, uint32_t gl, int q, int t, bool valid) {
+        if (!valid) return;
+        const T* __restrict__ la = (const T*)P.in + obase_in + (int64_t)gl * P.in_gs;
+        const T* __restrict__ lb = la + P.aux_u1;
+        const bool vb = (2 * gl + 1 < P.aux_u0);
+#pragma unroll 8
+        for (int j = t; j < N; j += TPL) {
+            const T a = la[j];
+            const T b = vb ? lb[j] : T(0);
+            B2_SMEM_ST(sm, sidx(q, C::RMODE == 3 ? unmakhoul(j) : j), mk<T>(a, b));
+        }
+    }
+    // DCT-III legs from the raw staged lines:  z_p = swap( (a_p + b_{N-p}, b_p - a_{N-p}) * conj-phase_p )
+    template <int s>
+    B2_D static void load_smem_dct3(X* x, const X* sm, const X* __restrict__ c, int q, int t) {
+        constexpr int r = Sch::r(s), NB = nbut<s>(), BPT = bpt<s>();
+#pragma unroll
+        for (int m = 0; m < BPT; ++m) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const int b = V * (t + m * TPL) + v;
+                if (guarded<s>() && b >= NB) continue;
+#pragma unroll
+                for (int k = 0; k < r; ++k) {
+                    const int p = b + k * NB;
+                    const X u = B2_SMEM_LD(sm, sidx(q, p));
+                    X w2 = mk<T>(T(0), T(0));
+                    if (p != 0) w2 = B2_SMEM_LD(sm, sidx(q, N - p));
+                    x[(m * V + v) * r + k] = swp(mulc(mk<T>(u.x + w2.y, u.y - w2.x), ld_lut(c + p)));
+                }
+            }
+        }
+    }
+
     // ---- DCT-II / DCT-III: first-stage legs (RMODE 3 / 4) --------------------------------------------------------------
     template <int s>
     B2_D static void load_global_dct(X* x, const b2_pass_params& P, int64_t obase_in, uint32_t gl, int t, bool valid) {
@@ -371,7 +420,31 @@ struct Engine {
         } else {
             oc = (X*)P.out + obase_out + (int64_t)gl * P.out_gs;
         }
-        if constexpr (C::RMODE == 4) {
+        if constexpr (C::RMODE == 4 && C::LAYOUT == LAY_LINE && B2_DCT3_STAGE_OUT) {
+            // Makhoul scatter through the tile: natural-order spectrum in, coalesced 4-byte stores out
+#pragma unroll
+            for (int m = 0; m < BPT; ++m) {
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    const int b = V * (t + m * TPL) + v;
+                    if (guarded<s>() && b >= NB) continue;
+#pragma unroll
+                    for (int k = 0; k < r; ++k) {
+                        X u = swp(x[(m * V + v) * r + k]);
+                        if (do_scale) u = u * sc;
+                        B2_SMEM_ST(sm, sidx(q, b + k * NB), u);
+                    }
+                }
+            }
+            __syncthreads();
+            if (!valid) return;
+#pragma unroll 8
+            for (int j = t; j < N; j += TPL) {
+                const X u = B2_SMEM_LD(sm, sidx(q, unmakhoul(j)));
+                oa[j] = u.x;
+                if (vb) ob[j] = u.y;
+            }
+        } else if constexpr (C::RMODE == 4) {
 #pragma unroll
             for (int m = 0; m < BPT; ++m) {
 #pragma unroll
@@ -612,7 +685,39 @@ struct Engine {
 
         const X* __restrict__ rw = (const X*)P.aux0;   // e^{-2 pi i k/2n} for the fused real transforms
         const uint32_t psel = (P.tw_sel == 1 ? o0 : (P.tw_sel == 2 ? o1 : o2));   // n2 / k1 of the long strided DCT launches
-        if constexpr (NS == 1) {
+        if constexpr (C::RMODE == 4 && C::LAYOUT == LAY_LINE && B2_DCT3_STAGE_IN) {
+            // real lines staged through the tile (see stage_in_dct); every stage reads its legs from shared memory
+            stage_in_dct(sm, P, obase_in, gl, ql, tl, gl < P.G);
+            __syncthreads();
+            if constexpr (NS == 1) {
+                X x[bpt<0>() * V * Sch::r(0)];
+                if constexpr (C::RMODE == 3) load_smem<0>(x, sm, ql, tl);
+                else load_smem_dct3<0>(x, sm, rw, ql, tl);
+                compute<0>(x, lut, tl);
+                __syncthreads();
+                store_global_dct<0>(x, sm, P, obase_out, gl, ql, tl, gl < P.G);
+            } else {
+                {
+                    X x[bpt<0>() * V * Sch::r(0)];
+                    if constexpr (C::RMODE == 3) load_smem<0>(x, sm, ql, tl);
+                    else load_smem_dct3<0>(x, sm, rw, ql, tl);
+                    compute<0>(x, lut, tl);
+                    __syncthreads();
+                    store_smem<0>(x, sm, ql, tl);
+                }
+                __syncthreads();
+                middle<1>(sm, lut, tid);
+                constexpr int s = NS - 1;
+                int qs, ts;
+                tmap<C::SMAP>(tid, qs, ts);
+                const uint32_t gs = grp * Q + qs;
+                X x[bpt<s>() * V * Sch::r(s)];
+                load_smem<s>(x, sm, qs, ts);
+                compute<s>(x, lut, ts);
+                __syncthreads();
+                store_global_dct<s>(x, sm, P, obase_out, gs, qs, ts, gs < P.G);
+            }
+        } else if constexpr (NS == 1) {
             X x[bpt<0>() * V * Sch::r(0)];
             if constexpr (C::RMODE == 2) load_global_c2r<0>(x, in_line, rw, tl, gl < P.G);
             else if constexpr (C::RMODE == 3 || C::RMODE == 4) load_global_dct<0>(x, P, obase_in, gl, tl, gl < P.G);
@@ -652,7 +757,7 @@ struct Engine {
                     __syncthreads();     // every last-stage read of the tile is done before it is overwritten
                     store_global_r2c<s>(x, sm, out_line, rw, qs, ts, gs < P.G, P);
                 } else if constexpr (C::RMODE == 3 || C::RMODE == 4) {
-                    if constexpr (C::RMODE == 3) __syncthreads();
+                    if constexpr (C::RMODE == 3 || C::LAYOUT == LAY_LINE) __syncthreads();   // the store goes through the tile
                     store_global_dct<s>(x, sm, P, obase_out, gs, qs, ts, gs < P.G);
                 } else if constexpr (C::RMODE == 6) {
                     store_global_perm<s>(x, out_line, P.out_es / P.aux_u1, psel, P.aux_u1, P.aux_u0, ts, gs < P.G, P);

@@ -316,13 +316,13 @@ std::vector<uint64_t> split_four_step(const PlanGraph& g, uint64_t N, bool dist 
     }
     const uint64_t cap = std::min<uint64_t>(max_single_env(), 4096);
     auto fast = [&](int kind, uint64_t n, int ops) { return b2_find_kernel(kind, g.prec, (int)n, 0, ops) != nullptr; };
-    // measured cost of one full pass over a 2 GiB FP32 buffer on B200, microseconds (profiles/r1/ktune_f32_phase_chain.log);
+    // measured cost of one full pass over a 2 GiB FP32 buffer on B200, microseconds (profiles/r1/ktune_f32_tw_chain.log);
     // used to rank factorizations.  Unknown sizes / FP64 fall back to "balanced factors".
     auto pass_us = [&](int kind, uint64_t n) -> uint64_t {
         if (g.prec != B2_PREC_F32) return 0;
         static const struct { uint64_t n; uint64_t cols, tout; } t[] = {
-            {16, 625, 1029}, {32, 750, 622}, {64, 725, 646}, {128, 783, 657}, {256, 805, 650},
-            {512, 908, 717}, {1024, 1044, 759}, {2048, 1214, 872}};
+            {16, 624, 1028}, {32, 764, 632}, {64, 706, 652}, {128, 753, 630}, {256, 782, 618},
+            {512, 862, 715}, {1024, 1013, 744}, {2048, 1197, 876}};
         for (const auto& e : t)
             if (e.n == n) return kind == B2_KIND_COLS ? e.cols : e.tout;
         return 0;

@@ -123,6 +123,10 @@ struct KCfg {
     //    viewed as one complex column on strided axes) -- vkFFT_R2R.h:193-229, :784-859 as fused load/store stages
     static constexpr int SMEM_ELEMS = (Sch::ns <= 1 && RMODE != 1 && RMODE != 3 && RMODE != 4) ? 0 : ((LAYOUT == LAY_LINE) ? Q * LS : N * QP);
     static constexpr int SMEM_BYTES = SMEM_ELEMS * 2 * (int)sizeof(T);
+    // stage twiddles w^k generated from w^1, w^2, w^4, w^8 (Engine::compute).  Measured per kernel on B200
+    // (profiles/r1/ktune_f32_tw_chain.log): -1...-10 % for most shapes (N = 4096: 687 -> 655 us per 2 GiB pass), but
+    // +9 % for the contiguous 8192-point kernels, which keep one table load per twiddle.
+    static constexpr bool TWCHAIN = !(N == 8192 && LAYOUT_ == 0 && sizeof(T_) == 4);
 };
 
 template <class C>
@@ -314,6 +318,9 @@ struct Engine {
     // Measured on B200 (fused DCT-III rows, N = 8192, 1 GiB of traffic): direct loads + direct scatter 599 us, staged
     // stores only 577, staged loads only 416, both staged 394.  The DCT-II kernel keeps its direct Makhoul gather
     // (313 us; staging its input as well: 388).
+#ifndef B2_TW_CHAIN
+#define B2_TW_CHAIN 1
+#endif
 #ifndef B2_DCT3_STAGE_IN
 #define B2_DCT3_STAGE_IN 1
 #endif
@@ -548,8 +555,21 @@ struct Engine {
                 if constexpr (s > 0) {
                     const int j = b % S;
                     const X* l = lut + Sch::lut_off(s) + j;
+                    if constexpr (B2_TW_CHAIN && C::TWCHAIN) {
+                    // only w^1, w^2, w^4, ... come from the table; w^k = w^(lowest set bit of k) * w^(rest), <= 3
+                    // multiplies deep for r <= 16: 4 loads instead of 15 per radix-16 butterfly (the LSU pipe, not
+                    // the FMA pipe, is what these kernels run out of)
+                    X w[r];
+#pragma unroll
+                    for (int k = 1; k < r; ++k) {
+                        if ((k & (k - 1)) == 0) w[k] = ld_lut(l + (k - 1) * S);
+                        else w[k] = w[k & -k] * w[k - (k & -k)];
+                        xb[k] = xb[k] * w[k];
+                    }
+                    } else {
 #pragma unroll
                     for (int k = 1; k < r; ++k) xb[k] = xb[k] * ld_lut(l + (k - 1) * S);
+                    }
                 }
                 dft<r, T>(xb);
             }

@@ -198,8 +198,6 @@ def test_r2c_c2r(gpu, shape, batch, double):
 @pytest.mark.parametrize("inverse", [-1, 1])
 def test_dct(gpu, kind, shape, batch, double, inverse):
     import vkfft_b200 as vk
-    if kind == 4 and any(s % 2 for s in shape):
-        pytest.skip("odd-length DCT-IV not built yet")
     if kind == 1 and not all(_smooth13(2 * s - 2) for s in shape):
         pytest.skip("DCT-I whose 2N-2 has a prime factor > 127: not built yet")
     rdt = np.float64 if double else np.float32
@@ -247,7 +245,8 @@ def test_out_of_place_formatted_buffers(gpu):
 
 
 @pytest.mark.parametrize("kind", [1, 2, 3, 4])
-@pytest.mark.parametrize("shape,batch,double", [((64,), 5, False), ((32, 16), 3, False), ((100,), 3, True), ((4096,), 2, False)])
+@pytest.mark.parametrize("shape,batch,double", [((64,), 5, False), ((32, 16), 3, False), ((100,), 3, True), ((4096,), 2, False),
+                                                ((33,), 4, True), ((45, 21), 2, False)])
 @pytest.mark.parametrize("inverse", [-1, 1])
 def test_dst(gpu, kind, shape, batch, double, inverse):
     import vkfft_b200 as vk

@@ -279,6 +279,18 @@ struct Generic {
                     B2_SMEM_ST(sl, pad(m), v);
                 }
             } break;
+            case B2_IO_DCT4_ODD: {
+                // one real line of odd length L = aux_u1, n = 2L:  y[p] = x[p] e^{-i pi p/(2L)} (aux0[p]) for p < L, 0 above.
+                //   X_k = 2 sum x_p cos(pi (2p+1)(2k+1)/(4L)) = 2 Re( e^{-i pi (2k+1)/(4L)} FFT_2L(y)[k] ),  k < L
+                const T* in = (const T*)P.in + line_off;
+                const X* w = (const X*)P.aux0;
+                const int L = (int)P.aux_u1;
+                for (int p = t; p < n; p += step) {
+                    X v = zero;
+                    if (valid && p < L) v = ld_lut(w + p) * in[(int64_t)dst_src(P, p, L) * P.in_es];
+                    B2_SMEM_ST(sl, pad(p), v);
+                }
+            } break;
         }
     }
 
@@ -400,6 +412,17 @@ struct Generic {
                     if (do_scale) { y0 *= sc; y1 *= sc; }
                     out[(int64_t)(2 * q2) * P.out_es] = dst_sgn_out(P, 2 * q2) * y0;
                     out[(int64_t)(2 * n - 1 - 2 * q2) * P.out_es] = dst_sgn_out(P, 2 * n - 1 - 2 * q2) * y1;
+                }
+            } break;
+            case B2_IO_DCT4_ODD: {
+                T* out = (T*)P.out + line_off;
+                const X* w = (const X*)P.aux1;
+                const int L = (int)P.aux_u1;
+                for (int k = t; k < L; k += step) {
+                    const X v = B2_SMEM_LD(sl, pad(k)) * ld_lut(w + k);
+                    T y = T(2) * v.x;
+                    if (do_scale) y *= sc;
+                    out[(int64_t)k * P.out_es] = dst_sgn_out(P, k) * y;
                 }
             } break;
         }

@@ -112,7 +112,9 @@ enum AuxKind {
     AUX_R2C = 1,          // a = N : e^{-2 pi i k/N},           k = 0..N/2           (vkFFT_ManageLUT.h:1418 R2C LUT)
     AUX_DCT23 = 2,        // a = n : e^{-i pi k/(2n)},           k = 0..n-1           (vkFFT_ManageLUT.h:800-806)
     AUX_DCT4_PRE = 3,     // a = N : e^{-i pi m/N},              m = 0..N/2-1         (vkFFT_ManageLUT.h:807-820)
-    AUX_DCT4_POST = 4,    // a = N : e^{-i pi (4q+1)/(4N)},      q = 0..N/2-1
+    AUX_DCT4_POST = 4,
+    AUX_DCT4ODD_PRE = 9,  // a = N : e^{-i pi n/(2N)},           n = 0..N-1   (odd-length DCT-IV through a 2N-point transform)
+    AUX_DCT4ODD_POST = 10,// a = N : e^{-i pi (2k+1)/(4N)},      k = 0..N-1    // a = N : e^{-i pi (4q+1)/(4N)},      q = 0..N/2-1
     AUX_BLUE_CHIRP = 5,   // a = N : e^{-i pi n^2/N},            n = 0..N-1           (vkFFT_RecursiveFFTGenerators.h:140)
     AUX_BLUE_FILTER = 6,  // a = N, b = M : FFT_M(e^{+i pi m^2/N} wrapped) / M        (vkFFT_RecursiveFFTGenerators.h:241-298)
 };
@@ -156,6 +158,12 @@ inline std::vector<T> make_aux(int kind, uint64_t a, uint64_t b) {
             break;
         case AUX_DCT4_POST:
             for (uint64_t q = 0; q < a / 2; ++q) { unit_root(4 * q + 1, 8 * a, c, s); push(c, s); }
+            break;
+        case AUX_DCT4ODD_PRE:
+            for (uint64_t n = 0; n < a; ++n) { unit_root(n, 4 * a, c, s); push(c, s); }
+            break;
+        case AUX_DCT4ODD_POST:
+            for (uint64_t k = 0; k < a; ++k) { unit_root(2 * k + 1, 8 * a, c, s); push(c, s); }
             break;
         case AUX_BLUE_CHIRP:
             for (uint64_t n = 0; n < a; ++n) { unit_root((n * n) % (2 * a), 2 * a, c, s); push(c, s); }

@@ -48,7 +48,8 @@ enum {
     B2_IO_DCT4 = 6,          // pre/post phases around a half-length complex transform (vkFFT_Scheduler.h:2277-2280)
     B2_IO_REAL = 7,          // odd-length R2C/C2R fallback: real line <-> complex line with zero imaginary part
     B2_IO_HERM = 8,          // load only: rebuild the full spectrum from the Hermitian half (odd-length C2R)
-    B2_IO_DST1 = 9,          // odd extension to 2n+2 on load, -Im / Re on store (DST-I, API guide :581-583)
+    B2_IO_DST1 = 9,
+    B2_IO_DCT4_ODD = 10,     // odd-length DCT-IV: pre-phase + zero-pad to 2N on load, post-phase + real part of the first N outputs on store          // odd extension to 2n+2 on load, -Im / Re on store (DST-I, API guide :581-583)
 };
 
 // DST-II/III/IV are the DCT operators with sign / index-reversal wrappers (vkFFT_R2R.h:769-780):

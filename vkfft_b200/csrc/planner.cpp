@@ -271,7 +271,7 @@ int emit(PlanGraph& g, std::vector<PassPlan>& list, const PassReq& rq) {
         if (rq.ops & B2_OP_TWIDDLE_OUT) pp.tw_id = tw_for(g, rq.twM);
         pp.aux0_id = rq.aux0; pp.aux1_id = rq.aux1;
         // specialised kernels: intra-tile factor of the four-step phase (coalesced table, see stockham.cuh)
-        auto scalar_io = [](int io) { return io == B2_IO_DCT1 || io == B2_IO_DCT2 || io == B2_IO_DCT3 || io == B2_IO_DCT4 || io == B2_IO_REAL || io == B2_IO_DST1; };
+        auto scalar_io = [](int io) { return io == B2_IO_DCT1 || io == B2_IO_DCT2 || io == B2_IO_DCT3 || io == B2_IO_DCT4 || io == B2_IO_DCT4_ODD || io == B2_IO_REAL || io == B2_IO_DST1; };
         pp.in_scalar = scalar_io(rq.load_io) || rq.scalar_units; pp.out_scalar = scalar_io(rq.store_io) || rq.scalar_units;
         char buf[320];
         std::string rs;
@@ -1022,7 +1022,10 @@ int plan_direction_dct(PlanGraph& g, std::vector<PassPlan>& list, int inv) {
             case 3: n = N; rq.load_io = rq.store_io = B2_IO_DCT3; rq.aux0 = aux_for(g, AUX_DCT23, N); rq.real_pairs = true;
                     rq.inner_inverse = 1; break;
             case 4:
-                if (N % 2) return R_UNSUPPORTED_FFT_LENGTH_R2R;
+                if (N % 2) {   // odd length: no half-length trick; phases around a zero-padded 2N-point transform
+                    n = 2 * N; rq.load_io = rq.store_io = B2_IO_DCT4_ODD; rq.aux_u1 = (uint32_t)N;
+                    rq.aux0 = aux_for(g, AUX_DCT4ODD_PRE, N); rq.aux1 = aux_for(g, AUX_DCT4ODD_POST, N); break;
+                }
                 n = N / 2; rq.load_io = rq.store_io = B2_IO_DCT4;
                 rq.aux0 = aux_for(g, AUX_DCT4_PRE, N); rq.aux1 = aux_for(g, AUX_DCT4_POST, N); break;
             default: return R_UNSUPPORTED_FFT_LENGTH_R2R;

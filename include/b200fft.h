@@ -66,7 +66,18 @@ typedef struct b200fft_desc {
      * of every Four-Step launch and exchanges data through loads/stores to peer memory inside those launches. */
     uint32_t dist_world;
     uint32_t dist_rank;
-    uint64_t reserved[7];
+    /* Convolution / cross-correlation (API guide "Convolution parameters", :1809-1852): one VkFFTAppend(app, -1) runs
+     * forward transform -> product with the pre-transformed kernel -> inverse transform, result in `buffer`.
+     * The kernel holds the natural-order spectrum a plan created with kernel_convolution=1 produces. */
+    uint32_t perform_convolution;         /* performConvolution */
+    uint32_t kernel_convolution;          /* kernelConvolution: this plan only transforms the kernel (plain forward plan) */
+    uint32_t matrix_convolution;          /* matrixConvolution: 0/1 = per-feature product, 2 / 3 = matrix-vector product */
+    uint32_t symmetric_kernel;            /* symmetricKernel: upper triangle stored (xx,xy,yy / xx,xy,xz,yy,yz,zz) */
+    uint32_t number_kernels;              /* numberKernels: one input, this many outputs (0 -> 1) */
+    uint32_t conjugate_convolution;       /* conjugateConvolution: 1 conjugates the sequence spectrum, 2 the kernel */
+    uint32_t cross_power_spectrum_normalization; /* crossPowerSpectrumNormalization */
+    uint32_t reserved1;
+    uint64_t reserved[3];
 } b200fft_desc;
 
 /* Buffers for one execution == VkFFTLaunchParams (vkFFT_Structs.h:326-379) with plain pointers.
@@ -78,6 +89,8 @@ typedef struct b200fft_buffers {
     void* output_buffer;   /* only when is_output_formatted=1 */
     uint64_t buffer_offset, temp_buffer_offset, input_buffer_offset, output_buffer_offset;
     void* stream;          /* overrides desc.stream when non-NULL */
+    void* kernel;          /* only when perform_convolution=1 */
+    uint64_t kernel_offset;
 } b200fft_buffers;
 
 typedef struct b200fft_plan b200fft_plan; /* opaque */

@@ -223,7 +223,6 @@ static inline VkFFTResult initializeVkFFT(VkFFTApplication* app, VkFFTConfigurat
     if (c->FFTdim > VKFFT_MAX_FFT_DIMENSIONS) return VKFFT_ERROR_FFTdim_GT_MAX_FFT_DIMENSIONS;
     if (c->size[0] == 0) return VKFFT_ERROR_EMPTY_size;
     /* features of the reference outside this engine's hot path */
-    if (c->performConvolution || c->kernelConvolution || c->matrixConvolution) return VKFFT_ERROR_UNSUPPORTED_FFT_LENGTH;
     if (c->halfPrecision || c->halfPrecisionMemoryOnly || c->quadDoubleDoublePrecision ||
         c->quadDoubleDoublePrecisionDoubleMemory || c->doublePrecisionFloatMemory)
         return VKFFT_ERROR_UNSUPPORTED_FFT_LENGTH;
@@ -259,6 +258,13 @@ static inline VkFFTResult initializeVkFFT(VkFFTApplication* app, VkFFTConfigurat
     d.is_output_formatted = (uint32_t)c->isOutputFormatted;
     d.inverse_return_to_input = (uint32_t)c->inverseReturnToInputBuffer;
     d.user_temp_buffer = (uint32_t)c->userTempBuffer;
+    d.perform_convolution = (uint32_t)c->performConvolution;
+    d.kernel_convolution = (uint32_t)c->kernelConvolution;
+    d.matrix_convolution = (uint32_t)c->matrixConvolution;
+    d.symmetric_kernel = (uint32_t)c->symmetricKernel;
+    d.number_kernels = (uint32_t)c->numberKernels;
+    d.conjugate_convolution = (uint32_t)c->conjugateConvolution;
+    d.cross_power_spectrum_normalization = (uint32_t)c->crossPowerSpectrumNormalization;
     if (c->bufferSize) d.buffer_size = c->bufferSize[0];
     if (c->userTempBuffer && c->tempBufferSize) d.temp_buffer_size = c->tempBufferSize[0];
     {   /* CUdevice handle -> runtime ordinal */
@@ -306,6 +312,8 @@ static inline VkFFTResult VkFFTAppend(VkFFTApplication* app, int inverse, VkFFTL
     void** tmp = (launchParams && launchParams->tempBuffer) ? launchParams->tempBuffer : c->tempBuffer;
     void** inb = (launchParams && launchParams->inputBuffer) ? launchParams->inputBuffer : c->inputBuffer;
     void** oub = (launchParams && launchParams->outputBuffer) ? launchParams->outputBuffer : c->outputBuffer;
+    void** ker = (launchParams && launchParams->kernel) ? launchParams->kernel : c->kernel;
+    b.kernel = ker ? *ker : 0;
     b.buffer = buf ? *buf : 0;
     b.temp_buffer = tmp ? *tmp : 0;
     b.input_buffer = inb ? *inb : 0;
@@ -313,7 +321,9 @@ static inline VkFFTResult VkFFTAppend(VkFFTApplication* app, int inverse, VkFFTL
     if (c->specifyOffsetsAtLaunch && launchParams) {
         b.buffer_offset = launchParams->bufferOffset; b.temp_buffer_offset = launchParams->tempBufferOffset;
         b.input_buffer_offset = launchParams->inputBufferOffset; b.output_buffer_offset = launchParams->outputBufferOffset;
+        b.kernel_offset = launchParams->kernelOffset;
     } else {
+        b.kernel_offset = c->kernelOffset;
         b.buffer_offset = c->bufferOffset; b.temp_buffer_offset = c->tempBufferOffset;
         b.input_buffer_offset = c->inputBufferOffset; b.output_buffer_offset = c->outputBufferOffset;
     }

@@ -64,7 +64,10 @@ class Desc(ctypes.Structure):
         ("buffer_stride", ctypes.c_uint64 * 4), ("input_stride", ctypes.c_uint64 * 4), ("output_stride", ctypes.c_uint64 * 4),
         ("omit_dimension", ctypes.c_uint32 * 4), ("buffer_size", ctypes.c_uint64), ("temp_buffer_size", ctypes.c_uint64),
         ("device", ctypes.c_int32), ("reserved0", ctypes.c_uint32), ("stream", ctypes.c_void_p),
-        ("dist_world", ctypes.c_uint32), ("dist_rank", ctypes.c_uint32), ("reserved", ctypes.c_uint64 * 7),
+        ("dist_world", ctypes.c_uint32), ("dist_rank", ctypes.c_uint32),
+        ("perform_convolution", ctypes.c_uint32), ("kernel_convolution", ctypes.c_uint32), ("matrix_convolution", ctypes.c_uint32),
+        ("symmetric_kernel", ctypes.c_uint32), ("number_kernels", ctypes.c_uint32), ("conjugate_convolution", ctypes.c_uint32),
+        ("cross_power_spectrum_normalization", ctypes.c_uint32), ("reserved1", ctypes.c_uint32), ("reserved", ctypes.c_uint64 * 3),
     ]
 
 
@@ -85,8 +88,9 @@ def make_desc(shape_xyz, batches=1, prec=0, **kw):
     return d
 
 
-def exec_plan(desc, inverse, buffer, inp=None, out=None):
+def exec_plan(desc, inverse, buffer, inp=None, out=None, kernel=None):
     L = lib()
+    L.emu_set_kernel(kernel.ctypes.data_as(ctypes.c_void_p) if kernel is not None else None)
     L.emu_exec_plan.restype = ctypes.c_int
     npass = ctypes.c_int(0)
     vp = lambda a: a.ctypes.data_as(ctypes.c_void_p) if a is not None else None

@@ -65,6 +65,9 @@ extern "C" int emu_run_pass(int kind, int prec, int n, int inv, int ops, int var
 
 // Execute a whole plan (planner.cpp + emulated kernels) on host memory.  bufs[ROLE_*] are host pointers;
 // the temp buffer is allocated here.  Returns the planner's VkFFTResult code.
+static void* g_emu_kernel = nullptr;
+extern "C" void emu_set_kernel(void* k) { g_emu_kernel = k; }
+
 static int emu_run_one(PlanGraph& g, PassPlan& pp, void* const* base) {
     const size_t esz = g.prec == B2_PREC_F64 ? 16 : 8;
     b2_pass_params P = pp.P;
@@ -89,6 +92,7 @@ static int emu_run_one(PlanGraph& g, PassPlan& pp, void* const* base) {
         if (g.prec == B2_PREC_F32) { a1f = make_aux<float>(a.kind, a.a, a.b); P.aux1 = a1f.data(); }
         else { a1d = make_aux<double>(a.kind, a.a, a.b); P.aux1 = a1d.data(); }
     }
+    if (pp.aux0_role == ROLE_KERNEL) P.aux0 = g_emu_kernel;
     P.in = (const unsigned char*)base[pp.in_role] + pp.in_off * (pp.in_scalar ? esz / 2 : esz);
     P.out = (unsigned char*)base[pp.out_role] + pp.out_off * (pp.out_scalar ? esz / 2 : esz);
     return pp.k->launch(&P, pp.grid, nullptr) ? 4039 : 0;
@@ -99,9 +103,11 @@ extern "C" int emu_exec_plan(const b200fft_desc* d, int inverse, void* buffer, v
     PlanGraph g;
     int rc = build_plan(*d, g);
     if (rc != 0) return rc;
+    if (inverse == 1 && !g.has_inv) return R_ONLY_FORWARD;      // same checks as b200fft_exec
+    if (inverse != 1 && !g.has_fwd) return R_ONLY_INVERSE;
     const size_t esz = g.prec == B2_PREC_F64 ? 16 : 8;
     std::vector<unsigned char> temp(g.temp_elems * esz + 16);
-    void* base[ROLE_COUNT] = {buffer, temp.data(), input, output};
+    void* base[ROLE_COUNT] = {buffer, temp.data(), input, output, g_emu_kernel};
     std::vector<PassPlan>& list = (inverse == 1) ? g.inv : g.fwd;
     if (npasses) *npasses = (int)list.size();
     for (PassPlan& pp : list)
@@ -117,7 +123,7 @@ extern "C" int emu_exec_plan_pass(const b200fft_desc* d, int inverse, void* buff
     PlanGraph g;
     int rc = build_plan(*d, g);
     if (rc != 0) return rc;
-    void* base[ROLE_COUNT] = {buffer, temp, nullptr, nullptr};
+    void* base[ROLE_COUNT] = {buffer, temp, nullptr, nullptr, g_emu_kernel};
     std::vector<PassPlan>& list = (inverse == 1) ? g.inv : g.fwd;
     if (npasses) *npasses = (int)list.size();
     if (sync_before)
@@ -133,7 +139,7 @@ extern "C" int emu_describe(const b200fft_desc* d, int inverse, char* dst, int c
     int rc = build_plan(*d, g);
     if (rc != 0) return rc;
     std::string s;
-    static const char* role[] = {"buffer", "temp", "input", "output"};
+    static const char* role[] = {"buffer", "temp", "input", "output", "kernel"};
     for (const PassPlan& pp : (inverse == 1 ? g.inv : g.fwd))
         s += pp.note + "  " + role[pp.in_role] + " -> " + role[pp.out_role] + (pp.sync_before ? "  [barrier before]" : "") + "\n";
     snprintf(dst, cap, "%s", s.c_str());

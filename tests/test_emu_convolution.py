@@ -1,0 +1,114 @@
+"""CPU: performConvolution plans (forward transform -> product with the kernel spectrum -> inverse transform behind one
+VkFFTAppend(app, -1)) on the kernel-body emulation, against numpy.  Mirrors the reference's samples 50-52
+(benchmark_scripts/vkFFT_scripts/src/sample_50/51/52_convolution_*.cpp) with random kernels instead of identities."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+import emu  # noqa: E402
+
+T32 = 2e-6
+
+
+def _rel(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+def _rand(shape, seed, cplx=True):
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(-1, 1, shape)
+    return (x + 1j * rng.uniform(-1, 1, shape)).astype(np.complex64) if cplx else x.astype(np.float32)
+
+
+@pytest.mark.parametrize("shape", [(256,), (48, 20), (16, 8, 12), (1 << 13,)])
+def test_per_feature_convolution_c2c(shape):
+    """coordinateFeatures = 2, 1x1 product per feature, two batches sharing the kernel"""
+    C, B = 2, 2
+    env = {"B200FFT_MAX_SINGLE_PASS": "1024"} if shape == (1 << 13,) else {}
+    os.environ.update(env)
+    try:
+        nd = len(shape)
+        np_shape = tuple(reversed(shape))
+        axes = tuple(range(-nd, 0))
+        k = _rand((C,) + np_shape, 1)
+        x = _rand((B, C) + np_shape, 2)
+        # kernel application: a plain forward plan with the same layout (kernelConvolution = 1)
+        K = k.copy()
+        rc, _ = emu.exec_plan(emu.make_desc(shape, 1, 0, coordinate_features=C, kernel_convolution=1), -1, K)
+        assert rc == 0 and _rel(K, np.fft.fftn(k.astype(np.complex128), axes=axes)) < T32
+        buf = x.copy()
+        d = emu.make_desc(shape, B, 0, coordinate_features=C, perform_convolution=1, normalize=1)
+        rc, _ = emu.exec_plan(d, -1, buf, kernel=K)
+        assert rc == 0
+        ref = np.fft.ifftn(np.fft.fftn(x.astype(np.complex128), axes=axes) * np.fft.fftn(k.astype(np.complex128), axes=axes)[None], axes=axes)
+        assert _rel(buf, ref) < T32
+        assert emu.exec_plan(d, 1, buf, kernel=K)[0] == 1006      # a convolution application only runs "forward"
+    finally:
+        for key in env:
+            os.environ.pop(key, None)
+
+
+@pytest.mark.parametrize("M,sym", [(2, 0), (2, 1), (3, 0), (3, 1)])
+def test_matrix_vector_convolution(M, sym):
+    """sample 50: out_r = sum_c K_rc (*) in_c, kernel stored row-major (or as its upper triangle when symmetric)"""
+    n = 512
+    x = _rand((M, n), 3)
+    kfull = _rand((M, M, n), 4)
+    if sym:
+        for r in range(M):
+            for c in range(r):
+                kfull[r, c] = kfull[c, r]
+        planes = [kfull[r, c] for r in range(M) for c in range(r, M)]
+    else:
+        planes = [kfull[r, c] for r in range(M) for c in range(M)]
+    K = np.fft.fft(np.stack(planes).astype(np.complex128), axis=-1).astype(np.complex64)
+    buf = x.copy()
+    d = emu.make_desc((n,), 1, 0, coordinate_features=M, matrix_convolution=M, symmetric_kernel=sym, perform_convolution=1, normalize=1)
+    rc, _ = emu.exec_plan(d, -1, buf, kernel=K)
+    assert rc == 0
+    X = np.fft.fft(x.astype(np.complex128), axis=-1)
+    KK = np.fft.fft(kfull.astype(np.complex128), axis=-1)
+    ref = np.fft.ifft(np.einsum("rcf,cf->rf", KK, X), axis=-1)
+    assert _rel(buf, ref) < T32
+
+
+def test_one_input_many_kernels_r2c_out_of_place():
+    """sample 52: real input in its own unpadded buffer, numberKernels outputs in the padded R2C layout"""
+    nx, ny, C, NK = 32, 24, 2, 3
+    x = _rand((C, ny, nx), 5, cplx=False)
+    k = _rand((NK, C, ny, nx), 6, cplx=False)
+    K = np.fft.rfft2(k.astype(np.float64)).astype(np.complex64)                      # [NK][C][ny][nx/2+1]
+    buf = np.zeros((NK, C, ny, nx + 2), np.float32)
+    d = emu.make_desc((nx, ny), 1, 0, coordinate_features=C, perform_r2c=1, is_input_formatted=1, number_kernels=NK,
+                      perform_convolution=1, normalize=1)
+    rc, _ = emu.exec_plan(d, -1, buf, inp=x.copy(), kernel=K)
+    assert rc == 0
+    ref = np.fft.irfft2(np.fft.rfft2(x.astype(np.float64))[None] * np.fft.rfft2(k.astype(np.float64)), s=(ny, nx))
+    assert _rel(buf[..., :nx], ref) < T32
+
+
+def test_cross_correlation_and_phase_correlation():
+    n = 1024
+    x, k = _rand((n,), 7), _rand((n,), 8)
+    K = np.fft.fft(k.astype(np.complex128)).astype(np.complex64)
+    X = np.fft.fft(x.astype(np.complex128))
+    buf = x.copy()
+    rc, _ = emu.exec_plan(emu.make_desc((n,), 1, 0, perform_convolution=1, conjugate_convolution=2, normalize=1), -1, buf, kernel=K)
+    assert rc == 0 and _rel(buf, np.fft.ifft(X * np.conj(K))) < T32                  # cross-correlation
+    buf = x.copy()
+    rc, _ = emu.exec_plan(emu.make_desc((n,), 1, 0, perform_convolution=1, conjugate_convolution=1, normalize=1), -1, buf, kernel=K)
+    assert rc == 0 and _rel(buf, np.fft.ifft(np.conj(X) * K)) < T32
+    buf = x.copy()
+    d = emu.make_desc((n,), 1, 0, perform_convolution=1, conjugate_convolution=2, cross_power_spectrum_normalization=1, normalize=1)
+    rc, _ = emu.exec_plan(d, -1, buf, kernel=K)
+    P = X * np.conj(K)
+    assert rc == 0 and _rel(buf, np.fft.ifft(P / np.abs(P))) < 1e-5                  # phase correlation
+
+
+def test_convolution_rejects_what_the_reference_rejects():
+    buf = np.zeros(256, np.complex64)
+    assert emu.exec_plan(emu.make_desc((16, 16), 1, 0, perform_convolution=1, omit_dimension=[0, 1]), -1, buf, kernel=buf)[0] == 3005
+    assert emu.exec_plan(emu.make_desc((256,), 1, 0, perform_convolution=1, coordinate_features=2, matrix_convolution=3), -1, buf, kernel=buf)[0] == 3002

@@ -27,7 +27,10 @@ class b200fft_desc(ctypes.Structure):
         ("omit_dimension", ctypes.c_uint32 * MAX_DIMS), ("buffer_size", ctypes.c_uint64),
         ("temp_buffer_size", ctypes.c_uint64),
         ("device", ctypes.c_int32), ("reserved0", ctypes.c_uint32), ("stream", ctypes.c_void_p),
-        ("dist_world", ctypes.c_uint32), ("dist_rank", ctypes.c_uint32), ("reserved", ctypes.c_uint64 * 7),
+        ("dist_world", ctypes.c_uint32), ("dist_rank", ctypes.c_uint32),
+        ("perform_convolution", ctypes.c_uint32), ("kernel_convolution", ctypes.c_uint32), ("matrix_convolution", ctypes.c_uint32),
+        ("symmetric_kernel", ctypes.c_uint32), ("number_kernels", ctypes.c_uint32), ("conjugate_convolution", ctypes.c_uint32),
+        ("cross_power_spectrum_normalization", ctypes.c_uint32), ("reserved1", ctypes.c_uint32), ("reserved", ctypes.c_uint64 * 3),
     ]
 
 
@@ -38,6 +41,7 @@ class b200fft_buffers(ctypes.Structure):
         ("buffer_offset", ctypes.c_uint64), ("temp_buffer_offset", ctypes.c_uint64),
         ("input_buffer_offset", ctypes.c_uint64), ("output_buffer_offset", ctypes.c_uint64),
         ("stream", ctypes.c_void_p),
+        ("kernel", ctypes.c_void_p), ("kernel_offset", ctypes.c_uint64),
     ]
 
 

@@ -32,6 +32,7 @@ VKFFT_ERROR_EMPTY_buffer = 2004
 VKFFT_ERROR_EMPTY_tempBuffer = 2006
 VKFFT_ERROR_EMPTY_inputBuffer = 2008
 VKFFT_ERROR_EMPTY_outputBuffer = 2010
+VKFFT_ERROR_EMPTY_kernel = 2012
 VKFFT_ERROR_EMPTY_app = 2015
 VKFFT_ERROR_UNSUPPORTED_RADIX = 3001
 VKFFT_ERROR_UNSUPPORTED_FFT_LENGTH = 3002
@@ -95,8 +96,17 @@ class VkFFTConfiguration:
     specifyOffsetsAtLaunch: int = 0
     bufferSize: int = 0
     tempBufferSize: int = 0
-    # reference features outside the engine's scope: accepted here so that setting them fails like the C shim
+    # convolution / cross-correlation (API guide "Convolution parameters"): VkFFTAppend(app, -1) = FFT -> x kernel -> iFFT
     performConvolution: int = 0
+    kernelConvolution: int = 0
+    matrixConvolution: int = 0
+    symmetricKernel: int = 0
+    numberKernels: int = 0
+    conjugateConvolution: int = 0
+    crossPowerSpectrumNormalization: int = 0
+    kernel: Any = None
+    kernelOffset: int = 0
+    # reference features outside the engine's scope: accepted here so that setting them fails like the C shim
     halfPrecision: int = 0
     performZeropadding: List[int] = field(default_factory=list)
     # engine extension (no reference counterpart, the reference is single-device): one sequence over peer windows,
@@ -116,6 +126,8 @@ class VkFFTLaunchParams:
     inputBufferOffset: int = 0
     outputBufferOffset: int = 0
     stream: Optional[int] = None
+    kernel: Any = None
+    kernelOffset: int = 0
 
 
 class VkFFTApplication:
@@ -159,6 +171,13 @@ def _to_desc(cfg: VkFFTConfiguration) -> "_lib.b200fft_desc":
     d.stream = cfg.stream
     d.dist_world = cfg.distWorld
     d.dist_rank = cfg.distRank
+    d.perform_convolution = cfg.performConvolution
+    d.kernel_convolution = cfg.kernelConvolution
+    d.matrix_convolution = cfg.matrixConvolution
+    d.symmetric_kernel = cfg.symmetricKernel
+    d.number_kernels = cfg.numberKernels
+    d.conjugate_convolution = cfg.conjugateConvolution
+    d.cross_power_spectrum_normalization = cfg.crossPowerSpectrumNormalization
     return d
 
 
@@ -176,7 +195,7 @@ def initializeVkFFT(app: VkFFTApplication, inputLaunchConfiguration: VkFFTConfig
         return VKFFT_ERROR_FFTdim_GT_MAX_FFT_DIMENSIONS
     if not cfg.size or cfg.size[0] == 0:
         return VKFFT_ERROR_EMPTY_size
-    if cfg.performConvolution or cfg.halfPrecision or any(cfg.performZeropadding):
+    if cfg.halfPrecision or any(cfg.performZeropadding):
         return VKFFT_ERROR_UNSUPPORTED_FFT_LENGTH
     L = _lib.load()
     d = _to_desc(cfg)
@@ -207,6 +226,8 @@ def VkFFTAppend(app: VkFFTApplication, inverse: int, launchParams: Optional[VkFF
     b.input_buffer_offset = src.inputBufferOffset
     b.output_buffer_offset = src.outputBufferOffset
     b.stream = lp.stream
+    b.kernel = _ptr(lp.kernel if lp.kernel is not None else c.kernel)
+    b.kernel_offset = src.kernelOffset
     return _lib.load().b200fft_exec(app._plan, int(inverse), ctypes.byref(b))
 
 

@@ -4,6 +4,8 @@
 // of long even-length R2C / C2R (the reference's separate VkFFT_main_R2C kernel,
 // vkFFT_R2C_even_decomposition.h:40-241, launched at vkFFT_RunApp.h:205-231).
 #pragma once
+#include <math.h>
+
 #include "pass_params.h"
 #include "stockham.cuh"
 
@@ -11,7 +13,11 @@ namespace b200fft {
 
 enum { B2_EW_COPY_MUL = 0, B2_EW_R2C_POST = 1, B2_EW_C2R_PRE = 2,
        B2_EW_DCT2_POST_COLS = 3,   // long strided DCT-II: split + phase of rows (k, N-k); items = neighbouring columns
-       B2_EW_DCT3_PRE_COLS = 4 };  // long strided DCT-III: phase + merge of rows (k, N-k)
+       B2_EW_DCT3_PRE_COLS = 4,    // long strided DCT-III: phase + merge of rows (k, N-k)
+       B2_EW_CONV = 5 };           // convolution: spectrum (x) kernel, per feature or as a 2x2 / 3x3 matrix-vector product
+// B2_EW_CONV packs its options into aux_u0: bits 0-7 features per vector, 8-11 matrix size (0 = per-feature product),
+// 12 symmetric kernel, 13-14 conjugation (1 sequence, 2 kernel), 15 cross-power-spectrum normalisation; aux_u1 = kernels
+enum { B2_CONV_SYM = 1u << 12, B2_CONV_CONJ_SEQ = 1u << 13, B2_CONV_CONJ_KER = 1u << 14, B2_CONV_XPS = 1u << 15 };
 enum { B2_EW_THREADS = 256, B2_EW_PER_THREAD = 8 };
 
 template <typename T>
@@ -48,6 +54,56 @@ struct Elementwise {
                 if (do_scale) v = v * sc;
                 if (P.inner_inverse) v = swp(v);
                 out[(int64_t)j * P.out_es] = v;
+            }
+        } else if (P.load_io == B2_EW_CONV) {
+            // (vkFFT_Convolution.h:125 does this inside the last-axis kernel)  One thread = one frequency point j of
+            // input batch gl: every feature of the point is read before anything is written, so the product runs in place.
+            //   in_es / out_es = distance between feature planes of the buffer / of the kernel; in_gs = batch stride
+            const uint32_t C = P.aux_u0 & 0xff, M = (P.aux_u0 >> 8) & 0xf, NK = P.aux_u1 ? P.aux_u1 : 1;
+            const bool sym = (P.aux_u0 & B2_CONV_SYM) != 0, cseq = (P.aux_u0 & B2_CONV_CONJ_SEQ) != 0,
+                       cker = (P.aux_u0 & B2_CONV_CONJ_KER) != 0, xps = (P.aux_u0 & B2_CONV_XPS) != 0;
+            const X* __restrict__ ker = (const X*)P.aux0;
+            const uint32_t kplanes = M >= 2 ? (sym ? M * (M + 1) / 2 : M * M) : C;
+            auto finish = [&](X v) {
+                if (xps) {
+                    const T a = sqrt(v.x * v.x + v.y * v.y);
+                    if (a > T(0)) v = v * (T(1) / a);
+                }
+                return v;
+            };
+#pragma unroll 2
+            for (int i = 0; i < B2_EW_PER_THREAD; ++i) {
+                const uint32_t j = j0 + i * B2_EW_THREADS;
+                if (j >= P.n) break;
+                if (M >= 2) {
+                    X x[3];
+                    for (uint32_t c = 0; c < M; ++c) { x[c] = in[(int64_t)c * P.in_es + j]; if (cseq) x[c] = conj(x[c]); }
+                    for (uint32_t k = 0; k < NK; ++k) {
+                        const X* kk = ker + (int64_t)k * kplanes * P.out_es + j;
+                        for (uint32_t r = 0; r < M; ++r) {
+                            X acc = mk<T>(T(0), T(0));
+                            for (uint32_t c = 0; c < M; ++c) {
+                                uint32_t idx;
+                                if (sym) { const uint32_t a = r < c ? r : c, b = r < c ? c : r; idx = a * M - a * (a - 1) / 2 + (b - a); }
+                                else idx = r * M + c;
+                                X w = kk[(int64_t)idx * P.out_es];
+                                if (cker) w = conj(w);
+                                acc = acc + w * x[c];
+                            }
+                            out[(int64_t)k * P.out_gs + (int64_t)r * P.in_es + j] = finish(acc);
+                        }
+                    }
+                } else {
+                    for (uint32_t c = 0; c < C; ++c) {
+                        X xv = in[(int64_t)c * P.in_es + j];
+                        if (cseq) xv = conj(xv);
+                        for (uint32_t k = 0; k < NK; ++k) {
+                            X w = ker[(int64_t)(k * kplanes + c) * P.out_es + j];
+                            if (cker) w = conj(w);
+                            out[(int64_t)k * P.out_gs + (int64_t)c * P.in_es + j] = finish(w * xv);
+                        }
+                    }
+                }
             }
         } else if (P.load_io == B2_EW_DCT2_POST_COLS || P.load_io == B2_EW_DCT3_PRE_COLS) {
             // this CTA's "line" is row k = gl of a complex-view column block; its partner is row N-k (N = aux_u0);

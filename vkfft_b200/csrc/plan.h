@@ -31,6 +31,7 @@ enum {
     R_EMPTY_TEMPBUFFER = 2006,
     R_EMPTY_INPUTBUFFER = 2008,
     R_EMPTY_OUTPUTBUFFER = 2010,
+    R_EMPTY_KERNEL = 2012,
     R_EMPTY_APP = 2015,
     R_USER_TEMP_TOO_SMALL = 2016,
     R_UNSUPPORTED_RADIX = 3001,
@@ -45,7 +46,7 @@ enum {
     R_FAILED_TO_LAUNCH_KERNEL = 4039,
 };
 
-enum BufRole { ROLE_BUFFER = 0, ROLE_TEMP = 1, ROLE_INPUT = 2, ROLE_OUTPUT = 3, ROLE_COUNT = 4 };
+enum BufRole { ROLE_BUFFER = 0, ROLE_TEMP = 1, ROLE_INPUT = 2, ROLE_OUTPUT = 3, ROLE_KERNEL = 4, ROLE_COUNT = 5 };
 
 struct LutSpec {       // stage twiddles of one kernel schedule
     int prec;
@@ -72,6 +73,7 @@ struct PassPlan {
     int lut_id_unaligned = -1;   // stage twiddles of k_unaligned (its radix schedule may differ)
     int tw_id = -1;
     int aux0_id = -1, aux1_id = -1;
+    int aux0_role = -1;          // >= 0: aux0 is a caller buffer (the convolution kernel), not a plan-owned table
     bool sync_before = false;    // distributed plans: barrier over all ranks of the window before this launch
     bool in_scalar = false, out_scalar = false;   // offsets (and strides) of that side count scalars, not complex elements
     std::string note;            // human readable (plan_describe)

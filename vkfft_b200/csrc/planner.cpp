@@ -1245,6 +1245,44 @@ int build_plan(const b200fft_desc& din, PlanGraph& g) {
         return plan_direction_c2c(g, list, inv);
     };
     int rc;
+    if (d.perform_convolution) {
+        // forward transform -> product with the kernel spectrum -> inverse transform, all behind VkFFTAppend(app, -1)
+        // (vkFFT_RunApp.h:111-321 runs the same chain; the reference fuses the product into the last-axis kernel,
+        // vkFFT_Convolution.h:125 -- here it is its own streaming launch)
+        const uint64_t C = d.coordinate_features, B = d.number_batches, NK = d.number_kernels ? d.number_kernels : 1;
+        const uint32_t M = d.matrix_convolution >= 2 ? d.matrix_convolution : 0;
+        if (d.perform_dct || d.perform_dst || d.is_output_formatted || d.dist_world > 1) return R_UNSUPPORTED_FFT_LENGTH;
+        for (uint32_t a = 0; a < d.fft_dim; ++a) if (d.omit_dimension[a]) return R_UNSUPPORTED_FFT_OMIT;
+        if (M > 3 || (M && C != M) || C > 255 || (NK > 1 && B > 1)) return R_UNSUPPORTED_FFT_LENGTH;
+        g.has_fwd = true; g.has_inv = false;
+        g.batches = B * C;
+        if ((rc = plan(g.fwd, 0)) != R_SUCCESS) return rc;
+        const uint64_t plane = d.buffer_stride[d.fft_dim - 1];
+        PassReq cv;
+        cv.elementwise = true; cv.ew_op = 5 /* B2_EW_CONV */;
+        cv.n = (int)std::min<uint64_t>(plane, 0x7fffffff); cv.ew_items = (uint32_t)plane;
+        if (plane > 0x7fffffffull) return R_UNSUPPORTED_FFT_LENGTH;
+        cv.in_es = cv.out_es = (int64_t)plane;
+        cv.aux_u0 = (uint32_t)C | (M << 8) | (d.symmetric_kernel ? (1u << 12) : 0) | (d.conjugate_convolution == 1 ? (1u << 13) : 0) |
+                    (d.conjugate_convolution == 2 ? (1u << 14) : 0) | (d.cross_power_spectrum_normalization ? (1u << 15) : 0);
+        cv.aux_u1 = (uint32_t)NK;
+        cv.in_role = cv.out_role = ROLE_BUFFER;
+        cv.what = "convolution: spectrum x kernel";
+        if ((rc = emit_ew(g, g.fwd, cv, std::vector<Dim>{Dim{B, (int64_t)(C * plane), (int64_t)(C * plane)}})) != R_SUCCESS) return rc;
+        g.fwd.back().aux0_role = ROLE_KERNEL;
+        g.fwd.back().P.out_gs = (int64_t)(C * plane);     // kernel k writes output batch k (one input, NK outputs)
+        // the inverse runs in `buffer` on every output batch
+        b200fft_desc back = g.desc;
+        g.desc.is_input_formatted = 0; g.desc.inverse_return_to_input = 0;
+        g.batches = std::max(B, NK) * C;
+        std::vector<PassPlan> tail;
+        rc = plan(tail, 1);
+        g.desc = back;
+        if (rc != R_SUCCESS) return rc;
+        g.fwd.insert(g.fwd.end(), tail.begin(), tail.end());
+        g.total_elems = g.total_elems / B * std::max(B, NK);
+        return R_SUCCESS;
+    }
     if (g.has_fwd && (rc = plan(g.fwd, 0)) != R_SUCCESS) return rc;
     if (g.has_inv && (rc = plan(g.inv, 1)) != R_SUCCESS) return rc;
     if (d.user_temp_buffer && g.temp_elems * esz > d.temp_buffer_size && d.temp_buffer_size != 0)

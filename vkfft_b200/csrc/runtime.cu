@@ -179,8 +179,10 @@ static int exec_impl(b200fft_plan* p, int inverse, const b200fft_buffers* b, std
                                               : (unsigned char*)p->d_temp;
     base[ROLE_INPUT] = (unsigned char*)b->input_buffer + b->input_buffer_offset;
     base[ROLE_OUTPUT] = (unsigned char*)b->output_buffer + b->output_buffer_offset;
-    bool used[ROLE_COUNT] = {false, false, false, false};
-    for (const PassPlan& pp : list) { used[pp.in_role] = true; used[pp.out_role] = true; }
+    base[ROLE_KERNEL] = g.desc.perform_convolution ? (unsigned char*)b->kernel + b->kernel_offset : nullptr;
+    bool used[ROLE_COUNT] = {false, false, false, false, false};
+    for (const PassPlan& pp : list) { used[pp.in_role] = true; used[pp.out_role] = true; if (pp.aux0_role >= 0) used[pp.aux0_role] = true; }
+    if (used[ROLE_KERNEL] && !b->kernel) return R_EMPTY_KERNEL;
     if (used[ROLE_BUFFER] && !b->buffer) return R_EMPTY_BUFFER;
     if (used[ROLE_TEMP] && !(g.desc.user_temp_buffer ? b->temp_buffer : p->d_temp)) return R_EMPTY_TEMPBUFFER;
     if (used[ROLE_INPUT] && !b->input_buffer) return R_EMPTY_INPUTBUFFER;
@@ -209,6 +211,7 @@ static int exec_impl(b200fft_plan* p, int inverse, const b200fft_buffers* b, std
         P.out = base[pp.out_role] + pp.out_off * (int64_t)(pp.out_scalar ? esz / 2 : esz);
         if (pp.aux0_id >= 0) P.aux0 = p->d_auxs[pp.aux0_id];
         if (pp.aux1_id >= 0) P.aux1 = p->d_auxs[pp.aux1_id];
+        if (pp.aux0_role >= 0) P.aux0 = base[pp.aux0_role];
         P.lut = p->d_luts[pp.lut_id];
         if (pp.tw_id >= 0) {
             P.tw_hi = p->d_tws[pp.tw_id].hi;
@@ -258,7 +261,7 @@ extern "C" size_t b200fft_plan_describe(const b200fft_plan* p, int inverse, char
     if (!p || !dst || cap == 0) return 0;
     std::string s;
     const std::vector<PassPlan>& list = (inverse == 1) ? p->g.inv : p->g.fwd;
-    static const char* role[] = {"buffer", "temp", "input", "output"};
+    static const char* role[] = {"buffer", "temp", "input", "output", "kernel"};
     for (size_t i = 0; i < list.size(); ++i) {
         s += "pass " + std::to_string(i) + ": " + list[i].note + "  " + role[list[i].in_role] + " -> " +
              role[list[i].out_role] + "\n";
@@ -321,6 +324,7 @@ extern "C" const char* b200fft_error_string(int code) {
         case R_EMPTY_TEMPBUFFER: return "VKFFT_ERROR_EMPTY_tempBuffer";
         case R_EMPTY_INPUTBUFFER: return "VKFFT_ERROR_EMPTY_inputBuffer";
         case R_EMPTY_OUTPUTBUFFER: return "VKFFT_ERROR_EMPTY_outputBuffer";
+        case R_EMPTY_KERNEL: return "VKFFT_ERROR_EMPTY_kernel";
         case R_EMPTY_APP: return "VKFFT_ERROR_EMPTY_app";
         case R_USER_TEMP_TOO_SMALL: return "VKFFT_ERROR_INVALID_user_tempBuffer_too_small";
         case R_UNSUPPORTED_RADIX: return "VKFFT_ERROR_UNSUPPORTED_RADIX";

@@ -112,3 +112,45 @@ def test_convolution_rejects_what_the_reference_rejects():
     buf = np.zeros(256, np.complex64)
     assert emu.exec_plan(emu.make_desc((16, 16), 1, 0, perform_convolution=1, omit_dimension=[0, 1]), -1, buf, kernel=buf)[0] == 3005
     assert emu.exec_plan(emu.make_desc((256,), 1, 0, perform_convolution=1, coordinate_features=2, matrix_convolution=3), -1, buf, kernel=buf)[0] == 3002
+
+
+@pytest.mark.parametrize("n,prec", [(64, 0), (128, 0), (256, 0), (512, 0), (1024, 0), (2048, 0), (4096, 0), (8192, 0),
+                                    (64, 1), (256, 1), (512, 1), (1024, 1), (4096, 1)])
+def test_fused_convolution_single_launch(n, prec):
+    """1-D C2C with a palindromic schedule: FFT, kernel product and iFFT in ONE launch; same numbers as the three-launch chain"""
+    C, B = 3, 2
+    cdt = np.complex64 if prec == 0 else np.complex128
+    k = _rand((C, n), 11).astype(cdt)
+    x = _rand((B, C, n), 12).astype(cdt)
+    K = np.fft.fft(k.astype(np.complex128), axis=-1).astype(cdt)
+    d = emu.make_desc((n,), B, prec, coordinate_features=C, perform_convolution=1, normalize=1)
+    assert "fused convolution" in emu.describe(d, -1)[1]
+    buf = x.copy()
+    rc, npass = emu.exec_plan(d, -1, buf, kernel=K)
+    assert rc == 0 and npass == 1
+    ref = np.fft.ifft(np.fft.fft(x.astype(np.complex128), axis=-1) * K.astype(np.complex128)[None], axis=-1)
+    assert _rel(buf, ref) < (T32 if prec == 0 else 1e-13)
+    os.environ["B200FFT_NO_FUSED_CONV"] = "1"
+    try:
+        chain = x.copy()
+        rc, npass3 = emu.exec_plan(d, -1, chain, kernel=K)
+    finally:
+        os.environ.pop("B200FFT_NO_FUSED_CONV")
+    assert rc == 0 and npass3 == 3 and _rel(buf, chain) < (T32 if prec == 0 else 1e-13)
+
+
+def test_fused_convolution_options_and_ragged_lines():
+    n, C, B = 1024, 1, 5          # 5 lines, 4 per CTA: the last CTA is ragged
+    x, k = _rand((B, C, n), 13), _rand((C, n), 14)
+    K = np.fft.fft(k.astype(np.complex128), axis=-1).astype(np.complex64)
+    X = np.fft.fft(x.astype(np.complex128), axis=-1)
+    for conj, xps, ref in ((2, 0, X * np.conj(K)[None]), (1, 0, np.conj(X) * K[None]), (2, 1, None)):
+        buf = x.copy()
+        d = emu.make_desc((n,), B, 0, coordinate_features=C, perform_convolution=1, conjugate_convolution=conj,
+                          cross_power_spectrum_normalization=xps)          # no normalize: unnormalised inverse
+        rc, npass = emu.exec_plan(d, -1, buf, kernel=K)
+        assert rc == 0 and npass == 1
+        if ref is None:
+            P = X * np.conj(K.astype(np.complex128))[None]
+            ref = P / np.abs(P)
+        assert _rel(buf, np.fft.ifft(ref, axis=-1) * n) < 1e-5

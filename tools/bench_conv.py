@@ -1,0 +1,36 @@
+#!/usr/bin/env python3
+"""1-D convolution (performConvolution) on a 2 GiB buffer: fused single-launch plan vs the three-launch chain."""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import vkfft_b200 as vk
+
+PEAK = 6575.4
+for n in (256, 1024, 4096, 8192):
+    batch = (1 << 28) // n
+    buf = torch.zeros(batch, n, dtype=torch.complex64, device="cuda")
+    torch.view_as_real(buf).uniform_(-1, 1)
+    ker = torch.fft.fft(torch.randn(1, n, dtype=torch.complex64, device="cuda"))
+    res = {}
+    for mode in ("fused", "chain"):
+        if mode == "chain":
+            os.environ["B200FFT_NO_FUSED_CONV"] = "1"
+        else:
+            os.environ.pop("B200FFT_NO_FUSED_CONV", None)
+        app = vk.VkFFTApplication()
+        assert vk.initializeVkFFT(app, vk.VkFFTConfiguration(FFTdim=1, size=[n], numberBatches=batch, device=0, performConvolution=1, normalize=1)) == 0
+        lp = vk.VkFFTLaunchParams(buffer=buf, kernel=ker)
+        for _ in range(3):
+            assert vk.VkFFTAppend(app, -1, lp) == 0
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            vk.VkFFTAppend(app, -1, lp)
+        b.record(); torch.cuda.synchronize()
+        res[mode] = a.elapsed_time(b) / 10
+        res[mode + "_launches"] = vk.planInfo(app)["num_passes_forward"]
+        vk.deleteVkFFT(app)
+    os.environ.pop("B200FFT_NO_FUSED_CONV", None)
+    res.update(n=n, fused_frac_of_copy_peak=round(2 * buf.numel() * 8 / (res["fused"] * 1e-3) / 1e9 / PEAK, 3))
+    print(json.dumps(res), flush=True)

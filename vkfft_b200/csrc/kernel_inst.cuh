@@ -132,7 +132,7 @@ struct Registrar {
     using KT = KindTraits<KIND>;
     using Sch = RList<Rs...>;
     static constexpr int RMODE = (OPS & B2_OP_REAL_EVEN) ? (INV ? 2 : 1)
-                               : ((OPS & B2_OP_DCT23) ? (INV ? 4 : 3) : ((OPS & B2_OP_PERM_IN) ? 5 : ((OPS & B2_OP_PERM_OUT) ? 6 : ((OPS & B2_OP_BLUESTEIN) ? (INV ? 8 : 7) : 0))));
+                               : ((OPS & B2_OP_DCT23) ? (INV ? 4 : 3) : ((OPS & B2_OP_PERM_IN) ? 5 : ((OPS & B2_OP_PERM_OUT) ? 6 : ((OPS & B2_OP_BLUESTEIN) ? (INV ? 8 : 7) : ((OPS & B2_OP_CONV) ? 9 : 0)))));
     using C = KCfg<T, Sch, TPL, Q, V, KT::LMAP, KT::SMAP, KT::LAYOUT, INV, (OPS & B2_OP_TWIDDLE_OUT), KT::IN_UNIT, KT::OUT_UNIT,
                    MINB, RMODE>;
     b2_kernel_info info;
@@ -303,6 +303,22 @@ struct MaybeBlue<true, T, TPL, Q, V, MINB, Rs...> {
 #define B2_KB(shard, T, TPL, Q, V, MINB, ...)                                                              \
     static ::b200fft::MaybeBlue<B2_SHARD_ON(shard), T, TPL, Q, V, MINB, __VA_ARGS__>                      \
         B2_CAT(b2_regb_, __COUNTER__)("BLUESTEIN_ROWS<" #T "," #TPL "x" #Q ",V" #V ";" #__VA_ARGS__ ">");
+
+// fused convolution (forward transform, kernel product, inverse transform in one launch) on a palindromic schedule
+namespace b200fft {
+template <bool EN, typename T, int TPL, int Q, int V, int MINB, int... Rs>
+struct MaybeConv {
+    explicit MaybeConv(const char*) {}
+};
+template <typename T, int TPL, int Q, int V, int MINB, int... Rs>
+struct MaybeConv<true, T, TPL, Q, V, MINB, Rs...> {
+    Registrar<B2_KIND_ROWS, T, TPL, Q, V, MINB, false, B2_OP_CONV, Rs...> a;
+    explicit MaybeConv(const char* n) : a(n) {}
+};
+}  // namespace b200fft
+#define B2_KC(shard, T, TPL, Q, V, MINB, ...)                                                              \
+    static ::b200fft::MaybeConv<B2_SHARD_ON(shard), T, TPL, Q, V, MINB, __VA_ARGS__>                      \
+        B2_CAT(b2_regc_, __COUNTER__)("CONV_ROWS<" #T "," #TPL "x" #Q ",V" #V ";" #__VA_ARGS__ ">");
 
 #define B2_KD(shard, KIND, T, TPL, Q, V, MINB, ...)                                                       \
     static ::b200fft::MaybeDct<B2_SHARD_ON(shard), B2_KIND_##KIND, T, TPL, Q, V, MINB, __VA_ARGS__>       \

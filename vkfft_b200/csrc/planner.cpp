@@ -151,7 +151,7 @@ int emit(PlanGraph& g, std::vector<PassPlan>& list, const PassReq& rq) {
     const bool plain = !rq.force_generic && rq.load_io == B2_IO_C2C && rq.store_io == B2_IO_C2C &&
                        !(rq.ops & (B2_OP_MUL_IN | B2_OP_MUL_OUT)) &&
                        ((rq.in_len == 0 && rq.out_len == 0) || (rq.ops & B2_OP_BLUESTEIN)) && !rq.inner_inverse;
-    if (plain) k = b2_find_kernel(rq.kind, g.prec, rq.n, rq.inv, rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN | B2_OP_DCT23 | B2_OP_PERM_IN | B2_OP_PERM_OUT | B2_OP_BLUESTEIN));
+    if (plain) k = b2_find_kernel(rq.kind, g.prec, rq.n, rq.inv, rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN | B2_OP_DCT23 | B2_OP_PERM_IN | B2_OP_PERM_OUT | B2_OP_BLUESTEIN | B2_OP_CONV));
     std::vector<int> radices;
     bool generic = false;
     if (!k) {
@@ -220,12 +220,12 @@ int emit(PlanGraph& g, std::vector<PassPlan>& list, const PassReq& rq) {
         pp.k = k;
         if (k->pipelined) {   // TMA needs 16-byte aligned sources: keep the first non-pipelined kernel of the same key as a stand-in
             for (int v = 0; v < 16 && !pp.k_unaligned; ++v) {
-                const b2_kernel_info* alt = b2_find_kernel_variant(rq.kind, g.prec, rq.n, rq.inv, rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN | B2_OP_DCT23 | B2_OP_PERM_IN | B2_OP_PERM_OUT | B2_OP_BLUESTEIN), v);
+                const b2_kernel_info* alt = b2_find_kernel_variant(rq.kind, g.prec, rq.n, rq.inv, rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN | B2_OP_DCT23 | B2_OP_PERM_IN | B2_OP_PERM_OUT | B2_OP_BLUESTEIN | B2_OP_CONV), v);
                 if (alt && !alt->pipelined && alt->q == k->q) pp.k_unaligned = alt;
             }
             if (!pp.k_unaligned) {    // no drop-in with the same tile height: do not use the pipelined kernel at all
                 for (int v = 0; v < 16; ++v) {
-                    const b2_kernel_info* alt = b2_find_kernel_variant(rq.kind, g.prec, rq.n, rq.inv, rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN | B2_OP_DCT23 | B2_OP_PERM_IN | B2_OP_PERM_OUT | B2_OP_BLUESTEIN), v);
+                    const b2_kernel_info* alt = b2_find_kernel_variant(rq.kind, g.prec, rq.n, rq.inv, rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN | B2_OP_DCT23 | B2_OP_PERM_IN | B2_OP_PERM_OUT | B2_OP_BLUESTEIN | B2_OP_CONV), v);
                     if (alt && !alt->pipelined) { pp.k = k = alt; break; }
                 }
                 tpl = k->tpl; q = k->q;
@@ -1255,6 +1255,28 @@ int build_plan(const b200fft_desc& din, PlanGraph& g) {
         for (uint32_t a = 0; a < d.fft_dim; ++a) if (d.omit_dimension[a]) return R_UNSUPPORTED_FFT_OMIT;
         if (M > 3 || (M && C != M) || C > 255 || (NK > 1 && B > 1)) return R_UNSUPPORTED_FFT_LENGTH;
         g.has_fwd = true; g.has_inv = false;
+        // 1-D C2C, per-feature product, packed lines, a fused kernel for this length: one launch does everything
+        if (d.fft_dim == 1 && !d.perform_r2c && !M && NK == 1 && !d.is_input_formatted && d.buffer_stride[0] == d.size[0] &&
+            d.size[0] <= 0x7fffffff && !getenv("B200FFT_NO_FUSED_CONV")) {
+            const b2_kernel_info* ck = b2_find_kernel(B2_KIND_ROWS, g.prec, (int)d.size[0], 0, B2_OP_CONV);
+            if (ck) {
+                const uint64_t N = d.size[0];
+                PassReq f;
+                f.kind = B2_KIND_ROWS; f.n = (int)N; f.inv = 0;
+                f.ops = B2_OP_CONV | (d.normalize ? B2_OP_SCALE : 0);
+                f.scale = d.normalize ? 1.0 / (double)N : 1.0;
+                f.in_es = f.out_es = 1;
+                f.group = Dim{B * C, (int64_t)N, (int64_t)N};
+                f.aux_u0 = (uint32_t)C;
+                f.aux_u1 = (d.conjugate_convolution == 1 ? (1u << 13) : 0) | (d.conjugate_convolution == 2 ? (1u << 14) : 0) |
+                           (d.cross_power_spectrum_normalization ? (1u << 15) : 0);
+                f.in_role = f.out_role = ROLE_BUFFER;
+                f.what = "fused convolution (fft, kernel product, ifft)";
+                if ((rc = emit(g, g.fwd, f)) != R_SUCCESS) return rc;
+                g.fwd.back().aux0_role = ROLE_KERNEL;
+                return R_SUCCESS;
+            }
+        }
         g.batches = B * C;
         if ((rc = plan(g.fwd, 0)) != R_SUCCESS) return rc;
         const uint64_t plane = d.buffer_stride[d.fft_dim - 1];

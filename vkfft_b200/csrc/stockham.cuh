@@ -12,6 +12,8 @@
 // write is coalesced), all shapes are template constants (AOT for sm_100a, nothing is JIT-compiled), and the
 // inverse transform is the forward code with re/im swapped at the HBM boundary.
 #pragma once
+#include <math.h>
+
 #include "pass_params.h"
 #include "radix.cuh"
 
@@ -705,7 +707,70 @@ struct Engine {
 
         const X* __restrict__ rw = (const X*)P.aux0;   // e^{-2 pi i k/2n} for the fused real transforms
         const uint32_t psel = (P.tw_sel == 1 ? o0 : (P.tw_sel == 2 ? o1 : o2));   // n2 / k1 of the long strided DCT launches
-        if constexpr (C::RMODE == 4 && C::LAYOUT == LAY_LINE && B2_DCT3_STAGE_IN) {
+        if constexpr (C::RMODE == 9) {
+            // ---- fused convolution (vkFFT_Convolution.h:125 fuses the same three steps into the last-axis kernel) ----------
+            // forward transform; the last stage leaves element p = b + k*NB in the registers of the thread that would read
+            // exactly these legs for the first stage of another transform, because the schedule starts and ends with the
+            // same radix.  So: multiply by the kernel line in registers, swap re/im (inverse = swap, forward, swap) and run
+            // the stages again.  One HBM read and one write of the data for FFT -> product -> iFFT.
+            static_assert(Sch::r(0) == Sch::r(NS - 1), "fused convolution needs a schedule with equal first and last radix");
+            static_assert(C::LAYOUT == LAY_LINE && C::LMAP == C::SMAP && V == 1, "contiguous lines only");
+            constexpr int s = NS - 1, r = Sch::r(0), NB = nbut<0>(), BPT = bpt<0>();
+            const bool valid = gl < P.G;
+            const uint32_t flags = P.aux_u1;
+            const X* __restrict__ kline = (const X*)P.aux0 + (int64_t)(gl % (P.aux_u0 ? P.aux_u0 : 1)) * N;
+            X* out_line = (X*)P.out + obase_out + (int64_t)gl * P.out_gs;
+            X x[BPT * r];
+            load_global<0>(x, in_line, P.in_es, tl, valid);
+            compute<0>(x, lut, tl);
+            if constexpr (NS > 1) {
+                store_smem<0>(x, sm, ql, tl);
+                __syncthreads();
+                middle<1>(sm, lut, tid);
+                load_smem<s>(x, sm, ql, tl);
+                compute<s>(x, lut, tl);
+            }
+#pragma unroll
+            for (int m = 0; m < BPT; ++m) {
+                const int b = tl + m * TPL;
+#pragma unroll
+                for (int k = 0; k < r; ++k) {
+                    X w = mk<T>(T(1), T(0));
+                    if (valid && (!guarded<0>() || b < NB)) w = ld_lut(kline + b + k * NB);
+                    X a = x[m * r + k];
+                    if (flags & (1u << 13)) a = conj(a);      // B2_CONV_CONJ_SEQ
+                    if (flags & (1u << 14)) w = conj(w);      // B2_CONV_CONJ_KER
+                    a = a * w;
+                    if (flags & (1u << 15)) {                  // B2_CONV_XPS
+                        const T mag = sqrt(a.x * a.x + a.y * a.y);
+                        if (mag > T(0)) a = a * (T(1) / mag);
+                    }
+                    x[m * r + k] = swp(a);
+                }
+            }
+            compute<0>(x, lut, tl);
+            if constexpr (NS > 1) {
+                __syncthreads();       // every last-stage read of the forward transform is done
+                store_smem<0>(x, sm, ql, tl);
+                __syncthreads();
+                middle<1>(sm, lut, tid);
+                load_smem<s>(x, sm, ql, tl);
+                compute<s>(x, lut, tl);
+            }
+            const bool do_scale = (P.ops & B2_OP_SCALE) != 0;
+            const T sc = (T)P.scale;
+#pragma unroll
+            for (int m = 0; m < BPT; ++m) {
+                const int b = tl + m * TPL;
+                if (!valid || (guarded<0>() && b >= NB)) continue;
+#pragma unroll
+                for (int k = 0; k < r; ++k) {
+                    X a = swp(x[m * r + k]);
+                    if (do_scale) a = a * sc;
+                    out_line[b + k * NB] = a;
+                }
+            }
+        } else if constexpr (C::RMODE == 4 && C::LAYOUT == LAY_LINE && B2_DCT3_STAGE_IN) {
             // real lines staged through the tile (see stage_in_dct); every stage reads its legs from shared memory
             stage_in_dct(sm, P, obase_in, gl, ql, tl, gl < P.G);
             __syncthreads();

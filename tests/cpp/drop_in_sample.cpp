@@ -49,6 +49,41 @@ int main() {
             worst_inv = fmax(worst_inv, hypot(h[2 * (b * N + k)] - (k == S ? (double)N : 0.0), h[2 * (b * N + k) + 1]) / (double)N);
     deleteVkFFT(&app);
     cudaFree(buffer);
-    printf("forward max abs err %.3e, inverse max rel err %.3e, version %d\n", worst, worst_inv, VkFFTGetVersion());
-    return (worst < 2e-6 && worst_inv < 2e-6 && app.b200fftPlan == 0) ? 0 : 1;
+
+    // convolution, the call sequence of the reference's sample_50_convolution_VkFFT_single_1d_matrix.cpp:100-330:
+    // a kernel application transforms the kernel (here: a delta shifted by 5), the convolution application then does
+    // FFT -> product -> iFFT in one VkFFTAppend.  Convolving with a shifted delta is a circular shift.
+    const uint64_t M = 4096, C = 2, SH = 5;
+    std::vector<float> hk(2 * M * C, 0.f), hx(2 * M * C), hy(2 * M * C);
+    for (uint64_t c = 0; c < C; c++) hk[2 * (c * M + SH)] = 1.f;
+    for (uint64_t i = 0; i < M * C; i++) { hx[2 * i] = (float)(i % 8) - 3.5f; hx[2 * i + 1] = (float)(i % 4) - 1.5f; }
+    void *kernel = 0, *cbuf = 0;
+    if (cudaMalloc(&kernel, sizeof(float) * 2 * M * C) != cudaSuccess || cudaMalloc(&cbuf, sizeof(float) * 2 * M * C) != cudaSuccess) return 2;
+    cudaMemcpy(kernel, hk.data(), sizeof(float) * 2 * M * C, cudaMemcpyHostToDevice);
+    cudaMemcpy(cbuf, hx.data(), sizeof(float) * 2 * M * C, cudaMemcpyHostToDevice);
+    VkFFTConfiguration kcfg = {};
+    VkFFTApplication app_kernel = {}, app_conv = {};
+    kcfg.FFTdim = 1; kcfg.size[0] = M; kcfg.coordinateFeatures = C; kcfg.kernelConvolution = 1; kcfg.normalize = 1;
+    kcfg.device = &dev; kcfg.buffer = &kernel;
+    if ((res = initializeVkFFT(&app_kernel, kcfg)) != VKFFT_SUCCESS) { printf("kernel init: %s\n", getVkFFTErrorString(res)); return 1; }
+    if ((res = VkFFTAppend(&app_kernel, -1, 0)) != VKFFT_SUCCESS) { printf("kernel fft: %s\n", getVkFFTErrorString(res)); return 1; }
+    VkFFTConfiguration ccfg = kcfg;
+    ccfg.kernelConvolution = 0; ccfg.performConvolution = 1; ccfg.buffer = &cbuf; ccfg.kernel = &kernel;
+    if ((res = initializeVkFFT(&app_conv, ccfg)) != VKFFT_SUCCESS) { printf("conv init: %s\n", getVkFFTErrorString(res)); return 1; }
+    if ((res = VkFFTAppend(&app_conv, -1, 0)) != VKFFT_SUCCESS) { printf("conv: %s\n", getVkFFTErrorString(res)); return 1; }
+    cudaDeviceSynchronize();
+    cudaMemcpy(hy.data(), cbuf, sizeof(float) * 2 * M * C, cudaMemcpyDeviceToHost);
+    double worst_conv = 0;
+    for (uint64_t c = 0; c < C; c++)
+        for (uint64_t i = 0; i < M; i++) {
+            const uint64_t src = c * M + (i + M - SH) % M;
+            worst_conv = fmax(worst_conv, hypot(hy[2 * (c * M + i)] - hx[2 * src], hy[2 * (c * M + i) + 1] - hx[2 * src + 1]));
+        }
+    deleteVkFFT(&app_kernel);
+    deleteVkFFT(&app_conv);
+    cudaFree(kernel);
+    cudaFree(cbuf);
+    printf("forward max abs err %.3e, inverse max rel err %.3e, convolution max abs err %.3e, version %d\n", worst, worst_inv,
+           worst_conv, VkFFTGetVersion());
+    return (worst < 2e-6 && worst_inv < 2e-6 && worst_conv < 2e-5 && app.b200fftPlan == 0) ? 0 : 1;
 }

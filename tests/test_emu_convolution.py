@@ -154,3 +154,35 @@ def test_fused_convolution_options_and_ragged_lines():
             P = X * np.conj(K.astype(np.complex128))[None]
             ref = P / np.abs(P)
         assert _rel(buf, np.fft.ifft(ref, axis=-1) * n) < 1e-5
+
+
+@pytest.mark.parametrize("shape,r2c,prec", [((48, 64), 0, 0), ((20, 6, 256), 0, 0), ((64, 128), 1, 0), ((32, 8, 16), 1, 0), ((24, 512), 0, 1),
+                                            ((16, 2048), 0, 0), ((40, 8), 1, 1)])
+def test_fused_last_axis_of_nd_convolution(shape, r2c, prec):
+    """N-D: the last axis runs forward + product + inverse in one launch, the other axes keep their passes: 2*nd-1 launches"""
+    C, B = 2, 2
+    nd = len(shape)
+    np_shape = tuple(reversed(shape))
+    axes = tuple(range(-nd, 0))
+    tol = T32 if prec == 0 else 1e-13
+    rdt, cdt = (np.float32, np.complex64) if prec == 0 else (np.float64, np.complex128)
+    if r2c:
+        k = _rand((C,) + np_shape, 21, cplx=False).astype(rdt)
+        x = _rand((B, C) + np_shape, 22, cplx=False).astype(rdt)
+        K = np.fft.rfftn(k.astype(np.float64), axes=axes).astype(cdt)
+        buf = np.zeros((B, C) + np_shape[:-1] + (shape[0] + 2,), rdt)
+        buf[..., :shape[0]] = x
+        ref = np.fft.irfftn(np.fft.rfftn(x.astype(np.float64), axes=axes) * K.astype(np.complex128)[None], s=np_shape, axes=axes)
+    else:
+        k = _rand((C,) + np_shape, 21).astype(cdt)
+        x = _rand((B, C) + np_shape, 22).astype(cdt)
+        K = np.fft.fftn(k.astype(np.complex128), axes=axes).astype(cdt)
+        buf = x.copy()
+        ref = np.fft.ifftn(np.fft.fftn(x.astype(np.complex128), axes=axes) * K.astype(np.complex128)[None], axes=axes)
+    d = emu.make_desc(shape, B, prec, coordinate_features=C, perform_convolution=1, perform_r2c=r2c, normalize=1)
+    listing = emu.describe(d, -1)[1]
+    assert "fused convolution" in listing, listing
+    rc, npass = emu.exec_plan(d, -1, buf, kernel=K)
+    assert rc == 0 and npass == 2 * nd - 1, (npass, listing)
+    got = buf[..., :shape[0]] if r2c else buf
+    assert _rel(got, ref) < tol

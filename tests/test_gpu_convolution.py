@@ -38,7 +38,7 @@ def _run(torch, cfg_kw, buf_np, kernel_np, inp_np=None):
     return buf.cpu().numpy()
 
 
-@pytest.mark.parametrize("shape", [(4096,), (256, 64), (1 << 18,), (1000,)])
+@pytest.mark.parametrize("shape", [(4096,), (256, 64), (1 << 18,), (1000,), (48, 32, 256), (8192,), (20, 2048)])
 def test_convolution_c2c(torch_cuda, shape):
     import vkfft_b200 as vk
     torch = torch_cuda
@@ -73,6 +73,30 @@ def test_matrix_convolution_3x3_symmetric(torch_cuda):
     out = _run(torch_cuda, dict(FFTdim=1, size=[n], coordinateFeatures=M, matrixConvolution=M, symmetricKernel=1), x, K)
     ref = np.fft.ifft(np.einsum("rcf,cf->rf", np.fft.fft(kfull.astype(np.complex128), axis=-1), np.fft.fft(x.astype(np.complex128), axis=-1)), axis=-1)
     assert _rel(out, ref) < 2e-6
+
+
+@pytest.mark.parametrize("shape", [(64, 128), (256, 16, 64)])
+def test_convolution_r2c_fused_last_axis(torch_cuda, shape):
+    """padded in-place R2C layout; the last axis runs forward + product + inverse in one launch"""
+    import vkfft_b200 as vk
+    rng = np.random.default_rng(6)
+    C, B = 2, 3
+    np_shape = tuple(reversed(shape))
+    axes = tuple(range(-len(shape), 0))
+    x = rng.uniform(-1, 1, (B, C) + np_shape).astype(np.float32)
+    k = rng.uniform(-1, 1, (C,) + np_shape).astype(np.float32)
+    K = np.fft.rfftn(k.astype(np.float64), axes=axes).astype(np.complex64)
+    buf = np.zeros((B, C) + np_shape[:-1] + (shape[0] + 2,), np.float32)
+    buf[..., :shape[0]] = x
+    cfg = dict(FFTdim=len(shape), size=list(shape), coordinateFeatures=C, numberBatches=B, performR2C=1)
+    app = vk.VkFFTApplication()
+    assert vk.initializeVkFFT(app, vk.VkFFTConfiguration(device=0, performConvolution=1, normalize=1, **cfg)) == 0
+    info = vk.planInfo(app)
+    vk.deleteVkFFT(app)
+    assert "fused convolution" in info["forward"] and info["num_passes_forward"] == 2 * len(shape) - 1
+    out = _run(torch_cuda, cfg, buf, K)
+    ref = np.fft.irfftn(np.fft.rfftn(x.astype(np.float64), axes=axes) * K.astype(np.complex128)[None], s=np_shape, axes=axes)
+    assert _rel(out[..., :shape[0]], ref) < 2e-6
 
 
 def test_one_input_many_kernels_r2c(torch_cuda):

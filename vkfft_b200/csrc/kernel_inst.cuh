@@ -315,7 +315,19 @@ struct MaybeConv<true, T, TPL, Q, V, MINB, Rs...> {
     Registrar<B2_KIND_ROWS, T, TPL, Q, V, MINB, false, B2_OP_CONV, Rs...> a;
     explicit MaybeConv(const char* n) : a(n) {}
 };
+template <bool EN, typename T, int TPL, int Q, int V, int MINB, int... Rs>
+struct MaybeConvCols {
+    explicit MaybeConvCols(const char*) {}
+};
+template <typename T, int TPL, int Q, int V, int MINB, int... Rs>
+struct MaybeConvCols<true, T, TPL, Q, V, MINB, Rs...> {
+    Registrar<B2_KIND_COLS, T, TPL, Q, V, MINB, false, B2_OP_CONV, Rs...> a;
+    explicit MaybeConvCols(const char* n) : a(n) {}
+};
 }  // namespace b200fft
+#define B2_KCC(shard, T, TPL, Q, V, MINB, ...)                                                             \
+    static ::b200fft::MaybeConvCols<B2_SHARD_ON(shard), T, TPL, Q, V, MINB, __VA_ARGS__>                  \
+        B2_CAT(b2_regcc_, __COUNTER__)("CONV_COLS<" #T "," #TPL "x" #Q ",V" #V ";" #__VA_ARGS__ ">");
 #define B2_KC(shard, T, TPL, Q, V, MINB, ...)                                                              \
     static ::b200fft::MaybeConv<B2_SHARD_ON(shard), T, TPL, Q, V, MINB, __VA_ARGS__>                      \
         B2_CAT(b2_regc_, __COUNTER__)("CONV_ROWS<" #T "," #TPL "x" #Q ",V" #V ";" #__VA_ARGS__ ">");

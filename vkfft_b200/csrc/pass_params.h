@@ -34,7 +34,7 @@ enum {
                              // chirp aux0 on load, filter aux1 on store); inverse kernel = second launch (chirp aux0 + truncation to
                              // out_len on store).  P.inverse selects the direction of the WHOLE transform at run time (outer re/im swap)
     B2_OP_CONV = 512,        // specialised kernels, contiguous lines: forward transform, product with the kernel line
-                             // (aux0, line index modulo aux_u0 features; aux_u1 = B2_CONV_* option bits of ew.cuh), inverse
+                             // (aux0, data offset modulo aux_u0 = features x plane elements; aux_u1 = B2_CONV_* option bits of ew.cuh), inverse
                              // transform, all in one launch -- needs a schedule whose first and last radix agree
     B2_OP_PERM_OUT = 128,    // strided Four-Step last launch of a long DCT-III: result k1 + N1*p is scattered to row makhoul(k)
                              // (aux_u0 = full length, aux_u1 = N1, k1 = coordinate tw_sel)

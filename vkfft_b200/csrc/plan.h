@@ -95,6 +95,7 @@ struct PlanGraph {
     uint64_t temp_elems_real = 0;   // (unused placeholder for real-sized scratch accounting)
     double flops = 0;
     uint64_t algorithmic_bytes = 0;
+    int skip_axis = -1;          // convolution plans: this axis is transformed by the fused kernel, the direction planners leave it out
     bool distributed = false;    // desc.dist_world > 1: one more barrier follows the last launch of a direction
 };
 

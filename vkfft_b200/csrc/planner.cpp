@@ -395,6 +395,9 @@ struct C2CJob {
     int64_t in_base = 0, out_base = 0, tmp_base = 0;   // element offsets into the roles' buffers
     // distributed sequence: this plan covers rank `rank` of `world` (buffer and temp are peer windows, plan.h)
     uint32_t world = 1, rank = 0;
+    // fused convolution along this axis (single launch only): B2_OP_CONV + its operands
+    int extra_ops = 0;
+    uint32_t aux_u0 = 0, aux_u1 = 0;
 };
 
 // keep rank `rank`'s share of dimension d (contiguous block of d.n/world coordinates); returns the first coordinate
@@ -600,6 +603,10 @@ int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
         if (kk && kk->q < 8 && N >= 2048) poor_strided = true;
     }
     bool try_single = !dist && N <= max_single_env() && single_ok(g, kind, N, 0);
+    if (job.extra_ops & B2_OP_CONV) {
+        if (!b2_find_kernel(kind, g.prec, (int)std::min<uint64_t>(N, 0x7fffffff), 0, B2_OP_CONV)) return R_UNSUPPORTED_FFT_LENGTH;
+        try_single = true; poor_strided = false;
+    }
     if (try_single && poor_strided) {
         // only if a split exists
         bool can_split = false;
@@ -611,7 +618,8 @@ int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
     }
     if (try_single) {
         PassReq rq;
-        rq.kind = kind; rq.n = (int)N; rq.inv = job.inv; rq.ops = sc_ops;
+        rq.kind = kind; rq.n = (int)N; rq.inv = job.inv; rq.ops = sc_ops | job.extra_ops;
+        rq.aux_u0 = job.aux_u0; rq.aux_u1 = job.aux_u1;
         rq.in_es = job.es_in; rq.out_es = job.es_out;
         if (job.unit_lines) {
             // keep the unit-stride dimension as the grouped one
@@ -842,6 +850,7 @@ int plan_direction_c2c(PlanGraph& g, std::vector<PassPlan>& list, int inv) {
     double norm = 1.0;
     if (inv && d.normalize)
         for (uint32_t a : axes) norm /= (double)d.size[a];
+    axes.erase(std::remove_if(axes.begin(), axes.end(), [&](uint32_t a) { return (int)a == g.skip_axis; }), axes.end());
     // out-of-place plumbing (API guide :365-376): the first launch reads the formatted input, the last launch
     // writes the formatted output, everything in between lives in `buffer`.  The inverse mirrors the forward
     // data flow (outputBuffer -> ... -> buffer, or -> inputBuffer with inverseReturnToInputBuffer).
@@ -977,12 +986,12 @@ int plan_direction_r2c(PlanGraph& g, std::vector<PassPlan>& list, int inv) {
     if (!inv) {
         if ((rc = axis0_any(true, 1.0)) != R_SUCCESS) return rc;
         for (uint32_t a = 1; a < d.fft_dim; ++a) {
-            if (d.omit_dimension[a] || d.size[a] == 1) continue;
+            if (d.omit_dimension[a] || d.size[a] == 1 || (int)a == g.skip_axis) continue;
             if ((rc = plan_c2c_axis(g, list, csize, a, 0, buf, buf, 1.0)) != R_SUCCESS) return rc;
         }
     } else {
         for (uint32_t a = d.fft_dim; a-- > 1;) {
-            if (d.omit_dimension[a] || d.size[a] == 1) continue;
+            if (d.omit_dimension[a] || d.size[a] == 1 || (int)a == g.skip_axis) continue;
             if ((rc = plan_c2c_axis(g, list, csize, a, 1, buf, buf, 1.0)) != R_SUCCESS) return rc;
         }
         if ((rc = axis0_any(false, norm)) != R_SUCCESS) return rc;
@@ -1255,25 +1264,50 @@ int build_plan(const b200fft_desc& din, PlanGraph& g) {
         for (uint32_t a = 0; a < d.fft_dim; ++a) if (d.omit_dimension[a]) return R_UNSUPPORTED_FFT_OMIT;
         if (M > 3 || (M && C != M) || C > 255 || (NK > 1 && B > 1)) return R_UNSUPPORTED_FFT_LENGTH;
         g.has_fwd = true; g.has_inv = false;
-        // 1-D C2C, per-feature product, packed lines, a fused kernel for this length: one launch does everything
-        if (d.fft_dim == 1 && !d.perform_r2c && !M && NK == 1 && !d.is_input_formatted && d.buffer_stride[0] == d.size[0] &&
-            d.size[0] <= 0x7fffffff && !getenv("B200FFT_NO_FUSED_CONV")) {
-            const b2_kernel_info* ck = b2_find_kernel(B2_KIND_ROWS, g.prec, (int)d.size[0], 0, B2_OP_CONV);
-            if (ck) {
-                const uint64_t N = d.size[0];
-                PassReq f;
-                f.kind = B2_KIND_ROWS; f.n = (int)N; f.inv = 0;
-                f.ops = B2_OP_CONV | (d.normalize ? B2_OP_SCALE : 0);
-                f.scale = d.normalize ? 1.0 / (double)N : 1.0;
-                f.in_es = f.out_es = 1;
-                f.group = Dim{B * C, (int64_t)N, (int64_t)N};
-                f.aux_u0 = (uint32_t)C;
-                f.aux_u1 = (d.conjugate_convolution == 1 ? (1u << 13) : 0) | (d.conjugate_convolution == 2 ? (1u << 14) : 0) |
-                           (d.cross_power_spectrum_normalization ? (1u << 15) : 0);
-                f.in_role = f.out_role = ROLE_BUFFER;
-                f.what = "fused convolution (fft, kernel product, ifft)";
-                if ((rc = emit(g, g.fwd, f)) != R_SUCCESS) return rc;
+        // Fused last axis: per-feature product, one kernel set, packed layout, and a fused kernel for the length of the
+        // last transformed axis (contiguous lines in 1-D, strided axis otherwise).  That launch runs the axis forward,
+        // multiplies and runs it inverse; the remaining axes keep their ordinary forward / inverse passes around it.
+        {
+            const uint32_t la = d.fft_dim - 1;
+            bool packed = !d.is_output_formatted && (la > 0 || (!d.perform_r2c && !d.is_input_formatted));
+            uint64_t want = d.perform_r2c ? d.size[0] / 2 + 1 : d.size[0];
+            for (uint32_t a = 0; a < d.fft_dim && packed; ++a) { packed = d.buffer_stride[a] == want; want *= (a + 1 < d.fft_dim ? d.size[a + 1] : 1); }
+            const uint64_t plane = d.buffer_stride[la], KS = C * plane;
+            const int ckind = la == 0 ? B2_KIND_ROWS : B2_KIND_COLS;
+            if (packed && !M && NK == 1 && d.size[la] > 1 && d.size[la] <= 0x7fffffff && KS < (1ull << 32) && !getenv("B200FFT_NO_FUSED_CONV") &&
+                b2_find_kernel(ckind, g.prec, (int)d.size[la], 0, B2_OP_CONV)) {
+                g.batches = B * C;
+                g.skip_axis = (int)la;
+                if ((rc = plan(g.fwd, 0)) != R_SUCCESS) return rc;
+                uint64_t csize[B200FFT_MAX_DIMS];
+                for (int a = 0; a < B200FFT_MAX_DIMS; ++a) csize[a] = d.size[a];
+                if (d.perform_r2c) csize[0] = d.size[0] / 2 + 1;
+                const Layout bl = layout_of(ROLE_BUFFER, d.buffer_stride, d.fft_dim);
+                C2CJob job;
+                job.N = d.size[la]; job.inv = 0;
+                job.es_in = job.es_out = la == 0 ? 1 : (int64_t)bl.stride[la - 1];
+                job.lines = other_dims(g, csize, la, bl, bl);
+                job.unit_lines = (la != 0);
+                job.in_role = job.out_role = ROLE_BUFFER;
+                job.scale = 1.0;         // the inverse passes of the other axes (or this one, below) carry the normalisation
+                job.extra_ops = B2_OP_CONV;
+                job.aux_u0 = (uint32_t)KS;
+                job.aux_u1 = (d.conjugate_convolution == 1 ? (1u << 13) : 0) | (d.conjugate_convolution == 2 ? (1u << 14) : 0) |
+                             (d.cross_power_spectrum_normalization ? (1u << 15) : 0);
+                std::vector<PassPlan> tail;
+                b200fft_desc back = g.desc;
+                g.desc.is_input_formatted = 0; g.desc.inverse_return_to_input = 0;
+                rc = plan(tail, 1);
+                g.desc = back;
+                if (rc != R_SUCCESS) return rc;
+                // the direction planners put the whole 1/N on their last pass; with nothing left for them (1-D) the fused
+                // launch scales itself
+                if (tail.empty() && d.normalize) job.scale = 1.0 / (double)d.size[la];
+                if ((rc = plan_c2c(g, g.fwd, job)) != R_SUCCESS) return rc;
                 g.fwd.back().aux0_role = ROLE_KERNEL;
+                g.fwd.back().note = "fused convolution (fft, kernel product, ifft)  " + g.fwd.back().note;
+                g.fwd.insert(g.fwd.end(), tail.begin(), tail.end());
+                g.skip_axis = -1;
                 return R_SUCCESS;
             }
         }

@@ -714,11 +714,14 @@ struct Engine {
             // same radix.  So: multiply by the kernel line in registers, swap re/im (inverse = swap, forward, swap) and run
             // the stages again.  One HBM read and one write of the data for FFT -> product -> iFFT.
             static_assert(Sch::r(0) == Sch::r(NS - 1), "fused convolution needs a schedule with equal first and last radix");
-            static_assert(C::LAYOUT == LAY_LINE && C::LMAP == C::SMAP && V == 1, "contiguous lines only");
+            static_assert(C::LMAP == C::SMAP && V == 1, "same thread map on both sides");
             constexpr int s = NS - 1, r = Sch::r(0), NB = nbut<0>(), BPT = bpt<0>();
             const bool valid = gl < P.G;
             const uint32_t flags = P.aux_u1;
-            const X* __restrict__ kline = (const X*)P.aux0 + (int64_t)(gl % (P.aux_u0 ? P.aux_u0 : 1)) * N;
+            // kernel operand: same offsets as the data inside one block of aux_u0 elements (features x plane), shared by
+            // every batch -- a line never leaves its feature plane, so one modulo per line is enough
+            const int64_t es = C::IN_UNIT ? 1 : P.in_es;
+            const X* __restrict__ kline = (const X*)P.aux0 + (int64_t)((uint64_t)(obase_in + (int64_t)gl * P.in_gs) % (uint64_t)(P.aux_u0 ? P.aux_u0 : 1));
             X* out_line = (X*)P.out + obase_out + (int64_t)gl * P.out_gs;
             X x[BPT * r];
             load_global<0>(x, in_line, P.in_es, tl, valid);
@@ -736,7 +739,7 @@ struct Engine {
 #pragma unroll
                 for (int k = 0; k < r; ++k) {
                     X w = mk<T>(T(1), T(0));
-                    if (valid && (!guarded<0>() || b < NB)) w = ld_lut(kline + b + k * NB);
+                    if (valid && (!guarded<0>() || b < NB)) w = ld_lut(kline + (int64_t)(b + k * NB) * es);
                     X a = x[m * r + k];
                     if (flags & (1u << 13)) a = conj(a);      // B2_CONV_CONJ_SEQ
                     if (flags & (1u << 14)) w = conj(w);      // B2_CONV_CONJ_KER
@@ -767,7 +770,7 @@ struct Engine {
                 for (int k = 0; k < r; ++k) {
                     X a = swp(x[m * r + k]);
                     if (do_scale) a = a * sc;
-                    out_line[b + k * NB] = a;
+                    out_line[C::OUT_UNIT ? (int64_t)(b + k * NB) : (int64_t)(b + k * NB) * P.out_es] = a;
                 }
             }
         } else if constexpr (C::RMODE == 4 && C::LAYOUT == LAY_LINE && B2_DCT3_STAGE_IN) {

@@ -27,6 +27,7 @@ struct State {
     std::barrier<>* bar = nullptr;
     unsigned char* smem = nullptr;
     bool log = false;
+    bool launch_refused = false;             // set by launch() when the configuration exceeds the device limits
     std::vector<std::vector<SmemRec>> recs;  // per thread (block 0 only)
 };
 inline State& st() { static State s; return s; }
@@ -94,6 +95,8 @@ inline ConflictReport analyse(unsigned nthreads) {
 template <class F>
 inline void launch(unsigned grid, unsigned block, size_t smem_bytes, F&& f, bool log = false) {
     State& s = st();
+    // what cudaLaunchKernel would refuse on sm_100 (1024 threads, 227 KiB opt-in shared memory, 2^31-1 CTAs)
+    if (block == 0 || block > 1024 || smem_bytes > 232448 || grid == 0 || grid > 0x7fffffffu) { s.launch_refused = true; return; }
     s.blockDim = {block, 1, 1};
     s.gridDim = {grid, 1, 1};
     std::vector<unsigned char> smem(smem_bytes + 64);

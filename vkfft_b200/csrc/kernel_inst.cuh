@@ -41,12 +41,18 @@ template <> struct PrecOf<float> { static constexpr int value = B2_PREC_F32; };
 template <> struct PrecOf<double> { static constexpr int value = B2_PREC_F64; };
 
 #if defined(B2_EMU)
+// the emulation refuses what cudaLaunchKernel would refuse (block size, shared memory, grid): report it like a failed launch
+inline int emu_refused() {
+    const bool r = b2emu::st().launch_refused;
+    b2emu::st().launch_refused = false;
+    return r ? 1 : 0;
+}
 template <class C>
 int launch_impl(const b2_pass_params* P, unsigned grid, void*) {
     const b2_pass_params PP = *P;
     b2emu::launch(grid, C::THREADS, C::SMEM_BYTES, [&](unsigned char* sm) { Engine<C>::run(PP, sm); },
                   b2emu::st().log);
-    return 0;
+    return emu_refused();
 }
 template <class C> int prepare_impl() { return 0; }
 #else
@@ -73,7 +79,7 @@ int generic_launch(const b2_pass_params* P, unsigned grid, void*) {
     const b2_pass_params PP = *P;
     b2emu::launch(grid, PP.tpl * PP.q, generic_smem_bytes<T>(P), [&](unsigned char* sm) { Generic<T, RMAX>::run(PP, sm); },
                   b2emu::st().log);
-    return 0;
+    return emu_refused();
 }
 template <typename T, int RMAX> int generic_prepare() { return 0; }
 #else
@@ -106,7 +112,7 @@ template <typename T>
 int ew_launch(const b2_pass_params* P, unsigned grid, void*) {
     const b2_pass_params PP = *P;
     b2emu::launch(grid, B2_EW_THREADS, 0, [&](unsigned char*) { Elementwise<T>::run(PP); }, false);
-    return 0;
+    return emu_refused();
 }
 #else
 template <typename T>
@@ -158,7 +164,7 @@ int pipe_launch_impl(const b2_pass_params* P, unsigned grid, void*) {
     const unsigned g = grid < 3 ? grid : 3;       // few persistent CTAs so that the buffer ring wraps
     b2emu::launch(g, C::THREADS, PipeEngine<C, NBUF>::SMEM_BYTES, [&](unsigned char* sm) { PipeEngine<C, NBUF>::run(PP, sm); },
                   b2emu::st().log);
-    return 0;
+    return emu_refused();
 }
 template <class C, int NBUF> int pipe_prepare_impl() { return 0; }
 #else

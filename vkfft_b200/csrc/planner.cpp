@@ -890,7 +890,7 @@ int plan_direction_r2c(PlanGraph& g, std::vector<PassPlan>& list, int inv) {
     if (inv && d.normalize)
         for (uint32_t a = 0; a < d.fft_dim; ++a)
             if (!d.omit_dimension[a]) norm /= (double)d.size[a];
-    const bool even = (N0 % 2 == 0);
+    const bool even = (N0 % 2 == 0) && N0 > 2;   // N0 = 2 has no half-length transform: it takes the zero-imaginary path of the odd lengths
     const uint64_t n = even ? N0 / 2 : N0;
     const bool fused = n >= 2 && ((is_smooth(n) && generic_fits(g, n)) ||
                                   (even && b2_find_kernel(B2_KIND_ROWS, g.prec, (int)n, 0, B2_OP_REAL_EVEN) != nullptr));
@@ -1031,7 +1031,7 @@ int plan_direction_dct(PlanGraph& g, std::vector<PassPlan>& list, int inv) {
             case 3: n = N; rq.load_io = rq.store_io = B2_IO_DCT3; rq.aux0 = aux_for(g, AUX_DCT23, N); rq.real_pairs = true;
                     rq.inner_inverse = 1; break;
             case 4:
-                if (N % 2) {   // odd length: no half-length trick; phases around a zero-padded 2N-point transform
+                if (N % 2 || N == 2) {   // odd length (or N = 2): no half-length trick; phases around a zero-padded 2N-point transform
                     n = 2 * N; rq.load_io = rq.store_io = B2_IO_DCT4_ODD; rq.aux_u1 = (uint32_t)N;
                     rq.aux0 = aux_for(g, AUX_DCT4ODD_PRE, N); rq.aux1 = aux_for(g, AUX_DCT4ODD_POST, N); break;
                 }

@@ -22,7 +22,8 @@ CASES = [
     ("1D C2C FP32 N=1000 batch 2^18", (1000,), 1 << 18, False, {}, {}, False),
     ("1D C2C FP32 N=2187 batch 2^16", (2187,), 1 << 16, False, {}, {}, False),
     ("1D C2C FP32 N=509 (Bluestein) batch 2^18", (509,), 1 << 18, False, {}, {}, False),
-    ("1D C2C FP32 N=1088 (Rader 17) batch 2^17", (1088,), 1 << 17, False, {}, {}, False),
+    ("1D C2C FP32 N=1088 (17 x 64, prime-radix kernel) batch 2^17", (1088,), 1 << 17, False, {}, {}, False),
+    ("1D C2C FP32 N=2032 (16 x 127, Rader stage in the runtime-scheduled kernel) batch 2^16", (2032,), 1 << 16, False, {}, {}, False),
 ]
 
 

@@ -32,6 +32,11 @@ template <typename T, int R> B2_HD constexpr T wcos_r(int k) {
     else if constexpr (R == 14) return rc::wcos14<T>(k);
     else if constexpr (R == 15) return rc::wcos15<T>(k);
     else if constexpr (R == 16) return rc::wcos16<T>(k);
+    else if constexpr (R == 17) return rc::wcos17<T>(k);
+    else if constexpr (R == 19) return rc::wcos19<T>(k);
+    else if constexpr (R == 23) return rc::wcos23<T>(k);
+    else if constexpr (R == 29) return rc::wcos29<T>(k);
+    else if constexpr (R == 31) return rc::wcos31<T>(k);
     else return rc::wcos32<T>(k);
 }
 template <typename T, int R> B2_HD constexpr T wsin_r(int k) {
@@ -50,6 +55,11 @@ template <typename T, int R> B2_HD constexpr T wsin_r(int k) {
     else if constexpr (R == 14) return rc::wsin14<T>(k);
     else if constexpr (R == 15) return rc::wsin15<T>(k);
     else if constexpr (R == 16) return rc::wsin16<T>(k);
+    else if constexpr (R == 17) return rc::wsin17<T>(k);
+    else if constexpr (R == 19) return rc::wsin19<T>(k);
+    else if constexpr (R == 23) return rc::wsin23<T>(k);
+    else if constexpr (R == 29) return rc::wsin29<T>(k);
+    else if constexpr (R == 31) return rc::wsin31<T>(k);
     else return rc::wsin32<T>(k);
 }
 

@@ -162,3 +162,21 @@ def test_long_and_non_smooth_even_r2c(shape, b, prec):
 def test_unsupported_requests_return_reference_error_codes():
     assert emu.exec_plan(emu.make_desc((130,), 1, 0, perform_dst=1), -1, np.zeros(130, np.float32))[0] == 3004
     assert emu.exec_plan(emu.make_desc((131,), 1, 0, perform_dct=4), -1, np.zeros(131, np.float32))[0] == 3004   # 2N = 2*131: prime factor > 127
+
+
+@pytest.mark.parametrize("shape,b,prec", [((131,), 3, 0), ((263,), 2, 1), ((4391,), 2, 0), ((19683,), 1, 0), ((131, 6), 2, 0), ((139, 4, 3), 1, 1)])
+def test_odd_r2c_composed_with_a_c2c_plan(shape, b, prec):
+    """odd lengths the single-launch kernel cannot take (prime factor > 127, or too long): real -> complex scratch, C2C plan
+    (Bluestein / Four-Step), first n/2+1 points; inverse: Hermitian expansion, C2C, real part"""
+    rdt = np.float32 if prec == 0 else np.float64
+    cdt = np.complex64 if prec == 0 else np.complex128
+    tol = T32 if prec == 0 else T64
+    nx, H = shape[0], shape[0] // 2 + 1
+    x = orc.random_input((b,) + tuple(reversed(shape)), rdt, seed=sum(shape))
+    buf = np.zeros(x.shape[:-1] + (2 * H,), rdt)
+    buf[..., :nx] = x
+    d = emu.make_desc(shape, b, prec, perform_r2c=1, normalize=1)
+    assert emu.exec_plan(d, -1, buf)[0] == 0
+    assert orc.error_metrics(buf.view(cdt), orc.r2c(x, len(shape)))["l2_rel"] < tol
+    assert emu.exec_plan(d, 1, buf)[0] == 0
+    assert orc.error_metrics(buf[..., :nx], x)["l2_rel"] < tol

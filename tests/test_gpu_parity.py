@@ -174,7 +174,8 @@ def _run_plan(torch, arr, cfg, inverse):
 
 @pytest.mark.parametrize("shape,batch,double", [((64,), 7, False), ((4096,), 5, False), ((4096, 4096), 1, False),
                                                 ((30,), 3, True), ((15,), 3, False), ((128, 8, 4), 2, True),
-                                                ((1000, 6), 2, False), ((8192,), 3, False)])
+                                                ((1000, 6), 2, False), ((8192,), 3, False), ((131,), 3, False), ((4391,), 2, False),
+                                                ((263, 5), 2, True)])
 def test_r2c_c2r(gpu, shape, batch, double):
     import vkfft_b200 as vk
     rdt, cdt = (np.float64, np.complex128) if double else (np.float32, np.complex64)

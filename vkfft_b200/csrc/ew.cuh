@@ -14,7 +14,11 @@ namespace b200fft {
 enum { B2_EW_COPY_MUL = 0, B2_EW_R2C_POST = 1, B2_EW_C2R_PRE = 2,
        B2_EW_DCT2_POST_COLS = 3,   // long strided DCT-II: split + phase of rows (k, N-k); items = neighbouring columns
        B2_EW_DCT3_PRE_COLS = 4,    // long strided DCT-III: phase + merge of rows (k, N-k)
-       B2_EW_CONV = 5 };           // convolution: spectrum (x) kernel, per feature or as a 2x2 / 3x3 matrix-vector product
+       B2_EW_CONV = 5,             // convolution: spectrum (x) kernel, per feature or as a 2x2 / 3x3 matrix-vector product
+       // odd-length R2C / C2R of lengths the single-launch kernel cannot take (composed with a C2C plan on scratch):
+       B2_EW_REAL_TO_CPLX = 6,     // real line (scalar strides) -> complex line with zero imaginary part
+       B2_EW_HERM_EXPAND = 7,      // half spectrum (n/2+1 points) -> full spectrum of n points, X[n-k] = conj X[k]
+       B2_EW_CPLX_TO_REAL = 8 };   // real part of a complex line -> real line (scalar strides), optional scale
 // B2_EW_CONV packs its options into aux_u0: bits 0-7 features per vector, 8-11 matrix size (0 = per-feature product),
 // 12 symmetric kernel, 13-14 conjugation (1 sequence, 2 kernel), 15 cross-power-spectrum normalisation; aux_u1 = kernels
 enum { B2_CONV_SYM = 1u << 12, B2_CONV_CONJ_SEQ = 1u << 13, B2_CONV_CONJ_KER = 1u << 14, B2_CONV_XPS = 1u << 15 };
@@ -54,6 +58,27 @@ struct Elementwise {
                 if (do_scale) v = v * sc;
                 if (P.inner_inverse) v = swp(v);
                 out[(int64_t)j * P.out_es] = v;
+            }
+        } else if (P.load_io == B2_EW_REAL_TO_CPLX || P.load_io == B2_EW_CPLX_TO_REAL || P.load_io == B2_EW_HERM_EXPAND) {
+            // the real side is addressed in scalars: in_off / out_off were accumulated from scalar strides
+            const T* rin = (const T*)P.in + in_off;
+            T* rout = (T*)P.out + out_off;
+#pragma unroll
+            for (int i = 0; i < B2_EW_PER_THREAD; ++i) {
+                const uint32_t j = j0 + i * B2_EW_THREADS;
+                if (j >= P.n) break;
+                if (P.load_io == B2_EW_REAL_TO_CPLX) {
+                    out[j] = mk<T>(rin[(int64_t)j * P.in_es], T(0));
+                } else if (P.load_io == B2_EW_CPLX_TO_REAL) {
+                    T v = in[j].x;
+                    if (do_scale) v *= sc;
+                    rout[(int64_t)j * P.out_es] = v;
+                } else {
+                    // j runs over the n/2+1 stored points; P.aux_u0 = n
+                    const X v = in[j];
+                    out[j] = v;
+                    if (j != 0 && 2 * j != P.aux_u0) out[P.aux_u0 - j] = conj(v);
+                }
             }
         } else if (P.load_io == B2_EW_CONV) {
             // (vkFFT_Convolution.h:125 does this inside the last-axis kernel)  One thread = one frequency point j of

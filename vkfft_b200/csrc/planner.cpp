@@ -894,7 +894,8 @@ int plan_direction_r2c(PlanGraph& g, std::vector<PassPlan>& list, int inv) {
     const uint64_t n = even ? N0 / 2 : N0;
     const bool fused = n >= 2 && ((is_smooth(n) && generic_fits(g, n)) ||
                                   (even && b2_find_kernel(B2_KIND_ROWS, g.prec, (int)n, 0, B2_OP_REAL_EVEN) != nullptr));
-    if (!fused && (!even || n < 2)) return R_UNSUPPORTED_FFT_LENGTH_R2C;   // long / non-smooth odd lengths: not yet
+    const bool odd_composed = !fused && !even && n >= 3;   // long / non-smooth odd lengths: C2C plan on scratch + copy launches
+    if (!fused && !even && !odd_composed) return R_UNSUPPORTED_FFT_LENGTH_R2C;
 
     // real side of the axis-0 launch, in units of the pointer type the operator uses
     const bool real_ext = d.is_input_formatted && (!inv || d.inverse_return_to_input);
@@ -981,7 +982,56 @@ int plan_direction_r2c(PlanGraph& g, std::vector<PassPlan>& list, int inv) {
         job.inv = 1; job.in_role = ROLE_BUFFER; job.out_role = real_role; job.scale = scale;
         return plan_c2c(g, list, job);
     };
-    auto axis0_any = [&](bool forward, double scale) -> int { return fused ? axis0(forward, scale) : axis0_composed(forward, scale); };
+    // odd lengths the single-launch kernel cannot take (prime factors above 127, or too long for shared memory): the real
+    // lines are widened to complex lines in scratch, transformed by an ordinary C2C plan (Bluestein / Four-Step as needed)
+    // and the first n/2+1 points copied out; the inverse rebuilds the full Hermitian spectrum first.  Three extra streaming
+    // launches -- the reference's generated kernels read the real data directly (vkFFT_ReadWrite.h:411).
+    auto axis0_odd = [&](bool forward, double scale) -> int {
+        std::vector<Dim> r2t, t2t, t2c;   // real<->scratch, scratch<->scratch, scratch<->complex buffer line dims
+        uint64_t ts = N0, nlines = 1;
+        for (uint32_t a = 1; a <= d.fft_dim; ++a) {
+            const bool isb = (a == d.fft_dim);
+            const uint64_t cnt = isb ? g.batches : d.size[a];
+            const int64_t rs = (int64_t)(isb ? rbatch : rstride[a - 1]), cs = (int64_t)(isb ? buf.batch_stride : d.buffer_stride[a - 1]);
+            r2t.push_back(forward ? Dim{cnt, rs, (int64_t)ts} : Dim{cnt, (int64_t)ts, rs});
+            t2t.push_back(Dim{cnt, (int64_t)ts, (int64_t)ts});
+            t2c.push_back(forward ? Dim{cnt, (int64_t)ts, cs} : Dim{cnt, cs, (int64_t)ts});
+            ts *= cnt; nlines *= cnt;
+        }
+        const uint64_t region = nlines * N0;
+        g.temp_elems = std::max<uint64_t>(g.temp_elems, region);
+        PassReq ew;
+        ew.elementwise = true; ew.in_es = ew.out_es = 1;
+        C2CJob job;
+        job.N = N0; job.es_in = job.es_out = 1; job.lines = t2t; job.unit_lines = false;
+        job.in_role = job.out_role = ROLE_TEMP; job.tmp_base = (int64_t)region;
+        int r;
+        if (forward) {
+            ew.ew_op = 6; ew.n = (int)N0; ew.ew_items = (uint32_t)N0; ew.in_role = real_role; ew.out_role = ROLE_TEMP;
+            ew.what = "odd r2c: real -> complex scratch";
+            if ((r = emit_ew(g, list, ew, r2t)) != R_SUCCESS) return r;
+            list.back().in_scalar = true;
+            job.inv = 0; job.scale = 1.0;
+            if ((r = plan_c2c(g, list, job)) != R_SUCCESS) return r;
+            ew.ew_op = 0; ew.n = (int)H; ew.ew_items = (uint32_t)H; ew.in_len = ew.out_len = (uint32_t)H;
+            ew.in_role = ROLE_TEMP; ew.out_role = ROLE_BUFFER; ew.what = "odd r2c: first n/2+1 points";
+            return emit_ew(g, list, ew, t2c);
+        }
+        ew.ew_op = 7; ew.n = (int)H; ew.ew_items = (uint32_t)H; ew.aux_u0 = (uint32_t)N0; ew.in_role = ROLE_BUFFER; ew.out_role = ROLE_TEMP;
+        ew.what = "odd c2r: hermitian expansion";
+        if ((r = emit_ew(g, list, ew, t2c)) != R_SUCCESS) return r;
+        job.inv = 1; job.scale = 1.0;
+        if ((r = plan_c2c(g, list, job)) != R_SUCCESS) return r;
+        ew.ew_op = 8; ew.n = (int)N0; ew.ew_items = (uint32_t)N0; ew.aux_u0 = 0; ew.in_role = ROLE_TEMP; ew.out_role = real_role;
+        ew.ops = (scale != 1.0) ? B2_OP_SCALE : 0; ew.scale = scale;
+        ew.what = "odd c2r: real part";
+        if ((r = emit_ew(g, list, ew, r2t)) != R_SUCCESS) return r;
+        list.back().out_scalar = true;
+        return R_SUCCESS;
+    };
+    auto axis0_any = [&](bool forward, double scale) -> int {
+        return fused ? axis0(forward, scale) : (odd_composed ? axis0_odd(forward, scale) : axis0_composed(forward, scale));
+    };
     int rc;
     if (!inv) {
         if ((rc = axis0_any(true, 1.0)) != R_SUCCESS) return rc;

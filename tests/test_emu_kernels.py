@@ -91,7 +91,7 @@ def test_whole_plans_on_emulation(case):
 
 
 def test_planner_rejects_what_it_cannot_do():
-    d = emu.make_desc((130,), 1, 0, perform_dst=1)     # DST-I of 130 needs a 262 = 2*131 point transform: not built
+    d = emu.make_desc((130,), 1, 0, perform_dst=1, perform_dct=2)     # two real-to-real kinds at once
     rc, _ = emu.exec_plan(d, -1, np.zeros(130, np.float32))
     assert rc == 3004
     d = emu.make_desc((8,), 1, 0)

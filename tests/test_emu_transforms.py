@@ -159,9 +159,18 @@ def test_long_and_non_smooth_even_r2c(shape, b, prec):
     assert orc.error_metrics(buf[..., :nx], x.astype(np.float64) * np.prod(shape))["l2_rel"] < tol
 
 
-def test_unsupported_requests_return_reference_error_codes():
-    assert emu.exec_plan(emu.make_desc((130,), 1, 0, perform_dst=1), -1, np.zeros(130, np.float32))[0] == 3004
-    assert emu.exec_plan(emu.make_desc((131,), 1, 0, perform_dct=4), -1, np.zeros(131, np.float32))[0] == 3004   # 2N = 2*131: prime factor > 127
+def test_r2r_composed_with_a_c2c_plan_for_lengths_the_single_launch_kernel_cannot_take():
+    """transform lengths with a prime factor above 127 (DST-I 130 -> 262 = 2*131, DCT-IV 131 -> 262) or too long for one
+    shared-memory pass: operator load side, C2C plan on scratch, operator store side"""
+    import scipy.fft as sfft
+    rng = np.random.default_rng(3)
+    for mode, kind, n in (("dst", 1, 130), ("dct", 4, 131), ("dct", 2, 131), ("dct", 3, 262), ("dct", 1, 132), ("dst", 4, 139), ("dct", 2, 20000)):
+        x = rng.uniform(-1, 1, (2, n)).astype(np.float32)
+        buf = x.copy()
+        rc, npass = emu.exec_plan(emu.make_desc((n,), 2, 0, **{"perform_" + mode: kind}), -1, buf)
+        assert rc == 0 and npass >= 3, (mode, kind, n, rc, npass)
+        f = sfft.dst if mode == "dst" else sfft.dct
+        assert orc.error_metrics(buf, f(x.astype(np.float64), type=kind, axis=-1))["l2_rel"] < T32, (mode, kind, n)
 
 
 @pytest.mark.parametrize("shape,b,prec", [((131,), 3, 0), ((263,), 2, 1), ((4391,), 2, 0), ((19683,), 1, 0), ((131, 6), 2, 0), ((139, 4, 3), 1, 1)])

@@ -18,7 +18,11 @@ enum { B2_EW_COPY_MUL = 0, B2_EW_R2C_POST = 1, B2_EW_C2R_PRE = 2,
        // odd-length R2C / C2R of lengths the single-launch kernel cannot take (composed with a C2C plan on scratch):
        B2_EW_REAL_TO_CPLX = 6,     // real line (scalar strides) -> complex line with zero imaginary part
        B2_EW_HERM_EXPAND = 7,      // half spectrum (n/2+1 points) -> full spectrum of n points, X[n-k] = conj X[k]
-       B2_EW_CPLX_TO_REAL = 8 };   // real part of a complex line -> real line (scalar strides), optional scale
+       B2_EW_CPLX_TO_REAL = 8,     // real part of a complex line -> real line (scalar strides), optional scale
+       // DCT / DST of lengths the single-launch kernel cannot take: the operator's load side and store side as launches of
+       // their own around a C2C plan on scratch (one real line per complex line).  store_io = B2_IO_DCT1/2/3/DCT4_ODD/DST1,
+       // aux_u0 = logical real length N, aux_u1 = complex length, dst_flags as in generic.cuh
+       B2_EW_R2R_PRE = 9, B2_EW_R2R_POST = 10 };
 // B2_EW_CONV packs its options into aux_u0: bits 0-7 features per vector, 8-11 matrix size (0 = per-feature product),
 // 12 symmetric kernel, 13-14 conjugation (1 sequence, 2 kernel), 15 cross-power-spectrum normalisation; aux_u1 = kernels
 enum { B2_CONV_SYM = 1u << 12, B2_CONV_CONJ_SEQ = 1u << 13, B2_CONV_CONJ_KER = 1u << 14, B2_CONV_XPS = 1u << 15 };
@@ -78,6 +82,58 @@ struct Elementwise {
                     const X v = in[j];
                     out[j] = v;
                     if (j != 0 && 2 * j != P.aux_u0) out[P.aux_u0 - j] = conj(v);
+                }
+            }
+        } else if (P.load_io == B2_EW_R2R_PRE || P.load_io == B2_EW_R2R_POST) {
+            const T* rin = (const T*)P.in + in_off;       // real side in scalars
+            T* rout = (T*)P.out + out_off;
+            const int N = (int)P.aux_u0, nc = (int)P.aux_u1, type = (int)P.store_io;
+            const X* __restrict__ tab = (const X*)P.aux0;
+            auto mak = [&](int p2) { return (p2 < (nc + 1) / 2) ? 2 * p2 : 2 * (nc - 1 - p2) + 1; };
+            auto src_i = [&](int i2, int L) { return (P.dst_flags & B2_DST_REV_IN) ? L - 1 - i2 : i2; };
+            auto sg_in = [&](int i2) { return ((P.dst_flags & B2_DST_NEG_ODD_IN) && (i2 & 1)) ? T(-1) : T(1); };
+            auto dst_i = [&](int k2, int L) { return (P.dst_flags & B2_DST_REV_OUT) ? L - 1 - k2 : k2; };
+            auto sg_out = [&](int k2) { return ((P.dst_flags & B2_DST_ALT_OUT) && (k2 & 1)) ? T(-1) : T(1); };
+#pragma unroll 2
+            for (int i = 0; i < B2_EW_PER_THREAD; ++i) {
+                const int j = (int)(j0 + i * B2_EW_THREADS);
+                if ((uint32_t)j >= P.n) break;
+                if (P.load_io == B2_EW_R2R_PRE) {            // j runs over the nc complex points
+                    X v = mk<T>(T(0), T(0));
+                    if (type == B2_IO_DCT2) {
+                        const int sidx = mak(j);
+                        v.x = sg_in(sidx) * rin[(int64_t)src_i(sidx, N) * P.in_es];
+                    } else if (type == B2_IO_DCT3) {
+                        const T a0 = rin[(int64_t)src_i(j, N) * P.in_es];
+                        const T a1 = j == 0 ? T(0) : rin[(int64_t)src_i(N - j, N) * P.in_es];
+                        v = mulc(mk<T>(a0, -a1), ld_lut(tab + j));
+                    } else if (type == B2_IO_DCT1) {
+                        v.x = rin[(int64_t)(j < N ? j : nc - j) * P.in_es];
+                    } else if (type == B2_IO_DST1) {
+                        if (j != 0 && j != N + 1) v.x = (j <= N ? T(1) : T(-1)) * rin[(int64_t)(j <= N ? j - 1 : nc - j - 1) * P.in_es];
+                    } else {                                  // B2_IO_DCT4_ODD (any N)
+                        if (j < N) v = ld_lut(tab + j) * rin[(int64_t)src_i(j, N) * P.in_es];
+                    }
+                    out[j] = v;
+                } else {                                       // j runs over the N real outputs (DCT-III: over the nc points)
+                    T y;
+                    int o = j;
+                    if (type == B2_IO_DCT2) {
+                        const X a = in[j], b = conj(in[j == 0 ? 0 : nc - j]);
+                        y = (ld_lut(tab + j) * (a + b)).x;
+                        o = dst_i(j, N);
+                    } else if (type == B2_IO_DCT3) {
+                        o = mak(j);
+                        y = sg_out(o) * in[j].x;
+                    } else if (type == B2_IO_DCT1) {
+                        y = in[j].x;
+                    } else if (type == B2_IO_DST1) {
+                        y = -in[j + 1].y;
+                    } else {
+                        y = sg_out(j) * T(2) * (in[j] * ld_lut((const X*)P.aux1 + j)).x;
+                    }
+                    if (do_scale) y *= sc;
+                    rout[(int64_t)o * P.out_es] = y;
                 }
             }
         } else if (P.load_io == B2_EW_CONV) {

@@ -437,14 +437,14 @@ int emit_ew(PlanGraph& g, std::vector<PassPlan>& list, PassReq rq, const std::ve
     if (grid == 0 || grid > 0x7fffffffull) return R_UNSUPPORTED_FFT_LENGTH;
     pp.grid = (unsigned)grid;
     P.tpl = chunks;
-    P.n = rq.n; P.load_io = rq.ew_op; P.ops = rq.ops; P.scale = rq.scale;
+    P.n = rq.n; P.load_io = rq.ew_op; P.store_io = rq.store_io; P.dst_flags = rq.dst_flags; P.ops = rq.ops; P.scale = rq.scale;
     P.inverse = rq.inv; P.inner_inverse = rq.inner_inverse;
     P.in_len = rq.in_len; P.out_len = rq.out_len;
     P.aux_u0 = rq.aux_u0; P.aux_u1 = rq.aux_u1;
     pp.in_role = rq.in_role; pp.out_role = rq.out_role;
     pp.in_off = rq.in_base; pp.out_off = rq.out_base;
     pp.lut_id = lut_for(g, std::vector<int>{});
-    pp.aux0_id = rq.aux0;
+    pp.aux0_id = rq.aux0; pp.aux1_id = rq.aux1;
     char buf[200];
     snprintf(buf, sizeof buf, "%s elementwise op=%d items=%u grid=%u", rq.what, rq.ew_op, rq.ew_items, pp.grid);
     pp.note = buf;
@@ -1206,7 +1206,52 @@ int plan_direction_dct(PlanGraph& g, std::vector<PassPlan>& list, int inv) {
                 continue;
             }
         }
-        if (n < 2 || !is_smooth(n) || !generic_fits(g, n)) return R_UNSUPPORTED_FFT_LENGTH_R2R;
+        if (n < 2) return R_UNSUPPORTED_FFT_LENGTH_R2R;
+        if (!is_smooth(n) || !generic_fits(g, n)) {
+            // transform length with a prime factor above 127, or too long for one shared-memory pass: the operator's load
+            // and store sides become launches of their own around an ordinary C2C plan on scratch (one real line per
+            // complex line; DCT-IV always in its zero-padded 2N form here)
+            uint32_t dflags = 0;
+            if (is_dst) dflags = type == 2 ? (B2_DST_NEG_ODD_IN | B2_DST_REV_OUT) : ((type == 3 || type == 4) ? (B2_DST_REV_IN | B2_DST_ALT_OUT) : 0);
+            int io; uint64_t nc; int a0 = -1, a1 = -1;
+            switch (type) {
+                case 1: io = is_dst ? B2_IO_DST1 : B2_IO_DCT1; nc = is_dst ? 2 * N + 2 : 2 * N - 2; break;
+                case 2: io = B2_IO_DCT2; nc = N; a0 = aux_for(g, AUX_DCT23, N); break;
+                case 3: io = B2_IO_DCT3; nc = N; a0 = aux_for(g, AUX_DCT23, N); break;
+                default: io = B2_IO_DCT4_ODD; nc = 2 * N; a0 = aux_for(g, AUX_DCT4ODD_PRE, N); a1 = aux_for(g, AUX_DCT4ODD_POST, N); break;
+            }
+            if (nc > 0x7fffffffull) return R_UNSUPPORTED_FFT_LENGTH_R2R;
+            const int64_t es_r = axis == 0 ? 1 : (int64_t)buf.stride[axis - 1];
+            std::vector<Dim> real_lines = other_dims(g, d.size, axis, buf, buf), r2t, t2t, t2r;
+            uint64_t ts = nc, nlines = 1;
+            for (const Dim& rl : real_lines) {
+                r2t.push_back(Dim{rl.n, rl.is, (int64_t)ts});
+                t2t.push_back(Dim{rl.n, (int64_t)ts, (int64_t)ts});
+                t2r.push_back(Dim{rl.n, (int64_t)ts, rl.os});
+                ts *= rl.n; nlines *= rl.n;
+            }
+            const uint64_t region = nlines * nc;
+            g.temp_elems = std::max<uint64_t>(g.temp_elems, region);
+            PassReq ew;
+            ew.elementwise = true; ew.store_io = io; ew.dst_flags = dflags; ew.aux0 = a0; ew.aux1 = a1;
+            ew.aux_u0 = (uint32_t)N; ew.aux_u1 = (uint32_t)nc;
+            ew.ew_op = 9; ew.n = (int)nc; ew.ew_items = (uint32_t)nc; ew.in_es = es_r; ew.out_es = 1;
+            ew.in_role = ROLE_BUFFER; ew.out_role = ROLE_TEMP; ew.what = "r2r (composed): operator load side";
+            int rc2;
+            if ((rc2 = emit_ew(g, list, ew, r2t)) != R_SUCCESS) return rc2;
+            list.back().in_scalar = true;
+            C2CJob job;
+            job.N = nc; job.inv = (type == 3) ? 1 : 0; job.es_in = job.es_out = 1; job.lines = t2t; job.unit_lines = false;
+            job.in_role = job.out_role = ROLE_TEMP; job.tmp_base = (int64_t)region; job.scale = 1.0;
+            if ((rc2 = plan_c2c(g, list, job)) != R_SUCCESS) return rc2 == R_UNSUPPORTED_FFT_LENGTH ? R_UNSUPPORTED_FFT_LENGTH_R2R : rc2;
+            const uint64_t items = (type == 3) ? nc : N;
+            ew.ew_op = 10; ew.n = (int)items; ew.ew_items = (uint32_t)items; ew.in_es = 1; ew.out_es = es_r;
+            ew.in_role = ROLE_TEMP; ew.out_role = ROLE_BUFFER; ew.what = "r2r (composed): operator store side";
+            ew.ops = (scale != 1.0) ? B2_OP_SCALE : 0; ew.scale = scale;
+            if ((rc2 = emit_ew(g, list, ew, t2r)) != R_SUCCESS) return rc2;
+            list.back().out_scalar = true;
+            continue;
+        }
         if (is_dst) {   // sign / reversal wrappers (API guide :581-583)
             if (type == 2) rq.dst_flags = B2_DST_NEG_ODD_IN | B2_DST_REV_OUT;
             if (type == 3) rq.dst_flags = B2_DST_REV_IN | B2_DST_ALT_OUT;

@@ -78,6 +78,16 @@ typedef struct b200fft_desc {
     uint32_t cross_power_spectrum_normalization; /* crossPowerSpectrumNormalization */
     uint32_t reserved1;
     uint64_t reserved[3];
+    /* ---- fields added after the first release of the struct: only read when struct_size covers them ---- */
+    /* Zero padding (API guide "Zero padding parameters", :1786-1807): elements [zeropad_left, zeropad_right) of every line along
+     * a flagged axis count as zero on the first read of the forward transform (of the inverse one with frequency_zeropadding).
+     * The engine clears those ranges in `buffer` with a streaming launch before the transform and then runs the ordinary
+     * plan: same results as the reference, without its saving from skipped lines. */
+    uint32_t perform_zeropadding[B200FFT_MAX_DIMS];   /* performZeropadding[] */
+    uint64_t zeropad_left[B200FFT_MAX_DIMS];          /* fft_zeropad_left[] */
+    uint64_t zeropad_right[B200FFT_MAX_DIMS];         /* fft_zeropad_right[] */
+    uint32_t frequency_zeropadding;                   /* frequencyZeroPadding */
+    uint32_t reserved2[3];
 } b200fft_desc;
 
 /* Buffers for one execution == VkFFTLaunchParams (vkFFT_Structs.h:326-379) with plain pointers.

@@ -226,8 +226,6 @@ static inline VkFFTResult initializeVkFFT(VkFFTApplication* app, VkFFTConfigurat
     if (c->halfPrecision || c->halfPrecisionMemoryOnly || c->quadDoubleDoublePrecision ||
         c->quadDoubleDoublePrecisionDoubleMemory || c->doublePrecisionFloatMemory)
         return VKFFT_ERROR_UNSUPPORTED_FFT_LENGTH;
-    for (int i = 0; i < VKFFT_MAX_FFT_DIMENSIONS; i++)
-        if (c->performZeropadding[i]) return VKFFT_ERROR_UNSUPPORTED_FFT_LENGTH;
     if (c->bufferNum > 1 || c->tempBufferNum > 1 || c->inputBufferNum > 1 || c->outputBufferNum > 1)
         return VKFFT_ERROR_UNSUPPORTED_FFT_LENGTH;
     if (c->loadApplicationFromString && c->saveApplicationToString) return VKFFT_ERROR_ENABLED_saveApplicationToString;
@@ -243,7 +241,11 @@ static inline VkFFTResult initializeVkFFT(VkFFTApplication* app, VkFFTConfigurat
         d.input_stride[i] = c->inputBufferStride[i];
         d.output_stride[i] = c->outputBufferStride[i];
         d.omit_dimension[i] = (uint32_t)c->omitDimension[i];
+        d.perform_zeropadding[i] = (uint32_t)c->performZeropadding[i];
+        d.zeropad_left[i] = c->fft_zeropad_left[i];
+        d.zeropad_right[i] = c->fft_zeropad_right[i];
     }
+    d.frequency_zeropadding = (uint32_t)c->frequencyZeroPadding;
     d.number_batches = c->numberBatches;
     d.coordinate_features = c->coordinateFeatures;
     d.precision = c->doublePrecision ? B200FFT_F64 : B200FFT_F32;

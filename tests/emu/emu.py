@@ -68,6 +68,8 @@ class Desc(ctypes.Structure):
         ("perform_convolution", ctypes.c_uint32), ("kernel_convolution", ctypes.c_uint32), ("matrix_convolution", ctypes.c_uint32),
         ("symmetric_kernel", ctypes.c_uint32), ("number_kernels", ctypes.c_uint32), ("conjugate_convolution", ctypes.c_uint32),
         ("cross_power_spectrum_normalization", ctypes.c_uint32), ("reserved1", ctypes.c_uint32), ("reserved", ctypes.c_uint64 * 3),
+        ("perform_zeropadding", ctypes.c_uint32 * 4), ("zeropad_left", ctypes.c_uint64 * 4), ("zeropad_right", ctypes.c_uint64 * 4),
+        ("frequency_zeropadding", ctypes.c_uint32), ("reserved2", ctypes.c_uint32 * 3),
     ]
 
 

@@ -186,3 +186,21 @@ def test_fused_last_axis_of_nd_convolution(shape, r2c, prec):
     assert rc == 0 and npass == 2 * nd - 1, (npass, listing)
     got = buf[..., :shape[0]] if r2c else buf
     assert _rel(got, ref) < tol
+
+
+def test_zero_padded_convolution_like_sample_51():
+    """sample_51_convolution_VkFFT_single_3d_matrix_zeropadding_r2c.cpp: an open system -- only the first half of every axis
+    carries data, the rest is padding that may hold anything; circular convolution of the padded system = linear convolution"""
+    nx, ny, C = 32, 16, 2
+    rng = np.random.default_rng(51)
+    x = rng.uniform(-1, 1, (C, ny, nx)).astype(np.float32)            # garbage in the padded half on purpose
+    clean = x.copy(); clean[..., nx // 2:] = 0; clean[:, ny // 2:, :] = 0
+    k = rng.uniform(-1, 1, (C, ny, nx)).astype(np.float32)
+    K = np.fft.rfft2(k.astype(np.float64)).astype(np.complex64)
+    buf = np.full((C, ny, nx + 2), 3.0, np.float32); buf[..., :nx] = x
+    d = emu.make_desc((nx, ny), 1, 0, coordinate_features=C, perform_r2c=1, perform_convolution=1, normalize=1,
+                      perform_zeropadding=[1, 1], zeropad_left=[nx // 2, ny // 2], zeropad_right=[nx, ny])
+    rc, _ = emu.exec_plan(d, -1, buf, kernel=K)
+    assert rc == 0
+    ref = np.fft.irfft2(np.fft.rfft2(clean.astype(np.float64)) * K.astype(np.complex128), s=(ny, nx))
+    assert _rel(buf[..., :nx], ref) < T32

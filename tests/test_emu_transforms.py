@@ -189,3 +189,46 @@ def test_odd_r2c_composed_with_a_c2c_plan(shape, b, prec):
     assert orc.error_metrics(buf.view(cdt), orc.r2c(x, len(shape)))["l2_rel"] < tol
     assert emu.exec_plan(d, 1, buf)[0] == 0
     assert orc.error_metrics(buf[..., :nx], x)["l2_rel"] < tol
+
+
+@pytest.mark.parametrize("case", ["c2c3d", "r2c2d", "dct1d", "freq"])
+def test_zero_padding_clears_the_flagged_ranges_before_the_first_read(case):
+    """performZeropadding (API guide :1786-1807, sample_4 / sample_51): the padded ranges may hold anything, the transform
+    must behave as if they were zero"""
+    rng = np.random.default_rng(5)
+    if case == "c2c3d":
+        shape = (16, 12, 8)
+        x = (rng.uniform(-1, 1, (2, 8, 12, 16)) + 1j * rng.uniform(-1, 1, (2, 8, 12, 16))).astype(np.complex64)
+        left, right = [8, 6, 4], [16, 12, 8]
+        clean = x.copy(); clean[..., 8:] = 0; clean[:, :, 6:, :] = 0; clean[:, 4:, :, :] = 0
+        buf = x.copy()
+        d = emu.make_desc(shape, 2, 0, perform_zeropadding=[1, 1, 1], zeropad_left=left, zeropad_right=right)
+        assert emu.exec_plan(d, -1, buf)[0] == 0
+        assert orc.error_metrics(buf, np.fft.fftn(clean.astype(np.complex128), axes=(1, 2, 3)))["l2_rel"] < T32
+    elif case == "r2c2d":
+        nx, ny = 32, 10
+        x = rng.uniform(-1, 1, (3, ny, nx)).astype(np.float32)
+        clean = x.copy(); clean[..., 20:] = 0; clean[:, 5:8, :] = 0
+        buf = np.full((3, ny, nx + 2), 7.0, np.float32); buf[..., :nx] = x
+        d = emu.make_desc((nx, ny), 3, 0, perform_r2c=1, perform_zeropadding=[1, 1], zeropad_left=[20, 5], zeropad_right=[32, 8])
+        assert emu.exec_plan(d, -1, buf)[0] == 0
+        assert orc.error_metrics(buf.view(np.complex64), np.fft.rfft2(clean.astype(np.float64)))["l2_rel"] < T32
+    elif case == "dct1d":
+        n = 64
+        x = rng.uniform(-1, 1, (4, n)).astype(np.float32)
+        clean = x.copy(); clean[:, 40:] = 0
+        buf = x.copy()
+        d = emu.make_desc((n,), 4, 0, perform_dct=2, perform_zeropadding=[1], zeropad_left=[40], zeropad_right=[64])
+        assert emu.exec_plan(d, -1, buf)[0] == 0
+        assert orc.error_metrics(buf, orc.dct(clean, 2, 1))["l2_rel"] < T32
+    else:
+        n = 256
+        x = (rng.uniform(-1, 1, (2, n)) + 1j * rng.uniform(-1, 1, (2, n))).astype(np.complex64)
+        clean = x.copy(); clean[:, 64:192] = 0
+        d = emu.make_desc((n,), 2, 0, perform_zeropadding=[1], zeropad_left=[64], zeropad_right=[192], frequency_zeropadding=1)
+        buf = x.copy()
+        assert emu.exec_plan(d, -1, buf)[0] == 0                    # forward: untouched by frequency-domain padding
+        assert orc.error_metrics(buf, np.fft.fft(x.astype(np.complex128), axis=-1))["l2_rel"] < T32
+        buf = x.copy()
+        assert emu.exec_plan(d, 1, buf)[0] == 0
+        assert orc.error_metrics(buf, np.fft.ifft(clean.astype(np.complex128), axis=-1) * n)["l2_rel"] < T32

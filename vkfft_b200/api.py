@@ -109,6 +109,9 @@ class VkFFTConfiguration:
     # reference features outside the engine's scope: accepted here so that setting them fails like the C shim
     halfPrecision: int = 0
     performZeropadding: List[int] = field(default_factory=list)
+    fft_zeropad_left: List[int] = field(default_factory=list)
+    fft_zeropad_right: List[int] = field(default_factory=list)
+    frequencyZeroPadding: int = 0
     # engine extension (no reference counterpart, the reference is single-device): one sequence over peer windows,
     # see b200fft_desc.dist_world in include/b200fft.h and vkfft_b200/dist.py FusedDistributedFFT1D
     distWorld: int = 0
@@ -171,6 +174,13 @@ def _to_desc(cfg: VkFFTConfiguration) -> "_lib.b200fft_desc":
     d.stream = cfg.stream
     d.dist_world = cfg.distWorld
     d.dist_rank = cfg.distRank
+    for i, v in enumerate(cfg.performZeropadding[:4]):
+        d.perform_zeropadding[i] = int(v)
+    for i, v in enumerate(cfg.fft_zeropad_left[:4]):
+        d.zeropad_left[i] = int(v)
+    for i, v in enumerate(cfg.fft_zeropad_right[:4]):
+        d.zeropad_right[i] = int(v)
+    d.frequency_zeropadding = cfg.frequencyZeroPadding
     d.perform_convolution = cfg.performConvolution
     d.kernel_convolution = cfg.kernelConvolution
     d.matrix_convolution = cfg.matrixConvolution
@@ -195,7 +205,7 @@ def initializeVkFFT(app: VkFFTApplication, inputLaunchConfiguration: VkFFTConfig
         return VKFFT_ERROR_FFTdim_GT_MAX_FFT_DIMENSIONS
     if not cfg.size or cfg.size[0] == 0:
         return VKFFT_ERROR_EMPTY_size
-    if cfg.halfPrecision or any(cfg.performZeropadding):
+    if cfg.halfPrecision:
         return VKFFT_ERROR_UNSUPPORTED_FFT_LENGTH
     L = _lib.load()
     d = _to_desc(cfg)

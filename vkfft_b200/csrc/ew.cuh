@@ -22,7 +22,8 @@ enum { B2_EW_COPY_MUL = 0, B2_EW_R2C_POST = 1, B2_EW_C2R_PRE = 2,
        // DCT / DST of lengths the single-launch kernel cannot take: the operator's load side and store side as launches of
        // their own around a C2C plan on scratch (one real line per complex line).  store_io = B2_IO_DCT1/2/3/DCT4_ODD/DST1,
        // aux_u0 = logical real length N, aux_u1 = complex length, dst_flags as in generic.cuh
-       B2_EW_R2R_PRE = 9, B2_EW_R2R_POST = 10 };
+       B2_EW_R2R_PRE = 9, B2_EW_R2R_POST = 10,
+       B2_EW_ZERO = 11 };          // clear P.n items of every line (aux_u0 = 1: items and strides count scalars, not complex elements)
 // B2_EW_CONV packs its options into aux_u0: bits 0-7 features per vector, 8-11 matrix size (0 = per-feature product),
 // 12 symmetric kernel, 13-14 conjugation (1 sequence, 2 kernel), 15 cross-power-spectrum normalisation; aux_u1 = kernels
 enum { B2_CONV_SYM = 1u << 12, B2_CONV_CONJ_SEQ = 1u << 13, B2_CONV_CONJ_KER = 1u << 14, B2_CONV_XPS = 1u << 15 };
@@ -83,6 +84,15 @@ struct Elementwise {
                     out[j] = v;
                     if (j != 0 && 2 * j != P.aux_u0) out[P.aux_u0 - j] = conj(v);
                 }
+            }
+        } else if (P.load_io == B2_EW_ZERO) {
+            T* rout = (T*)P.out + out_off;
+#pragma unroll
+            for (int i = 0; i < B2_EW_PER_THREAD; ++i) {
+                const uint32_t j = j0 + i * B2_EW_THREADS;
+                if (j >= P.n) break;
+                if (P.aux_u0) rout[(int64_t)j * P.out_es] = T(0);
+                else out[(int64_t)j * P.out_es] = mk<T>(T(0), T(0));
             }
         } else if (P.load_io == B2_EW_R2R_PRE || P.load_io == B2_EW_R2R_POST) {
             const T* rin = (const T*)P.in + in_off;       // real side in scalars

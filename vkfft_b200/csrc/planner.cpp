@@ -1343,7 +1343,49 @@ int build_plan(const b200fft_desc& din, PlanGraph& g) {
 
     g.has_fwd = !d.make_inverse_plan_only;
     g.has_inv = !d.make_forward_plan_only;
+    // zero padding: clear the flagged ranges before the first read of the direction they apply to
+    bool any_zp = false;
+    for (uint32_t a = 0; a < d.fft_dim; ++a) any_zp = any_zp || (d.perform_zeropadding[a] && d.zeropad_right[a] > d.zeropad_left[a]);
+    auto zero_fill = [&](std::vector<PassPlan>& list, int inv) -> int {
+        if (!any_zp || (inv != 0) != (d.frequency_zeropadding != 0)) return R_SUCCESS;
+        if (d.dist_world > 1) return R_UNSUPPORTED_FFT_LENGTH;
+        // the data being read lives in `buffer` (a formatted input / output buffer of the caller is never modified)
+        if ((!inv && d.is_input_formatted) || (inv && d.is_output_formatted)) return R_UNSUPPORTED_FFT_LENGTH;
+        const bool real_buf = (d.perform_dct || d.perform_dst) || (d.perform_r2c && !inv);   // R2C: real rows before the forward transform
+        const uint64_t unit = (d.perform_r2c && !inv) ? 2 : 1;                                // real rows of R2C: 2 * complex stride
+        for (uint32_t a = 0; a < d.fft_dim; ++a) {
+            if (!d.perform_zeropadding[a] || d.zeropad_right[a] <= d.zeropad_left[a]) continue;
+            const uint64_t extent = (d.perform_r2c && inv && a == 0) ? d.size[0] / 2 + 1 : d.size[a];
+            const uint64_t L = d.zeropad_left[a], R = std::min<uint64_t>(d.zeropad_right[a], extent);
+            if (L >= R) continue;
+            auto stride_of = [&](uint32_t ax) -> int64_t { return ax == 0 ? 1 : (int64_t)(d.buffer_stride[ax - 1] * unit); };
+            PassReq z;
+            z.elementwise = true; z.ew_op = 11; z.in_es = z.out_es = 1;
+            z.in_role = z.out_role = ROLE_BUFFER;
+            z.aux_u0 = real_buf ? 1 : 0;
+            std::vector<Dim> lines;
+            uint64_t items;
+            if (a == 0) { items = R - L; z.out_base = (int64_t)L; }
+            else {
+                items = (d.perform_r2c && inv) ? d.size[0] / 2 + 1 : d.size[0];
+                z.out_base = (int64_t)L * stride_of(a);
+                lines.push_back(Dim{R - L, stride_of(a), stride_of(a)});
+            }
+            for (uint32_t b = 1; b < d.fft_dim; ++b)
+                if (b != a) lines.push_back(Dim{d.size[b], stride_of(b), stride_of(b)});
+            const int64_t bstride = (int64_t)(d.buffer_stride[d.fft_dim - 1] * unit);
+            lines.push_back(Dim{g.batches, bstride, bstride});
+            z.in_base = z.out_base;
+            z.n = (int)std::min<uint64_t>(items, 0x7fffffff); z.ew_items = (uint32_t)items;
+            z.what = "zero padding: clear the padded range";
+            int zr = emit_ew(g, list, z, lines);
+            if (zr != R_SUCCESS) return zr;
+            list.back().in_scalar = list.back().out_scalar = real_buf;
+        }
+        return R_SUCCESS;
+    };
     auto plan = [&](std::vector<PassPlan>& list, int inv) {
+        if (int zr = zero_fill(list, inv)) return zr;
         if (d.perform_r2c) return plan_direction_r2c(g, list, inv);
         if (d.perform_dct || d.perform_dst) return plan_direction_dct(g, list, inv);
         return plan_direction_c2c(g, list, inv);

@@ -94,7 +94,14 @@ extern "C" int b200fft_plan_create(const b200fft_desc* desc, b200fft_plan** out)
     if (!p) return R_MALLOC_FAILED;
     p->device = desc->device;
     p->stream = (cudaStream_t)desc->stream;
-    int rc = build_plan(*desc, p->g);
+    // callers built against an older header pass a shorter struct: everything beyond struct_size reads as zero
+    b200fft_desc full;
+    memset(&full, 0, sizeof full);
+    {
+        const size_t have = (desc->struct_size >= 64 && desc->struct_size <= sizeof full) ? desc->struct_size : sizeof full;
+        memcpy(&full, desc, have);
+    }
+    int rc = build_plan(full, p->g);
     if (rc != R_SUCCESS) { delete p; return rc; }
     DeviceGuard dg(p->device);
     if (!dg.ok) { delete p; return R_INVALID_DEVICE; }

@@ -28,6 +28,8 @@ struct State {
     unsigned char* smem = nullptr;
     bool log = false;
     bool launch_refused = false;             // set by launch() when the configuration exceeds the device limits
+    size_t smem_bytes = 0;
+    bool smem_oob = false;                   // a shared-memory access outside the CTA's allocation (reported as a failed launch)
     std::vector<std::vector<SmemRec>> recs;  // per thread (block 0 only)
 };
 inline State& st() { static State s; return s; }
@@ -37,8 +39,11 @@ inline thread_local idx3 t_blockIdx{0, 0, 0};
 inline void syncthreads() { st().bar->arrive_and_wait(); }
 inline void log_access(const void* base, size_t index, size_t elem_bytes, bool store) {
     State& s = st();
+    {   // bounds of the dynamic shared-memory allocation (what compute-sanitizer memcheck would flag on the device)
+        const unsigned char* a = (const unsigned char*)base + index * elem_bytes;
+        if (a < s.smem || a + elem_bytes > s.smem + s.smem_bytes) s.smem_oob = true;
+    }
     if (!s.log || t_blockIdx.x != 0) return;
-    (void)base;
     s.recs[t_threadIdx.x].push_back(SmemRec{(uint32_t)(index * elem_bytes), (uint16_t)elem_bytes, (uint16_t)store});
 }
 
@@ -99,8 +104,9 @@ inline void launch(unsigned grid, unsigned block, size_t smem_bytes, F&& f, bool
     if (block == 0 || block > 1024 || smem_bytes > 232448 || grid == 0 || grid > 0x7fffffffu) { s.launch_refused = true; return; }
     s.blockDim = {block, 1, 1};
     s.gridDim = {grid, 1, 1};
-    std::vector<unsigned char> smem(smem_bytes + 64);
+    std::vector<unsigned char> smem(smem_bytes + 65536);   // slack: an out-of-bounds access is reported, not a host crash
     s.smem = smem.data();
+    s.smem_bytes = smem_bytes;
     std::barrier<> bar((std::ptrdiff_t)block);
     s.bar = &bar;
     s.log = log;

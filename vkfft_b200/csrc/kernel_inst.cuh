@@ -43,8 +43,9 @@ template <> struct PrecOf<double> { static constexpr int value = B2_PREC_F64; };
 #if defined(B2_EMU)
 // the emulation refuses what cudaLaunchKernel would refuse (block size, shared memory, grid): report it like a failed launch
 inline int emu_refused() {
-    const bool r = b2emu::st().launch_refused;
+    const bool r = b2emu::st().launch_refused || b2emu::st().smem_oob;
     b2emu::st().launch_refused = false;
+    b2emu::st().smem_oob = false;
     return r ? 1 : 0;
 }
 template <class C>

@@ -8,7 +8,10 @@
 // shared-memory access log lets the tests assert "bank-conflict free" per configuration.
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <barrier>
+#include <cstdlib>
+#include <memory>
 #include <cstdint>
 #include <cstring>
 #include <functional>
@@ -31,17 +34,50 @@ struct State {
     size_t smem_bytes = 0;
     bool smem_oob = false;                   // a shared-memory access outside the CTA's allocation (reported as a failed launch)
     std::vector<std::vector<SmemRec>> recs;  // per thread (block 0 only)
+    // race check (what compute-sanitizer racecheck reports on the device): per 4-byte word of shared memory the last
+    // writer and the last reader(s) with the barrier interval ("epoch") they acted in; two different threads touching a
+    // word in the same interval, at least one of them writing, is a hazard
+    struct WordMeta { std::atomic<uint64_t> w{0}, r{0}; };
+    std::unique_ptr<WordMeta[]> meta;
+    size_t meta_words = 0;
+    bool racecheck = true;
+    std::atomic<int> hazards{0};
+    uint32_t hazard_addr = 0, hazard_kind = 0;   // first hazard: byte offset, 1 = write-write, 2 = write-after-read, 3 = read-after-write
 };
 inline State& st() { static State s; return s; }
 inline thread_local idx3 t_threadIdx{0, 0, 0};
 inline thread_local idx3 t_blockIdx{0, 0, 0};
+inline thread_local uint64_t t_epoch = 1;
 
-inline void syncthreads() { st().bar->arrive_and_wait(); }
+inline void syncthreads() { st().bar->arrive_and_wait(); ++t_epoch; }
 inline void log_access(const void* base, size_t index, size_t elem_bytes, bool store) {
     State& s = st();
     {   // bounds of the dynamic shared-memory allocation (what compute-sanitizer memcheck would flag on the device)
         const unsigned char* a = (const unsigned char*)base + index * elem_bytes;
         if (a < s.smem || a + elem_bytes > s.smem + s.smem_bytes) s.smem_oob = true;
+    }
+    if (s.racecheck && s.meta && !s.smem_oob) {
+        const size_t off = (size_t)((const unsigned char*)base - s.smem) + index * elem_bytes;
+        const uint64_t tid = t_threadIdx.x, key = (t_epoch << 20) | tid;
+        for (size_t wd = off / 4; wd < (off + elem_bytes + 3) / 4 && wd < s.meta_words; ++wd) {
+            State::WordMeta& m = s.meta[wd];
+            int kind = 0;
+            if (store) {
+                const uint64_t ow = m.w.exchange(key);
+                if ((ow >> 20) == t_epoch && (ow & 0x7ffff) != tid) kind = 1;
+                const uint64_t rd = m.r.load();
+                if ((rd >> 20) == t_epoch && ((rd & 0x7ffff) != tid || (rd & 0x80000))) kind = kind ? kind : 2;
+            } else {
+                uint64_t old = m.r.load(), want;
+                do {
+                    want = key;
+                    if ((old >> 20) == t_epoch && ((old & 0x7ffff) != tid || (old & 0x80000))) want |= 0x80000;   // several readers
+                } while (!m.r.compare_exchange_weak(old, want));
+                const uint64_t wv = m.w.load();
+                if ((wv >> 20) == t_epoch && (wv & 0x7ffff) != tid) kind = 3;
+            }
+            if (kind && s.hazards.fetch_add(1) == 0) { s.hazard_addr = (uint32_t)(wd * 4); s.hazard_kind = (uint32_t)kind; }
+        }
     }
     if (!s.log || t_blockIdx.x != 0) return;
     s.recs[t_threadIdx.x].push_back(SmemRec{(uint32_t)(index * elem_bytes), (uint16_t)elem_bytes, (uint16_t)store});
@@ -107,6 +143,9 @@ inline void launch(unsigned grid, unsigned block, size_t smem_bytes, F&& f, bool
     std::vector<unsigned char> smem(smem_bytes + 65536);   // slack: an out-of-bounds access is reported, not a host crash
     s.smem = smem.data();
     s.smem_bytes = smem_bytes;
+    s.racecheck = !getenv("B2EMU_NO_RACECHECK");
+    s.meta_words = smem_bytes / 4 + 16;
+    s.meta.reset(s.racecheck && smem_bytes ? new State::WordMeta[s.meta_words] : nullptr);
     std::barrier<> bar((std::ptrdiff_t)block);
     s.bar = &bar;
     s.log = log;
@@ -120,6 +159,7 @@ inline void launch(unsigned grid, unsigned block, size_t smem_bytes, F&& f, bool
                 t_blockIdx = {b, 0, 0};
                 f(s.smem);
                 s.bar->arrive_and_wait();
+                ++t_epoch;
             }
         });
     }

@@ -145,3 +145,25 @@ extern "C" int emu_describe(const b200fft_desc* d, int inverse, char* dst, int c
     snprintf(dst, cap, "%s", s.c_str());
     return 0;
 }
+
+// self test of the emulation's checkers: mode 0 = correct exchange through shared memory (own slot, barrier, neighbour's slot),
+// 1 = the barrier is missing (read-after-write hazard), 2 = two threads write one word, 3 = write beyond the allocation.
+// Returns hazards (modes 0-2) or the out-of-bounds flag (mode 3).
+extern "C" int emu_selftest_checkers(int mode) {
+    b2emu::State& s = b2emu::st();
+    s.hazards = 0; s.smem_oob = false;
+    b2emu::launch(2, 64, 64 * sizeof(float), [&](unsigned char* raw) {
+        float* sm = reinterpret_cast<float*>(raw);
+        const unsigned t = threadIdx.x;
+        if (mode == 2) { B2_SMEM_ST(sm, t / 2, 1.0f); return; }
+        if (mode == 3) { if (t == 0) B2_SMEM_ST(sm, 64, 1.0f); return; }
+        B2_SMEM_ST(sm, t, (float)t);
+        if (mode == 0) __syncthreads();
+        volatile float v = B2_SMEM_LD(sm, (t + 1) % 64);
+        (void)v;
+        if (mode == 0) __syncthreads();
+    }, false);
+    const int r = mode == 3 ? (s.smem_oob ? 1 : 0) : s.hazards.load();
+    s.hazards = 0; s.smem_oob = false;
+    return r;
+}

@@ -100,3 +100,13 @@ def test_planner_rejects_what_it_cannot_do():
     d = emu.make_desc((8,), 1, 0)
     d.fft_dim = 5
     assert emu.exec_plan(d, -1, np.zeros(8, np.complex64))[0] == 7
+
+
+def test_emulation_checkers_catch_races_and_out_of_bounds_accesses():
+    """the emulation's racecheck / bounds check must fire on deliberately broken kernels (and stay quiet on a correct one),
+    otherwise "0 hazards" in the kernel tests above would mean nothing"""
+    L = emu.lib()
+    assert L.emu_selftest_checkers(0) == 0          # write own slot, barrier, read the neighbour's
+    assert L.emu_selftest_checkers(1) > 0           # same without the barrier: read-after-write hazard
+    assert L.emu_selftest_checkers(2) > 0           # two threads write the same word
+    assert L.emu_selftest_checkers(3) == 1          # store one element past the allocation

@@ -1,6 +1,8 @@
 // Expands kernel_list.def into registry entries.  Included by the CUDA shard translation units (product)
 // and, with B2_EMU defined, by the CPU emulation used in tests.
 #pragma once
+#include <cstdio>
+
 #include "kernel_registry.h"
 #include "stockham.cuh"
 #include "generic.cuh"
@@ -43,9 +45,13 @@ template <> struct PrecOf<double> { static constexpr int value = B2_PREC_F64; };
 #if defined(B2_EMU)
 // the emulation refuses what cudaLaunchKernel would refuse (block size, shared memory, grid): report it like a failed launch
 inline int emu_refused() {
-    const bool r = b2emu::st().launch_refused || b2emu::st().smem_oob;
+    const bool r = b2emu::st().launch_refused || b2emu::st().smem_oob || b2emu::st().hazards.load() != 0;
+    if (b2emu::st().hazards.load())
+        fprintf(stderr, "b2emu racecheck: %d shared-memory hazards, first at byte %u (kind %u: 1 WAW, 2 WAR, 3 RAW)\n",
+                b2emu::st().hazards.load(), b2emu::st().hazard_addr, b2emu::st().hazard_kind);
     b2emu::st().launch_refused = false;
     b2emu::st().smem_oob = false;
+    b2emu::st().hazards = 0;
     return r ? 1 : 0;
 }
 template <class C>

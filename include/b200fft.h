@@ -122,6 +122,9 @@ int b200fft_exec(b200fft_plan* plan, int inverse, const b200fft_buffers* buffers
 /* == deleteVkFFT */
 void b200fft_plan_destroy(b200fft_plan* plan);
 int b200fft_plan_get_info(const b200fft_plan* plan, b200fft_plan_info* info);
+/* kernel launches per axis of one direction == VkFFTPlan.numAxisUploads (vkFFT_Structs.h:1118-1130), which the reference's
+ * benchmark samples read to convert time into "bandwidth" (sample_0_benchmark_VkFFT_single.cpp:234-237) */
+int b200fft_plan_axis_uploads(const b200fft_plan* plan, int inverse, uint32_t uploads[B200FFT_MAX_DIMS]);
 /* human-readable list of the plan's passes; returns bytes written (excluding NUL) */
 size_t b200fft_plan_describe(const b200fft_plan* plan, int inverse, char* dst, size_t cap);
 

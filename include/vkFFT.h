@@ -179,23 +179,55 @@ typedef enum VkFFTResult {
     VKFFT_ERROR_UNSUPPORTED_FFT_LENGTH_R2R = 3004,
     VKFFT_ERROR_UNSUPPORTED_FFT_OMIT = 3005,
     VKFFT_ERROR_FAILED_TO_ALLOCATE = 4001,
+    /* 4002-4027, 4030-4034: codes of the other backends; never returned here, present so that code switching on them compiles */
+    VKFFT_ERROR_FAILED_TO_MAP_MEMORY = 4002, VKFFT_ERROR_FAILED_TO_ALLOCATE_COMMAND_BUFFERS = 4003,
+    VKFFT_ERROR_FAILED_TO_BEGIN_COMMAND_BUFFER = 4004, VKFFT_ERROR_FAILED_TO_END_COMMAND_BUFFER = 4005,
+    VKFFT_ERROR_FAILED_TO_SUBMIT_QUEUE = 4006, VKFFT_ERROR_FAILED_TO_WAIT_FOR_FENCES = 4007,
+    VKFFT_ERROR_FAILED_TO_RESET_FENCES = 4008, VKFFT_ERROR_FAILED_TO_CREATE_DESCRIPTOR_POOL = 4009,
+    VKFFT_ERROR_FAILED_TO_CREATE_DESCRIPTOR_SET_LAYOUT = 4010, VKFFT_ERROR_FAILED_TO_ALLOCATE_DESCRIPTOR_SETS = 4011,
+    VKFFT_ERROR_FAILED_TO_CREATE_PIPELINE_LAYOUT = 4012, VKFFT_ERROR_FAILED_SHADER_PREPROCESS = 4013,
+    VKFFT_ERROR_FAILED_SHADER_PARSE = 4014, VKFFT_ERROR_FAILED_SHADER_LINK = 4015, VKFFT_ERROR_FAILED_SPIRV_GENERATE = 4016,
+    VKFFT_ERROR_FAILED_TO_CREATE_SHADER_MODULE = 4017, VKFFT_ERROR_FAILED_TO_CREATE_INSTANCE = 4018,
+    VKFFT_ERROR_FAILED_TO_SETUP_DEBUG_MESSENGER = 4019, VKFFT_ERROR_FAILED_TO_FIND_PHYSICAL_DEVICE = 4020,
+    VKFFT_ERROR_FAILED_TO_CREATE_DEVICE = 4021, VKFFT_ERROR_FAILED_TO_CREATE_FENCE = 4022,
+    VKFFT_ERROR_FAILED_TO_CREATE_COMMAND_POOL = 4023, VKFFT_ERROR_FAILED_TO_CREATE_BUFFER = 4024,
+    VKFFT_ERROR_FAILED_TO_ALLOCATE_MEMORY = 4025, VKFFT_ERROR_FAILED_TO_BIND_BUFFER_MEMORY = 4026,
+    VKFFT_ERROR_FAILED_TO_FIND_MEMORY = 4027,
     VKFFT_ERROR_FAILED_TO_SYNCHRONIZE = 4028,
     VKFFT_ERROR_FAILED_TO_COPY = 4029,
+    VKFFT_ERROR_FAILED_TO_CREATE_PROGRAM = 4030, VKFFT_ERROR_FAILED_TO_COMPILE_PROGRAM = 4031,
+    VKFFT_ERROR_FAILED_TO_GET_CODE_SIZE = 4032, VKFFT_ERROR_FAILED_TO_GET_CODE = 4033, VKFFT_ERROR_FAILED_TO_DESTROY_PROGRAM = 4034,
     VKFFT_ERROR_FAILED_TO_LOAD_MODULE = 4035,
     VKFFT_ERROR_FAILED_TO_GET_FUNCTION = 4036,
     VKFFT_ERROR_FAILED_TO_SET_DYNAMIC_SHARED_MEMORY = 4037,
     VKFFT_ERROR_FAILED_TO_MODULE_GET_GLOBAL = 4038,
     VKFFT_ERROR_FAILED_TO_LAUNCH_KERNEL = 4039,
     VKFFT_ERROR_FAILED_TO_EVENT_RECORD = 4040,
+    VKFFT_ERROR_FAILED_TO_ADD_NAME_EXPRESSION = 4041, VKFFT_ERROR_FAILED_TO_INITIALIZE = 4042,
+    VKFFT_ERROR_FAILED_TO_SET_DEVICE_ID = 4043, VKFFT_ERROR_FAILED_TO_GET_DEVICE = 4044,
+    VKFFT_ERROR_FAILED_TO_CREATE_CONTEXT = 4045, VKFFT_ERROR_FAILED_TO_CREATE_PIPELINE = 4046,
+    VKFFT_ERROR_FAILED_TO_SET_KERNEL_ARG = 4047, VKFFT_ERROR_FAILED_TO_CREATE_COMMAND_QUEUE = 4048,
+    VKFFT_ERROR_FAILED_TO_RELEASE_COMMAND_QUEUE = 4049, VKFFT_ERROR_FAILED_TO_ENUMERATE_DEVICES = 4050,
     VKFFT_ERROR_FAILED_TO_GET_ATTRIBUTE = 4051,
-    VKFFT_ERROR_FAILED_TO_CREATE_EVENT = 4052
+    VKFFT_ERROR_FAILED_TO_CREATE_EVENT = 4052,
+    VKFFT_ERROR_FAILED_TO_CREATE_COMMAND_LIST = 4053, VKFFT_ERROR_FAILED_TO_DESTROY_COMMAND_LIST = 4054,
+    VKFFT_ERROR_FAILED_TO_SUBMIT_BARRIER = 4055
 } VkFFTResult;
 
 static inline const char* getVkFFTErrorString(VkFFTResult result) { return b200fft_error_string((int)result); }
 
 /* ---- application handle ---------------------------------------------------------------------------------- */
+/* What callers read from the reference's VkFFTPlan (vkFFT_Structs.h:1118-1130): how many launches each axis takes.  The
+ * reference's own benchmark samples use it to turn time into "bandwidth" (sample_0_benchmark_VkFFT_single.cpp:234-237). */
+typedef struct {
+    pfUINT actualFFTSizePerAxis[VKFFT_MAX_FFT_DIMENSIONS][VKFFT_MAX_FFT_DIMENSIONS];
+    pfUINT numAxisUploads[VKFFT_MAX_FFT_DIMENSIONS];
+} VkFFTPlan;
+
 typedef struct {
     VkFFTConfiguration configuration;   /* normalised copy of what the caller passed (as in the reference) */
+    VkFFTPlan* localFFTPlan;            /* forward / inverse launch counts (allocated by initializeVkFFT) */
+    VkFFTPlan* localFFTPlan_inverse;
     b200fft_plan* b200fftPlan;          /* the engine's plan: owns tables, scratch, kernel selection */
     pfUINT actualNumBatches;
     pfUINT applicationStringSize;       /* saveApplicationToString: opaque blob, nothing to cache (no JIT) */
@@ -208,6 +240,8 @@ static inline void deleteVkFFT(VkFFTApplication* app) {
     if (!app) return;
     if (app->b200fftPlan) b200fft_plan_destroy(app->b200fftPlan);
     if (app->saveApplicationString) free(app->saveApplicationString);
+    if (app->localFFTPlan) free(app->localFFTPlan);
+    if (app->localFFTPlan_inverse) free(app->localFFTPlan_inverse);
     memset(app, 0, sizeof(VkFFTApplication));
 }
 
@@ -292,6 +326,17 @@ static inline VkFFTResult initializeVkFFT(VkFFTApplication* app, VkFFTConfigurat
     app->configuration.vendorID = 0x10DE;
     app->actualNumBatches = app->configuration.numberBatches;
     app->b200fftPlan = plan;
+    for (int dir = 0; dir < 2; dir++) {
+        VkFFTPlan* pl = (VkFFTPlan*)calloc(1, sizeof(VkFFTPlan));
+        if (!pl) { deleteVkFFT(app); return VKFFT_ERROR_MALLOC_FAILED; }
+        uint32_t up[B200FFT_MAX_DIMS] = {0, 0, 0, 0};
+        b200fft_plan_axis_uploads(plan, dir ? 1 : -1, up);
+        for (int a = 0; a < VKFFT_MAX_FFT_DIMENSIONS; a++) {
+            pl->numAxisUploads[a] = up[a];
+            for (int b = 0; b < VKFFT_MAX_FFT_DIMENSIONS; b++) pl->actualFFTSizePerAxis[a][b] = c->size[b] ? c->size[b] : 1;
+        }
+        if (dir) app->localFFTPlan_inverse = pl; else app->localFFTPlan = pl;
+    }
     if (c->saveApplicationToString) {   /* nothing is compiled at plan time, so the "binary" is a tag */
         static const char tag[] = "b200fft:aot:sm_100a";
         app->saveApplicationString = malloc(sizeof tag);

@@ -106,3 +106,19 @@ def test_reference_style_cpp_program_runs(built_lib):
     with tempfile.TemporaryDirectory() as td:
         out = subprocess.run([_build_sample(td)], capture_output=True, text=True)
         assert out.returncode == 0, out.stdout + out.stderr
+
+
+def test_reference_testsuite_sources_build_against_the_shim(built_lib):
+    """drop-in at source level: the reference's own VkFFT_TestSuite.cpp with its benchmark / convolution samples and utilities
+    (unmodified, where they lie) compiles against include/vkFFT.h and links to libb200fft.so"""
+    if not os.path.isdir("/root/reference/benchmark_scripts"):
+        pytest.skip("reference tree not present")
+    exe = os.path.join(ROOT, "oracle", "_ref", "VkFFT_TestSuite_b200")
+    if os.path.exists(exe):
+        os.unlink(exe)
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "testsuite"], stdout=subprocess.DEVNULL)
+    assert os.path.exists(exe)
+    syms = subprocess.run(["nm", "-D", "--undefined-only", exe], capture_output=True, text=True).stdout
+    for s in ("b200fft_plan_create", "b200fft_exec", "b200fft_plan_destroy", "b200fft_plan_axis_uploads"):
+        assert s in syms, s                      # the samples' initializeVkFFT / VkFFTAppend / deleteVkFFT end in the C ABI
+    assert "nvrtcCompileProgram" not in syms     # nothing is JIT-compiled any more

@@ -62,7 +62,7 @@ EXPORTS = [
     "b200fft_error_string", "b200fft_version", "b200fft_kernel_count",
     "b200fft_window_granularity", "b200fft_window_create", "b200fft_window_export", "b200fft_window_import",
     "b200fft_window_base", "b200fft_window_local", "b200fft_window_barrier", "b200fft_window_status",
-    "b200fft_window_destroy", "b200fft_plan_attach_window",
+    "b200fft_window_destroy", "b200fft_plan_attach_window", "b200fft_plan_axis_uploads",
 ]
 
 _lib = None

@@ -95,6 +95,7 @@ struct PlanGraph {
     uint64_t temp_elems_real = 0;   // (unused placeholder for real-sized scratch accounting)
     double flops = 0;
     uint64_t algorithmic_bytes = 0;
+    uint32_t axis_uploads[2][B200FFT_MAX_DIMS] = {{0, 0, 0, 0}, {0, 0, 0, 0}};   // launches per axis, [0] forward / [1] inverse (the reference's numAxisUploads)
     int skip_axis = -1;          // convolution plans: this axis is transformed by the fused kernel, the direction planners leave it out
     bool distributed = false;    // desc.dist_world > 1: one more barrier follows the last launch of a direction
 };

@@ -867,8 +867,10 @@ int plan_direction_c2c(PlanGraph& g, std::vector<PassPlan>& list, int inv) {
             if (first && d.is_output_formatted) in = outl;
             if (last && d.is_input_formatted && d.inverse_return_to_input) out = inl;
         }
+        const size_t before = list.size();
         int rc = plan_c2c_axis(g, list, d.size, axes[i], inv, in, out, last ? norm : 1.0);
         if (rc != R_SUCCESS) return rc;
+        g.axis_uploads[inv ? 1 : 0][axes[i]] += (uint32_t)(list.size() - before);
     }
     return R_SUCCESS;
 }
@@ -1033,18 +1035,24 @@ int plan_direction_r2c(PlanGraph& g, std::vector<PassPlan>& list, int inv) {
         return fused ? axis0(forward, scale) : (odd_composed ? axis0_odd(forward, scale) : axis0_composed(forward, scale));
     };
     int rc;
+    size_t mark = list.size();
+    auto count = [&](uint32_t a) { g.axis_uploads[inv ? 1 : 0][a] += (uint32_t)(list.size() - mark); mark = list.size(); };
     if (!inv) {
         if ((rc = axis0_any(true, 1.0)) != R_SUCCESS) return rc;
+        count(0);
         for (uint32_t a = 1; a < d.fft_dim; ++a) {
             if (d.omit_dimension[a] || d.size[a] == 1 || (int)a == g.skip_axis) continue;
             if ((rc = plan_c2c_axis(g, list, csize, a, 0, buf, buf, 1.0)) != R_SUCCESS) return rc;
+            count(a);
         }
     } else {
         for (uint32_t a = d.fft_dim; a-- > 1;) {
             if (d.omit_dimension[a] || d.size[a] == 1 || (int)a == g.skip_axis) continue;
             if ((rc = plan_c2c_axis(g, list, csize, a, 1, buf, buf, 1.0)) != R_SUCCESS) return rc;
+            count(a);
         }
         if ((rc = axis0_any(false, norm)) != R_SUCCESS) return rc;
+        count(0);
     }
     return R_SUCCESS;
 }
@@ -1064,8 +1072,14 @@ int plan_direction_dct(PlanGraph& g, std::vector<PassPlan>& list, int inv) {
         if (!d.omit_dimension[a] && d.size[a] > 1) axes.push_back(a);
     if (inv) std::reverse(axes.begin(), axes.end());
     const Layout buf = layout_of(ROLE_BUFFER, d.buffer_stride, d.fft_dim);
-    for (size_t i = 0; i < axes.size(); ++i) {
+    size_t dct_mark = list.size();
+    uint32_t dct_prev_axis = ~0u;
+    for (size_t i = 0; i <= axes.size(); ++i) {
+        if (dct_prev_axis != ~0u) g.axis_uploads[inv ? 1 : 0][dct_prev_axis] += (uint32_t)(list.size() - dct_mark);
+        dct_mark = list.size();
+        if (i == axes.size()) break;
         const uint32_t axis = axes[i];
+        dct_prev_axis = axis;
         const uint64_t N = d.size[axis];
         double scale = 1.0;
         if (inv && d.normalize) scale = 1.0 / (type == 1 ? (is_dst ? 2.0 * (double)(N + 1) : 2.0 * (double)(N - 1)) : 2.0 * (double)N);

@@ -264,6 +264,12 @@ extern "C" int b200fft_plan_get_info(const b200fft_plan* p, b200fft_plan_info* i
     return R_SUCCESS;
 }
 
+extern "C" int b200fft_plan_axis_uploads(const b200fft_plan* p, int inverse, uint32_t uploads[B200FFT_MAX_DIMS]) {
+    if (!p || !uploads) return R_EMPTY_APP;
+    for (int a = 0; a < B200FFT_MAX_DIMS; ++a) uploads[a] = p->g.axis_uploads[inverse == 1 ? 1 : 0][a];
+    return R_SUCCESS;
+}
+
 extern "C" size_t b200fft_plan_describe(const b200fft_plan* p, int inverse, char* dst, size_t cap) {
     if (!p || !dst || cap == 0) return 0;
     std::string s;

@@ -204,3 +204,30 @@ def test_zero_padded_convolution_like_sample_51():
     assert rc == 0
     ref = np.fft.irfft2(np.fft.rfft2(clean.astype(np.float64)) * K.astype(np.complex128), s=(ny, nx))
     assert _rel(buf[..., :nx], ref) < T32
+
+
+def test_sample_51_configuration_3d_r2c_matrix_kernel_with_zero_padding():
+    """the exact option set of sample_51_convolution_VkFFT_single_3d_matrix_zeropadding_r2c.cpp:77-206 on a smaller grid:
+    kernel application (kernelConvolution, 9 features, R2C, zero padding), then 3x3 non-symmetric matrix convolution of a
+    3-vector field with zero padding on all axes"""
+    n = 16
+    rng = np.random.default_rng(510)
+    zp = dict(perform_zeropadding=[1, 1, 1], zeropad_left=[n // 2] * 3, zeropad_right=[n] * 3)
+    # kernel: 9 real fields, garbage in the padded half, transformed by the kernel application
+    kr = rng.uniform(-1, 1, (9, n, n, n)).astype(np.float32)
+    kclean = kr.copy(); kclean[..., n // 2:] = 0; kclean[:, :, n // 2:, :] = 0; kclean[:, n // 2:, :, :] = 0
+    kbuf = np.zeros((9, n, n, n + 2), np.float32); kbuf[..., :n] = kr
+    dk = emu.make_desc((n, n, n), 1, 0, coordinate_features=9, perform_r2c=1, kernel_convolution=1, normalize=1, **zp)
+    assert emu.exec_plan(dk, -1, kbuf)[0] == 0
+    K = kbuf.view(np.complex64).copy()                                       # [9][n][n][n/2+1]
+    assert _rel(K, np.fft.rfftn(kclean.astype(np.float64), axes=(1, 2, 3))) < T32
+    x = rng.uniform(-1, 1, (3, n, n, n)).astype(np.float32)
+    xclean = x.copy(); xclean[..., n // 2:] = 0; xclean[:, :, n // 2:, :] = 0; xclean[:, n // 2:, :, :] = 0
+    buf = np.zeros((3, n, n, n + 2), np.float32); buf[..., :n] = x
+    dc = emu.make_desc((n, n, n), 1, 0, coordinate_features=3, matrix_convolution=3, perform_r2c=1, perform_convolution=1, normalize=1, **zp)
+    rc, _ = emu.exec_plan(dc, -1, buf, kernel=K)
+    assert rc == 0
+    X = np.fft.rfftn(xclean.astype(np.float64), axes=(1, 2, 3))
+    KK = K.astype(np.complex128).reshape(3, 3, n, n, n // 2 + 1)
+    ref = np.fft.irfftn(np.einsum("rczyx,czyx->rzyx", KK, X), s=(n, n, n), axes=(1, 2, 3))
+    assert _rel(buf[..., :n], ref) < T32

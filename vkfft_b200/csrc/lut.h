@@ -119,6 +119,31 @@ enum AuxKind {
     AUX_BLUE_FILTER = 6,  // a = N, b = M : FFT_M(e^{+i pi m^2/N} wrapped) / M        (vkFFT_RecursiveFFTGenerators.h:241-298)
 };
 
+// mixed-radix DFT in long double for any length (host, table generation only): decimation in time by the smallest prime factor
+inline void host_fft_any(std::vector<long double>& re, std::vector<long double>& im) {
+    const size_t n = re.size();
+    if (n <= 1) return;
+    size_t p = 2;
+    while (p * p <= n && n % p) ++p;
+    if (n % p) p = n;
+    const size_t m = n / p;
+    std::vector<std::vector<long double>> sr(p, std::vector<long double>(m)), si(p, std::vector<long double>(m));
+    for (size_t r = 0; r < p; ++r)
+        for (size_t j = 0; j < m; ++j) { sr[r][j] = re[j * p + r]; si[r][j] = im[j * p + r]; }
+    for (size_t r = 0; r < p; ++r) host_fft_any(sr[r], si[r]);
+    for (size_t k = 0; k < m; ++k)
+        for (size_t q = 0; q < p; ++q) {
+            long double ar = 0, ai = 0;
+            for (size_t r = 0; r < p; ++r) {
+                long double c, s;
+                unit_root((r * (k + m * q)) % n, n, c, s);      // e^{-2 pi i r (k + m q)/n}
+                ar += sr[r][k] * c - si[r][k] * s;
+                ai += sr[r][k] * s + si[r][k] * c;
+            }
+            re[k + m * q] = ar; im[k + m * q] = ai;
+        }
+}
+
 // in-place radix-2 FFT in long double (host, table generation only); n must be a power of two
 inline void host_fft_pow2(std::vector<long double>& re, std::vector<long double>& im) {
     const size_t n = re.size();
@@ -175,7 +200,7 @@ inline std::vector<T> make_aux(int kind, uint64_t a, uint64_t b) {
                 re[m] = c; im[m] = -s;
                 if (m) { re[b - m] = c; im[b - m] = -s; }
             }
-            host_fft_pow2(re, im);
+            if ((b & (b - 1)) == 0) host_fft_pow2(re, im); else host_fft_any(re, im);
             for (uint64_t k = 0; k < b; ++k) push(re[k] / (long double)b, im[k] / (long double)b);
         } break;
         default: break;

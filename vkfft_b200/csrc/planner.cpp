@@ -464,6 +464,15 @@ int plan_bluestein(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job)
     const uint64_t N = job.N;
     uint64_t M = 1;
     while (M < 2 * N - 1) M <<= 1;
+    // contiguous lines: a smooth padded length between the powers of two when both specialised Bluestein launches exist for it
+    if (!job.unit_lines && job.es_in == 1 && job.es_out == 1 && !getenv("B200FFT_BLUESTEIN_POW2")) {
+        for (int i = 0; i < b2_kernel_count(); ++i) {
+            const b2_kernel_info* k = b2_kernel_at(i);
+            if (k->kind != B2_KIND_ROWS || k->prec != g.prec || k->ops != B2_OP_BLUESTEIN || k->inv != 0) continue;
+            const uint64_t n = (uint64_t)k->n;
+            if (n >= 2 * N - 1 && n < M && b2_find_kernel(B2_KIND_ROWS, g.prec, k->n, 1, B2_OP_BLUESTEIN)) M = n;
+        }
+    }
     const uint64_t L = count_lines(job.lines);
     if (!generic_fits(g, M)) {
         // padded length beyond one shared-memory pass: chirp/zero-pad, FFT_M (Four-Step), filter, IFFT_M, post-chirp as

@@ -98,6 +98,35 @@ static int emu_run_one(PlanGraph& g, PassPlan& pp, void* const* base) {
     return pp.k->launch(&P, pp.grid, nullptr) ? 4039 : 0;
 }
 
+// both launches of a fused Four-Step pair through the fused kernel body (tables built per pass as above)
+static int emu_run_fused(PlanGraph& g, PassPlan& pa, PassPlan& pb, void* const* base) {
+    const size_t esz = g.prec == B2_PREC_F64 ? 16 : 8;
+    b2_fused_params F{};
+    std::vector<float> lutf[2], hif, lof;
+    std::vector<double> lutd[2], hid, lod;
+    PassPlan* pps[2] = {&pa, &pb};
+    b2_pass_params* Ps[2] = {&F.A, &F.B};
+    for (int i = 0; i < 2; ++i) {
+        PassPlan& pp = *pps[i];
+        b2_pass_params& P = *Ps[i];
+        P = pp.P;
+        const LutSpec& ls = g.luts[pp.lut_id];
+        if (g.prec == B2_PREC_F32) { lutf[i] = make_stage_lut<float>(ls.radices.data(), (int)ls.radices.size()); P.lut = lutf[i].data(); }
+        else { lutd[i] = make_stage_lut<double>(ls.radices.data(), (int)ls.radices.size()); P.lut = lutd[i].data(); }
+        if (pp.tw_id >= 0) {
+            uint64_t M = g.tws[pp.tw_id].M;
+            if (g.prec == B2_PREC_F32) { make_twolevel<float>(M, P.tw_shift, hif, lof); P.tw_hi = hif.data(); P.tw_lo = lof.data(); }
+            else { make_twolevel<double>(M, P.tw_shift, hid, lod); P.tw_hi = hid.data(); P.tw_lo = lod.data(); }
+        }
+        P.in = (const unsigned char*)base[pp.in_role] + pp.in_off * esz;
+        P.out = (unsigned char*)base[pp.out_role] + pp.out_off * esz;
+    }
+    std::vector<uint32_t> ctl(B2_FCTL_WORDS + 2 * (size_t)pa.fz_NU);
+    F.ctl = ctl.data();
+    F.nseq = pa.fz_nseq; F.U = pa.fz_U; F.NU = pa.fz_NU; F.R = pa.fz_R; F.TA = pa.fz_TA; F.TB = pa.fz_TB;
+    return pa.fused->launch(&F, 0, nullptr) ? 4039 : 0;
+}
+
 extern "C" int emu_exec_plan(const b200fft_desc* d, int inverse, void* buffer, void* input, void* output,
                              int* npasses) {
     PlanGraph g;
@@ -110,8 +139,14 @@ extern "C" int emu_exec_plan(const b200fft_desc* d, int inverse, void* buffer, v
     void* base[ROLE_COUNT] = {buffer, temp.data(), input, output, g_emu_kernel};
     std::vector<PassPlan>& list = (inverse == 1) ? g.inv : g.fwd;
     if (npasses) *npasses = (int)list.size();
-    for (PassPlan& pp : list)
-        if ((rc = emu_run_one(g, pp, base)) != 0) return rc;
+    for (size_t i = 0; i < list.size(); ++i) {
+        if (list[i].fused && i + 1 < list.size()) {
+            if ((rc = emu_run_fused(g, list[i], list[i + 1], base)) != 0) return rc;
+            ++i;
+            continue;
+        }
+        if ((rc = emu_run_one(g, list[i], base)) != 0) return rc;
+    }
     return 0;
 }
 

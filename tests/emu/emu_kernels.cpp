@@ -2,3 +2,4 @@
 #include "kernel_inst.cuh"
 #include "kernel_list.def"
 #include "kernel_list_nonpow2.def"
+#include "kernel_list_fused.def"

@@ -7,6 +7,7 @@
 #include "stockham.cuh"
 #include "generic.cuh"
 #include "pipe.cuh"
+#include "fused4.cuh"
 #include "ew.cuh"
 
 #if !defined(B2_EMU)
@@ -344,6 +345,85 @@ struct MaybeConvCols<true, T, TPL, Q, V, MINB, Rs...> {
 #define B2_KC(shard, T, TPL, Q, V, MINB, ...)                                                              \
     static ::b200fft::MaybeConv<B2_SHARD_ON(shard), T, TPL, Q, V, MINB, __VA_ARGS__>                      \
         B2_CAT(b2_regc_, __COUNTER__)("CONV_ROWS<" #T "," #TPL "x" #Q ",V" #V ";" #__VA_ARGS__ ">");
+
+// ---- fused Four-Step (fused4.cuh) -----------------------------------------------------------------------------------
+namespace b200fft {
+#if defined(B2_EMU)
+template <class CA, class CB>
+int fused_launch_impl(const b2_fused_params* F, unsigned, void*) {
+    b2_fused_params FF = *F;
+    const uint32_t words = B2_FCTL_WORDS + 2 * FF.NU;
+    for (uint32_t i = 0; i < words; ++i) FF.ctl[i] = 0;
+    FF.ctl[B2_FCTL_AVAIL_A] = (FF.R < FF.NU ? FF.R : FF.NU) * FF.TA;
+    // one CTA walks every tile in claim order (pass B first whenever a unit is complete): no cross-CTA waiting to emulate
+    b2emu::launch(1, CA::THREADS, Fused4<CA, CB>::SMEM_BYTES, [&](unsigned char* sm) { Fused4<CA, CB>::run(FF, sm); }, b2emu::st().log);
+    return emu_refused();
+}
+template <class CA, class CB> int fused_prepare_impl() { return 0; }
+#else
+template <class CA, class CB>
+int fused_launch_impl(const b2_fused_params* F, unsigned max_ctas, void* stream) {
+    static int resident = 0;
+    if (!resident) {
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused4_kernel<CA, CB>, CA::THREADS, Fused4<CA, CB>::SMEM_BYTES);
+        resident = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    const uint64_t tiles = (uint64_t)F->NU * (F->TA + F->TB);
+    unsigned g = (unsigned)(tiles < (uint64_t)resident ? tiles : (uint64_t)resident);
+    if (max_ctas && g > max_ctas) g = max_ctas;
+    const uint32_t words = B2_FCTL_WORDS + 2 * F->NU;
+    fused4_init_kernel<0><<<(words + 255) / 256 < 64 ? (words + 255) / 256 : 64, 256, 0, (cudaStream_t)stream>>>(
+        F->ctl, words, (F->R < F->NU ? F->R : F->NU) * F->TA);
+    void* args[] = {const_cast<b2_fused_params*>(F)};
+    return (int)cudaLaunchKernel((const void*)fused4_kernel<CA, CB>, dim3(g), dim3(CA::THREADS), args, Fused4<CA, CB>::SMEM_BYTES,
+                                 (cudaStream_t)stream);
+}
+template <class CA, class CB>
+int fused_prepare_impl() {
+    return (int)cudaFuncSetAttribute(fused4_kernel<CA, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fused4<CA, CB>::SMEM_BYTES);
+}
+#endif
+
+template <typename T, bool INV, int TPLA, int QA, class SchA, int TPLB, int QB, class SchB, int REGS>
+struct FusedRegistrar {
+    using KA = KindTraits<B2_KIND_COLS>;
+    using KB = KindTraits<B2_KIND_ROWS_TOUT>;
+    using CA = KCfg<T, SchA, TPLA, QA, 1, KA::LMAP, KA::SMAP, KA::LAYOUT, INV, B2_OP_TWIDDLE_OUT, KA::IN_UNIT, KA::OUT_UNIT, REGS, 0>;
+    using CB = KCfg<T, SchB, TPLB, QB, 1, KB::LMAP, KB::SMAP, KB::LAYOUT, INV, 0, KB::IN_UNIT, KB::OUT_UNIT, REGS, 0>;
+    static_assert(SchA::ns >= 2 && SchB::ns >= 2, "both passes exchange through shared memory");
+    b2_fused_info info;
+    explicit FusedRegistrar(const char* name) {
+        info = b2_fused_info{};
+        info.prec = PrecOf<T>::value; info.n1 = SchA::N; info.n2 = SchB::N; info.inv = INV;
+        info.threads = CA::THREADS; info.qa = QA; info.qb = QB; info.smem_bytes = Fused4<CA, CB>::SMEM_BYTES;
+        info.ns_a = SchA::ns; info.ns_b = SchB::ns;
+        for (int s = 0; s < SchA::ns; ++s) info.radices_a[s] = SchA::r(s);
+        for (int s = 0; s < SchB::ns; ++s) info.radices_b[s] = SchB::r(s);
+        info.launch = &fused_launch_impl<CA, CB>;
+        info.prepare = &fused_prepare_impl<CA, CB>;
+        info.name = name;
+        b2_register_fused(&info);
+    }
+};
+template <bool EN, typename T, int TPLA, int QA, class SchA, int TPLB, int QB, class SchB, int REGS>
+struct MaybeFused {
+    explicit MaybeFused(const char*) {}
+};
+template <typename T, int TPLA, int QA, class SchA, int TPLB, int QB, class SchB, int REGS>
+struct MaybeFused<true, T, TPLA, QA, SchA, TPLB, QB, SchB, REGS> {
+    FusedRegistrar<T, false, TPLA, QA, SchA, TPLB, QB, SchB, REGS> f;
+    FusedRegistrar<T, true, TPLA, QA, SchA, TPLB, QB, SchB, REGS> i;
+    explicit MaybeFused(const char* n) : f(n), i(n) {}
+};
+}  // namespace b200fft
+#define B2_R(...) ::b200fft::RList<__VA_ARGS__>
+//   B2_KF(shard, type, REGS, TPL_A, Q_A, B2_R(radices of n1), TPL_B, Q_B, B2_R(radices of n2))
+#define B2_KF(shard, T, REGS, TPLA, QA, SA, TPLB, QB, SB)                                                  \
+    static ::b200fft::MaybeFused<B2_SHARD_ON(shard), T, TPLA, QA, SA, TPLB, QB, SB, REGS>                  \
+        B2_CAT(b2_regf_, __COUNTER__)("FUSED4<" #T ";A " #TPLA "x" #QA " " #SA ";B " #TPLB "x" #QB " " #SB ">");
 
 #define B2_KD(shard, KIND, T, TPL, Q, V, MINB, ...)                                                       \
     static ::b200fft::MaybeDct<B2_SHARD_ON(shard), B2_KIND_##KIND, T, TPL, Q, V, MINB, __VA_ARGS__>       \

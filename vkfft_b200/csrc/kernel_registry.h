@@ -38,6 +38,24 @@ const b2_kernel_info* b2_find_kernel_variant(int kind, int prec, int n, int inv,
 int b2_kernel_count(void);
 const b2_kernel_info* b2_kernel_at(int i);
 
+// fused Four-Step kernels (fused4.cuh): both passes of n1 x n2 in one persistent launch
+typedef struct b2_fused_info {
+    int prec, n1, n2, inv;             // lookup key
+    int variant;
+    int threads, qa, qb, smem_bytes;   // CTA shape, columns per pass-A tile, rows per pass-B tile
+    int ns_a, ns_b;
+    int radices_a[8], radices_b[8];
+    // enqueue the control-block reset + the persistent kernel (at most max_ctas CTAs; 0 = as many as are resident)
+    int (*launch)(const b2_fused_params* F, unsigned max_ctas, void* stream);
+    int (*prepare)(void);
+    const char* name;
+} b2_fused_info;
+void b2_register_fused(const b2_fused_info* k);
+const b2_fused_info* b2_find_fused(int prec, int n1, int n2, int inv);
+const b2_fused_info* b2_find_fused_variant(int prec, int n1, int n2, int inv, int variant);
+int b2_fused_count(void);
+const b2_fused_info* b2_fused_at(int i);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,3 +7,4 @@
 
 #include "kernel_list.def"
 #include "kernel_list_nonpow2.def"
+#include "kernel_list_fused.def"

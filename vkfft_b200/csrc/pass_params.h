@@ -101,6 +101,31 @@ typedef struct b2_pass_params {
     uint32_t dst_flags;                    // B2_DST_* wrappers around the DCT operators
 } b2_pass_params;
 
+// One launch of the fused Four-Step kernel (fused4.cuh): both passes of a two-factor split N = n1*n2 in ONE persistent
+// launch.  Pass A (strided n1-point transforms + phase) writes into a small ring of scratch "units" that stays in L2,
+// pass B (contiguous n2-point transforms, transposed store) consumes a unit as soon as all of its A tiles are done.
+// The reference always runs the two uploads as separate dispatches with the whole intermediate going through DRAM
+// (vkFFT_Scheduler.h:2582-2893, vkFFT_DispatchPlan.h:157-225).
+typedef struct b2_fused_params {
+    b2_pass_params A, B;       // A.out / B.in = scratch ring base; their outer strides on the scratch side are ignored
+    uint32_t* ctl;             // B2_FCTL_* words followed by doneA[NU], doneB[NU]; zeroed before every launch
+    uint32_t nseq;             // sequences = product of the outer extents (same for A and B)
+    uint32_t U, NU;            // sequences per unit, units
+    uint32_t R;                // ring slots (units)
+    uint32_t TA, TB;           // tiles per unit of pass A / pass B
+    uint32_t reserved;
+} b2_fused_params;
+
+enum {
+    B2_FCTL_NEXT_A = 0,        // A tiles handed out
+    B2_FCTL_NEXT_B = 1,        // B tiles handed out
+    B2_FCTL_AVAIL_A = 2,       // (signed) A tiles that may be claimed: their ring slot is free
+    B2_FCTL_AVAIL_B = 3,       // (signed) B tiles that may be claimed: their unit's A tiles are all done
+    B2_FCTL_READY_UNITS = 4,   // prefix of units whose pass A is complete
+    B2_FCTL_FREED_UNITS = 5,   // prefix of units whose pass B is complete (their slot may be overwritten)
+    B2_FCTL_WORDS = 32,        // doneA starts here (128-byte aligned), doneB follows
+};
+
 #ifdef __cplusplus
 }
 #endif

@@ -76,6 +76,10 @@ struct PassPlan {
     int aux0_role = -1;          // >= 0: aux0 is a caller buffer (the convolution kernel), not a plan-owned table
     bool sync_before = false;    // distributed plans: barrier over all ranks of the window before this launch
     bool in_scalar = false, out_scalar = false;   // offsets (and strides) of that side count scalars, not complex elements
+    // fused Four-Step (fused4.cuh): this launch and the NEXT one of the list run as one persistent kernel; the two
+    // PassPlans stay in the list (the second is skipped at run time) so that un-fusing is a matter of clearing the pointer
+    const b2_fused_info* fused = nullptr;
+    uint32_t fz_nseq = 0, fz_U = 0, fz_NU = 0, fz_R = 0, fz_TA = 0, fz_TB = 0;
     std::string note;            // human readable (plan_describe)
 };
 
@@ -97,6 +101,7 @@ struct PlanGraph {
     uint64_t algorithmic_bytes = 0;
     uint32_t axis_uploads[2][B200FFT_MAX_DIMS] = {{0, 0, 0, 0}, {0, 0, 0, 0}};   // launches per axis, [0] forward / [1] inverse (the reference's numAxisUploads)
     int skip_axis = -1;          // convolution plans: this axis is transformed by the fused kernel, the direction planners leave it out
+    uint64_t ctl_words = 0;      // control block of the fused Four-Step launches (largest one of the plan)
     bool distributed = false;    // desc.dist_world > 1: one more barrier follows the last launch of a direction
 };
 

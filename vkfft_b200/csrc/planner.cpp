@@ -350,6 +350,17 @@ std::vector<uint64_t> split_four_step(const PlanGraph& g, uint64_t N, bool dist 
         if (!fast(B2_KIND_ROWS_TOUT, n2, 0)) cost += 1u << 20;
         if (!fast(B2_KIND_COLS, n1, B2_OP_TWIDDLE_OUT)) cost += 1u << 20;
         cost += short_runs(B2_KIND_COLS, n1, B2_OP_TWIDDLE_OUT) + short_runs(B2_KIND_ROWS_TOUT, n2, 0);
+        // splits that run as one fused launch (one HBM round trip instead of two) win over every two-launch split;
+        // among them the first registered pair of a length is the measured default (kernel_list_fused.def)
+        if (!dist && !getenv("B200FFT_NO_FUSED4")) {
+            const b2_fused_info* fk = b2_find_fused(g.prec, (int)n1, (int)n2, 0);
+            if (fk) {
+                int order = 0;
+                for (int i = 0; i < b2_fused_count() && b2_fused_at(i) != fk; ++i)
+                    if (b2_fused_at(i)->prec == g.prec && !b2_fused_at(i)->inv && (uint64_t)b2_fused_at(i)->n1 * b2_fused_at(i)->n2 == N) ++order;
+                cost = 1 + order;
+            }
+        }
         if (cost < best_cost) { best_cost = cost; best = {n1, n2}; }
     }
     const uint64_t two_level_limit = (g.prec == B2_PREC_F32) ? (1ull << 22) : (1ull << 21);
@@ -586,6 +597,48 @@ int plan_bluestein(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job)
     return R_SUCCESS;
 }
 
+// Two-factor Four-Step just emitted as list[ia] (strided + phase, -> temp) and list[ia + 1] (contiguous + transpose,
+// temp ->): run both as ONE persistent launch with the intermediate in an L2-resident ring (fused4.cuh) when a fused
+// kernel exists for (n1, n2).  B200FFT_NO_FUSED4=1 keeps the two launches; B200FFT_FUSED_UNIT_KB / B200FFT_FUSED_RING /
+// B200FFT_FUSED_RING_MB tune the ring (unit size, slots, total size).
+void try_fuse(PlanGraph& g, std::vector<PassPlan>& list, size_t ia) {
+    if (getenv("B200FFT_NO_FUSED4") || ia + 2 != list.size()) return;
+    PassPlan& a = list[ia];
+    PassPlan& b = list[ia + 1];
+    if (a.out_role != ROLE_TEMP || b.in_role != ROLE_TEMP || a.sync_before || b.sync_before) return;
+    if (!a.k || !b.k || a.k->kind != B2_KIND_COLS || b.k->kind != B2_KIND_ROWS_TOUT) return;
+    const b2_fused_info* fk = b2_find_fused(g.prec, (int)a.P.n, (int)b.P.n, a.k->inv);
+    if (!fk) return;
+    uint64_t nseq = 1, nseq_b = 1;
+    for (int d = 0; d < B2_MAX_OUTER; ++d) { nseq *= a.P.nb[d]; nseq_b *= b.P.nb[d]; }
+    if (nseq != nseq_b || nseq > 0x7fffffffull) return;
+    const uint64_t N = (uint64_t)a.P.n * b.P.n, esz = esize(g), seq_bytes = N * esz;
+    uint64_t unit_kb = 2048, ring_mb = 32, ring = 0;
+    if (const char* e = getenv("B200FFT_FUSED_UNIT_KB")) unit_kb = strtoull(e, nullptr, 10);
+    if (const char* e = getenv("B200FFT_FUSED_RING_MB")) ring_mb = strtoull(e, nullptr, 10);
+    if (const char* e = getenv("B200FFT_FUSED_RING")) ring = strtoull(e, nullptr, 10);
+    uint64_t U = std::max<uint64_t>(1, (unit_kb << 10) / seq_bytes);
+    U = std::min(U, nseq);
+    while (nseq % U) --U;                                  // whole units only
+    const uint64_t NU = nseq / U;
+    uint64_t R = ring ? ring : std::max<uint64_t>(3, (ring_mb << 20) / (U * seq_bytes));
+    if (!ring && R * U * seq_bytes > (64ull << 20)) R = std::max<uint64_t>(2, (64ull << 20) / (U * seq_bytes));   // very long sequences
+    R = std::max<uint64_t>(1, std::min(R, NU));
+    const uint64_t ga = (a.P.G + fk->qa - 1) / fk->qa, gb = (b.P.G + fk->qb - 1) / fk->qb;
+    if (NU * U * (ga + gb) > 0x7fffffffull) return;
+    a.fused = fk;
+    a.fz_nseq = (uint32_t)nseq; a.fz_U = (uint32_t)U; a.fz_NU = (uint32_t)NU; a.fz_R = (uint32_t)R;
+    a.fz_TA = (uint32_t)(U * ga); a.fz_TB = (uint32_t)(U * gb);
+    a.lut_id = lut_for(g, std::vector<int>(fk->radices_a, fk->radices_a + fk->ns_a));
+    b.lut_id = lut_for(g, std::vector<int>(fk->radices_b, fk->radices_b + fk->ns_b));
+    g.ctl_words = std::max<uint64_t>(g.ctl_words, B2_FCTL_WORDS + 2 * NU);
+    char buf[256];
+    snprintf(buf, sizeof buf, " [fused with the next launch: %s, %llu units of %llu sequences, ring of %llu units = %.1f MB]", fk->name,
+             (unsigned long long)NU, (unsigned long long)U, (unsigned long long)R, (double)(R * U * seq_bytes) / 1048576.0);
+    a.note += buf;
+    b.note += " [runs inside the previous launch]";
+}
+
 int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
     const uint64_t N = job.N;
     const int sc_ops = (job.scale != 1.0) ? B2_OP_SCALE : 0;
@@ -745,7 +798,10 @@ int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
             b.sync_before = true;
             b.what = "distributed four-step 2/2 contiguous+transpose (peer stores)";
         }
-        return emit(g, list, b);
+        const size_t ia = list.size() - 1;
+        if ((rc = emit(g, list, b)) != R_SUCCESS) return rc;
+        if (!dist && job.tmp_base % 16 == 0) try_fuse(g, list, ia);
+        return R_SUCCESS;
     }
     const uint64_t N1 = f[0], N2 = f[1], N3 = f[2], M = N2 * N3;
     PassReq a;

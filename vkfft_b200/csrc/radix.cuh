@@ -72,12 +72,13 @@ B2_HD cpx<T> mul_wconst(cpx<T> a, int e) {
     if (4 * e == R) return mul_mi(a);
     if (4 * e == 3 * R) return mul_pi(a);
     constexpr T h = T(7.07106781186547524400844362104849039e-01L);
-    if (8 * e == R) return mk<T>((a.x + a.y) * h, (a.y - a.x) * h);          // (1-i)/sqrt2
-    if (8 * e == 3 * R) return mk<T>((a.y - a.x) * h, -(a.x + a.y) * h);     // (-1-i)/sqrt2
-    if (8 * e == 5 * R) return mk<T>(-(a.x + a.y) * h, (a.x - a.y) * h);     // (-1+i)/sqrt2
-    if (8 * e == 7 * R) return mk<T>((a.x - a.y) * h, (a.x + a.y) * h);      // (1+i)/sqrt2
-    const T c = wcos_r<T, R>(e), s = wsin_r<T, R>(e);                        // W = c - i s
-    return mk<T>(a.x * c + a.y * s, a.y * c - a.x * s);
+    // eighth turns: one (packed) add with a quarter turn of the same value, one scale
+    if (8 * e == R) return (a + mul_mi(a)) * h;              // (1-i)/sqrt2 : ((x+y), (y-x)) h
+    if (8 * e == 3 * R) return (mul_mi(a) - a) * h;          // (-1-i)/sqrt2: ((y-x), -(x+y)) h
+    if (8 * e == 5 * R) return (mul_pi(a) - a) * h;          // (-1+i)/sqrt2: (-(x+y), (x-y)) h
+    if (8 * e == 7 * R) return (a + mul_pi(a)) * h;          // (1+i)/sqrt2 : ((x-y), (x+y)) h
+    const T c = wcos_r<T, R>(e), s = wsin_r<T, R>(e);        // W = c - i s :  a c + (-i a) s
+    return fma_s(mul_mi(a), s, a * c);
 }
 
 template <int R> struct radix_split { static constexpr int r1 = 1, r2 = R; };  // prime
@@ -115,12 +116,12 @@ B2_HD void dft_prime(cpx<T>* x) {
 #pragma unroll
         for (int j = 1; j <= h; ++j) {
             const T c = wcos_r<T, P>((j * k) % P), sn = wsin_r<T, P>((j * k) % P);
-            a.x += c * s[j - 1].x;  a.y += c * s[j - 1].y;
-            b.x += sn * d[j - 1].x; b.y += sn * d[j - 1].y;
+            a = fma_s(s[j - 1], c, a);
+            b = fma_s(d[j - 1], sn, b);
         }
         // X_k = A - iB ; X_{P-k} = A + iB
-        x[k] = mk<T>(a.x + b.y, a.y - b.x);
-        x[P - k] = mk<T>(a.x - b.y, a.y + b.x);
+        x[k] = a + mul_mi(b);
+        x[P - k] = a + mul_pi(b);
     }
 }
 

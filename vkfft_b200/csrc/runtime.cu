@@ -9,6 +9,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -34,6 +35,7 @@ struct b200fft_plan {
     std::vector<void*> d_auxs;
     void* d_temp = nullptr;
     uint64_t temp_bytes = 0;
+    void* d_ctl = nullptr;          // control block of the fused Four-Step launches
     uint64_t lut_bytes = 0;
     // exec_host staging
     void* d_stage = nullptr;
@@ -76,6 +78,7 @@ void free_plan(b200fft_plan* p) {
     for (TwDev& t : p->d_tws) { if (t.hi) cudaFree(t.hi); if (t.lo) cudaFree(t.lo); }
     for (void* d : p->d_auxs) if (d) cudaFree(d);
     if (p->d_temp) cudaFree(p->d_temp);
+    if (p->d_ctl) cudaFree(p->d_ctl);
     if (p->d_stage) cudaFree(p->d_stage);
     delete p;
 }
@@ -141,6 +144,10 @@ extern "C" int b200fft_plan_create(const b200fft_desc* desc, b200fft_plan** out)
                 rc = R_FAILED_TO_SET_DYNAMIC_SHARED_MEMORY;
                 break;
             }
+    for (int dir = 0; dir < 2 && rc == R_SUCCESS; ++dir)
+        for (const PassPlan& pp : (dir ? g.inv : g.fwd))
+            if (pp.fused && pp.fused->prepare && pp.fused->prepare() != 0) { rc = R_FAILED_TO_SET_DYNAMIC_SHARED_MEMORY; break; }
+    if (rc == R_SUCCESS && g.ctl_words && cudaMalloc(&p->d_ctl, g.ctl_words * 4) != cudaSuccess) rc = R_FAILED_TO_ALLOCATE;
     // scratch for Four-Step (the reference auto-allocates tempBuffer the same way, vkFFT_InitializeApp.h:1603-1637)
     if (rc == R_SUCCESS && g.temp_elems && !g.desc.user_temp_buffer) {
         p->temp_bytes = g.temp_elems * (g.prec == B2_PREC_F64 ? 16 : 8);
@@ -206,14 +213,8 @@ static int exec_impl(b200fft_plan* p, int inverse, const b200fft_buffers* b, std
         marks->push_back(e);
         if (kind_of_next >= 0) kinds->push_back(kind_of_next);
     };
-    for (const PassPlan& pp : list) {
-        if (pp.sync_before) {
-            mark(0);
-            int brc = b200fft_window_barrier(p->window, (void*)st);
-            if (brc != R_SUCCESS) return brc;
-        }
-        mark(1);
-        b2_pass_params P = pp.P;
+    auto resolve = [&](const PassPlan& pp, b2_pass_params& P) {
+        P = pp.P;
         P.in = base[pp.in_role] + pp.in_off * (int64_t)(pp.in_scalar ? esz / 2 : esz);
         P.out = base[pp.out_role] + pp.out_off * (int64_t)(pp.out_scalar ? esz / 2 : esz);
         if (pp.aux0_id >= 0) P.aux0 = p->d_auxs[pp.aux0_id];
@@ -225,6 +226,31 @@ static int exec_impl(b200fft_plan* p, int inverse, const b200fft_buffers* b, std
             P.tw_lo = p->d_tws[pp.tw_id].lo;
             P.tw_shift = p->d_tws[pp.tw_id].shift;
         }
+    };
+    const unsigned fused_max_ctas = [] { const char* e = getenv("B200FFT_FUSED_CTAS"); return e ? (unsigned)strtoul(e, nullptr, 10) : 0u; }();   // tuning knob
+    for (size_t ip = 0; ip < list.size(); ++ip) {
+        const PassPlan& pp = list[ip];
+        if (pp.fused && ip + 1 < list.size()) {
+            // both passes of a two-factor Four-Step in one persistent launch (fused4.cuh)
+            mark(1);
+            b2_fused_params F;
+            memset(&F, 0, sizeof F);
+            resolve(pp, F.A);
+            resolve(list[ip + 1], F.B);
+            F.ctl = (uint32_t*)p->d_ctl;
+            F.nseq = pp.fz_nseq; F.U = pp.fz_U; F.NU = pp.fz_NU; F.R = pp.fz_R; F.TA = pp.fz_TA; F.TB = pp.fz_TB;
+            if (!F.ctl || pp.fused->launch(&F, fused_max_ctas, (void*)st) != 0) return R_FAILED_TO_LAUNCH_KERNEL;
+            ++ip;
+            continue;
+        }
+        if (pp.sync_before) {
+            mark(0);
+            int brc = b200fft_window_barrier(p->window, (void*)st);
+            if (brc != R_SUCCESS) return brc;
+        }
+        mark(1);
+        b2_pass_params P;
+        resolve(pp, P);
         const b2_kernel_info* k = pp.k;
         if (k->pipelined && ((((uintptr_t)P.in) | (uintptr_t)(P.in_gs * (int64_t)esz) | (uintptr_t)(P.in_bs[0] * (int64_t)esz) |
                               (uintptr_t)(P.in_bs[1] * (int64_t)esz) | (uintptr_t)(P.in_bs[2] * (int64_t)esz)) & 15))

@@ -131,7 +131,24 @@ struct KCfg {
     static constexpr bool TWCHAIN = !(N == 8192 && LAYOUT_ == 0 && sizeof(T_) == 4);
 };
 
-template <class C>
+// XF (extra flags, fused Four-Step kernel):
+//   XF_LDCG      first-stage legs are read with ld.global.cg (L2 only): the data was written by other SMs during this launch
+//   XF_DISCARD   after the first-stage legs of a tile are in registers its lines are dropped from L2 without write-back
+//                (discard.global.L2): scratch that is never read again must not cost HBM write bandwidth
+enum { XF_LDCG = 1, XF_DISCARD = 2 };
+
+#if defined(__CUDA_ARCH__)
+template <typename T> B2_D cpx<T> ld_cg(const cpx<T>* p) {
+    if constexpr (sizeof(T) == 4) { float2 v = __ldcg(reinterpret_cast<const float2*>(p)); return mk<T>(v.x, v.y); }
+    else { double2 v = __ldcg(reinterpret_cast<const double2*>(p)); return mk<T>(v.x, v.y); }
+}
+#else
+template <typename T> B2_D cpx<T> ld_cg(const cpx<T>* p) { return *p; }
+#endif
+
+struct NoHook { B2_D void operator()() const {} };
+
+template <class C, int XF = 0>
 struct Engine {
     using T = typename C::T;
     using X = cpx<T>;
@@ -171,7 +188,10 @@ struct Engine {
 #pragma unroll
                     for (int v = 0; v < V; ++v) {
                         X a = mk<T>(T(0), T(0));
-                        if (ok) a = line[C::IN_UNIT ? (int64_t)(p + v) : (int64_t)(p + v) * es];
+                        if (ok) {
+                            const X* src = line + (C::IN_UNIT ? (int64_t)(p + v) : (int64_t)(p + v) * es);
+                            if constexpr (XF & XF_LDCG) a = ld_cg(src); else a = *src;
+                        }
                         x[(m * V + v) * r + k] = C::INV ? swp(a) : a;
                     }
                 }
@@ -664,6 +684,23 @@ struct Engine {
         }
     }
 
+    // drop the (contiguous-line) input tile from L2 without write-back: every thread of the CTA has its legs in registers
+    B2_D static void discard_tile(const b2_pass_params& P, int64_t obase_in, uint32_t grp, int tid) {
+#if defined(__CUDA_ARCH__)
+        static_assert(C::LAYOUT == LAY_LINE && C::IN_UNIT, "discard: contiguous input lines");
+        constexpr int LINES_PER_ROW = (N * 2 * (int)sizeof(T)) / 128;      // 128-byte cache lines per FFT line
+        static_assert(LINES_PER_ROW * 128 == N * 2 * (int)sizeof(T), "whole cache lines");
+        const uint32_t g0 = grp * Q;
+        const uint32_t nrows = (P.G - g0) < (uint32_t)Q ? (P.G - g0) : (uint32_t)Q;
+        const char* base = (const char*)((const X*)P.in + obase_in + (int64_t)g0 * P.in_gs);
+        if ((((uintptr_t)base) | (uintptr_t)(P.in_gs * 2 * (int64_t)sizeof(T))) & 127) return;   // unaligned scratch: keep the lines
+        for (uint32_t i = tid; i < nrows * LINES_PER_ROW; i += C::THREADS) {
+            const char* a = base + (int64_t)(i / LINES_PER_ROW) * P.in_gs * 2 * (int64_t)sizeof(T) + (size_t)(i % LINES_PER_ROW) * 128;
+            asm volatile("discard.global.L2 [%0], 128;" ::"l"(a) : "memory");
+        }
+#endif
+    }
+
     // coordinate that multiplies the element index in the four-step phase
     B2_D static uint32_t twl(const b2_pass_params& P, uint32_t g, uint32_t o0, uint32_t o1, uint32_t o2) {
         const uint32_t sel = P.tw_sel;
@@ -687,7 +724,6 @@ struct Engine {
     }
 
     B2_D static void run(const b2_pass_params& P, unsigned char* smem_raw) {
-        const int tid = threadIdx.x;
         // decode CTA -> (line group, outer batch coordinates)
         const uint32_t ngrp = (P.G + Q - 1) / Q;
         uint32_t rest = blockIdx.x;
@@ -697,6 +733,16 @@ struct Engine {
         const uint32_t o2 = rest;
         const int64_t obase_in = (int64_t)o0 * P.in_bs[0] + (int64_t)o1 * P.in_bs[1] + (int64_t)o2 * P.in_bs[2];
         const int64_t obase_out = (int64_t)o0 * P.out_bs[0] + (int64_t)o1 * P.out_bs[1] + (int64_t)o2 * P.out_bs[2];
+        run_at(P, smem_raw, grp, o0, o1, o2, obase_in, obase_out, NoHook{});
+    }
+
+    // one tile: line group `grp` of the lines at (o0, o1, o2); obase_* = element offsets of those coordinates.
+    // `hook` runs once, after the first-stage loads have been issued and before their values are used (the fused
+    // Four-Step kernel claims its next tile there, hidden behind the HBM latency)
+    template <class Hook>
+    B2_D static void run_at(const b2_pass_params& P, unsigned char* smem_raw, uint32_t grp, uint32_t o0, uint32_t o1, uint32_t o2,
+                            int64_t obase_in, int64_t obase_out, Hook hook) {
+        const int tid = threadIdx.x;
         const X* __restrict__ lut = (const X*)P.lut;
         X* sm = reinterpret_cast<X*>(smem_raw);
 
@@ -827,10 +873,12 @@ struct Engine {
                 else if constexpr (C::RMODE == 5) load_global_perm<0>(x, in_line, P.in_es / P.aux_u1, psel, P.aux_u1, P.aux_u0, tl, gl < P.G);
                 else if constexpr (C::RMODE == 7) load_global_blue<0>(x, in_line, P, tl, gl < P.G);
                 else load_global<0>(x, in_line, P.in_es, tl, gl < P.G);
+                hook();
                 compute<0>(x, lut, tl);
                 store_smem<0>(x, sm, ql, tl);
             }
             __syncthreads();
+            if constexpr ((XF & XF_DISCARD) != 0) discard_tile(P, obase_in, grp, tid);
             middle<1>(sm, lut, tid);
             {
                 constexpr int s = NS - 1;

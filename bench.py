@@ -9,7 +9,15 @@
   value    whole-job GFLOP/s with the buffer resident in HBM (CUDA events, max over ranks).
   e2e      the same step through the public API with HOST buffers: pinned-host -> HBM copy of the step's input,
            the sweep, and the HBM -> host read of the result, all inside the timed region.
-  roofline the dominant kernel (single-pass N=4096 forward): algorithmic bytes / CUDA-event time / measured peak.
+  roofline the dominant kernel = the kernel with the LARGEST SHARE of the step's device time (per-launch CUDA events
+           through b200fft_debug_exec_timed, aggregated by kernel over the sweep): algorithmic bytes per launch / mean
+           launch time / measured peak; `kernel_shares` lists the top kernels, `step_frac` is the whole step.
+  per_config  BASELINE configs 3-5 on one GPU (3-D FP64 256^3 / 512^3, 2-D R2C 4096^2, DCT-II 8192^2, 1-D 2^26): ms per
+           forward+inverse pair, roofline fraction, and the unmodified reference's CUDA backend on the same GPU.
+  sample0  the reference's own sample_0 benchmark binary (VkFFT_TestSuite -vkfft 0, "Benchmark score VkFFT") built from the
+           reference's sources against this engine (oracle/_ref/VkFFT_TestSuite_b200) and against stock VkFFT
+           (oracle/_ref/VkFFT_TestSuite_ref), both run here.
+  dist_2p26  (N >= 2 GPUs) config 5: one 2^26-point sequence over all ranks, exchange fused into the FFT launches.
   cpu_baseline  pocketfft (scipy.fft) on the box's host cores, bounded sample -- stand-in for the reference's
            FFTW precision-test path (FFTW is not installed in this image).  Reported, not a target.
   vkfft_cuda_ref  the UNMODIFIED reference (CUDA backend, oracle/_ref) timed on the same GPU in the same run.
@@ -134,14 +142,15 @@ def cpu_baseline(steps=1, warmup=0):
             "seconds_per_step": dt}, dt
 
 
-def vkfft_cuda_reference(torch, buf, ns, iters=3):
+def vkfft_cuda_reference(torch, buf, ns, iters=5, warm=2):
     """time the unmodified reference's CUDA backend (oracle/_ref) on the same buffer: ms per FFT+iFFT pair per N"""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import vkfft_oracle as orc
     if not orc.ref_available():
         return {"unavailable": "oracle/_ref/libvkfft_ref.so not built"}
     L = orc.ref_lib()
-    out = {"per_n": {}, "impl": "DTolm/VkFFT 1.3.4 CUDA backend (NVRTC), unmodified, same GPU, same buffer"}
+    out = {"per_n": {}, "impl": "DTolm/VkFFT 1.3.4 CUDA backend (NVRTC), unmodified, same GPU, same buffer",
+           "warmup_pairs": warm, "timed_pairs": iters}
     total_ms, total_fl = 0.0, 0.0
     pts = buf.numel()
     score_terms = []
@@ -153,7 +162,7 @@ def vkfft_cuda_reference(torch, buf, ns, iters=3):
             out["per_n"][str(n)] = {"error": rc}
             continue
         ms_e, ms_w = ctypes.c_double(), ctypes.c_double()
-        rc = L.vkref_bench_pairs(h, buf.data_ptr(), 1, iters, ctypes.byref(ms_e), ctypes.byref(ms_w))
+        rc = L.vkref_bench_pairs(h, buf.data_ptr(), warm, iters, ctypes.byref(ms_e), ctypes.byref(ms_w))
         up = L.vkref_axis0_uploads(h)
         L.vkref_close(h)
         buf.zero_()                      # unnormalised pairs overflow; reset (timing is data independent)
@@ -169,6 +178,217 @@ def vkfft_cuda_reference(torch, buf, ns, iters=3):
         out["ms_sweep"] = total_ms
         out["sample0_style_score"] = sum(score_terms) / len(score_terms)
     return out
+
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank's threads to the CPUs next to its GPU BEFORE the pinned host buffer is allocated (first touch puts the
+    pages on that NUMA node): 8 ranks copying 4 GiB per step each otherwise meet on one socket's memory controllers."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local_rank)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if bus.startswith("00000000:"):
+            bus = "0000:" + bus[len("00000000:"):]
+        base = f"/sys/bus/pci/devices/{bus}"
+        cpus = open(base + "/local_cpulist").read().strip()
+        node = open(base + "/numa_node").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        if ids:
+            os.sched_setaffinity(0, ids)
+            return {"numa_node": int(node), "cpus": cpus}
+    except Exception as e:
+        return {"error": repr(e)}
+    return {"error": "no local_cpulist"}
+
+
+def launch_labels(describe_text):
+    """plan_describe lines -> one label per actual launch (a fused pair is one launch)"""
+    import re
+    out = []
+    for l in describe_text.strip().split("\n"):
+        if "runs inside the previous launch" in l:
+            continue
+        m = re.search(r"fused with the next launch: (FUSED4<[^\]]*?>),", l)
+        if m:
+            out.append(m.group(1))
+            continue
+        m = re.search(r" n=(\d+) (\S+)\[", l)
+        what = l.split(": ", 1)[1].split(" n=")[0] if ": " in l else ""
+        out.append(f"{m.group(2)} n={m.group(1)} ({what})" if m else l[:80])
+    return out
+
+
+def timed_launches(vk, app, inv, buffers, reps=3):
+    """per-launch device times of one execution (CUDA events around every launch): [ms, ...], best of `reps`"""
+    from vkfft_b200 import _lib
+    L = _lib.load()
+    L.b200fft_debug_exec_timed.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.c_int, ctypes.c_void_p]
+    b = _lib.b200fft_buffers()
+    b.buffer = buffers["buffer"]
+    if buffers.get("temp"):
+        b.temp_buffer = buffers["temp"]
+    ms, kind, n = (ctypes.c_float * 64)(), (ctypes.c_int * 64)(), ctypes.c_int(0)
+    best = None
+    for _ in range(reps):
+        rc = L.b200fft_debug_exec_timed(app._plan, inv, ctypes.byref(b), ms, kind, 64, ctypes.byref(n))
+        if rc != 0:
+            raise RuntimeError(vk.getVkFFTErrorString(rc))
+        cur = [ms[i] for i in range(n.value) if kind[i] == 1]
+        best = cur if best is None else [min(a, c) for a, c in zip(best, cur)]
+    return best
+
+
+CONFIG_CASES = [
+    # BASELINE.json configs[2..4], single-GPU part: name, size_xyz, batch, double, engine kwargs, reference kwargs, real?
+    ("config3: 3D C2C FP64 256^3 x8", (256, 256, 256), 8, True, {}, {}, False),
+    ("config3: 3D C2C FP64 512^3 x1", (512, 512, 512), 1, True, {}, {}, False),
+    ("config4: 2D R2C/C2R FP32 4096^2 x16", (4096, 4096), 16, False, dict(performR2C=1), dict(perform_r2c=1), True),
+    ("config4: 2D DCT-II/III FP32 8192^2 x2", (8192, 8192), 2, False, dict(performDCT=2), dict(perform_dct=2), True),
+    ("config5 (one GPU): 1D C2C FP32 2^26 x4", (1 << 26,), 4, False, {}, {}, False),
+]
+
+
+def bench_configs(torch, vk, peak, dev, warm=2, reps=5):
+    """BASELINE configs 3-5 on this GPU: engine vs the unmodified reference's CUDA backend, same buffer, same warm-up/reps"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import vkfft_oracle as orc
+    rows = []
+    for name, size, batch, dbl, kw, rkw, real in CONFIG_CASES:
+        pts = batch
+        for s_ in size:
+            pts *= s_
+        if kw.get("performR2C"):
+            alloc = batch * (size[0] // 2 + 1) * 2
+            for s_ in size[1:]:
+                alloc *= s_
+        else:
+            alloc = pts * (1 if real else 2)
+        buf = torch.zeros(alloc, dtype=torch.float64 if dbl else torch.float32, device=dev).uniform_(-1, 1)
+        row = {"case": name}
+        app = vk.VkFFTApplication()
+        rc = vk.initializeVkFFT(app, vk.VkFFTConfiguration(FFTdim=len(size), size=list(size), numberBatches=batch, device=dev.index,
+                                                           doublePrecision=int(dbl), normalize=1, **kw))
+        if rc != 0:
+            row["error"] = vk.getVkFFTErrorString(rc)
+        else:
+            info = vk.planInfo(app)
+            lp = vk.VkFFTLaunchParams(buffer=buf)
+            for _ in range(warm):
+                vk.VkFFTAppend(app, -1, lp); vk.VkFFTAppend(app, 1, lp)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                vk.VkFFTAppend(app, -1, lp); vk.VkFFTAppend(app, 1, lp)
+            b.record(); torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / reps
+            alg = 2 * info["algorithmic_bytes"]       # one read + one write of the data per transformed axis, both directions
+            row.update(ms_pair=round(ms, 4), launches_forward=len(launch_labels(info["forward"])),
+                       algorithmic_gb_pair=round(alg / 1e9, 3), frac_of_peak=round(alg / (ms * 1e-3) / 1e9 / peak, 4))
+            vk.deleteVkFFT(app)
+        if orc.ref_available():
+            L = orc.ref_lib()
+            d = orc.ref_desc(size, batch, dbl, device=dev.index, **rkw)
+            h = ctypes.c_void_p()
+            rc = L.vkref_open(ctypes.byref(d), ctypes.byref(h))
+            if rc == 0:
+                e, w = ctypes.c_double(), ctypes.c_double()
+                buf.uniform_(-1e-3, 1e-3)
+                rc = L.vkref_bench_pairs(h, buf.data_ptr(), warm, reps, ctypes.byref(e), ctypes.byref(w))
+                row["reference_ms_pair"] = round(e.value, 4) if rc == 0 else f"error {rc}"
+                L.vkref_close(h)
+            else:
+                row["reference_ms_pair"] = f"init error {rc}"
+        rows.append(row)
+        del buf
+        torch.cuda.empty_cache()
+    return rows
+
+
+def sample0_scores(device_index):
+    """the reference's sample_0 benchmark binary (VkFFT_TestSuite -vkfft 0), once linked to this engine and once stock"""
+    import re
+    out = {"formula": "mean over N = 2^3..2^27 (1 GiB buffer) of buffer_KB / ms per FFT+iFFT "
+                      "(sample_0_benchmark_VkFFT_single.cpp:239-276)"}
+    for key, exe in (("b200fft", "VkFFT_TestSuite_b200"), ("reference_vkfft_cuda", "VkFFT_TestSuite_ref")):
+        path = os.path.join(ROOT, "oracle", "_ref", exe)
+        if not os.path.exists(path):
+            out[key] = {"unavailable": f"oracle/_ref/{exe} not built"}
+            continue
+        try:
+            t0 = time.time()
+            r = subprocess.run([path, "-d", str(device_index), "-vkfft", "0"], capture_output=True, text=True, timeout=900,
+                               cwd=os.path.join(ROOT, "oracle", "_ref"))
+            m = re.search(r"Benchmark score VkFFT: (\d+)", r.stdout)
+            per = {mm.group(1): float(mm.group(2)) for mm in re.finditer(r"VkFFT System: (\d+) .*?avg_time_per_step: ([0-9.]+) ms", r.stdout)}
+            out[key] = {"score": int(m.group(1)) if m else None, "rc": r.returncode, "seconds": round(time.time() - t0, 1),
+                        "ms_per_pair_by_log2n": per}
+            if not m:
+                out[key]["tail"] = (r.stdout + r.stderr)[-400:]
+        except Exception as e:
+            out[key] = {"error": repr(e)}
+    return out
+
+
+def bench_dist_2p26(torch, dist, vk, local_rank, rank, world):
+    """config 5: ONE 2^26-point sequence over all ranks; the exchange is the peer loads/stores of the FFT launches"""
+    from vkfft_b200.dist import FusedDistributedFFT1D
+    n = 1 << 26
+    dev = torch.device("cuda", local_rank)
+    rec = {"n": "2^26", "world": world}
+    f = FusedDistributedFFT1D(n, dist, local_rank, normalize=True)
+    g = torch.Generator(device=dev).manual_seed(99)
+    torch.view_as_real(f.local).uniform_(-1, 1, generator=g)
+    x0 = f.local.clone()
+
+    def pair():
+        f(inverse=False); f(inverse=True)
+    for _ in range(3):
+        pair()
+    dist.barrier(); torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    a.record()
+    for _ in range(reps):
+        pair()
+    b.record(); torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b) / reps / 2], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    f.check()
+    err = (f.local - x0).abs().double().norm() / x0.abs().double().norm()
+    e = torch.tensor([float(err)], device=dev, dtype=torch.float64)
+    dist.all_reduce(e, op=dist.ReduceOp.MAX)
+    dist.barrier()
+    f.timed(False)
+    br = f.timed(False)
+    rec.update(fused_ms_per_transform=round(t.item(), 4), gflops=round(5 * n * 26 / (t.item() * 1e-3) / 1e9, 1),
+               roundtrip_rel_err_after_26_transforms=e.item(), launches_rank0=[(k, round(m, 4)) for k, m in br],
+               nvlink_bytes_per_gpu_per_direction=int(n * 8 / world * (world - 1) / world) * 2,
+               note="bytes: launch 1 gathers (R-1)/R of its columns and scatters (R-1)/R of its results, the last launch scatters again")
+    f.close()
+    dist.barrier()
+    if rank == 0:
+        # the same transform on one GPU, for the speed-up
+        buf = torch.zeros(n, dtype=torch.complex64, device=dev)
+        app = vk.VkFFTApplication()
+        if vk.initializeVkFFT(app, vk.VkFFTConfiguration(FFTdim=1, size=[n], device=local_rank, normalize=1)) == 0:
+            lp = vk.VkFFTLaunchParams(buffer=buf)
+            for _ in range(3):
+                vk.VkFFTAppend(app, -1, lp); vk.VkFFTAppend(app, 1, lp)
+            a.record()
+            for _ in range(reps):
+                vk.VkFFTAppend(app, -1, lp); vk.VkFFTAppend(app, 1, lp)
+            b.record(); torch.cuda.synchronize()
+            rec["single_gpu_ms_per_transform"] = round(a.elapsed_time(b) / reps / 2, 4)
+            rec["speedup_vs_one_gpu"] = round(rec["single_gpu_ms_per_transform"] / rec["fused_ms_per_transform"], 3)
+            vk.deleteVkFFT(app)
+        del buf
+    dist.barrier()
+    return rec
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -209,6 +429,9 @@ def main():
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip timing the reference's CUDA backend")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE config 3-5 legs")
+    ap.add_argument("--no-sample0", action="store_true", help="skip the reference's sample_0 benchmark binaries")
+    ap.add_argument("--no-dist", action="store_true", help="skip the distributed 2^26 record (N >= 2)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -219,6 +442,7 @@ def main():
         run_reference_arm(args, rank, world)
         return
 
+    numa = bind_to_gpu_numa_node(local_rank)
     import torch
     import vkfft_b200 as vk
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
@@ -285,14 +509,15 @@ def main():
     fl_step = sum(flops_pair(n, pts) for n in ns)
     value = world * fl_step / (ms_step * 1e-3) / 1e9
 
-    # ---- per-N breakdown + dominant-kernel roofline (rank 0 reports) --------------------------------------------
+    # ---- per-N breakdown (rank 0 reports) ---------------------------------------------------------------------------
     peak, peak_src = measured_peaks()
     per_n = {}
     alg_bytes_dir = 2 * 8 * pts      # one read + one write of every complex64 point, per direction
     for n, app, info in apps:
         reps = 5
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        vk.VkFFTAppend(app, -1, lp); vk.VkFFTAppend(app, 1, lp)
+        for _ in range(2):
+            vk.VkFFTAppend(app, -1, lp); vk.VkFFTAppend(app, 1, lp)
         a.record()
         for _ in range(reps):
             vk.VkFFTAppend(app, -1, lp); vk.VkFFTAppend(app, 1, lp)
@@ -302,31 +527,46 @@ def main():
         gbs = 2 * alg_bytes_dir / (ms_pair * 1e-3) / 1e9
         per_n[str(n)] = {"ms_pair": round(ms_pair, 4), "gflops": round(flops_pair(n, pts) / (ms_pair * 1e-3) / 1e9, 1),
                          "alg_gbs": round(gbs, 1), "frac_of_peak": round(gbs / peak, 4),
-                         "passes": info["num_passes_forward"]}
-    # dominant kernel: the single-pass N=4096 forward launch, timed alone with events on the launch stream
-    dom_n = 4096
-    dom_app = [a for n, a, _ in apps if n == dom_n][0]
-    for _ in range(3):
-        vk.VkFFTAppend(dom_app, -1, lp)
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 20
-    a.record()
-    for _ in range(reps):
-        vk.VkFFTAppend(dom_app, -1, lp)
-    b.record()
-    torch.cuda.synchronize()
-    ms_dom = a.elapsed_time(b) / reps
-    ach = alg_bytes_dir / (ms_dom * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
-                "traffic": None, "kernel": "stockham_kernel<ROWS,float,N=4096,forward> (1 launch = 2^16 sequences)",
-                "algorithmic_bytes_per_launch": alg_bytes_dir, "ms_per_launch": round(ms_dom, 4), "peak_source": peak_src,
-                "step_frac": round((len(ns) * 2 * alg_bytes_dir) / (ms_step * 1e-3) / 1e9 / peak, 4)}
-    tr = os.path.join(ROOT, "profiles", "traffic_n4096.json")
-    if os.path.exists(tr):
-        try:
-            roofline["traffic"] = json.load(open(tr))["dram_bytes_per_launch"]
-        except Exception:
-            pass
+                         "launches": len(launch_labels(info["forward"]))}
+    # ---- which kernel dominates the step?  One execution of every plan with CUDA events around every launch, aggregated by
+    # kernel over the whole sweep (both directions).  The roofline line is about THAT kernel; every launch of the sweep reads
+    # and writes the 2 GiB buffer exactly once (a fused Four-Step launch included), so algorithmic bytes per launch are equal.
+    shares = {}
+    if rank == 0:
+        for n, app, info in apps:
+            for inv, key in ((-1, "forward"), (1, "inverse")):
+                labels = launch_labels(info[key])
+                times = timed_launches(vk, app, inv, {"buffer": buf.data_ptr(), "temp": tmp.data_ptr()})
+                for lab, t in zip(labels, times):
+                    if lab.startswith("FUSED4") or "init" in lab:
+                        pass
+                    e = shares.setdefault(lab.split(" (")[0], {"ms": 0.0, "launches": 0})
+                    e["ms"] += t; e["launches"] += 1
+    tot_ms = sum(e["ms"] for e in shares.values()) or 1.0
+    ranked = sorted(shares.items(), key=lambda kv: -kv[1]["ms"])
+    kernel_shares = [{"kernel": k, "share_of_step": round(e["ms"] / tot_ms, 4), "launches_per_step": e["launches"],
+                      "ms_per_launch": round(e["ms"] / e["launches"], 4),
+                      "frac_of_peak": round(alg_bytes_dir / (e["ms"] / e["launches"] * 1e-3) / 1e9 / peak, 4)} for k, e in ranked[:8]]
+    roofline = {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src, "traffic": None,
+                "step_frac": round((len(ns) * 2 * alg_bytes_dir) / (ms_step * 1e-3) / 1e9 / peak, 4),
+                "algorithmic_bytes_per_launch": alg_bytes_dir}
+    if ranked:
+        k, e = ranked[0]
+        ms_dom = e["ms"] / e["launches"]
+        ach = alg_bytes_dir / (ms_dom * 1e-3) / 1e9
+        roofline.update(kernel=k, share_of_step=round(e["ms"] / tot_ms, 4), achieved=round(ach, 1), frac=round(ach / peak, 4),
+                        ms_per_launch=round(ms_dom, 4), launches_per_step=e["launches"],
+                        how="largest share of the step's device time; per-launch CUDA events on the launch stream "
+                            "(b200fft_debug_exec_timed), mean over its launches in the sweep")
+        tr = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tr):
+            try:
+                for rec in json.load(open(tr)):
+                    if rec["kernel"] in k or k in rec["kernel"]:
+                        roofline["traffic"] = rec["dram_bytes_per_launch"]
+                        roofline["traffic_source"] = rec.get("source")
+            except Exception:
+                pass
 
     # restore a sane buffer and verify the round trip the bench has been doing (normalize=1 -> identity)
     torch.view_as_real(buf).uniform_(-1, 1, generator=g)
@@ -404,6 +644,17 @@ def main():
     for _, app, _ in apps:
         vk.deleteVkFFT(app)
 
+    # ---- config 5, distributed part: one 2^26-point sequence over all ranks (every rank takes part) ---------------------
+    dist_rec = None
+    if dist is not None and not args.no_dist:
+        del buf, tmp, host
+        torch.cuda.empty_cache()
+        try:
+            dist_rec = bench_dist_2p26(torch, dist, vk, local_rank, rank, world)
+        except Exception as e:
+            dist_rec = {"error": repr(e)}
+        buf = torch.zeros(1, dtype=torch.complex64, device=dev)
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -418,8 +669,10 @@ def main():
                    "l2": "inputs (2 GiB) larger than L2 (126 MB)", "parallelism": f"batch-sharded x{world}, no collective",
                    "points_per_gpu": pts},
         "roofline": roofline, "e2e": e2e, "gpu_launches": launches_per_step * args.steps * world, "clocks": clocks,
-        "per_n": per_n, "roundtrip_rel_err": rt_err,
+        "kernel_shares": kernel_shares, "per_n": per_n, "roundtrip_rel_err": rt_err, "numa": numa,
     }
+    if dist_rec is not None:
+        line["dist_2p26"] = dist_rec
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"], _ = cpu_baseline()
     else:
@@ -429,6 +682,15 @@ def main():
             line["vkfft_cuda_ref"] = vkfft_cuda_reference(torch, buf, ns)
         except Exception as e:
             line["vkfft_cuda_ref"] = {"unavailable": repr(e)}
+    if world == 1 and not args.no_configs:
+        del buf, tmp, host
+        torch.cuda.empty_cache()
+        try:
+            line["per_config"] = bench_configs(torch, vk, peak, dev)
+        except Exception as e:
+            line["per_config"] = {"error": repr(e)}
+    if world == 1 and not args.no_sample0:
+        line["sample0"] = sample0_scores(local_rank)
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

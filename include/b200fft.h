@@ -109,7 +109,10 @@ typedef struct b200fft_plan b200fft_plan; /* opaque */
 typedef struct b200fft_plan_info {
     uint32_t num_passes_forward;    /* kernel launches per forward execution */
     uint32_t num_passes_inverse;
-    uint64_t temp_bytes;            /* engine-owned scratch (0 when none / user supplied) */
+    uint64_t temp_bytes;            /* scratch this plan needs (engine-owned, or the minimum size of the caller's tempBuffer
+                                       when user_temp_buffer = 1).  NOTE: it can exceed the size of `buffer` (Bluestein pads
+                                       to M >= 2N-1 points per line, odd-length R2C and composed DCT/DST plans widen their
+                                       lines): a caller-owned tempBuffer must be at least this large */
     uint64_t lut_bytes;             /* twiddle tables resident in HBM */
     uint64_t algorithmic_bytes;     /* 2 * sizeof(elem) * points * transformed axes, per direction */
     double flops;                   /* 5 N log2 N convention, per direction */

@@ -123,7 +123,7 @@ static int emu_run_fused(PlanGraph& g, PassPlan& pa, PassPlan& pb, void* const* 
     }
     std::vector<uint32_t> ctl(B2_FCTL_WORDS + 2 * (size_t)pa.fz_NU);
     F.ctl = ctl.data();
-    F.nseq = pa.fz_nseq; F.U = pa.fz_U; F.NU = pa.fz_NU; F.R = pa.fz_R; F.TA = pa.fz_TA; F.TB = pa.fz_TB;
+    F.nseq = pa.fz_nseq; F.U = pa.fz_U; F.NU = pa.fz_NU; F.R = pa.fz_R; F.TA = pa.fz_TA; F.TB = pa.fz_TB; F.reserved = pa.fz_L;
     return pa.fused->launch(&F, 0, nullptr) ? 4039 : 0;
 }
 

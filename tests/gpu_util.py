@@ -26,3 +26,30 @@ def run_c2c(x_np, size_xyz, batches=1, inverse=-1, double=False, **cfgkw):
     finally:
         vk.deleteVkFFT(app)
     return out
+
+
+def assert_f32_parity(mine, exact, theirs_fn, tol=1e-6):
+    """north_star tolerance for FP32: 1e-6 relative (l2) against the exact result.  Where a transform's own conditioning puts
+    BOTH engines beyond that (the composed real transforms: the reference's FP32 error reaches ~1.4e-6, README.md:76-80),
+    the criterion of the C2C reference test applies instead: this engine is at least as close to the exact result as the
+    unmodified reference's CUDA backend on the same input (|mine - exact| <= 1.05 |reference - exact|) -- which needs the
+    reference (oracle/_ref); without it the 1e-6 bound stands."""
+    import vkfft_oracle as orc
+    e_m = orc.error_metrics(mine, exact)["l2_rel"]
+    if e_m < tol:
+        return e_m
+    assert orc.ref_available(), f"l2_rel {e_m:.3e} >= {tol:.0e} and no reference build to compare with"
+    theirs = theirs_fn()
+    e_t = orc.error_metrics(theirs, exact)["l2_rel"]
+    assert e_m <= 1.05 * e_t + 1e-8, f"l2_rel {e_m:.3e} vs reference {e_t:.3e} (north-star 1e-6)"
+    return e_m
+
+
+def ref_inplace(arr, size_xyz, batch, inverse, double=False, **kw):
+    """the unmodified reference's CUDA backend (oracle/_ref) on a copy of `arr`"""
+    import vkfft_oracle as orc
+    torch = torch_mod()
+    t = torch.from_numpy(np.ascontiguousarray(arr)).cuda()
+    rc = orc.ref_run(orc.ref_desc(size_xyz, batch, double, use_lut=1, **kw), inverse, t.data_ptr())
+    assert rc == 0, rc
+    return t.cpu().numpy()

@@ -41,30 +41,74 @@ def test_desc_struct_layout_matches_header(built_lib):
                     ctypes.sizeof(_lib.b200fft_plan_info)]
 
 
-@pytest.mark.parametrize("lang", ["c", "c++"])
-def test_vkfft_shim_header_layout(lang):
-    """sizeof/offsetof of the drop-in structs == the reference's VKFFT_BACKEND==1 build (SURVEY.md section 7:
-    VkFFTConfiguration 1168 B, VkFFTLaunchParams 80 B, buffer@152, numberBatches@272, doublePrecision@360,
-    performR2C@408; measured from the reference headers)."""
-    src = r'''
-    #include "vkFFT.h"
-    #include <stdio.h>
-    #include <stddef.h>
-    int main(void){ printf("%zu %zu %zu %zu %zu %zu\n", sizeof(VkFFTConfiguration), sizeof(VkFFTLaunchParams),
-        offsetof(VkFFTConfiguration, buffer), offsetof(VkFFTConfiguration, numberBatches),
-        offsetof(VkFFTConfiguration, doublePrecision), offsetof(VkFFTConfiguration, performR2C));
-        VkFFTApplication app = VKFFT_ZERO_INIT; VkFFTConfiguration cfg = VKFFT_ZERO_INIT;
-        (void)app; (void)cfg; return VkFFTGetVersion() == 10304 ? 0 : 1; }'''
+def _struct_members(header_text, struct_name):
+    """member names of `typedef struct { ... } struct_name;` in declaration order (handles `a, *b, c[N]` lists)"""
+    import re
+    end = header_text.index("} " + struct_name + ";")
+    start = header_text.rindex("typedef struct", 0, end)
+    body = re.sub(r"/\*.*?\*/", "", header_text[start:end], flags=re.S)
+    body = re.sub(r"//[^\n]*", "", body)
+    names = []
+    for decl in body[body.index("{") + 1:].split(";"):
+        decl = decl.strip()
+        if not decl or decl.startswith("#"):
+            continue
+        first, *rest = decl.split(",")
+        parts = [first.split()[-1]] + rest if first.split() else rest
+        for q in parts:
+            q = q.strip().lstrip("*").strip()
+            q = re.sub(r"\[.*", "", q)
+            if re.fullmatch(r"[A-Za-z_][A-Za-z0-9_]*", q):
+                names.append(q)
+    return names
+
+
+def _layout_dump(include_dirs, defines, members, lang):
+    """compile AND RUN a probe printing sizeof + offsetof of every member; returns {name: value}"""
     cuda = "/usr/local/cuda"
-    if not os.path.exists(os.path.join(cuda, "include", "cuda.h")):
-        pytest.skip("CUDA headers not present")
+    lines = ['#include "vkFFT.h"', "#include <stdio.h>", "#include <stddef.h>", "int main(void){",
+             'printf("sizeof.VkFFTConfiguration %zu\\n", sizeof(VkFFTConfiguration));',
+             'printf("sizeof.VkFFTLaunchParams %zu\\n", sizeof(VkFFTLaunchParams));']
+    for st, ms in members.items():
+        for m in ms:
+            lines.append(f'printf("{st}.{m} %zu\\n", offsetof({st}, {m}));')
+    lines.append("return 0; }")
     with tempfile.TemporaryDirectory() as td:
         ext = "c" if lang == "c" else "cpp"
         f = os.path.join(td, "t." + ext)
-        open(f, "w").write(src)
+        open(f, "w").write("\n".join(lines))
         cc = ["gcc", "-std=c99"] if lang == "c" else ["g++", "-std=c++11"]
-        subprocess.check_call(cc + ["-c", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(cuda, "include"), f,
-                                    "-o", os.path.join(td, "t.o")])
+        cmd = cc + ["-w"] + [f"-D{d}" for d in defines]
+        for d in include_dirs + [os.path.join(cuda, "include")]:
+            cmd += ["-I", d]
+        exe = os.path.join(td, "probe")
+        # the probe only uses sizeof/offsetof: the header's forwarding functions are never referenced, nothing to link
+        subprocess.check_call(cmd + [f, "-o", exe, "-Wl,--unresolved-symbols=ignore-all"])
+        out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+    return {l.split()[0]: int(l.split()[1]) for l in out.strip().split("\n")}
+
+
+@pytest.mark.parametrize("lang", ["c", "c++"])
+def test_vkfft_shim_header_layout(lang):
+    """sizeof/offsetof of the drop-in structs == the reference's VKFFT_BACKEND==1 build.  The probe is compiled, RUN and
+    compared: against the known numbers of the reference headers (VkFFTConfiguration 1168 B,
+    VkFFTLaunchParams 80 B, buffer@152, numberBatches@272, doublePrecision@360, performR2C@408) and -- when the reference
+    tree is present -- member by member against a probe compiled from the reference's own header."""
+    cuda = "/usr/local/cuda"
+    if not os.path.exists(os.path.join(cuda, "include", "cuda.h")):
+        pytest.skip("CUDA headers not present")
+    hdr = open(os.path.join(ROOT, "include", "vkFFT.h")).read()
+    members = {"VkFFTConfiguration": _struct_members(hdr, "VkFFTConfiguration"),
+               "VkFFTLaunchParams": _struct_members(hdr, "VkFFTLaunchParams")}
+    assert len(members["VkFFTConfiguration"]) > 100 and len(members["VkFFTLaunchParams"]) >= 9
+    mine = _layout_dump([os.path.join(ROOT, "include")], ["VKFFT_BACKEND=1"], members, lang)
+    assert mine["sizeof.VkFFTConfiguration"] == 1168 and mine["sizeof.VkFFTLaunchParams"] == 80
+    assert mine["VkFFTConfiguration.buffer"] == 152 and mine["VkFFTConfiguration.numberBatches"] == 272
+    assert mine["VkFFTConfiguration.doublePrecision"] == 360 and mine["VkFFTConfiguration.performR2C"] == 408
+    ref_inc = "/root/reference/vkFFT"
+    if lang == "c++" and os.path.exists(os.path.join(ref_inc, "vkFFT.h")):
+        theirs = _layout_dump([ref_inc], ["VKFFT_BACKEND=1"], members, lang)
+        assert mine == theirs, {k: (mine[k], theirs.get(k)) for k in mine if mine[k] != theirs.get(k)}
 
 
 def test_python_api_host_side_errors(built_lib):

@@ -1,8 +1,6 @@
-"""GPU, opt-in (B200FFT_RUN_REFERENCE_TESTSUITE=1): the reference's own test-suite binary, built unmodified against include/vkFFT.h
-and linked to libb200fft.so (oracle/_ref/VkFFT_TestSuite_b200, `make -C oracle testsuite`), running its convolution samples.
-
-Opt-in because the binary was first built after the GPU budget of round 1 was spent: it has not run on hardware yet and must
-not be able to stop the regular `pytest -m gpu` run.  Enable it in round 2 and drop the switch once it has passed."""
+"""GPU: the reference's own test-suite binary, built unmodified against include/vkFFT.h and linked to libb200fft.so
+(oracle/_ref/VkFFT_TestSuite_b200, `make -C oracle testsuite`), running its convolution samples and its sample_0 benchmark --
+the reference's user-facing programs running on this engine through the drop-in header."""
 import os
 import re
 import subprocess
@@ -12,8 +10,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "oracle", "_ref", "VkFFT_TestSuite_b200")
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("B200FFT_RUN_REFERENCE_TESTSUITE") != "1", reason="opt-in, see module docstring"),
-              pytest.mark.skipif(not os.path.exists(EXE), reason="oracle/_ref/VkFFT_TestSuite_b200 not built")]
+              pytest.mark.skipif(not os.path.exists(EXE), reason="oracle/_ref/VkFFT_TestSuite_b200 not built (needs /root/reference at build time)")]
 
 
 def _run(sample):

@@ -113,9 +113,14 @@ def test_dct_matches_reference(ref, kind, size_xyz, batch, inverse):
             while n % p == 0:
                 n //= p
         return n == 1
-    if kind == 1 and not all(smooth(2 * s - 2) for s in size_xyz):
-        pytest.skip("DCT-I whose 2N-2 has a prime factor > 127: not built yet")
     x = orc.random_input((batch,) + tuple(reversed(size_xyz)), np.float32, seed=kind + sum(size_xyz))
     mine = _mine_inplace(torch, x, size_xyz, batch, inverse, performDCT=kind)
     theirs = _ref_inplace(torch, x, size_xyz, batch, inverse, perform_dct=kind)
-    assert orc.error_metrics(mine, theirs)["l2_rel"] < 2e-6
+    # north-star 1e-6 between the two engines; where the transform's conditioning puts the reference itself further than
+    # that from the exact result, this engine must be at least as close to it as the reference is
+    d = orc.error_metrics(mine, theirs)["l2_rel"]
+    if d >= 1e-6:
+        exact = orc.dct(x, kind, len(size_xyz), inverse=(inverse == 1))
+        e_m = orc.error_metrics(mine, exact)["l2_rel"]
+        e_t = orc.error_metrics(theirs, exact)["l2_rel"]
+        assert e_m <= 1.05 * e_t + 1e-8 and d < e_m + e_t + 1e-9, (d, e_m, e_t)

@@ -354,7 +354,6 @@ int fused_launch_impl(const b2_fused_params* F, unsigned, void*) {
     b2_fused_params FF = *F;
     const uint32_t words = B2_FCTL_WORDS + 2 * FF.NU;
     for (uint32_t i = 0; i < words; ++i) FF.ctl[i] = 0;
-    FF.ctl[B2_FCTL_AVAIL_A] = (FF.R < FF.NU ? FF.R : FF.NU) * FF.TA;
     // one CTA walks every tile in claim order (pass B first whenever a unit is complete): no cross-CTA waiting to emulate
     b2emu::launch(1, CA::THREADS, Fused4<CA, CB>::SMEM_BYTES, [&](unsigned char* sm) { Fused4<CA, CB>::run(FF, sm); }, b2emu::st().log);
     return emu_refused();
@@ -376,7 +375,7 @@ int fused_launch_impl(const b2_fused_params* F, unsigned max_ctas, void* stream)
     if (max_ctas && g > max_ctas) g = max_ctas;
     const uint32_t words = B2_FCTL_WORDS + 2 * F->NU;
     fused4_init_kernel<0><<<(words + 255) / 256 < 64 ? (words + 255) / 256 : 64, 256, 0, (cudaStream_t)stream>>>(
-        F->ctl, words, (F->R < F->NU ? F->R : F->NU) * F->TA);
+        F->ctl, words);
     void* args[] = {const_cast<b2_fused_params*>(F)};
     return (int)cudaLaunchKernel((const void*)fused4_kernel<CA, CB>, dim3(g), dim3(CA::THREADS), args, Fused4<CA, CB>::SMEM_BYTES,
                                  (cudaStream_t)stream);
@@ -398,7 +397,7 @@ struct FusedRegistrar {
     explicit FusedRegistrar(const char* name) {
         info = b2_fused_info{};
         info.prec = PrecOf<T>::value; info.n1 = SchA::N; info.n2 = SchB::N; info.inv = INV;
-        info.threads = CA::THREADS; info.qa = QA; info.qb = QB; info.smem_bytes = Fused4<CA, CB>::SMEM_BYTES;
+        info.threads = CA::THREADS; info.qa = QA; info.qb = QB; info.smem_bytes = Fused4<CA, CB>::SMEM_BYTES; info.regs = REGS;
         info.ns_a = SchA::ns; info.ns_b = SchB::ns;
         for (int s = 0; s < SchA::ns; ++s) info.radices_a[s] = SchA::r(s);
         for (int s = 0; s < SchB::ns; ++s) info.radices_b[s] = SchB::r(s);

@@ -43,6 +43,7 @@ typedef struct b2_fused_info {
     int prec, n1, n2, inv;             // lookup key
     int variant;
     int threads, qa, qb, smem_bytes;   // CTA shape, columns per pass-A tile, rows per pass-B tile
+    int regs;                          // register budget per thread (bounds the resident CTAs per SM)
     int ns_a, ns_b;
     int radices_a[8], radices_b[8];
     // enqueue the control-block reset + the persistent kernel (at most max_ctas CTAs; 0 = as many as are resident)

@@ -108,22 +108,20 @@ typedef struct b2_pass_params {
 // (vkFFT_Scheduler.h:2582-2893, vkFFT_DispatchPlan.h:157-225).
 typedef struct b2_fused_params {
     b2_pass_params A, B;       // A.out / B.in = scratch ring base; their outer strides on the scratch side are ignored
-    uint32_t* ctl;             // B2_FCTL_* words followed by doneA[NU], doneB[NU]; zeroed before every launch
+    uint32_t* ctl;             // B2_FCTL_* words followed by doneA[NU], doneB[NU]; zeroed before every launch (fused4_init_kernel)
     uint32_t nseq;             // sequences = product of the outer extents (same for A and B)
     uint32_t U, NU;            // sequences per unit, units
     uint32_t R;                // ring slots (units)
     uint32_t TA, TB;           // tiles per unit of pass A / pass B
-    uint32_t reserved;
+    uint32_t reserved;         // L: pass B runs this many units behind pass A (L < R)
 } b2_fused_params;
 
 enum {
-    B2_FCTL_NEXT_A = 0,        // A tiles handed out
-    B2_FCTL_NEXT_B = 1,        // B tiles handed out
-    B2_FCTL_AVAIL_A = 2,       // (signed) A tiles that may be claimed: their ring slot is free
-    B2_FCTL_AVAIL_B = 3,       // (signed) B tiles that may be claimed: their unit's A tiles are all done
-    B2_FCTL_READY_UNITS = 4,   // prefix of units whose pass A is complete
-    B2_FCTL_FREED_UNITS = 5,   // prefix of units whose pass B is complete (their slot may be overwritten)
-    B2_FCTL_WORDS = 32,        // doneA starts here (128-byte aligned), doneB follows
+    B2_FCTL_NEXT_A = 0,        // tiles handed out: fetch-add tickets into the one ordered sequence of pass-A and pass-B tiles
+    B2_FCTL_NEXT_B = 32,       // (unused)                          (each hot word on its own 128-byte line)
+    B2_FCTL_READY_UNITS = 64,  // prefix of units whose pass A is complete  -> their pass-B tiles may run
+    B2_FCTL_FREED_UNITS = 96,  // prefix of units whose pass B is complete  -> unit + R may overwrite the ring slot
+    B2_FCTL_WORDS = 128,       // doneA[NU] starts here, doneB[NU] follows
 };
 
 #ifdef __cplusplus

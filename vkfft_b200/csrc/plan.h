@@ -79,7 +79,7 @@ struct PassPlan {
     // fused Four-Step (fused4.cuh): this launch and the NEXT one of the list run as one persistent kernel; the two
     // PassPlans stay in the list (the second is skipped at run time) so that un-fusing is a matter of clearing the pointer
     const b2_fused_info* fused = nullptr;
-    uint32_t fz_nseq = 0, fz_U = 0, fz_NU = 0, fz_R = 0, fz_TA = 0, fz_TB = 0;
+    uint32_t fz_nseq = 0, fz_U = 0, fz_NU = 0, fz_R = 0, fz_TA = 0, fz_TB = 0, fz_L = 1;
     std::string note;            // human readable (plan_describe)
 };
 

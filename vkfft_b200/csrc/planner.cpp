@@ -613,28 +613,37 @@ void try_fuse(PlanGraph& g, std::vector<PassPlan>& list, size_t ia) {
     for (int d = 0; d < B2_MAX_OUTER; ++d) { nseq *= a.P.nb[d]; nseq_b *= b.P.nb[d]; }
     if (nseq != nseq_b || nseq > 0x7fffffffull) return;
     const uint64_t N = (uint64_t)a.P.n * b.P.n, esz = esize(g), seq_bytes = N * esz;
-    uint64_t unit_kb = 2048, ring_mb = 32, ring = 0;
+    uint64_t unit_kb = 4096, ring = 0, lead = 0;
     if (const char* e = getenv("B200FFT_FUSED_UNIT_KB")) unit_kb = strtoull(e, nullptr, 10);
-    if (const char* e = getenv("B200FFT_FUSED_RING_MB")) ring_mb = strtoull(e, nullptr, 10);
     if (const char* e = getenv("B200FFT_FUSED_RING")) ring = strtoull(e, nullptr, 10);
+    if (const char* e = getenv("B200FFT_FUSED_LEAD")) lead = strtoull(e, nullptr, 10);
     uint64_t U = std::max<uint64_t>(1, (unit_kb << 10) / seq_bytes);
     U = std::min(U, nseq);
     while (nseq % U) --U;                                  // whole units only
     const uint64_t NU = nseq / U;
-    uint64_t R = ring ? ring : std::max<uint64_t>(3, (ring_mb << 20) / (U * seq_bytes));
-    if (!ring && R * U * seq_bytes > (64ull << 20)) R = std::max<uint64_t>(2, (64ull << 20) / (U * seq_bytes));   // very long sequences
-    R = std::max<uint64_t>(1, std::min(R, NU));
+    const uint64_t ga0 = (a.P.G + fk->qa - 1) / fk->qa, gb0 = (b.P.G + fk->qb - 1) / fk->qb;
+    // Lead L (units pass B trails pass A): the tiles handed out between the last pass-A tile of a unit and its first pass-B
+    // tile -- (L-1) blocks of TA+TB tiles -- must exceed what the resident CTAs have in flight (one running tile plus one
+    // ticket each), or pass-B tiles would be handed out before their unit is complete and CTAs would sit waiting.
+    const uint64_t per_sm = std::max<uint64_t>(1, std::min<uint64_t>({(227ull << 10) / (uint64_t)fk->smem_bytes, 2048ull / (uint64_t)fk->threads,
+                                                                     65536ull / ((uint64_t)fk->threads * (uint64_t)fk->regs)}));
+    const uint64_t in_flight = 148 * per_sm * 2;
+    uint64_t L = lead ? lead : 1 + (in_flight + U * (ga0 + gb0) - 1) / (U * (ga0 + gb0));
+    L = std::max<uint64_t>(1, std::min(L, NU));
+    uint64_t R = ring ? ring : L + 2;                      // two more slots: one being filled ahead, one draining behind
+    R = std::min(std::max(R, L + 1), NU);
     const uint64_t ga = (a.P.G + fk->qa - 1) / fk->qa, gb = (b.P.G + fk->qb - 1) / fk->qb;
     if (NU * U * (ga + gb) > 0x7fffffffull) return;
     a.fused = fk;
     a.fz_nseq = (uint32_t)nseq; a.fz_U = (uint32_t)U; a.fz_NU = (uint32_t)NU; a.fz_R = (uint32_t)R;
-    a.fz_TA = (uint32_t)(U * ga); a.fz_TB = (uint32_t)(U * gb);
+    a.fz_TA = (uint32_t)(U * ga); a.fz_TB = (uint32_t)(U * gb); a.fz_L = (uint32_t)L;
     a.lut_id = lut_for(g, std::vector<int>(fk->radices_a, fk->radices_a + fk->ns_a));
     b.lut_id = lut_for(g, std::vector<int>(fk->radices_b, fk->radices_b + fk->ns_b));
     g.ctl_words = std::max<uint64_t>(g.ctl_words, B2_FCTL_WORDS + 2 * NU);
     char buf[256];
-    snprintf(buf, sizeof buf, " [fused with the next launch: %s, %llu units of %llu sequences, ring of %llu units = %.1f MB]", fk->name,
-             (unsigned long long)NU, (unsigned long long)U, (unsigned long long)R, (double)(R * U * seq_bytes) / 1048576.0);
+    snprintf(buf, sizeof buf, " [fused with the next launch: %s, %llu units of %llu sequences, pass B %llu units behind, ring of %llu units = %.1f MB]",
+             fk->name, (unsigned long long)NU, (unsigned long long)U, (unsigned long long)L, (unsigned long long)R,
+             (double)(R * U * seq_bytes) / 1048576.0);
     a.note += buf;
     b.note += " [runs inside the previous launch]";
 }
@@ -1361,7 +1370,7 @@ int plan_direction_dct(PlanGraph& g, std::vector<PassPlan>& list, int inv) {
 
 }  // namespace
 
-int build_plan(const b200fft_desc& din, PlanGraph& g) {
+static int build_plan_impl(const b200fft_desc& din, PlanGraph& g) {
     g = PlanGraph{};
     b200fft_desc d = din;
     if (d.fft_dim == 0) return R_EMPTY_FFTDIM;
@@ -1557,8 +1566,21 @@ int build_plan(const b200fft_desc& din, PlanGraph& g) {
     }
     if (g.has_fwd && (rc = plan(g.fwd, 0)) != R_SUCCESS) return rc;
     if (g.has_inv && (rc = plan(g.inv, 1)) != R_SUCCESS) return rc;
-    if (d.user_temp_buffer && g.temp_elems * esz > d.temp_buffer_size && d.temp_buffer_size != 0)
-        return R_USER_TEMP_TOO_SMALL;
+    return R_SUCCESS;
+}
+
+int build_plan(const b200fft_desc& din, PlanGraph& g) {
+    const int rc = build_plan_impl(din, g);
+    if (rc != R_SUCCESS) return rc;
+    // Caller-owned scratch (userTempBuffer = 1): this engine's plans can need MORE scratch than `buffer` holds (Bluestein,
+    // odd-length R2C, composed DCT/DST), so the size is checked on every path, convolution plans included.  Without a
+    // tempBufferSize the reference's contract applies ("same size as buffer"): the buffer size stands in.  The required
+    // size is published through b200fft_plan_get_info().temp_bytes either way.
+    if (g.desc.user_temp_buffer && g.temp_elems) {
+        const uint64_t need = g.temp_elems * esize(g);
+        const uint64_t have = din.temp_buffer_size ? din.temp_buffer_size : din.buffer_size;
+        if (have != 0 && need > have) return R_USER_TEMP_TOO_SMALL;
+    }
     return R_SUCCESS;
 }
 

@@ -205,6 +205,11 @@ static int exec_impl(b200fft_plan* p, int inverse, const b200fft_buffers* b, std
     if (!dg.ok) return R_INVALID_DEVICE;
     cudaStream_t st = b->stream ? (cudaStream_t)b->stream : p->stream;
     if (g.distributed && !p->window) return R_PLAN_NOT_INITIALIZED;
+    // timed mode: events created so far are released on every failure path
+    auto fail = [&](int code) {
+        if (marks) { for (cudaEvent_t e : *marks) cudaEventDestroy(e); marks->clear(); }
+        return code;
+    };
     auto mark = [&](int kind_of_next) {
         if (!marks) return;
         cudaEvent_t e;
@@ -237,16 +242,17 @@ static int exec_impl(b200fft_plan* p, int inverse, const b200fft_buffers* b, std
             memset(&F, 0, sizeof F);
             resolve(pp, F.A);
             resolve(list[ip + 1], F.B);
+            if (const char* e = getenv("B200FFT_FUSED_FLAGS")) F.B.aux_u1 |= (uint32_t)strtoul(e, nullptr, 10);   // tuning: 1 = no discard
             F.ctl = (uint32_t*)p->d_ctl;
-            F.nseq = pp.fz_nseq; F.U = pp.fz_U; F.NU = pp.fz_NU; F.R = pp.fz_R; F.TA = pp.fz_TA; F.TB = pp.fz_TB;
-            if (!F.ctl || pp.fused->launch(&F, fused_max_ctas, (void*)st) != 0) return R_FAILED_TO_LAUNCH_KERNEL;
+            F.nseq = pp.fz_nseq; F.U = pp.fz_U; F.NU = pp.fz_NU; F.R = pp.fz_R; F.TA = pp.fz_TA; F.TB = pp.fz_TB; F.reserved = pp.fz_L;
+            if (!F.ctl || pp.fused->launch(&F, fused_max_ctas, (void*)st) != 0) return fail(R_FAILED_TO_LAUNCH_KERNEL);
             ++ip;
             continue;
         }
         if (pp.sync_before) {
             mark(0);
             int brc = b200fft_window_barrier(p->window, (void*)st);
-            if (brc != R_SUCCESS) return brc;
+            if (brc != R_SUCCESS) return fail(brc);
         }
         mark(1);
         b2_pass_params P;
@@ -258,7 +264,16 @@ static int exec_impl(b200fft_plan* p, int inverse, const b200fft_buffers* b, std
             k = pp.k_unaligned;
             if (pp.lut_id_unaligned >= 0) P.lut = p->d_luts[pp.lut_id_unaligned];
         }
-        if (!k || k->launch(&P, pp.grid, (void*)st) != 0) return R_FAILED_TO_LAUNCH_KERNEL;
+        if (!k || k->launch(&P, pp.grid, (void*)st) != 0) {
+            // a distributed plan that stops half way would leave the peers spinning in their next barrier until the device-side
+            // time-out: keep the barrier sequence complete (the data is lost either way, the error code says so)
+            if (g.distributed) {
+                for (size_t jp = ip + 1; jp < list.size(); ++jp)
+                    if (list[jp].sync_before) b200fft_window_barrier(p->window, (void*)st);
+                b200fft_window_barrier(p->window, (void*)st);
+            }
+            return fail(R_FAILED_TO_LAUNCH_KERNEL);
+        }
     }
     // every rank's stores into this rank's slab have landed once all ranks passed this point
     if (g.distributed) {
@@ -283,7 +298,7 @@ extern "C" int b200fft_plan_get_info(const b200fft_plan* p, b200fft_plan_info* i
     if (!p || !info) return R_EMPTY_APP;
     info->num_passes_forward = (uint32_t)p->g.fwd.size();
     info->num_passes_inverse = (uint32_t)p->g.inv.size();
-    info->temp_bytes = p->temp_bytes;
+    info->temp_bytes = p->g.temp_elems * (p->g.prec == B2_PREC_F64 ? 16 : 8);   // required scratch, whoever owns it
     info->lut_bytes = p->lut_bytes;
     info->algorithmic_bytes = p->g.algorithmic_bytes;
     info->flops = p->g.flops;
@@ -319,7 +334,12 @@ extern "C" int b200fft_exec_host(b200fft_plan* p, int inverse, const void* host_
     if (p->g.distributed) return R_UNSUPPORTED_FFT_LENGTH;
     DeviceGuard dg(p->device);
     if (!dg.ok) return R_INVALID_DEVICE;
-    const uint64_t need = bytes_in > bytes_out ? bytes_in : bytes_out;
+    // the staging buffer always covers the plan's own layout (strides x batches, counted in complex elements: an upper
+    // bound for the real-data layouts), whatever byte counts the caller passes: a short count can then neither make a
+    // kernel read or write past the allocation nor leave uninitialised input behind (the tail is cleared)
+    const uint64_t extent = p->g.batch_stride * p->g.batches * (p->g.prec == B2_PREC_F64 ? 16 : 8);
+    uint64_t need = bytes_in > bytes_out ? bytes_in : bytes_out;
+    if (extent > need) need = extent;
     if (need > p->stage_bytes) {
         if (p->d_stage) cudaFree(p->d_stage);
         p->d_stage = nullptr;
@@ -329,6 +349,7 @@ extern "C" int b200fft_exec_host(b200fft_plan* p, int inverse, const void* host_
     }
     cudaStream_t st = p->stream;
     if (cudaMemcpyAsync(p->d_stage, host_in, bytes_in, cudaMemcpyHostToDevice, st) != cudaSuccess) return R_FAILED_TO_COPY;
+    if (bytes_in < extent && cudaMemsetAsync((char*)p->d_stage + bytes_in, 0, extent - bytes_in, st) != cudaSuccess) return R_FAILED_TO_COPY;
     b200fft_buffers b;
     memset(&b, 0, sizeof b);
     b.buffer = p->d_stage;

@@ -138,6 +138,14 @@ struct KCfg {
 enum { XF_LDCG = 1, XF_DISCARD = 2 };
 
 #if defined(__CUDA_ARCH__)
+// the value becomes opaque to the optimiser (it stays in its register): keeps address chains additive without losing
+// the address space of the pointer they are added to
+#define B2_OPAQUE64(v) asm("" : "+l"(v))
+#else
+#define B2_OPAQUE64(v) ((void)0)
+#endif
+
+#if defined(__CUDA_ARCH__)
 template <typename T> B2_D cpx<T> ld_cg(const cpx<T>* p) {
     if constexpr (sizeof(T) == 4) { float2 v = __ldcg(reinterpret_cast<const float2*>(p)); return mk<T>(v.x, v.y); }
     else { double2 v = __ldcg(reinterpret_cast<const double2*>(p)); return mk<T>(v.x, v.y); }
@@ -148,12 +156,17 @@ template <typename T> B2_D cpx<T> ld_cg(const cpx<T>* p) { return *p; }
 
 struct NoHook { B2_D void operator()() const {} };
 
-template <class C, int XF = 0>
+// ESI / ESO: compile-time element strides of the input / output lines (0 = the runtime values of the pass descriptor).
+// The fused Four-Step kernel knows both (n2 on both sides of pass A, n1 on the store side of pass B), which turns the
+// per-access 64-bit address arithmetic into immediate offsets.
+template <class C, int XF = 0, int ESI = 0, int ESO = 0>
 struct Engine {
     using T = typename C::T;
     using X = cpx<T>;
     using Sch = typename C::Sch;
     static constexpr int N = C::N, TPL = C::TPL, Q = C::Q, V = C::V, NS = Sch::ns;
+    static constexpr bool RUNNING_IN = !C::IN_UNIT && ESI == 0;      // strides only known at run time
+    static constexpr bool RUNNING_OUT = !C::OUT_UNIT && ESO == 0;
 
     B2_D static int sidx(int q, int p) {
         if constexpr (C::LAYOUT == LAY_LINE) return q * C::LS + p + (p >> C::PAD_SHIFT);
@@ -169,18 +182,28 @@ struct Engine {
 
     // ---- HBM load of first-stage legs --------------------------------------------------------------
     template <int s>
-    B2_D static void load_global(X* x, const X* __restrict__ line, int64_t es, int t, bool valid) {
+    B2_D static void load_global(X* x, const X* __restrict__ line, int64_t es_rt, int t, bool valid) {
         constexpr int r = Sch::r(s), NB = nbut<s>(), BPT = bpt<s>();
+        // element stride: 1 (contiguous kinds), a compile-time constant (fused kernel) or the descriptor's value; the legs
+        // of one butterfly are `step` apart, so one multiply per butterfly and additions from there (the per-leg 64-bit
+        // multiply + LEA pair this replaces was a fifth of the instructions of the strided kernels)
+        const int64_t es = C::IN_UNIT ? 1 : (ESI ? (int64_t)ESI : es_rt);
+        const int64_t step = (int64_t)NB * es;
 #pragma unroll
         for (int m = 0; m < BPT; ++m) {
             const int b0 = V * (t + m * TPL);
             const bool ok = valid && (!guarded<s>() || b0 < NB);
+            const X* src = line + (int64_t)b0 * es;
 #pragma unroll
             for (int k = 0; k < r; ++k) {
-                const int p = b0 + k * NB;
+                // runtime stride: walk the legs with a running pointer the compiler may not re-associate into
+                // (b0 + k*NB) * es (it does otherwise: a 64-bit multiply + two LEA per leg); constant stride: immediates
+                const X* lp = src;
+                if constexpr (RUNNING_IN) { if (k + 1 < r) { int64_t st = step; B2_OPAQUE64(st); src += st; } }
+                else lp = src + k * step;
                 if constexpr (V == 2 && C::IN_UNIT) {
                     using G = typename gvec<T, 2>::type;
-                    G g = ok ? *reinterpret_cast<const G*>(line + p) : G{};
+                    G g = ok ? *reinterpret_cast<const G*>(lp) : G{};
                     X a = mk<T>(g.x, g.y), c = mk<T>(g.z, g.w);
                     x[(m * V + 0) * r + k] = C::INV ? swp(a) : a;
                     x[(m * V + 1) * r + k] = C::INV ? swp(c) : c;
@@ -189,8 +212,8 @@ struct Engine {
                     for (int v = 0; v < V; ++v) {
                         X a = mk<T>(T(0), T(0));
                         if (ok) {
-                            const X* src = line + (C::IN_UNIT ? (int64_t)(p + v) : (int64_t)(p + v) * es);
-                            if constexpr (XF & XF_LDCG) a = ld_cg(src); else a = *src;
+                            const X* q = lp + (int64_t)v * es;
+                            if constexpr ((XF & XF_LDCG) != 0) a = ld_cg(q); else a = *q;
                         }
                         x[(m * V + v) * r + k] = C::INV ? swp(a) : a;
                     }
@@ -625,13 +648,15 @@ struct Engine {
     // of these kernels.  Also measured on B200 and rejected (profiles/r1/README.md): a tile-factored scheme with
     // coalesced table reads and the reference-style full M-entry table.
     template <int s>
-    B2_D static void store_global(const X* x, X* __restrict__ line, int64_t es, int t, bool valid,
+    B2_D static void store_global(const X* x, X* __restrict__ line, int64_t es_rt, int t, bool valid,
                                   const b2_pass_params& P, uint32_t gline, uint32_t qline) {
         constexpr int r = Sch::r(s), NB = nbut<s>(), BPT = bpt<s>();
         static_assert(s == NS - 1, "global store only after the last stage");
         constexpr bool TW = (C::OPS & B2_OP_TWIDDLE_OUT) != 0;
         const bool do_scale = (P.ops & B2_OP_SCALE) != 0;   // runtime: normalize=1 on the last inverse pass
         const T sc = (T)P.scale;
+        const int64_t es = C::OUT_UNIT ? 1 : (ESO ? (int64_t)ESO : es_rt);
+        const int64_t step = (int64_t)NB * es;
         X s1 = mk<T>(T(1), T(0)), s2 = s1, s4 = s1;
         if constexpr (TW) {
             const uint64_t e1 = (uint64_t)gline * (uint64_t)NB;     // 4*e1 < M for r >= 4; unused otherwise
@@ -643,9 +668,14 @@ struct Engine {
         for (int m = 0; m < BPT; ++m) {
             const int b0 = V * (t + m * TPL);
             const bool ok = valid && (!guarded<s>() || b0 < NB);
+            if (!ok) continue;                     // one branch per butterfly, not one per output
+            X* dst = line + (int64_t)b0 * es;
             X w0[V], w2[V], w4[V], w6[V];
 #pragma unroll
             for (int k = 0; k < r; ++k) {
+                X* sp = dst;
+                if constexpr (RUNNING_OUT) { if (k + 1 < r) { int64_t st = step; B2_OPAQUE64(st); dst += st; } }
+                else sp = dst + k * step;
                 X o[V];
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
@@ -667,18 +697,14 @@ struct Engine {
                     if (do_scale) a = a * sc;
                     o[v] = C::INV ? swp(a) : a;
                 }
-                const int p0 = b0 + k * NB;
-                if (ok) {
-                    if constexpr (V == 2 && C::OUT_UNIT) {
-                        using G = typename gvec<T, 2>::type;
-                        G g;
-                        g.x = o[0].x; g.y = o[0].y; g.z = o[1].x; g.w = o[1].y;
-                        *reinterpret_cast<G*>(line + p0) = g;
-                    } else {
+                if constexpr (V == 2 && C::OUT_UNIT) {
+                    using G = typename gvec<T, 2>::type;
+                    G g;
+                    g.x = o[0].x; g.y = o[0].y; g.z = o[1].x; g.w = o[1].y;
+                    *reinterpret_cast<G*>(sp) = g;
+                } else {
 #pragma unroll
-                        for (int v = 0; v < V; ++v)
-                            line[C::OUT_UNIT ? (int64_t)(p0 + v) : (int64_t)(p0 + v) * es] = o[v];
-                    }
+                    for (int v = 0; v < V; ++v) sp[(int64_t)v * es] = o[v];
                 }
             }
         }
@@ -878,7 +904,7 @@ struct Engine {
                 store_smem<0>(x, sm, ql, tl);
             }
             __syncthreads();
-            if constexpr ((XF & XF_DISCARD) != 0) discard_tile(P, obase_in, grp, tid);
+            if constexpr ((XF & XF_DISCARD) != 0) { if (!(P.aux_u1 & 1u)) discard_tile(P, obase_in, grp, tid); }   // aux_u1 bit 0: tuning switch
             middle<1>(sm, lut, tid);
             {
                 constexpr int s = NS - 1;

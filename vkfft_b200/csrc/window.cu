@@ -112,7 +112,8 @@ struct b200fft_window {
     std::vector<CUmemGenericAllocationHandle> data_h, pad_h;
     std::vector<char> mapped;
     uint32_t epoch = 0;
-    int* d_err = nullptr;
+    int* d_err = nullptr;            // device alias of h_err
+    volatile int* h_err = nullptr;   // mapped pinned host word: a barrier that timed out sets it; read without synchronising
 };
 
 extern "C" uint64_t b200fft_window_granularity(int device) {
@@ -158,7 +159,7 @@ extern "C" void b200fft_window_destroy(b200fft_window* w) {
     }
     if (w->data_va) a.AddressFree(w->data_va, (size_t)w->world * w->slab_bytes);
     if (w->pad_va) a.AddressFree(w->pad_va, (size_t)w->world * w->pad_bytes);
-    if (w->d_err) cudaFree(w->d_err);
+    if (w->h_err) cudaFreeHost((void*)w->h_err);
     delete w;
 }
 
@@ -184,10 +185,17 @@ extern "C" int b200fft_window_create(int device, uint32_t world, uint32_t rank, 
     if (rc == R_SUCCESS && a.Create(&dh, slab_bytes, &p, 0) != CUDA_SUCCESS) rc = R_FAILED_TO_ALLOCATE;
     if (rc == R_SUCCESS && a.Create(&ph, w->pad_bytes, &p, 0) != CUDA_SUCCESS) { a.Release(dh); rc = R_FAILED_TO_ALLOCATE; }
     if (rc == R_SUCCESS) rc = map_slot(w, rank, dh, ph);
-    if (rc == R_SUCCESS && cudaMalloc(&w->d_err, sizeof(int)) != cudaSuccess) rc = R_FAILED_TO_ALLOCATE;
+    if (rc == R_SUCCESS) {
+        void* h = nullptr;
+        if (cudaHostAlloc(&h, sizeof(int), cudaHostAllocMapped) != cudaSuccess) rc = R_FAILED_TO_ALLOCATE;
+        else {
+            w->h_err = (volatile int*)h;
+            *w->h_err = 0;
+            if (cudaHostGetDevicePointer((void**)&w->d_err, h, 0) != cudaSuccess) rc = R_FAILED_TO_ALLOCATE;
+        }
+    }
     if (rc == R_SUCCESS &&
-        (cudaMemset(w->d_err, 0, sizeof(int)) != cudaSuccess ||
-         cudaMemset((void*)(w->pad_va + (CUdeviceptr)rank * w->pad_bytes), 0, w->pad_bytes) != cudaSuccess ||
+        (cudaMemset((void*)(w->pad_va + (CUdeviceptr)rank * w->pad_bytes), 0, w->pad_bytes) != cudaSuccess ||
          cudaDeviceSynchronize() != cudaSuccess))
         rc = R_FAILED_TO_COPY;
     if (rc != R_SUCCESS) { cudaGetLastError(); b200fft_window_destroy(w); return rc; }
@@ -224,6 +232,8 @@ extern "C" int b200fft_window_barrier(b200fft_window* w, void* stream) {
     if (!w) return R_EMPTY_APP;
     for (uint32_t s = 0; s < w->world; ++s)
         if (!w->mapped[s]) return R_PLAN_NOT_INITIALIZED;
+    // a barrier of an earlier call gave up (a peer stopped): every later exchange would consume stale data -- refuse
+    if (w->h_err && *w->h_err) return R_FAILED_TO_SYNCHRONIZE;
     Guard g(w->device);
     ++w->epoch;
     uint32_t* pads = (uint32_t*)w->pad_va;
@@ -236,8 +246,6 @@ extern "C" int b200fft_window_barrier(b200fft_window* w, void* stream) {
 extern "C" int b200fft_window_status(b200fft_window* w) {
     if (!w) return R_EMPTY_APP;
     Guard g(w->device);
-    int e = 0;
     if (cudaDeviceSynchronize() != cudaSuccess) return R_FAILED_TO_SYNCHRONIZE;
-    if (cudaMemcpy(&e, w->d_err, sizeof e, cudaMemcpyDeviceToHost) != cudaSuccess) return R_FAILED_TO_COPY;
-    return e ? R_FAILED_TO_SYNCHRONIZE : R_SUCCESS;
+    return (w->h_err && *w->h_err) ? R_FAILED_TO_SYNCHRONIZE : R_SUCCESS;
 }

@@ -70,8 +70,14 @@ def _scale_after(t, n, norm, inverse):
         raise ValueError("norm must be 0, 1 or 'ortho'")
 
 
+def _check_norm(norm):
+    if norm not in (0, 1, "ortho"):
+        raise ValueError("norm must be 0, 1 or 'ortho'")
+
+
 def _c2c(src, dest, ndim, norm, cuda_stream, inverse):
     import torch
+    _check_norm(norm)                      # before any launch
     _check(src, "src")
     if not src.is_complex():
         raise TypeError("complex tensor expected; use rfftn for real input")
@@ -84,6 +90,13 @@ def _c2c(src, dest, ndim, norm, cuda_stream, inverse):
     nd, sizes, batch = _split(src.shape, ndim)
     dbl = src.dtype == torch.complex128
     dev = src.device.index
+    if all(s == 1 for s in sizes):
+        # every transformed axis has one point: the plan has no launch (plan_direction_c2c skips such axes), so an
+        # out-of-place call would hand back uninitialised memory -- the transform is the identity
+        if not inplace:
+            with torch.cuda.stream(torch.cuda.ExternalStream(_stream(torch, cuda_stream))):
+                dest.copy_(src)
+        return dest
     # out of place (API guide :365-376): the forward transform reads inputBuffer, the inverse reads outputBuffer; both
     # leave the result in `buffer`
     fmt = {} if inplace else ({"isOutputFormatted": 1, "makeInversePlanOnly": 1} if inverse else
@@ -118,6 +131,7 @@ def ifftn(src, dest=None, ndim=None, norm=1, cuda_stream=None):
 def rfftn(src, dest=None, ndim=None, norm=1, cuda_stream=None):
     """real -> complex; the last axis of the result has n//2+1 points (even n only on the fast path, like the reference)"""
     import torch
+    _check_norm(norm)
     _check(src, "src")
     if src.is_complex():
         raise TypeError("real tensor expected")
@@ -147,6 +161,7 @@ def irfftn(src, dest=None, ndim=None, norm=1, cuda_stream=None, n_last=None):
     """half-Hermitian complex -> real; n_last = length of the real fast axis (default 2*(src.shape[-1]-1)).
     Like the reference's C2R, the transform may overwrite `src`."""
     import torch
+    _check_norm(norm)
     _check(src, "src")
     if not src.is_complex():
         raise TypeError("complex tensor expected")
@@ -177,6 +192,7 @@ def irfftn(src, dest=None, ndim=None, norm=1, cuda_stream=None, n_last=None):
 
 def _r2r(src, dest, ndim, norm, cuda_stream, inverse, kind, dst):
     import torch
+    _check_norm(norm)
     _check(src, "src")
     if src.is_complex():
         raise TypeError("real tensor expected")

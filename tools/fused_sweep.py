@@ -5,6 +5,7 @@ import os, sys, itertools
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import vkfft_b200 as vk
+os.environ["B200FFT_FUSED4"] = "1"
 
 PEAK = 6575.4e9
 pts = 1 << 28

@@ -19,6 +19,7 @@
 // to the two-launch plan bit for bit.
 #pragma once
 #include "stockham.cuh"
+#include "pipe.cuh"
 
 namespace b200fft {
 
@@ -72,18 +73,26 @@ B2_D uint32_t fz_cas_release(uint32_t* p, uint32_t cmp, uint32_t val) { return f
 B2_D void fz_sleep(unsigned) {}
 #endif
 
-template <class CA, class CB>
+// NBUF: tile buffers per CTA.  2: the NEXT tile is copied into the other buffer by TMA while this one is transformed;
+// 1 (tiles too large to double): the next tile is copied into the same buffer as soon as the last stage has its legs in
+// registers, i.e. it overlaps the last butterflies and the global stores.
+template <class CA, class CB, int NBUF = 2>
 struct Fused4 {
     // strides known at compile time: pass A walks columns of an n1 x n2 matrix (element stride n2 on both sides), pass B
     // stores transposed (element stride n1)
     using EA = Engine<CA, 0, CB::N, CB::N>;
     using EB = Engine<CB, XF_LDCG | XF_DISCARD, 0, CA::N>;
+    using T = typename CA::T;
+    using X = cpx<T>;
     static_assert(CA::THREADS == CB::THREADS, "both passes run in the same CTA shape");
     static_assert(CA::LAYOUT == LAY_ELEM && CB::LAYOUT == LAY_LINE, "pass A: interleaved columns, pass B: contiguous rows");
+    static_assert(CA::V == 1 && CB::V == 1, "one butterfly per thread and step");
+    static_assert(NBUF == 1 || NBUF == 2, "one or two tile buffers");
     static constexpr int THREADS = CA::THREADS;
     static constexpr int MINB = CA::MINB < CB::MINB ? CA::MINB : CB::MINB;
-    static constexpr int TILE_BYTES = ((CA::SMEM_BYTES > CB::SMEM_BYTES ? CA::SMEM_BYTES : CB::SMEM_BYTES) + 15) / 16 * 16;
-    static constexpr int SMEM_BYTES = TILE_BYTES + 32;     // + mailbox: two alternating slots of (kind, unit, tile, must-wait)
+    static constexpr int TILE_BYTES = ((CA::SMEM_BYTES > CB::SMEM_BYTES ? CA::SMEM_BYTES : CB::SMEM_BYTES) + 127) / 128 * 128;
+    static constexpr int SMEM_BYTES = NBUF * TILE_BYTES + 64;     // + two mbarriers + mailbox: two slots of (kind, unit, tile)
+    static constexpr uint32_t BYTES_A = (uint32_t)(CA::N * CA::Q * sizeof(X)), BYTES_B = (uint32_t)(CB::N * CB::Q * sizeof(X));
     enum { NONE = 0, TILE_A = 1, TILE_B = 2 };
 
     // ---- scheduler: ONE ordered queue, state in the registers of thread 0 --------------------------------------------------
@@ -101,7 +110,6 @@ struct Fused4 {
     // release of the PREVIOUS tile (one MEMBAR.GPU + one atomic) are issued while the tile's first loads are in flight
     // (Engine hook) and only looked at after its last store.
     struct Sched {
-        uint32_t next;                 // ticket of the following tile (fetched one tile ahead)
         uint32_t ready, freed;         // last values read of READY_UNITS / FREED_UNITS
         uint32_t pend_kind, pend_unit; // finished tile whose completion has not been published yet
         uint32_t newT, dcount;         // in flight: next-next ticket, done-counter before this CTA's increment
@@ -152,87 +160,202 @@ struct Fused4 {
         }
     }
 
-    struct Hook {
-        const b2_fused_params* F;
-        Sched* S;
-        B2_D void operator()() const {
-            if (threadIdx.x == 0) {
-                S->newT = fz_add(F->ctl + B2_FCTL_NEXT_A, 1u);
-                S->ready = fz_ld_relaxed(F->ctl + B2_FCTL_READY_UNITS);
-                S->freed = fz_ld_relaxed(F->ctl + B2_FCTL_FREED_UNITS);
-                publish(*F, *S);
-            }
-        }
-    };
+    // scheduler traffic of one tile, issued by thread 0 while the tile's first-stage legs are being read
+    B2_D static void sched_issue(const b2_fused_params& F, Sched& S) {
+        S.newT = fz_add(F.ctl + B2_FCTL_NEXT_A, 1u);
+        S.ready = fz_ld_relaxed(F.ctl + B2_FCTL_READY_UNITS);
+        S.freed = fz_ld_relaxed(F.ctl + B2_FCTL_FREED_UNITS);
+        publish(F, S);
+    }
 
     B2_D static void seq_coords(const b2_pass_params& P, uint32_t seq, uint32_t& o0, uint32_t& o1, uint32_t& o2) {
         o0 = seq % P.nb[0]; seq /= P.nb[0];
         o1 = seq % P.nb[1]; seq /= P.nb[1];
         o2 = seq;
     }
+    struct Where { uint32_t grp, o0, o1, o2; int64_t obase_in, obase_out; };
+    B2_D static Where locate(const b2_fused_params& F, uint32_t kind, uint32_t unit, uint32_t tile) {
+        constexpr uint64_t NN = (uint64_t)CA::N * (uint64_t)CB::N;              // points per sequence
+        Where w;
+        if (kind == TILE_A) {
+            const uint32_t ga = F.A.G / CA::Q, sq = tile / ga;
+            w.grp = tile % ga;
+            seq_coords(F.A, unit * F.U + sq, w.o0, w.o1, w.o2);
+            w.obase_in = (int64_t)w.o0 * F.A.in_bs[0] + (int64_t)w.o1 * F.A.in_bs[1] + (int64_t)w.o2 * F.A.in_bs[2];
+            w.obase_out = (int64_t)(((uint64_t)(unit % F.R) * F.U + sq) * NN);
+        } else {
+            const uint32_t gb = F.B.G / CB::Q, sq = tile / gb;
+            w.grp = tile % gb;
+            seq_coords(F.B, unit * F.U + sq, w.o0, w.o1, w.o2);
+            w.obase_in = (int64_t)(((uint64_t)(unit % F.R) * F.U + sq) * NN);
+            w.obase_out = (int64_t)w.o0 * F.B.out_bs[0] + (int64_t)w.o1 * F.B.out_bs[1] + (int64_t)w.o2 * F.B.out_bs[2];
+        }
+        return w;
+    }
 
-    B2_D static void run(const b2_fused_params& F, unsigned char* smem_raw) {
-        volatile uint32_t* mail = reinterpret_cast<volatile uint32_t*>(smem_raw + TILE_BYTES);    // [slot][kind, unit, tile, wait]
+    // ---- TMA: copy a tile into a shared-memory buffer; completion on the buffer's mbarrier ------------------------------------
+    //   pass A: Q_A neighbouring columns = n1 row segments of Q_A*8 bytes, n2*8 bytes apart -> buf[p*Q_A + q]  (the
+    //           interleaved-line layout the stages use, so they run in place); the 32 lanes of warp 0 share the row copies
+    //   pass B: Q_B contiguous rows of the scratch = ONE contiguous block                   -> buf[q*n2 + p]  (dense; the
+    //           first scatter moves it to the padded layout)
+    // Called by every lane of warp 0 (emulation: by thread 0 alone); the arguments are taken from lane 0.
+    B2_D static void warp_issue(const b2_fused_params& F, bool go, uint32_t kind, uint32_t unit, uint32_t tile, X* buf, uint64_t* bar) {
+#if defined(__CUDA_ARCH__)
+        const int lane = threadIdx.x & 31, nlanes = 32;
+        go = __shfl_sync(0xffffffffu, go ? 1 : 0, 0) != 0;
+        kind = __shfl_sync(0xffffffffu, kind, 0); unit = __shfl_sync(0xffffffffu, unit, 0); tile = __shfl_sync(0xffffffffu, tile, 0);
+#else
+        const int lane = 0, nlanes = 1;
+#endif
+        if (!go) return;
+        const Where w = locate(F, kind, unit, tile);
+        if (kind == TILE_A) {
+            if (lane == 0) mbar_expect_tx(bar, BYTES_A);
+#if defined(__CUDA_ARCH__)
+            __syncwarp();
+#endif
+            const X* src = (const X*)F.A.in + w.obase_in + (int64_t)w.grp * CA::Q * F.A.in_gs;
+            for (int p = lane; p < CA::N; p += nlanes)
+                tma_load_1d(buf + (size_t)p * CA::Q, src + (int64_t)p * CB::N, (uint32_t)(CA::Q * sizeof(X)), bar);
+        } else if (lane == 0) {
+            mbar_expect_tx(bar, BYTES_B);
+            const X* src = (const X*)F.B.in + w.obase_in + (int64_t)w.grp * CB::Q * CB::N;
+            tma_load_1d(buf, src, BYTES_B, bar);
+        }
+    }
+    // thread 0: hold back nothing, then wait until the tile may run (the slow path: its unit was not ready when looked at)
+    B2_D static void wait_runnable(const b2_fused_params& F, Sched& S, uint32_t kind, uint32_t unit) {
+        publish(F, S);
+        after_publish(F, S);
+        for (;;) {
+            S.ready = fz_ld_relaxed(F.ctl + B2_FCTL_READY_UNITS);
+            S.freed = fz_ld_relaxed(F.ctl + B2_FCTL_FREED_UNITS);
+            if (runnable(F, S, kind, unit)) return;
+            fz_sleep(100);
+        }
+    }
+
+    // first-stage legs from the tile as TMA delivered it
+    template <class E, class C>
+    B2_D static void load_raw(X* x, const X* sm, int q, int t) {
+        using Sch = typename C::Sch;
+        constexpr int r = Sch::r(0), NB = C::N / r, BPT = E::template bpt<0>();
+#pragma unroll
+        for (int m = 0; m < BPT; ++m) {
+            const int b = t + m * C::TPL;
+            if (E::template guarded<0>() && b >= NB) continue;
+#pragma unroll
+            for (int k = 0; k < r; ++k) {
+                const int p = b + k * NB;
+                X a = B2_SMEM_LD(sm, C::LAYOUT == LAY_ELEM ? p * C::Q + q : q * C::N + p);
+                x[m * r + k] = C::INV ? swp(a) : a;
+            }
+        }
+    }
+
+    // one tile of pass `C` from buffer `sm`.  `on_dead` runs (thread 0 .. 31) once every thread has read its last-stage legs
+    template <class E, class C, class Dead>
+    B2_D static void process(const b2_fused_params& F, const b2_pass_params& P, X* sm, const Where& w, Sched& S, bool discard, Dead on_dead) {
+        using Sch = typename C::Sch;
+        constexpr int NS = Sch::ns;
         const int tid = threadIdx.x;
-        const uint64_t NN = (uint64_t)CA::N * (uint64_t)CB::N;              // points per sequence
-        const uint32_t ga = (F.A.G + CA::Q - 1) / CA::Q, gb = (F.B.G + CB::Q - 1) / CB::Q;   // tiles per sequence
-        Sched S;
-        S.next = 0; S.ready = S.freed = 0; S.pend_kind = S.done_kind = NONE; S.pend_unit = S.done_unit = 0; S.newT = S.dcount = 0;
-        if (tid == 0) {
-            const uint32_t t0 = fz_add(F.ctl + B2_FCTL_NEXT_A, 1u);
-            S.next = fz_add(F.ctl + B2_FCTL_NEXT_A, 1u);
-            uint32_t u, t;
-            const uint32_t k = decode(F, t0, u, t);
-            mail[0] = k; mail[1] = u; mail[2] = t; mail[3] = (k != NONE && !runnable(F, S, k, u)) ? 1u : 0u;
+        const X* __restrict__ lut = (const X*)P.lut;
+        int ql, tl;
+        E::template tmap<C::LMAP>(tid, ql, tl);
+        {
+            X x[E::template bpt<0>() * Sch::r(0)];
+            load_raw<E, C>(x, sm, ql, tl);
+            if (tid == 0) sched_issue(F, S);         // atomics + limit loads in flight behind the first butterflies
+            E::template compute<0>(x, lut, tl);
+            __syncthreads();                         // every raw read of the buffer is done: switch to the stage layout
+            if constexpr (C::LAYOUT == LAY_LINE) { if (discard) E::discard_tile(P, w.obase_in, w.grp, tid); }   // pass B: the scratch lines are dead in L2 as well
+            E::template store_smem<0>(x, sm, ql, tl);
         }
         __syncthreads();
-        uint32_t slot = 0;
-        for (;;) {
-            const uint32_t kind = mail[4 * slot], unit = mail[4 * slot + 1], tile = mail[4 * slot + 2], wait = mail[4 * slot + 3];
+        E::template middle<1>(sm, lut, tid);
+        {
+            constexpr int s = NS - 1;
+            int qs, ts;
+            E::template tmap<C::SMAP>(tid, qs, ts);
+            const uint32_t gs = w.grp * C::Q + qs;
+            X x[E::template bpt<s>() * Sch::r(s)];
+            E::template load_smem<s>(x, sm, qs, ts);
+            if constexpr (NBUF == 1) {
+                fence_proxy_async_smem();
+                __syncthreads();                     // the buffer is dead: refill it while the last stage runs
+                on_dead();
+            }
+            E::template compute<s>(x, lut, ts);
+            X* out_line = (X*)P.out + w.obase_out + (int64_t)gs * P.out_gs;
+            E::template store_global<s>(x, out_line, P.out_es, ts, gs < P.G, P, E::twl(P, gs, w.o0, w.o1, w.o2), (uint32_t)qs);
+        }
+    }
+
+    B2_D static void run(const b2_fused_params& F, unsigned char* smem_raw) {
+        uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NBUF * TILE_BYTES);
+        volatile uint32_t* mail = reinterpret_cast<volatile uint32_t*>(smem_raw + (size_t)NBUF * TILE_BYTES + 16);   // [slot][kind, unit, tile]
+        const int tid = threadIdx.x;
+#if defined(__CUDA_ARCH__)
+        const bool w0 = tid < 32;                    // warp 0 issues the copies
+#else
+        const bool w0 = tid == 0;
+#endif
+        auto bufp = [&](uint32_t i) { return reinterpret_cast<X*>(smem_raw + (size_t)(i % NBUF) * TILE_BYTES); };
+        Sched S;
+        S.ready = S.freed = 0; S.pend_kind = S.done_kind = NONE; S.pend_unit = S.done_unit = 0; S.newT = S.dcount = 0;
+        // thread 0: the tile being transformed and the one after it (whose copy may already be running)
+        uint32_t ck = NONE, cu = 0, ct = 0, nk = NONE, nu = 0, nt = 0;
+        bool cissued = false, nissued = false;
+        if (tid == 0) {
+            for (int i = 0; i < NBUF; ++i) mbar_init(&bars[i], 1);
+            mbar_init_fence();
+            const uint32_t a = fz_add(F.ctl + B2_FCTL_NEXT_A, 1u), b = fz_add(F.ctl + B2_FCTL_NEXT_A, 1u);
+            ck = decode(F, a, cu, ct);
+            nk = decode(F, b, nu, nt);
+            mail[0] = ck; mail[1] = cu; mail[2] = ct;
+            if (ck != NONE) wait_runnable(F, S, ck, cu);
+        }
+        __syncthreads();                             // mbarriers initialised, mailbox written
+        if (w0) { warp_issue(F, ck != NONE, ck, cu, ct, bufp(0), &bars[0]); cissued = true; }
+        for (uint32_t it = 0;; ++it) {
+            const uint32_t slot = it & 1u;
+            const uint32_t kind = mail[3 * slot], unit = mail[3 * slot + 1], tile = mail[3 * slot + 2];
             if (kind == NONE) break;
-            if (wait) {
-                // the tile's unit is not ready yet.  Every store of the previous tile has been issued (barrier): publish it
-                // first -- others may be waiting for exactly that -- then poll the two limits
-                if (tid == 0) {
-                    publish(F, S);
-                    after_publish(F, S);
-                    for (;;) {
-                        S.ready = fz_ld_relaxed(F.ctl + B2_FCTL_READY_UNITS);
-                        S.freed = fz_ld_relaxed(F.ctl + B2_FCTL_FREED_UNITS);
-                        if (runnable(F, S, kind, unit)) break;
-                        fz_sleep(100);
-                    }
+            X* sm = bufp(it);
+            uint64_t* bar = &bars[it % NBUF];
+            if (w0) {
+                // this tile's copy could not be started ahead (its unit was not ready): wait for it now
+                if (tid == 0 && !cissued) wait_runnable(F, S, ck, cu);
+                warp_issue(F, !cissued, ck, cu, ct, sm, bar);
+                cissued = true;
+                if constexpr (NBUF == 2) {           // the other buffer is free: start the next tile's copy if its unit is ready
+                    const bool go = nk != NONE && runnable(F, S, nk, nu);
+                    warp_issue(F, go, nk, nu, nt, bufp(it + 1), &bars[(it + 1) % NBUF]);
+                    nissued = go;
                 }
-                __syncthreads();
             }
-            const Hook hk{&F, &S};
-            if (kind == TILE_A) {
-                const uint32_t sq = tile / ga, grp = tile % ga;
-                uint32_t o0, o1, o2;
-                seq_coords(F.A, unit * F.U + sq, o0, o1, o2);
-                const int64_t obase_in = (int64_t)o0 * F.A.in_bs[0] + (int64_t)o1 * F.A.in_bs[1] + (int64_t)o2 * F.A.in_bs[2];
-                const int64_t obase_out = (int64_t)(((uint64_t)(unit % F.R) * F.U + sq) * NN);
-                EA::run_at(F.A, smem_raw, grp, o0, o1, o2, obase_in, obase_out, hk);
-            } else {
-                const uint32_t sq = tile / gb, grp = tile % gb;
-                uint32_t o0, o1, o2;
-                seq_coords(F.B, unit * F.U + sq, o0, o1, o2);
-                const int64_t obase_in = (int64_t)(((uint64_t)(unit % F.R) * F.U + sq) * NN);
-                const int64_t obase_out = (int64_t)o0 * F.B.out_bs[0] + (int64_t)o1 * F.B.out_bs[1] + (int64_t)o2 * F.B.out_bs[2];
-                EB::run_at(F.B, smem_raw, grp, o0, o1, o2, obase_in, obase_out, hk);
-            }
+            mbar_wait(bar, (it / NBUF) & 1u);
+            const Where w = locate(F, kind, unit, tile);
+            auto dead = [&]() {                      // one buffer: refill it as soon as the last stage has its legs
+                if (w0) {
+                    const bool go = nk != NONE && runnable(F, S, nk, nu);
+                    warp_issue(F, go, nk, nu, nt, sm, bar);
+                    nissued = go;
+                }
+            };
+            if (kind == TILE_A) process<EA, CA>(F, F.A, sm, w, S, false, dead);
+            else process<EB, CB>(F, F.B, sm, w, S, !(F.B.aux_u1 & 1u), dead);
             if (tid == 0) {
-                // the atomics issued behind the first loads have long returned
                 after_publish(F, S);
-                S.pend_kind = kind; S.pend_unit = unit;      // published behind the next tile's loads (or on the wait / exit path)
-                uint32_t u, t;
-                const uint32_t k = decode(F, S.next, u, t);
-                S.next = S.newT;
-                volatile uint32_t* m = mail + 4 * (slot ^ 1);
-                m[0] = k; m[1] = u; m[2] = t; m[3] = (k != NONE && !runnable(F, S, k, u)) ? 1u : 0u;
+                S.pend_kind = kind; S.pend_unit = unit;          // published behind the next tile's first stage (or on the wait / exit path)
+                volatile uint32_t* m = mail + 3 * (slot ^ 1);
+                m[0] = nk; m[1] = nu; m[2] = nt;
+                ck = nk; cu = nu; ct = nt; cissued = nissued;
+                nk = decode(F, S.newT, nu, nt);                  // the ticket fetched behind this tile's first stage
+                nissued = false;
             }
-            __syncthreads();      // every store of this tile has been issued; its shared memory is dead; the next mailbox slot is visible
-            slot ^= 1;
+            fence_proxy_async_smem();
+            __syncthreads();      // stores issued; this buffer may be refilled; the next mailbox slot is visible
         }
         if (tid == 0) {
             publish(F, S);
@@ -242,10 +365,10 @@ struct Fused4 {
 };
 
 #if defined(__CUDACC__)
-template <class CA, class CB>
-__global__ void __launch_bounds__(CA::THREADS, Fused4<CA, CB>::MINB) fused4_kernel(const __grid_constant__ b2_fused_params F) {
-    extern __shared__ __align__(16) unsigned char b2_smem_fused[];
-    Fused4<CA, CB>::run(F, b2_smem_fused);
+template <class CA, class CB, int NBUF>
+__global__ void __launch_bounds__(CA::THREADS, Fused4<CA, CB, NBUF>::MINB) fused4_kernel(const __grid_constant__ b2_fused_params F) {
+    extern __shared__ __align__(128) unsigned char b2_smem_fused[];
+    Fused4<CA, CB, NBUF>::run(F, b2_smem_fused);
 }
 // control block: ticket counters, unit prefixes and per-unit done counters all start at zero
 template <int DUMMY = 0>

@@ -349,25 +349,32 @@ struct MaybeConvCols<true, T, TPL, Q, V, MINB, Rs...> {
 // ---- fused Four-Step (fused4.cuh) -----------------------------------------------------------------------------------
 namespace b200fft {
 #if defined(B2_EMU)
+// two tile buffers (the next tile is copied in while this one is transformed) when three such CTAs still fit an SM
+template <class CA, class CB> struct FusedNbuf { static constexpr int value = (Fused4<CA, CB, 1>::TILE_BYTES <= 36 * 1024) ? 2 : 1; };
+
 template <class CA, class CB>
 int fused_launch_impl(const b2_fused_params* F, unsigned, void*) {
+    constexpr int NBUF = FusedNbuf<CA, CB>::value;
     b2_fused_params FF = *F;
     const uint32_t words = B2_FCTL_WORDS + 2 * FF.NU;
     for (uint32_t i = 0; i < words; ++i) FF.ctl[i] = 0;
     // one CTA walks every tile in claim order (pass B first whenever a unit is complete): no cross-CTA waiting to emulate
-    b2emu::launch(1, CA::THREADS, Fused4<CA, CB>::SMEM_BYTES, [&](unsigned char* sm) { Fused4<CA, CB>::run(FF, sm); }, b2emu::st().log);
+    b2emu::launch(1, CA::THREADS, Fused4<CA, CB, NBUF>::SMEM_BYTES, [&](unsigned char* sm) { Fused4<CA, CB, NBUF>::run(FF, sm); }, b2emu::st().log);
     return emu_refused();
 }
 template <class CA, class CB> int fused_prepare_impl() { return 0; }
 #else
+template <class CA, class CB> struct FusedNbuf { static constexpr int value = (Fused4<CA, CB, 1>::TILE_BYTES <= 36 * 1024) ? 2 : 1; };
+
 template <class CA, class CB>
 int fused_launch_impl(const b2_fused_params* F, unsigned max_ctas, void* stream) {
+    constexpr int NBUF = FusedNbuf<CA, CB>::value;
     static int resident = 0;
     if (!resident) {
         int dev = 0, sms = 0, per_sm = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused4_kernel<CA, CB>, CA::THREADS, Fused4<CA, CB>::SMEM_BYTES);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused4_kernel<CA, CB, NBUF>, CA::THREADS, Fused4<CA, CB, NBUF>::SMEM_BYTES);
         resident = sms * (per_sm > 0 ? per_sm : 1);
     }
     const uint64_t tiles = (uint64_t)F->NU * (F->TA + F->TB);
@@ -377,12 +384,13 @@ int fused_launch_impl(const b2_fused_params* F, unsigned max_ctas, void* stream)
     fused4_init_kernel<0><<<(words + 255) / 256 < 64 ? (words + 255) / 256 : 64, 256, 0, (cudaStream_t)stream>>>(
         F->ctl, words);
     void* args[] = {const_cast<b2_fused_params*>(F)};
-    return (int)cudaLaunchKernel((const void*)fused4_kernel<CA, CB>, dim3(g), dim3(CA::THREADS), args, Fused4<CA, CB>::SMEM_BYTES,
+    return (int)cudaLaunchKernel((const void*)fused4_kernel<CA, CB, NBUF>, dim3(g), dim3(CA::THREADS), args, Fused4<CA, CB, NBUF>::SMEM_BYTES,
                                  (cudaStream_t)stream);
 }
 template <class CA, class CB>
 int fused_prepare_impl() {
-    return (int)cudaFuncSetAttribute(fused4_kernel<CA, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fused4<CA, CB>::SMEM_BYTES);
+    return (int)cudaFuncSetAttribute(fused4_kernel<CA, CB, FusedNbuf<CA, CB>::value>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Fused4<CA, CB, FusedNbuf<CA, CB>::value>::SMEM_BYTES);
 }
 #endif
 
@@ -397,7 +405,7 @@ struct FusedRegistrar {
     explicit FusedRegistrar(const char* name) {
         info = b2_fused_info{};
         info.prec = PrecOf<T>::value; info.n1 = SchA::N; info.n2 = SchB::N; info.inv = INV;
-        info.threads = CA::THREADS; info.qa = QA; info.qb = QB; info.smem_bytes = Fused4<CA, CB>::SMEM_BYTES; info.regs = REGS;
+        info.threads = CA::THREADS; info.qa = QA; info.qb = QB; info.smem_bytes = Fused4<CA, CB, FusedNbuf<CA, CB>::value>::SMEM_BYTES; info.regs = REGS;
         info.ns_a = SchA::ns; info.ns_b = SchB::ns;
         for (int s = 0; s < SchA::ns; ++s) info.radices_a[s] = SchA::r(s);
         for (int s = 0; s < SchB::ns; ++s) info.radices_b[s] = SchB::r(s);

@@ -292,6 +292,15 @@ bool single_ok(const PlanGraph& g, int kind, uint64_t n, int ops) {
     return generic_fits(g, n);
 }
 
+// Fused Four-Step (fused4.cuh).  Measured on B200 (profiles/r2): DRAM traffic is exactly one read + one write (the ring stays
+// in L2), but each SM now has to turn every tile over twice in the time HBM delivers it once, and with the loads of a tile
+// on its critical path the resident CTAs do not keep enough bytes in flight: 1.56 ms (2^16) / 1.83 ms (2^20) per 2 GiB
+// transform against 1.28 / 1.67 ms for the two launches.  Opt-in (B200FFT_FUSED4=1) until the asynchronous tile prefetch is in.
+bool fused4_enabled() {
+    const char* e = getenv("B200FFT_FUSED4");        // read per plan: tests and tuning scripts switch it between plans
+    return e && *e && *e != '0' && !getenv("B200FFT_NO_FUSED4");
+}
+
 uint64_t max_single_env() {
     if (const char* e = getenv("B200FFT_MAX_SINGLE_PASS")) return strtoull(e, nullptr, 10);
     return ~0ull;
@@ -316,13 +325,13 @@ std::vector<uint64_t> split_four_step(const PlanGraph& g, uint64_t N, bool dist 
     }
     const uint64_t cap = std::min<uint64_t>(max_single_env(), 4096);
     auto fast = [&](int kind, uint64_t n, int ops) { return b2_find_kernel(kind, g.prec, (int)n, 0, ops) != nullptr; };
-    // measured cost of one full pass over a 2 GiB FP32 buffer on B200, microseconds (profiles/r1/ktune_f32_tw_chain.log);
+    // measured cost of one full pass over a 2 GiB FP32 buffer on B200, microseconds (profiles/r2/ktune_f32.log);
     // used to rank factorizations.  Unknown sizes / FP64 fall back to "balanced factors".
     auto pass_us = [&](int kind, uint64_t n) -> uint64_t {
         if (g.prec != B2_PREC_F32) return 0;
-        static const struct { uint64_t n; uint64_t cols, tout; } t[] = {
-            {16, 624, 1028}, {32, 764, 632}, {64, 706, 652}, {128, 753, 630}, {256, 782, 618},
-            {512, 862, 715}, {1024, 1013, 744}, {2048, 1197, 876}};
+        static const struct { uint64_t n; uint64_t cols, tout; } t[] = {      // profiles/r2/ktune_f32.log
+            {16, 626, 1032}, {32, 627, 631}, {64, 635, 638}, {128, 635, 641}, {256, 685, 631},
+            {512, 775, 650}, {1024, 864, 685}, {2048, 1258, 900}};
         for (const auto& e : t)
             if (e.n == n) return kind == B2_KIND_COLS ? e.cols : e.tout;
         return 0;
@@ -352,7 +361,7 @@ std::vector<uint64_t> split_four_step(const PlanGraph& g, uint64_t N, bool dist 
         cost += short_runs(B2_KIND_COLS, n1, B2_OP_TWIDDLE_OUT) + short_runs(B2_KIND_ROWS_TOUT, n2, 0);
         // splits that run as one fused launch (one HBM round trip instead of two) win over every two-launch split;
         // among them the first registered pair of a length is the measured default (kernel_list_fused.def)
-        if (!dist && !getenv("B200FFT_NO_FUSED4")) {
+        if (!dist && fused4_enabled()) {
             const b2_fused_info* fk = b2_find_fused(g.prec, (int)n1, (int)n2, 0);
             if (fk) {
                 int order = 0;
@@ -602,7 +611,7 @@ int plan_bluestein(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job)
 // kernel exists for (n1, n2).  B200FFT_NO_FUSED4=1 keeps the two launches; B200FFT_FUSED_UNIT_KB / B200FFT_FUSED_RING /
 // B200FFT_FUSED_RING_MB tune the ring (unit size, slots, total size).
 void try_fuse(PlanGraph& g, std::vector<PassPlan>& list, size_t ia) {
-    if (getenv("B200FFT_NO_FUSED4") || ia + 2 != list.size()) return;
+    if (!fused4_enabled() || ia + 2 != list.size()) return;
     PassPlan& a = list[ia];
     PassPlan& b = list[ia + 1];
     if (a.out_role != ROLE_TEMP || b.in_role != ROLE_TEMP || a.sync_before || b.sync_before) return;
@@ -627,7 +636,7 @@ void try_fuse(PlanGraph& g, std::vector<PassPlan>& list, size_t ia) {
     // ticket each), or pass-B tiles would be handed out before their unit is complete and CTAs would sit waiting.
     const uint64_t per_sm = std::max<uint64_t>(1, std::min<uint64_t>({(227ull << 10) / (uint64_t)fk->smem_bytes, 2048ull / (uint64_t)fk->threads,
                                                                      65536ull / ((uint64_t)fk->threads * (uint64_t)fk->regs)}));
-    const uint64_t in_flight = 148 * per_sm * 2;
+    const uint64_t in_flight = 148 * per_sm * 3;          // per CTA: the tile being transformed, the one being copied in, one ticket
     uint64_t L = lead ? lead : 1 + (in_flight + U * (ga0 + gb0) - 1) / (U * (ga0 + gb0));
     L = std::max<uint64_t>(1, std::min(L, NU));
     uint64_t R = ring ? ring : L + 2;                      // two more slots: one being filled ahead, one draining behind

@@ -128,7 +128,7 @@ struct KCfg {
     // stage twiddles w^k generated from w^1, w^2, w^4, w^8 (Engine::compute).  Measured per kernel on B200
     // (profiles/r1/ktune_f32_tw_chain.log): -1...-10 % for most shapes (N = 4096: 687 -> 655 us per 2 GiB pass), but
     // +9 % for the contiguous 8192-point kernels, which keep one table load per twiddle.
-    static constexpr bool TWCHAIN = !(N == 8192 && LAYOUT_ == 0 && sizeof(T_) == 4);
+    static constexpr bool TWCHAIN = !(N == 8192 && LAYOUT_ == 0 && sizeof(T_) == 4 && REGS_ != 127);
 };
 
 // XF (extra flags, fused Four-Step kernel):

@@ -239,6 +239,11 @@ static inline int VkFFTGetVersion(void) { return 10304; /* API level of the refe
 static inline void deleteVkFFT(VkFFTApplication* app) {
     if (!app) return;
     if (app->b200fftPlan) b200fft_plan_destroy(app->b200fftPlan);
+    if (app->configuration.stream_event) {       /* num_streams > 1: the events that order the streams (below) */
+        for (pfUINT s_ = 0; s_ < app->configuration.num_streams; s_++)
+            if (app->configuration.stream_event[s_]) cudaEventDestroy(app->configuration.stream_event[s_]);
+        free(app->configuration.stream_event);
+    }
     if (app->saveApplicationString) free(app->saveApplicationString);
     if (app->localFFTPlan) free(app->localFFTPlan);
     if (app->localFFTPlan_inverse) free(app->localFFTPlan_inverse);
@@ -326,6 +331,20 @@ static inline VkFFTResult initializeVkFFT(VkFFTApplication* app, VkFFTConfigurat
     app->configuration.vendorID = 0x10DE;
     app->actualNumBatches = app->configuration.numberBatches;
     app->b200fftPlan = plan;
+    app->configuration.stream_event = 0;
+    if (c->stream && c->num_streams > 1) {
+        /* Several streams (vkFFT_DispatchPlan.h:218-225: the reference deals split dispatches round-robin over them and
+           records one event per stream).  The launches of one transform depend on each other, so they all go to stream[0];
+           the events make that equivalent for the caller: stream[0] first waits for everything already enqueued on the
+           other streams, and afterwards every other stream waits for the transform. */
+        app->configuration.stream_event = (cudaEvent_t*)calloc(c->num_streams, sizeof(cudaEvent_t));
+        if (!app->configuration.stream_event) { deleteVkFFT(app); return VKFFT_ERROR_MALLOC_FAILED; }
+        for (pfUINT s_ = 0; s_ < c->num_streams; s_++)
+            if (cudaEventCreateWithFlags(&app->configuration.stream_event[s_], cudaEventDisableTiming) != cudaSuccess) {
+                deleteVkFFT(app);
+                return VKFFT_ERROR_FAILED_TO_CREATE_EVENT;
+            }
+    }
     for (int dir = 0; dir < 2; dir++) {
         VkFFTPlan* pl = (VkFFTPlan*)calloc(1, sizeof(VkFFTPlan));
         if (!pl) { deleteVkFFT(app); return VKFFT_ERROR_MALLOC_FAILED; }
@@ -374,7 +393,20 @@ static inline VkFFTResult VkFFTAppend(VkFFTApplication* app, int inverse, VkFFTL
         b.buffer_offset = c->bufferOffset; b.temp_buffer_offset = c->tempBufferOffset;
         b.input_buffer_offset = c->inputBufferOffset; b.output_buffer_offset = c->outputBufferOffset;
     }
-    return (VkFFTResult)b200fft_exec(app->b200fftPlan, inverse, &b);
+    if (c->stream_event && c->stream) {
+        for (pfUINT s_ = 1; s_ < c->num_streams; s_++) {
+            if (cudaEventRecord(c->stream_event[s_], c->stream[s_]) != cudaSuccess) return VKFFT_ERROR_FAILED_TO_EVENT_RECORD;
+            if (cudaStreamWaitEvent(c->stream[0], c->stream_event[s_], 0) != cudaSuccess) return VKFFT_ERROR_FAILED_TO_SYNCHRONIZE;
+        }
+    }
+    VkFFTResult res_ = (VkFFTResult)b200fft_exec(app->b200fftPlan, inverse, &b);
+    if (res_ == VKFFT_SUCCESS && c->stream_event && c->stream) {
+        if (cudaEventRecord(c->stream_event[0], c->stream[0]) != cudaSuccess) return VKFFT_ERROR_FAILED_TO_EVENT_RECORD;
+        for (pfUINT s_ = 1; s_ < c->num_streams; s_++)
+            if (cudaStreamWaitEvent(c->stream[s_], c->stream_event[0], 0) != cudaSuccess) return VKFFT_ERROR_FAILED_TO_SYNCHRONIZE;
+        app->configuration.streamCounter++;
+    }
+    return res_;
 }
 
 #endif /* VKFFT_H */

@@ -83,7 +83,38 @@ int main() {
     deleteVkFFT(&app_conv);
     cudaFree(kernel);
     cudaFree(cbuf);
-    printf("forward max abs err %.3e, inverse max rel err %.3e, convolution max abs err %.3e, version %d\n", worst, worst_inv,
-           worst_conv, VkFFTGetVersion());
-    return (worst < 2e-6 && worst_inv < 2e-6 && worst_conv < 2e-5 && app.b200fftPlan == 0) ? 0 : 1;
+    // several streams (num_streams = 3): work enqueued on stream[2] BEFORE the transform (the fill) and on stream[1] AFTER it
+    // (the copy back) must be ordered with the transform without any host synchronisation in between
+    double worst_ms = 0;
+    {
+        const uint64_t L = 1 << 12, LB = 64;
+        cudaStream_t st[3];
+        for (int i = 0; i < 3; i++) cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking);
+        void* mb = 0;
+        float* pinned = 0;
+        if (cudaMalloc(&mb, sizeof(float) * 2 * L * LB) != cudaSuccess || cudaMallocHost((void**)&pinned, sizeof(float) * 2 * L * LB) != cudaSuccess) return 2;
+        for (uint64_t i = 0; i < 2 * L * LB; i++) pinned[i] = 0.f;
+        for (uint64_t b = 0; b < LB; b++) pinned[2 * (b * L + 1)] = 1.f;        // delta at 1 -> exp(-2 pi i k / L)
+        VkFFTConfiguration mcfg = {};
+        VkFFTApplication mapp = {};
+        mcfg.FFTdim = 1; mcfg.size[0] = L; mcfg.numberBatches = LB; mcfg.device = &dev; mcfg.stream = st; mcfg.num_streams = 3;
+        if ((res = initializeVkFFT(&mapp, mcfg)) != VKFFT_SUCCESS) { printf("multi-stream init: %s\n", getVkFFTErrorString(res)); return 1; }
+        VkFFTLaunchParams mlp = {};
+        mlp.buffer = &mb;
+        cudaMemcpyAsync(mb, pinned, sizeof(float) * 2 * L * LB, cudaMemcpyHostToDevice, st[2]);
+        if ((res = VkFFTAppend(&mapp, -1, &mlp)) != VKFFT_SUCCESS) { printf("multi-stream append: %s\n", getVkFFTErrorString(res)); return 1; }
+        cudaMemcpyAsync(pinned, mb, sizeof(float) * 2 * L * LB, cudaMemcpyDeviceToHost, st[1]);
+        cudaStreamSynchronize(st[1]);
+        for (uint64_t b = 0; b < LB; b++)
+            for (uint64_t k = 0; k < L; k++) {
+                const double a = -2.0 * M_PI * (double)k / (double)L;
+                worst_ms = fmax(worst_ms, hypot(pinned[2 * (b * L + k)] - cos(a), pinned[2 * (b * L + k) + 1] - sin(a)));
+            }
+        deleteVkFFT(&mapp);
+        cudaFree(mb); cudaFreeHost(pinned);
+        for (int i = 0; i < 3; i++) cudaStreamDestroy(st[i]);
+    }
+    printf("forward max abs err %.3e, inverse max rel err %.3e, convolution max abs err %.3e, multi-stream max abs err %.3e, version %d\n",
+           worst, worst_inv, worst_conv, worst_ms, VkFFTGetVersion());
+    return (worst < 2e-6 && worst_inv < 2e-6 && worst_conv < 2e-5 && worst_ms < 2e-6 && app.b200fftPlan == 0) ? 0 : 1;
 }

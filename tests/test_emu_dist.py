@@ -92,3 +92,65 @@ def test_distributed_plan_rejects_what_it_cannot_shard():
     assert emu.exec_plan_pass(d, -1, buf, buf.copy(), -1)[0] == 3002   # batches are sharded whole, not distributed
     d = emu.make_desc((1 << 15,), 1, 0, user_temp_buffer=1, dist_world=2, dist_rank=2)
     assert emu.exec_plan_pass(d, -1, buf, buf.copy(), -1)[0] == 1002
+
+
+# ---- distributed N-D transforms: slabs along the last dimension ---------------------------------------
+def _play_nd(shape_xyz, world, inverse, order, env=None, normalize=0):
+    """every rank's launches of the slab plan on one host array standing for the peer window (+ a temp window)"""
+    env = env or {}
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        total = int(np.prod(shape_xyz))
+        rng = np.random.default_rng(total + world)
+        x = (rng.uniform(-1, 1, total) + 1j * rng.uniform(-1, 1, total)).astype(np.complex64)
+        buf, tmp = x.copy(), np.zeros(total, dtype=np.complex64)
+        descs = [emu.make_desc(shape_xyz, 1, 0, user_temp_buffer=1, dist_world=world, dist_rank=r, normalize=normalize) for r in range(world)]
+        rc, npass, sync = emu.exec_plan_pass(descs[0], inverse, buf, tmp, -1)
+        assert rc == 0, rc
+        segs, cur = [], []
+        for p in range(npass):
+            if sync[p] and cur:
+                segs.append(cur)
+                cur = []
+            cur.append(p)
+        segs.append(cur)
+        for seg in segs:
+            for r in (range(world) if order == "up" else range(world - 1, -1, -1)):
+                for p in seg:
+                    rc, _, _ = emu.exec_plan_pass(descs[r], inverse, buf, tmp, p)
+                    assert rc == 0, rc
+        nd = x.astype(np.complex128).reshape(tuple(reversed(shape_xyz)))
+        ref = np.fft.ifftn(nd) * total if inverse == 1 else np.fft.fftn(nd)
+        if normalize and inverse == 1:
+            ref = ref / total
+        return np.linalg.norm(buf.reshape(ref.shape) - ref) / np.linalg.norm(ref), npass, len(segs)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("shape,world", [((64, 32), 2), ((128, 64), 4), ((32, 16, 8), 2), ((64, 32, 16), 4), ((48, 40, 12), 2),
+                                         ((256, 8), 8)])
+@pytest.mark.parametrize("inverse", [-1, 1])
+def test_distributed_nd_slab_plans(shape, world, inverse):
+    for order in ("up", "down"):
+        err, npass, nseg = _play_nd(shape, world, inverse, order)
+        assert npass == len(shape) and nseg == 2      # local axes | barrier | the axis across the slabs (inverse: the other way round)
+        assert err < 2e-6, err
+
+
+def test_distributed_nd_long_last_axis_runs_as_strided_four_step():
+    """the axis across the slabs is too long for one strided launch: two launches along the stride, still one barrier segment"""
+    for inverse in (-1, 1):
+        err, npass, nseg = _play_nd((32, 4096), 2, inverse, "up", env={"B200FFT_MAX_SINGLE_PASS": "1024"})
+        assert npass == 3 and nseg == 2
+        assert err < 2e-6, err
+
+
+def test_distributed_nd_rejects_what_it_cannot_slice():
+    d = emu.make_desc((64, 30), 1, 0, user_temp_buffer=1, dist_world=4, dist_rank=0)      # 30 rows over 4 ranks
+    assert emu.exec_plan_pass(d, -1, np.zeros(64 * 30, np.complex64), np.zeros(64 * 30, np.complex64), -1)[0] == 3002

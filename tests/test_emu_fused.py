@@ -1,8 +1,8 @@
 """CPU: the fused Four-Step launch (csrc/fused4.cuh) on the kernel-body emulation.
 
-One CTA walks every tile in claim order (pass B whenever a unit is complete, otherwise the next pass-A tile whose ring
-slot is free), so the scheduler's bookkeeping -- semaphores, in-order prefixes, ring wrap-around -- is exercised exactly
-as on the device, minus the concurrency.  Results are compared with the oracle and, bit for bit, with the two-launch plan
+One CTA (a group of one) walks every tile of the static schedule, so the tile bookkeeping -- phases, the two scratch slots,
+the tile counters, the TMA-style tile copies (synchronous here) and the double-buffered tile loop -- is exercised exactly as
+on the device, minus the concurrency.  Results are compared with the oracle and, bit for bit, with the two-launch plan
 (both run the same stage code)."""
 import os
 
@@ -40,17 +40,17 @@ def run(shape, batch, inv, x, **kw):
     return buf, txt
 
 
-# (log2 N, batch, ring settings): one unit; pass B one unit behind with the smallest legal ring (2 slots: every slot is
-# rewritten as soon as it has drained); deeper lead; units of several sequences; more slots than units; lead larger than
-# the number of units (clamped)
+# (log2 N, batch, extra environment).  The emulation runs one CTA at a time, so the launch is played by ONE group of one
+# CTA that walks every sequence in phase order (pass B of sequence j-1, then pass A of sequence j, alternating between the two
+# scratch slots); odd and even numbers of sequences, one sequence, every fused pair up to 2^17
 CASES = [
     (15, 5, dict()),
-    (15, 6, dict(B200FFT_FUSED_UNIT_KB=512, B200FFT_FUSED_LEAD=1, B200FFT_FUSED_RING=2)),
-    (15, 8, dict(B200FFT_FUSED_UNIT_KB=256, B200FFT_FUSED_LEAD=2, B200FFT_FUSED_RING=3)),
-    (16, 3, dict(B200FFT_FUSED_UNIT_KB=512, B200FFT_FUSED_LEAD=1, B200FFT_FUSED_RING=2)),
-    (16, 4, dict(B200FFT_FUSED_UNIT_KB=1024, B200FFT_FUSED_LEAD=1, B200FFT_FUSED_RING=8)),
-    (17, 2, dict(B200FFT_FUSED_UNIT_KB=1024, B200FFT_FUSED_LEAD=5)),
-    (15, 12, dict(B200FFT_FUSED_UNIT_KB=256, B200FFT_FUSED_LEAD=3, B200FFT_FUSED_RING=4)),
+    (15, 6, dict(B200FFT_FUSED_GROUP=4)),
+    (15, 1, dict()),
+    (15, 2, dict()),
+    (16, 3, dict()),
+    (16, 4, dict(B200FFT_FUSED_GROUP=64)),
+    (17, 2, dict()),
 ]
 
 

@@ -40,9 +40,9 @@ def _worker(rank, world, port, n, q):
         f.check()
         back = ((f.local.cpu() - full[lo:hi]).abs().norm() / full[lo:hi].abs().norm()).item()
         f.close()
-        q.put((rank, err, back, None))
+        q.put((rank, err, back, None, dev))
     except Exception as e:  # noqa: BLE001
-        q.put((rank, None, None, repr(e)))
+        q.put((rank, None, None, repr(e), -1))
     finally:
         dist.destroy_process_group()
 
@@ -62,7 +62,71 @@ def test_fused_distributed_fft_two_ranks(logn):
     res = [q.get(timeout=300) for _ in procs]
     for p in procs:
         p.join(timeout=120)
-    for rank, err, back, exc in res:
+    for rank, err, back, exc, dev in res:
         assert exc is None, exc
         assert err < 1e-6, (rank, err)        # FP32 tolerance of north_star
+        assert back < 1e-6, (rank, back)
+    # on a box with two or more GPUs the two ranks sit on DIFFERENT devices: the peer traffic really crosses NVLink
+    import torch
+    if torch.cuda.device_count() >= 2:
+        assert len({dev for *_, dev in res}) == 2, res
+
+
+def _worker_nd(rank, world, port, shape_xyz, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from vkfft_b200.dist import FusedDistributedFFTND
+        dev = rank % torch.cuda.device_count()
+        torch.cuda.set_device(dev)
+        g = torch.Generator(device="cpu").manual_seed(13)
+        np_shape = tuple(reversed(shape_xyz))
+        total = 1
+        for v in shape_xyz:
+            total *= v
+        full = torch.view_as_complex(torch.empty(total, 2, dtype=torch.float32).uniform_(-1, 1, generator=g)).reshape(np_shape)
+        sl = np_shape[0] // world
+        f = FusedDistributedFFTND(shape_xyz, dist, dev, normalize=True)
+        f.local.copy_(full[rank * sl:(rank + 1) * sl])
+        torch.cuda.synchronize()
+        dist.barrier()
+        f(inverse=False)
+        f.check()
+        ref = torch.fft.fftn(full.to(torch.complex128))[rank * sl:(rank + 1) * sl]
+        got = f.local.cpu().to(torch.complex128)
+        err = ((got - ref).abs().norm() / ref.abs().norm()).item()
+        f(inverse=True)
+        f.check()
+        mine = full[rank * sl:(rank + 1) * sl]
+        back = ((f.local.cpu() - mine).abs().norm() / mine.abs().norm()).item()
+        f.close()
+        q.put((rank, err, back, None))
+    except Exception as e:  # noqa: BLE001
+        q.put((rank, None, None, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shape_xyz", [(512, 256), (128, 64, 32), (64, 8192)])      # 2-D, 3-D, a Four-Step across the slabs
+def test_fused_distributed_nd_two_ranks(shape_xyz):
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_nd, args=(r, 2, port, shape_xyz, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=120)
+    for rank, err, back, exc in res:
+        assert exc is None, exc
+        assert err < 1e-6, (rank, err)
         assert back < 1e-6, (rank, back)

@@ -15,7 +15,7 @@ SWEEP = {
     15: [("128", "COLS"), ("256", "ROWS_TOUT")], 16: [("128", "COLS"), ("512", "ROWS_TOUT")],
     17: [("128", "COLS"), ("1024", "ROWS_TOUT")], 18: [("256", "COLS"), ("1024", "ROWS_TOUT")],
     19: [("512", "COLS"), ("1024", "ROWS_TOUT")], 20: [("1024", "COLS"), ("1024", "ROWS_TOUT")],
-    21: [("1024", "COLS"), ("2048", "PIPE1_ROWS_TOUT")], 22: [("2048", "COLS"), ("2048", "PIPE1_ROWS_TOUT")],
+    21: [("1024", "COLS"), ("2048", "PIPE1_ROWS_TOUT")], 22: [("128", "COLS"), ("128", "COLS"), ("256", "ROWS_TOUT")],
 }
 
 

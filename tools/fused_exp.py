@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""Time the fused Four-Step for explicit settings: python tools/fused_exp.py "log2n:unit_kb:lead:ring:ctas[:flags]" ...   (0 = default)"""
+"""Time the fused Four-Step for explicit settings: python tools/fused_exp.py "log2n:group:ctas:flags" ...   (0 = default;
+group = CTAs per group, ctas = cap on resident CTAs, flags: 1 no discard, 2 ignore dependencies)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -13,9 +14,8 @@ torch.view_as_real(buf).uniform_(-1, 1)
 lp = vk.VkFFTLaunchParams(buffer=buf)
 for spec in sys.argv[1:]:
     f = [int(x) for x in spec.split(":")] + [0] * 6
-    logn, unit, lead, ring, ctas, flags = f[:6]
-    env = {"B200FFT_FUSED_UNIT_KB": unit, "B200FFT_FUSED_LEAD": lead, "B200FFT_FUSED_RING": ring, "B200FFT_FUSED_CTAS": ctas,
-           "B200FFT_FUSED_FLAGS": flags}
+    logn, group, ctas, flags = f[:4]
+    env = {"B200FFT_FUSED_GROUP": group, "B200FFT_FUSED_CTAS": ctas, "B200FFT_FUSED_FLAGS": flags}
     for k, v in env.items():
         if v: os.environ[k] = str(v)
         else: os.environ.pop(k, None)
@@ -23,7 +23,7 @@ for spec in sys.argv[1:]:
     app = vk.VkFFTApplication()
     assert vk.initializeVkFFT(app, vk.VkFFTConfiguration(FFTdim=1, size=[n], numberBatches=pts // n, device=0)) == 0
     note = vk.planInfo(app)["forward"].split("\n")[0]
-    note = note[note.index("units of"):note.index("]")] if "units of" in note else "NOT FUSED"
+    note = note[note.index("groups of"):note.index("]")] if "groups of" in note else "NOT FUSED"
     for _ in range(2): vk.VkFFTAppend(app, -1, lp)
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -42,7 +42,7 @@ for logn in range(15, 23):
     # ---- correctness: ring smaller than the number of units, both directions
     batch = max(24, (96 << 20) // (n * 8))
     x = torch.view_as_complex(torch.empty(batch * n, 2, device="cuda").uniform_(-1, 1)).reshape(batch, n)
-    a_f = plan(n, batch, B200FFT_FUSED_UNIT_KB=max(1024, n * 8 // 1024), B200FFT_FUSED_LEAD=1, B200FFT_FUSED_RING=2)
+    a_f = plan(n, batch)
     a_u = plan(n, batch, B200FFT_NO_FUSED4=1)
     desc = vk.planInfo(a_f)["forward"].split("\n")[0]
     ok = True
@@ -68,19 +68,16 @@ for logn in range(15, 23):
     line = f"N=2^{logn}: two launches {t_u*1e3:7.1f} us ({4*pts*8/1e6/t_u/PEAK*1e9:.2f})"
     best = None
     seq_kb = n * 8 // 1024
-    units = sorted({max(seq_kb, u) for u in ((2048, 8192) if quick else (1024, 2048, 4096, 8192, 16384))})
-    leads = (0, 6) if quick else (0, 2, 3, 4, 6, 8)          # 0 = the planner's own choice
-    for unit_kb, lead in itertools.product(units, leads):
+    for group in ((0,) if quick else (0, 8, 16, 32, 64, 128)):
         torch.view_as_real(buf).uniform_(-1, 1)
-        env = dict(B200FFT_FUSED_UNIT_KB=unit_kb)
-        if lead: env["B200FFT_FUSED_LEAD"] = lead
+        env = dict(B200FFT_FUSED_GROUP=group) if group else {}
         a_f = plan(n, pts // n, **env)
         note = vk.planInfo(a_f)["forward"].split("\n")[0]
-        note = note[note.index("units of"):note.index("]")] if "units of" in note else note[-80:]
+        note = note[note.index("groups of"):note.index("]")] if "groups of" in note else note[-80:]
         t = timed(lambda: vk.VkFFTAppend(a_f, -1, lp))
         vk.deleteVkFFT(a_f)
-        print(f"      unit {unit_kb:5d} KB lead {lead}: {t*1e3:7.1f} us  frac {2*pts*8/1e6/t/PEAK*1e9:.3f}   [{note}]", flush=True)
-        if best is None or t < best[0]: best = (t, unit_kb, lead)
+        print(f"      group {group:3d}: {t*1e3:7.1f} us  frac {2*pts*8/1e6/t/PEAK*1e9:.3f}   [{note}]", flush=True)
+        if best is None or t < best[0]: best = (t, group, 0)
     if best is None:
         print(line + " | fused: no configuration ran"); continue
-    print(line + f" | fused best {best[0]*1e3:7.1f} us frac {2*pts*8/1e6/best[0]/PEAK*1e9:.3f} (unit {best[1]} KB, lead {best[2]})  ok={ok}", flush=True)
+    print(line + f" | fused best {best[0]*1e3:7.1f} us frac {2*pts*8/1e6/best[0]/PEAK*1e9:.3f} (group {best[1]})  ok={ok}", flush=True)

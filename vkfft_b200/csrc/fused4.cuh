@@ -8,11 +8,10 @@
 //   * persistent CTAs take TILES from two ordered queues.  A tile of pass A (Q_A neighbouring columns of one sequence:
 //     strided n1-point transforms + the Four-Step phase) may be taken when its unit's ring slot is free; a tile of pass B
 //     (Q_B rows: contiguous n2-point transforms, transposed store to the final place) when ALL A tiles of its unit are
-//     done.  All tiles form ONE ordered sequence (pass A of unit u interleaved with pass B of unit u-L) that the CTAs walk
-//     with fetch-add tickets, so pass B trails pass A by L units and reads and writes overlap; all scheduler traffic (the
-//     next ticket, the two readiness limits, the release of the previous tile) is issued while the current tile's first
-//     loads are in flight (Engine::run_at hook) and only looked at after its last store, so no memory round trip sits on
-//     the tile path;
+//     done.  The schedule is static: groups of K CTAs own whole sequences and two private scratch slots each and walk them
+//     in phases (pass B of the previous sequence, then pass A of the next), synchronised by two tile counters per group;
+//     every CTA knows its tile list in advance, so the next tile is always being copied in by TMA while the current one is
+//     transformed, and the counter traffic rides behind the first butterflies of the following tile;
 //   * pass B reads the scratch with ld.global.cg (it was written by other SMs in this launch) and, once the legs are in
 //     registers, drops the lines from L2 (discard.global.L2) so that dead scratch is never written back to HBM.
 // Both passes run the very same stage code as the stand-alone kernels (Engine<C>::run_at), so results are identical
@@ -76,6 +75,16 @@ B2_D void fz_sleep(unsigned) {}
 // NBUF: tile buffers per CTA.  2: the NEXT tile is copied into the other buffer by TMA while this one is transformed;
 // 1 (tiles too large to double): the next tile is copied into the same buffer as soon as the last stage has its legs in
 // registers, i.e. it overlaps the last butterflies and the global stores.
+#if defined(__CUDA_ARCH__)
+// 2-D tensor copy global -> shared (TMA, SASS UTMALDG): box of the tensor map at element coordinates (c0, c1)
+B2_D void tma_load_2d(void* dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+#endif
+
 template <class CA, class CB, int NBUF = 2>
 struct Fused4 {
     // strides known at compile time: pass A walks columns of an n1 x n2 matrix (element stride n2 on both sides), pass B
@@ -93,78 +102,68 @@ struct Fused4 {
     static constexpr int TILE_BYTES = ((CA::SMEM_BYTES > CB::SMEM_BYTES ? CA::SMEM_BYTES : CB::SMEM_BYTES) + 127) / 128 * 128;
     static constexpr int SMEM_BYTES = NBUF * TILE_BYTES + 64;     // + two mbarriers + mailbox: two slots of (kind, unit, tile)
     static constexpr uint32_t BYTES_A = (uint32_t)(CA::N * CA::Q * sizeof(X)), BYTES_B = (uint32_t)(CB::N * CB::Q * sizeof(X));
+    static constexpr int BOX_ROWS = CA::N < 256 ? CA::N : 256;      // rows per TMA box (hardware limit 256 per dimension)
     enum { NONE = 0, TILE_A = 1, TILE_B = 2 };
 
-    // ---- scheduler: ONE ordered queue, state in the registers of thread 0 --------------------------------------------------
-    // All tiles of the launch form one sequence that every CTA walks with a fetch-add ticket:
-    //      block b = 0 .. NU+L-1 :   the pass-A tiles of unit b  interleaved with  the pass-B tiles of unit b-L
-    // so pass B runs L units behind pass A -- far enough that a unit's pass-A tiles have normally all finished by the time
-    // its first pass-B tile is handed out (L is sized from the number of resident CTAs by the planner), and HBM reads
-    // (pass A) and HBM writes (pass B) are always in flight together.  A tile may START when
-    //      pass B:  unit <  READY_UNITS            (in-order prefix of units whose pass A is complete)
-    //      pass A:  unit <  FREED_UNITS + R        (the ring slot it overwrites has been drained; R > L)
-    // otherwise thread 0 polls the two words (both monotonic).  A tile only ever waits for tiles EARLIER in the sequence and
-    // a CTA holds one started tile plus one ticket it has not started, so the lowest unfinished tile can always run: no
-    // deadlock, whatever the number of resident CTAs.
-    // Nothing here waits for a memory round trip on the tile path: the next ticket, the refresh of the two limits and the
-    // release of the PREVIOUS tile (one MEMBAR.GPU + one atomic) are issued while the tile's first loads are in flight
-    // (Engine hook) and only looked at after its last store.
+    // ---- schedule: static, per GROUP of K CTAs -------------------------------------------------------------------------------
+    // The resident CTAs are split into groups of K (F.U); group g owns the sequences g, g+NG, g+2NG, ... and a private pair
+    // of scratch slots, and walks them in phases:
+    //      phase j :  pass-B tiles of its (j-1)-th sequence (slot (j-1)&1)   then   pass-A tiles of its j-th sequence (slot j&1)
+    // CTA r of the group takes tiles r, r+K, ... of each part, so every CTA knows its whole tile list in advance (the TMA
+    // copy of the next tile can always be started early) and nothing is handed out at run time.  Two counters per group
+    // count finished tiles:
+    //      a pass-B tile of phase j may start when  cntA >= TA*j      (every pass-A tile of that sequence is done)
+    //      a pass-A tile of phase j may start when  cntB >= TB*(j-1)  (the slot it overwrites has been read completely)
+    // Both conditions refer to work that ended at least half a phase earlier, so CTAs rarely wait; the scratch of all groups
+    // together is 2 * NG sequences (tens of MB at most: K is chosen by the planner so that it stays far below the L2 size)
+    // and is rewritten in place for the whole launch, so it never leaves L2.  (Three dynamic schedulers -- semaphores,
+    // reserved tickets, one ordered queue -- were measured first: every ticket a CTA holds ahead of its work widens the
+    // window of units that must stay resident and the CTAs ended up waiting for each other, profiles/r2/fused_*.log.)
+    // The counter updates of a tile (one MEMBAR.GPU + one atomic) and the refresh of the two counters are issued behind the
+    // NEXT tile's first butterflies and only looked at after its last store: no memory round trip on the tile path.
     struct Sched {
-        uint32_t ready, freed;         // last values read of READY_UNITS / FREED_UNITS
-        uint32_t pend_kind, pend_unit; // finished tile whose completion has not been published yet
-        uint32_t newT, dcount;         // in flight: next-next ticket, done-counter before this CTA's increment
-        uint32_t done_kind, done_unit;
+        uint32_t cntA, cntB;           // last values read of the group's counters
+        uint32_t pend_kind;            // finished tile whose completion has not been published yet
     };
+    struct Tile { uint32_t kind, m, t; };      // pass, ordinal of the sequence within the group, tile within the sequence
 
-    // ticket -> (pass, unit, tile within the unit's pass)
-    B2_D static uint32_t decode(const b2_fused_params& F, uint32_t item, uint32_t& unit, uint32_t& tile) {
-        const uint32_t TA = F.TA, TB = F.TB, NU = F.NU, L = F.reserved;       // reserved = lead L (units)
-        const uint32_t headA = L * TA, mid = (NU - L) * (TA + TB);
-        if (item < headA) { unit = item / TA; tile = item % TA; return TILE_A; }
-        if (item < headA + mid) {
-            const uint32_t r = item - headA, blk = L + r / (TA + TB), pos = r % (TA + TB);
-            const uint32_t a0 = (uint32_t)(((uint64_t)pos * TA) / (TA + TB)), a1 = (uint32_t)(((uint64_t)(pos + 1) * TA) / (TA + TB));
-            if (a1 > a0) { unit = blk; tile = a0; return TILE_A; }
-            unit = blk - L; tile = pos - a1; return TILE_B;
+    B2_D static uint32_t* counters(const b2_fused_params& F) { return F.ctl + (size_t)(blockIdx.x / F.U) * 64; }
+    B2_D static uint32_t nseq_of_group(const b2_fused_params& F) {
+        const uint32_t g = blockIdx.x / F.U;
+        return g < F.nseq ? (F.nseq - g + F.NU - 1) / F.NU : 0u;
+    }
+    // the CTA's next tile after `c` (c.kind == NONE: its first one)
+    B2_D static Tile advance(const b2_fused_params& F, Tile c, uint32_t P) {
+        const uint32_t K = F.U, r = blockIdx.x % K;
+        uint32_t j, part, t;                    // phase, part (0: B of sequence j-1, 1: A of sequence j), tile
+        if (c.kind == NONE) { j = 0; part = 0; t = r; }
+        else { part = c.kind == TILE_B ? 0u : 1u; j = part ? c.m : c.m + 1; t = c.t + K; }
+        for (;;) {
+            if (j > P) return Tile{NONE, 0, 0};
+            if (part == 0) {
+                if (j >= 1 && t < F.TB) return Tile{TILE_B, j - 1, t};
+                part = 1; t = r;
+            } else {
+                if (j < P && t < F.TA) return Tile{TILE_A, j, t};
+                part = 0; t = r; ++j;
+            }
         }
-        const uint32_t r = item - headA - mid;
-        if (r >= L * TB) { unit = 0; tile = 0; return NONE; }
-        unit = NU - L + r / TB; tile = r % TB;
-        return TILE_B;
     }
-    B2_D static bool runnable(const b2_fused_params& F, const Sched& S, uint32_t kind, uint32_t unit) {
-        return kind == TILE_B ? unit < S.ready : unit < S.freed + F.R;
+    B2_D static bool runnable(const b2_fused_params& F, const Sched& S, const Tile& c) {
+        if (F.B.aux_u1 & 2u) return true;      // tuning switch: ignore the dependencies (wrong results, upper bound of the tile pipeline)
+        if (c.kind == TILE_B) return S.cntA >= F.TA * (c.m + 1);
+        return c.m < 2 || S.cntB >= F.TB * (c.m - 1);
     }
-
-    B2_D static void publish(const b2_fused_params& F, Sched& S) {      // release the pending tile (if any); async result in S.dcount
-        S.done_kind = S.pend_kind; S.done_unit = S.pend_unit;
+    B2_D static void publish(const b2_fused_params& F, Sched& S) {      // release the pending tile (if any)
         if (S.pend_kind != NONE) {
-            uint32_t* done = F.ctl + B2_FCTL_WORDS + (S.pend_kind == TILE_B ? F.NU : 0u);
-            S.dcount = fz_add_release(done + S.pend_unit, 1u);
+            fz_add_release(counters(F) + (S.pend_kind == TILE_B ? 32 : 0), 1u);
             S.pend_kind = NONE;
         }
     }
-    // the unit just published was completed by this CTA's increment: advance the in-order prefix (once per unit and pass)
-    B2_D static void after_publish(const b2_fused_params& F, Sched& S) {
-        if (S.done_kind == NONE) return;
-        const uint32_t per_unit = S.done_kind == TILE_A ? F.TA : F.TB;
-        if (S.dcount + 1 != per_unit) { S.done_kind = NONE; return; }
-        const uint32_t word = S.done_kind == TILE_A ? B2_FCTL_READY_UNITS : B2_FCTL_FREED_UNITS;
-        const uint32_t* done = F.ctl + B2_FCTL_WORDS + (S.done_kind == TILE_B ? F.NU : 0u);
-        S.done_kind = NONE;
-        for (;;) {
-            const uint32_t p = fz_ld_acquire(F.ctl + word);
-            if (p >= F.NU) return;
-            if (fz_ld_acquire(done + p) != per_unit) return;
-            fz_cas_release(F.ctl + word, p, p + 1);
-        }
-    }
-
     // scheduler traffic of one tile, issued by thread 0 while the tile's first-stage legs are being read
     B2_D static void sched_issue(const b2_fused_params& F, Sched& S) {
-        S.newT = fz_add(F.ctl + B2_FCTL_NEXT_A, 1u);
-        S.ready = fz_ld_relaxed(F.ctl + B2_FCTL_READY_UNITS);
-        S.freed = fz_ld_relaxed(F.ctl + B2_FCTL_FREED_UNITS);
+        S.cntA = fz_ld_relaxed(counters(F));
+        S.cntB = fz_ld_relaxed(counters(F) + 32);
         publish(F, S);
     }
 
@@ -173,21 +172,21 @@ struct Fused4 {
         o1 = seq % P.nb[1]; seq /= P.nb[1];
         o2 = seq;
     }
-    struct Where { uint32_t grp, o0, o1, o2; int64_t obase_in, obase_out; };
-    B2_D static Where locate(const b2_fused_params& F, uint32_t kind, uint32_t unit, uint32_t tile) {
+    struct Where { uint32_t grp, seq, o0, o1, o2; int64_t obase_in, obase_out; };
+    B2_D static Where locate(const b2_fused_params& F, const Tile& c) {
         constexpr uint64_t NN = (uint64_t)CA::N * (uint64_t)CB::N;              // points per sequence
+        const uint32_t g = blockIdx.x / F.U;
+        const int64_t slot = (int64_t)(((uint64_t)g * 2 + (c.m & 1u)) * NN);  // this group's scratch slot of that sequence
         Where w;
-        if (kind == TILE_A) {
-            const uint32_t ga = F.A.G / CA::Q, sq = tile / ga;
-            w.grp = tile % ga;
-            seq_coords(F.A, unit * F.U + sq, w.o0, w.o1, w.o2);
+        w.grp = c.t;
+        w.seq = g + F.NU * c.m;
+        if (c.kind == TILE_A) {
+            seq_coords(F.A, w.seq, w.o0, w.o1, w.o2);
             w.obase_in = (int64_t)w.o0 * F.A.in_bs[0] + (int64_t)w.o1 * F.A.in_bs[1] + (int64_t)w.o2 * F.A.in_bs[2];
-            w.obase_out = (int64_t)(((uint64_t)(unit % F.R) * F.U + sq) * NN);
+            w.obase_out = slot;
         } else {
-            const uint32_t gb = F.B.G / CB::Q, sq = tile / gb;
-            w.grp = tile % gb;
-            seq_coords(F.B, unit * F.U + sq, w.o0, w.o1, w.o2);
-            w.obase_in = (int64_t)(((uint64_t)(unit % F.R) * F.U + sq) * NN);
+            seq_coords(F.B, w.seq, w.o0, w.o1, w.o2);
+            w.obase_in = slot;
             w.obase_out = (int64_t)w.o0 * F.B.out_bs[0] + (int64_t)w.o1 * F.B.out_bs[1] + (int64_t)w.o2 * F.B.out_bs[2];
         }
         return w;
@@ -199,38 +198,46 @@ struct Fused4 {
     //   pass B: Q_B contiguous rows of the scratch = ONE contiguous block                   -> buf[q*n2 + p]  (dense; the
     //           first scatter moves it to the padded layout)
     // Called by every lane of warp 0 (emulation: by thread 0 alone); the arguments are taken from lane 0.
-    B2_D static void warp_issue(const b2_fused_params& F, bool go, uint32_t kind, uint32_t unit, uint32_t tile, X* buf, uint64_t* bar) {
+    B2_D static void warp_issue(const b2_fused_params& F, bool go, Tile c, X* buf, uint64_t* bar) {
 #if defined(__CUDA_ARCH__)
         const int lane = threadIdx.x & 31, nlanes = 32;
         go = __shfl_sync(0xffffffffu, go ? 1 : 0, 0) != 0;
-        kind = __shfl_sync(0xffffffffu, kind, 0); unit = __shfl_sync(0xffffffffu, unit, 0); tile = __shfl_sync(0xffffffffu, tile, 0);
+        c.kind = __shfl_sync(0xffffffffu, c.kind, 0); c.m = __shfl_sync(0xffffffffu, c.m, 0); c.t = __shfl_sync(0xffffffffu, c.t, 0);
 #else
         const int lane = 0, nlanes = 1;
 #endif
         if (!go) return;
-        const Where w = locate(F, kind, unit, tile);
-        if (kind == TILE_A) {
-            if (lane == 0) mbar_expect_tx(bar, BYTES_A);
+        const Where w = locate(F, c);
+        if (c.kind == TILE_A) {
 #if defined(__CUDA_ARCH__)
-            __syncwarp();
-#endif
+            // one tensor copy per box of up to 256 rows: the TMA unit walks the rows (row-by-row bulk copies cost ~50 cycles
+            // of the unit each and made the launch several times slower, profiles/r2/fused_exp_bulk_rows.log)
+            if (lane == 0) {
+                mbar_expect_tx(bar, BYTES_A);
+#pragma unroll
+                for (int r0 = 0; r0 < CA::N; r0 += BOX_ROWS)
+                    tma_load_2d(buf + (size_t)r0 * CA::Q, &F.tmap_a, (int)(2 * w.grp * CA::Q), (int)(w.seq * CA::N + r0), bar);
+            }
+            (void)nlanes;
+#else
+            if (lane == 0) mbar_expect_tx(bar, BYTES_A);
             const X* src = (const X*)F.A.in + w.obase_in + (int64_t)w.grp * CA::Q * F.A.in_gs;
             for (int p = lane; p < CA::N; p += nlanes)
                 tma_load_1d(buf + (size_t)p * CA::Q, src + (int64_t)p * CB::N, (uint32_t)(CA::Q * sizeof(X)), bar);
+#endif
         } else if (lane == 0) {
             mbar_expect_tx(bar, BYTES_B);
             const X* src = (const X*)F.B.in + w.obase_in + (int64_t)w.grp * CB::Q * CB::N;
             tma_load_1d(buf, src, BYTES_B, bar);
         }
     }
-    // thread 0: hold back nothing, then wait until the tile may run (the slow path: its unit was not ready when looked at)
-    B2_D static void wait_runnable(const b2_fused_params& F, Sched& S, uint32_t kind, uint32_t unit) {
+    // thread 0: hold back nothing, then wait until the tile may run (the slow path: its sequence was not ready when looked at)
+    B2_D static void wait_runnable(const b2_fused_params& F, Sched& S, const Tile& c) {
         publish(F, S);
-        after_publish(F, S);
         for (;;) {
-            S.ready = fz_ld_relaxed(F.ctl + B2_FCTL_READY_UNITS);
-            S.freed = fz_ld_relaxed(F.ctl + B2_FCTL_FREED_UNITS);
-            if (runnable(F, S, kind, unit)) return;
+            S.cntA = fz_ld_relaxed(counters(F));
+            S.cntB = fz_ld_relaxed(counters(F) + 32);
+            if (runnable(F, S, c)) return;
             fz_sleep(100);
         }
     }
@@ -293,7 +300,7 @@ struct Fused4 {
 
     B2_D static void run(const b2_fused_params& F, unsigned char* smem_raw) {
         uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NBUF * TILE_BYTES);
-        volatile uint32_t* mail = reinterpret_cast<volatile uint32_t*>(smem_raw + (size_t)NBUF * TILE_BYTES + 16);   // [slot][kind, unit, tile]
+        volatile uint32_t* mail = reinterpret_cast<volatile uint32_t*>(smem_raw + (size_t)NBUF * TILE_BYTES + 16);   // [slot][kind, m, t]
         const int tid = threadIdx.x;
 #if defined(__CUDA_ARCH__)
         const bool w0 = tid < 32;                    // warp 0 issues the copies
@@ -301,66 +308,62 @@ struct Fused4 {
         const bool w0 = tid == 0;
 #endif
         auto bufp = [&](uint32_t i) { return reinterpret_cast<X*>(smem_raw + (size_t)(i % NBUF) * TILE_BYTES); };
+        const uint32_t P = nseq_of_group(F);
         Sched S;
-        S.ready = S.freed = 0; S.pend_kind = S.done_kind = NONE; S.pend_unit = S.done_unit = 0; S.newT = S.dcount = 0;
+        S.cntA = S.cntB = 0; S.pend_kind = NONE;
         // thread 0: the tile being transformed and the one after it (whose copy may already be running)
-        uint32_t ck = NONE, cu = 0, ct = 0, nk = NONE, nu = 0, nt = 0;
+        Tile cur{NONE, 0, 0}, nxt{NONE, 0, 0};
         bool cissued = false, nissued = false;
         if (tid == 0) {
             for (int i = 0; i < NBUF; ++i) mbar_init(&bars[i], 1);
             mbar_init_fence();
-            const uint32_t a = fz_add(F.ctl + B2_FCTL_NEXT_A, 1u), b = fz_add(F.ctl + B2_FCTL_NEXT_A, 1u);
-            ck = decode(F, a, cu, ct);
-            nk = decode(F, b, nu, nt);
-            mail[0] = ck; mail[1] = cu; mail[2] = ct;
-            if (ck != NONE) wait_runnable(F, S, ck, cu);
+            cur = advance(F, Tile{NONE, 0, 0}, P);
+            nxt = cur.kind != NONE ? advance(F, cur, P) : cur;
+            mail[0] = cur.kind; mail[1] = cur.m; mail[2] = cur.t;
+            if (cur.kind != NONE) wait_runnable(F, S, cur);
         }
         __syncthreads();                             // mbarriers initialised, mailbox written
-        if (w0) { warp_issue(F, ck != NONE, ck, cu, ct, bufp(0), &bars[0]); cissued = true; }
+        if (w0) { warp_issue(F, cur.kind != NONE, cur, bufp(0), &bars[0]); cissued = true; }
         for (uint32_t it = 0;; ++it) {
             const uint32_t slot = it & 1u;
-            const uint32_t kind = mail[3 * slot], unit = mail[3 * slot + 1], tile = mail[3 * slot + 2];
-            if (kind == NONE) break;
+            const Tile c{mail[3 * slot], mail[3 * slot + 1], mail[3 * slot + 2]};
+            if (c.kind == NONE) break;
             X* sm = bufp(it);
             uint64_t* bar = &bars[it % NBUF];
             if (w0) {
-                // this tile's copy could not be started ahead (its unit was not ready): wait for it now
-                if (tid == 0 && !cissued) wait_runnable(F, S, ck, cu);
-                warp_issue(F, !cissued, ck, cu, ct, sm, bar);
+                // this tile's copy could not be started ahead (its sequence was not ready): wait for it now
+                if (tid == 0 && !cissued) wait_runnable(F, S, cur);
+                warp_issue(F, !cissued, cur, sm, bar);
                 cissued = true;
-                if constexpr (NBUF == 2) {           // the other buffer is free: start the next tile's copy if its unit is ready
-                    const bool go = nk != NONE && runnable(F, S, nk, nu);
-                    warp_issue(F, go, nk, nu, nt, bufp(it + 1), &bars[(it + 1) % NBUF]);
+                if constexpr (NBUF == 2) {           // the other buffer is free: start the next tile's copy if it may run
+                    const bool go = nxt.kind != NONE && runnable(F, S, nxt);
+                    warp_issue(F, go, nxt, bufp(it + 1), &bars[(it + 1) % NBUF]);
                     nissued = go;
                 }
             }
             mbar_wait(bar, (it / NBUF) & 1u);
-            const Where w = locate(F, kind, unit, tile);
+            const Where w = locate(F, c);
             auto dead = [&]() {                      // one buffer: refill it as soon as the last stage has its legs
                 if (w0) {
-                    const bool go = nk != NONE && runnable(F, S, nk, nu);
-                    warp_issue(F, go, nk, nu, nt, sm, bar);
+                    const bool go = nxt.kind != NONE && runnable(F, S, nxt);
+                    warp_issue(F, go, nxt, sm, bar);
                     nissued = go;
                 }
             };
-            if (kind == TILE_A) process<EA, CA>(F, F.A, sm, w, S, false, dead);
+            if (c.kind == TILE_A) process<EA, CA>(F, F.A, sm, w, S, false, dead);
             else process<EB, CB>(F, F.B, sm, w, S, !(F.B.aux_u1 & 1u), dead);
             if (tid == 0) {
-                after_publish(F, S);
-                S.pend_kind = kind; S.pend_unit = unit;          // published behind the next tile's first stage (or on the wait / exit path)
+                S.pend_kind = c.kind;                // published behind the next tile's first stage (or on the wait / exit path)
                 volatile uint32_t* m = mail + 3 * (slot ^ 1);
-                m[0] = nk; m[1] = nu; m[2] = nt;
-                ck = nk; cu = nu; ct = nt; cissued = nissued;
-                nk = decode(F, S.newT, nu, nt);                  // the ticket fetched behind this tile's first stage
+                m[0] = nxt.kind; m[1] = nxt.m; m[2] = nxt.t;
+                cur = nxt; cissued = nissued;
+                nxt = cur.kind != NONE ? advance(F, cur, P) : cur;
                 nissued = false;
             }
             fence_proxy_async_smem();
             __syncthreads();      // stores issued; this buffer may be refilled; the next mailbox slot is visible
         }
-        if (tid == 0) {
-            publish(F, S);
-            after_publish(F, S);
-        }
+        if (tid == 0) publish(F, S);
     }
 };
 

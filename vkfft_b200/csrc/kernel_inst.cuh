@@ -356,9 +356,8 @@ template <class CA, class CB>
 int fused_launch_impl(const b2_fused_params* F, unsigned, void*) {
     constexpr int NBUF = FusedNbuf<CA, CB>::value;
     b2_fused_params FF = *F;
-    const uint32_t words = B2_FCTL_WORDS + 2 * FF.NU;
-    for (uint32_t i = 0; i < words; ++i) FF.ctl[i] = 0;
-    // one CTA walks every tile in claim order (pass B first whenever a unit is complete): no cross-CTA waiting to emulate
+    FF.U = 1; FF.NU = 1;                       // one group of one CTA walks every tile of every sequence in phase order
+    for (uint32_t i = 0; i < 64; ++i) FF.ctl[i] = 0;
     b2emu::launch(1, CA::THREADS, Fused4<CA, CB, NBUF>::SMEM_BYTES, [&](unsigned char* sm) { Fused4<CA, CB, NBUF>::run(FF, sm); }, b2emu::st().log);
     return emu_refused();
 }
@@ -377,14 +376,22 @@ int fused_launch_impl(const b2_fused_params* F, unsigned max_ctas, void* stream)
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused4_kernel<CA, CB, NBUF>, CA::THREADS, Fused4<CA, CB, NBUF>::SMEM_BYTES);
         resident = sms * (per_sm > 0 ? per_sm : 1);
     }
-    const uint64_t tiles = (uint64_t)F->NU * (F->TA + F->TB);
-    unsigned g = (unsigned)(tiles < (uint64_t)resident ? tiles : (uint64_t)resident);
-    if (max_ctas && g > max_ctas) g = max_ctas;
-    const uint32_t words = B2_FCTL_WORDS + 2 * F->NU;
-    fused4_init_kernel<0><<<(words + 255) / 256 < 64 ? (words + 255) / 256 : 64, 256, 0, (cudaStream_t)stream>>>(
-        F->ctl, words);
-    void* args[] = {const_cast<b2_fused_params*>(F)};
-    return (int)cudaLaunchKernel((const void*)fused4_kernel<CA, CB, NBUF>, dim3(g), dim3(CA::THREADS), args, Fused4<CA, CB, NBUF>::SMEM_BYTES,
+    // groups of K = F->U CTAs, all resident at once (they synchronise with each other); at most nseq/2 groups so that the two
+    // scratch slots of every group fit the sequences' own footprint in the temp buffer
+    b2_fused_params FF = *F;
+    const uint32_t K = FF.U ? FF.U : 1;
+    uint32_t cap = (uint32_t)resident;
+    if (max_ctas && cap > max_ctas) cap = max_ctas;
+    uint32_t NG = cap / K;
+    const uint32_t ng_max = FF.nseq >= 2 ? FF.nseq / 2 : 1;
+    if (NG > ng_max) NG = ng_max;
+    if (NG > B2_FCTL_MAX_GROUPS) NG = B2_FCTL_MAX_GROUPS;
+    if (NG < 1) return (int)cudaErrorLaunchOutOfResources;        // a group does not fit the device: the plan must not be fused
+    FF.NU = NG;
+    const uint32_t words = NG * 64;
+    fused4_init_kernel<0><<<(words + 255) / 256 < 64 ? (words + 255) / 256 : 64, 256, 0, (cudaStream_t)stream>>>(FF.ctl, words);
+    void* args[] = {&FF};
+    return (int)cudaLaunchKernel((const void*)fused4_kernel<CA, CB, NBUF>, dim3(NG * K), dim3(CA::THREADS), args, Fused4<CA, CB, NBUF>::SMEM_BYTES,
                                  (cudaStream_t)stream);
 }
 template <class CA, class CB>
@@ -431,6 +438,40 @@ struct MaybeFused<true, T, TPLA, QA, SchA, TPLB, QB, SchB, REGS> {
 #define B2_KF(shard, T, REGS, TPLA, QA, SA, TPLB, QB, SB)                                                  \
     static ::b200fft::MaybeFused<B2_SHARD_ON(shard), T, TPLA, QA, SA, TPLB, QB, SB, REGS>                  \
         B2_CAT(b2_regf_, __COUNTER__)("FUSED4<" #T ";A " #TPLA "x" #QA " " #SA ";B " #TPLB "x" #QB " " #SB ">");
+
+// short contiguous lines staged through shared memory (stockham.cuh RMODE 10): same registry key as the plain kernels
+namespace b200fft {
+template <typename T, int Q, int REGS, bool INV, int N>
+struct StagedRegistrar {
+    using KT = KindTraits<B2_KIND_ROWS>;
+    using C = KCfg<T, RList<N>, 1, Q, 1, KT::LMAP, KT::SMAP, KT::LAYOUT, INV, 0, KT::IN_UNIT, KT::OUT_UNIT, REGS, 10>;
+    b2_kernel_info info;
+    explicit StagedRegistrar(const char* name) {
+        info = b2_kernel_info{};
+        info.kind = B2_KIND_ROWS; info.prec = PrecOf<T>::value; info.n = N; info.inv = INV; info.ops = 0;
+        info.threads = C::THREADS; info.q = Q; info.tpl = 1; info.v = 1; info.smem_bytes = C::SMEM_BYTES;
+        info.ns = 1; info.radices[0] = N; info.lut_size = 0;
+        info.launch = &launch_impl<C>;
+        info.prepare = &prepare_impl<C>;
+        info.name = name;
+        b2_register_kernel(&info);
+    }
+};
+template <bool EN, typename T, int Q, int REGS, int N>
+struct MaybeStaged {
+    explicit MaybeStaged(const char*) {}
+};
+template <typename T, int Q, int REGS, int N>
+struct MaybeStaged<true, T, Q, REGS, N> {
+    StagedRegistrar<T, Q, REGS, false, N> f;
+    StagedRegistrar<T, Q, REGS, true, N> i;
+    explicit MaybeStaged(const char* n) : f(n), i(n) {}
+};
+}  // namespace b200fft
+//   B2_KS(shard, type, Q lines per CTA (= threads), REGS, N)
+#define B2_KS(shard, T, Q, REGS, N)                                                                        \
+    static ::b200fft::MaybeStaged<B2_SHARD_ON(shard), T, Q, REGS, N>                                       \
+        B2_CAT(b2_regs_, __COUNTER__)("STAGED_ROWS<" #T "," #Q " lines;" #N ">");
 
 #define B2_KD(shard, KIND, T, TPL, Q, V, MINB, ...)                                                       \
     static ::b200fft::MaybeDct<B2_SHARD_ON(shard), B2_KIND_##KIND, T, TPL, Q, V, MINB, __VA_ARGS__>       \

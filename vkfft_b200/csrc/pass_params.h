@@ -107,21 +107,25 @@ typedef struct b2_pass_params {
 // The reference always runs the two uploads as separate dispatches with the whole intermediate going through DRAM
 // (vkFFT_Scheduler.h:2582-2893, vkFFT_DispatchPlan.h:157-225).
 typedef struct b2_fused_params {
+    // TMA descriptor (CUtensorMap, 128 bytes, filled in by the runtime at launch) of pass A's input seen as a 2-D array of
+    // floats: [sequences * n1 rows][2 * n2 floats]; a pass-A tile is a box of 2*Q_A floats x n1 rows of it
+    unsigned long long tmap_a[16]
+#if defined(__GNUC__) || defined(__CUDACC__)
+        __attribute__((aligned(64)))
+#endif
+        ;
     b2_pass_params A, B;       // A.out / B.in = scratch ring base; their outer strides on the scratch side are ignored
-    uint32_t* ctl;             // B2_FCTL_* words followed by doneA[NU], doneB[NU]; zeroed before every launch (fused4_init_kernel)
+    uint32_t* ctl;             // per group 64 words: [0] finished pass-A tiles, [32] finished pass-B tiles; zeroed before every launch
     uint32_t nseq;             // sequences = product of the outer extents (same for A and B)
-    uint32_t U, NU;            // sequences per unit, units
-    uint32_t R;                // ring slots (units)
-    uint32_t TA, TB;           // tiles per unit of pass A / pass B
-    uint32_t reserved;         // L: pass B runs this many units behind pass A (L < R)
+    uint32_t U, NU;            // K = CTAs per group (planner), number of groups (launch: as many as are resident)
+    uint32_t R;                // (unused)
+    uint32_t TA, TB;           // tiles per SEQUENCE of pass A / pass B
+    uint32_t reserved;
 } b2_fused_params;
 
 enum {
-    B2_FCTL_NEXT_A = 0,        // tiles handed out: fetch-add tickets into the one ordered sequence of pass-A and pass-B tiles
-    B2_FCTL_NEXT_B = 32,       // (unused)                          (each hot word on its own 128-byte line)
-    B2_FCTL_READY_UNITS = 64,  // prefix of units whose pass A is complete  -> their pass-B tiles may run
-    B2_FCTL_FREED_UNITS = 96,  // prefix of units whose pass B is complete  -> unit + R may overwrite the ring slot
-    B2_FCTL_WORDS = 128,       // doneA[NU] starts here, doneB[NU] follows
+    B2_FCTL_MAX_GROUPS = 1024,
+    B2_FCTL_WORDS = 64 * B2_FCTL_MAX_GROUPS,
 };
 
 #ifdef __cplusplus

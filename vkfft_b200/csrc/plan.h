@@ -80,6 +80,7 @@ struct PassPlan {
     // PassPlans stay in the list (the second is skipped at run time) so that un-fusing is a matter of clearing the pointer
     const b2_fused_info* fused = nullptr;
     uint32_t fz_nseq = 0, fz_U = 0, fz_NU = 0, fz_R = 0, fz_TA = 0, fz_TB = 0, fz_L = 1;
+    int lut_id_plain = -1;       // stage tables of the stand-alone kernel `k` when lut_id belongs to the fused pair
     std::string note;            // human readable (plan_describe)
 };
 

@@ -70,6 +70,18 @@ std::vector<Dim> merge_dims(const std::vector<Dim>& d) {
 // stages (the reference inlines Rader kernels for radix primes from 17, vkFFT_InitializeApp.h:1257-1292); empty if
 // n has a prime factor above that (-> Bluestein).
 const int RADER_MAX_PRIME = 127;
+const int RADER_DEFAULT_MAX_PRIME = 127;
+// largest prime factor the runtime-scheduled kernel takes as a Rader stage; lengths with a larger one go through Bluestein.
+// B200FFT_RADER_MAX_PRIME overrides it (tuning)
+// Measured on B200 (profiles/r2/rader_vs_bluestein.log, ~512 MiB per pair): the Rader stage of the runtime-scheduled kernel is
+// a direct O(p^2) product and loses to the two fused Bluestein launches for every length that has them (padded length
+// M <= 4096, i.e. N <= 2048: 34: 2.68 vs 2.03 ms, 323: 4.71 vs 1.85, 2032: 13.0 vs 1.38, 113: 10.2 vs 1.80); above that
+// Bluestein needs 5-7 launches and the two are comparable (4416: 4.31 vs 6.54, 12167: 8.77 vs 5.90).  So: no Rader stages up
+// to 2048 points (those lengths run as Bluestein unless a curated kernel with a direct prime butterfly exists), Rader above.
+int rader_max_prime(uint64_t n) {
+    if (const char* e = getenv("B200FFT_RADER_MAX_PRIME")) { const int v = atoi(e); return v < 13 ? 13 : (v > RADER_MAX_PRIME ? RADER_MAX_PRIME : v); }
+    return n <= 2048 ? 13 : RADER_DEFAULT_MAX_PRIME;
+}
 std::vector<int> generic_radices(uint64_t n) {
     std::vector<int> r, primes;
     static const int cand16[] = {16, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2};
@@ -78,7 +90,8 @@ std::vector<int> generic_radices(uint64_t n) {
     // split off prime factors > 13 first
     uint64_t m = n;
     for (int f : {2, 3, 5, 7, 11, 13}) while (m % f == 0) m /= f;
-    for (uint64_t f = 17; m > 1 && f <= (uint64_t)RADER_MAX_PRIME; f += 2)
+    const uint64_t n_whole = n;
+    for (uint64_t f = 17; m > 1 && f <= (uint64_t)rader_max_prime(n_whole); f += 2)
         while (m % f == 0) { primes.push_back((int)f); m /= f; n /= f; }
     if (m != 1) return {};
     // greedy factorisation per radix class; keep the leanest class that does not need more stages than the widest one
@@ -372,7 +385,9 @@ std::vector<uint64_t> split_four_step(const PlanGraph& g, uint64_t N, bool dist 
         }
         if (cost < best_cost) { best_cost = cost; best = {n1, n2}; }
     }
-    const uint64_t two_level_limit = (g.prec == B2_PREC_F32) ? (1ull << 22) : (1ull << 21);
+    // three launches of fast 128/256-point factors beat two launches with a 2048-point strided pass from 2^22 on (FP32, B200:
+    // 635 + 635 + 631 us against 1258 + 900 us per 2 GiB pass, profiles/r2/ktune_f32.log)
+    const uint64_t two_level_limit = 1ull << 21;
     if (!best.empty() && N <= two_level_limit) return best;
     std::vector<uint64_t> best3;
     uint64_t best3_cost = ~0ull;
@@ -415,6 +430,10 @@ struct C2CJob {
     int64_t in_base = 0, out_base = 0, tmp_base = 0;   // element offsets into the roles' buffers
     // distributed sequence: this plan covers rank `rank` of `world` (buffer and temp are peer windows, plan.h)
     uint32_t world = 1, rank = 0;
+    // distributed N-D transform, the axis that crosses the slabs: this rank transforms 1/line_world of the lines (a slice
+    // of the outermost line dimension); its strided loads and stores reach into every rank's slab of the peer window
+    uint32_t line_world = 1, line_rank = 0;
+    bool sync_first = false;            // a barrier over all ranks precedes the first launch of this job
     // fused convolution along this axis (single launch only): B2_OP_CONV + its operands
     int extra_ops = 0;
     uint32_t aux_u0 = 0, aux_u1 = 0;
@@ -621,38 +640,30 @@ void try_fuse(PlanGraph& g, std::vector<PassPlan>& list, size_t ia) {
     uint64_t nseq = 1, nseq_b = 1;
     for (int d = 0; d < B2_MAX_OUTER; ++d) { nseq *= a.P.nb[d]; nseq_b *= b.P.nb[d]; }
     if (nseq != nseq_b || nseq > 0x7fffffffull) return;
+    // the tiles are copied in by TMA: whole tiles only, and pass A's input must be ONE dense [sequence][n1][n2] array
+    if (a.P.G % fk->qa || b.P.G % fk->qb || a.in_scalar || b.out_scalar) return;
+    if (a.P.nb[1] != 1 || a.P.nb[2] != 1 || (a.P.nb[0] > 1 && a.P.in_bs[0] != (int64_t)((uint64_t)a.P.n * b.P.n)) || a.P.in_gs != 1) return;
     const uint64_t N = (uint64_t)a.P.n * b.P.n, esz = esize(g), seq_bytes = N * esz;
-    uint64_t unit_kb = 4096, ring = 0, lead = 0;
-    if (const char* e = getenv("B200FFT_FUSED_UNIT_KB")) unit_kb = strtoull(e, nullptr, 10);
-    if (const char* e = getenv("B200FFT_FUSED_RING")) ring = strtoull(e, nullptr, 10);
-    if (const char* e = getenv("B200FFT_FUSED_LEAD")) lead = strtoull(e, nullptr, 10);
-    uint64_t U = std::max<uint64_t>(1, (unit_kb << 10) / seq_bytes);
-    U = std::min(U, nseq);
-    while (nseq % U) --U;                                  // whole units only
-    const uint64_t NU = nseq / U;
-    const uint64_t ga0 = (a.P.G + fk->qa - 1) / fk->qa, gb0 = (b.P.G + fk->qb - 1) / fk->qb;
-    // Lead L (units pass B trails pass A): the tiles handed out between the last pass-A tile of a unit and its first pass-B
-    // tile -- (L-1) blocks of TA+TB tiles -- must exceed what the resident CTAs have in flight (one running tile plus one
-    // ticket each), or pass-B tiles would be handed out before their unit is complete and CTAs would sit waiting.
-    const uint64_t per_sm = std::max<uint64_t>(1, std::min<uint64_t>({(227ull << 10) / (uint64_t)fk->smem_bytes, 2048ull / (uint64_t)fk->threads,
-                                                                     65536ull / ((uint64_t)fk->threads * (uint64_t)fk->regs)}));
-    const uint64_t in_flight = 148 * per_sm * 3;          // per CTA: the tile being transformed, the one being copied in, one ticket
-    uint64_t L = lead ? lead : 1 + (in_flight + U * (ga0 + gb0) - 1) / (U * (ga0 + gb0));
-    L = std::max<uint64_t>(1, std::min(L, NU));
-    uint64_t R = ring ? ring : L + 2;                      // two more slots: one being filled ahead, one draining behind
-    R = std::min(std::max(R, L + 1), NU);
+    // K = CTAs per group: every CTA of a group takes tiles r, r+K, ... of both passes of one sequence per phase.  One or two
+    // tiles of each pass per CTA and phase keep the groups small enough to fill the device evenly and large enough that the
+    // scratch of all groups (2 sequences each) stays well inside L2:  K = max(TA, TB) / 2, at least 8, at most 148.
     const uint64_t ga = (a.P.G + fk->qa - 1) / fk->qa, gb = (b.P.G + fk->qb - 1) / fk->qb;
-    if (NU * U * (ga + gb) > 0x7fffffffull) return;
+    uint64_t K = std::max<uint64_t>(std::max(ga, gb) / 2, 8);
+    if (seq_bytes >= (4ull << 20)) K = std::max(ga, gb);              // long sequences: one tile per CTA and phase, fewer groups
+    K = std::min<uint64_t>(K, 148);
+    if (const char* e = getenv("B200FFT_FUSED_GROUP")) K = std::max<uint64_t>(1, strtoull(e, nullptr, 10));
+    const uint64_t U = K, NU = 0, R = 2, L = 0;
+    if (nseq * (ga + gb) > 0x7fffffffull) return;
     a.fused = fk;
     a.fz_nseq = (uint32_t)nseq; a.fz_U = (uint32_t)U; a.fz_NU = (uint32_t)NU; a.fz_R = (uint32_t)R;
-    a.fz_TA = (uint32_t)(U * ga); a.fz_TB = (uint32_t)(U * gb); a.fz_L = (uint32_t)L;
+    a.fz_TA = (uint32_t)ga; a.fz_TB = (uint32_t)gb; a.fz_L = (uint32_t)L;
+    a.lut_id_plain = a.lut_id; b.lut_id_plain = b.lut_id;
     a.lut_id = lut_for(g, std::vector<int>(fk->radices_a, fk->radices_a + fk->ns_a));
     b.lut_id = lut_for(g, std::vector<int>(fk->radices_b, fk->radices_b + fk->ns_b));
-    g.ctl_words = std::max<uint64_t>(g.ctl_words, B2_FCTL_WORDS + 2 * NU);
+    g.ctl_words = std::max<uint64_t>(g.ctl_words, B2_FCTL_WORDS);
     char buf[256];
-    snprintf(buf, sizeof buf, " [fused with the next launch: %s, %llu units of %llu sequences, pass B %llu units behind, ring of %llu units = %.1f MB]",
-             fk->name, (unsigned long long)NU, (unsigned long long)U, (unsigned long long)L, (unsigned long long)R,
-             (double)(R * U * seq_bytes) / 1048576.0);
+    snprintf(buf, sizeof buf, " [fused with the next launch: %s, groups of %llu CTAs, %llu + %llu tiles per sequence]", fk->name,
+             (unsigned long long)K, (unsigned long long)ga, (unsigned long long)gb);
     a.note += buf;
     b.note += " [runs inside the previous launch]";
 }
@@ -660,9 +671,25 @@ void try_fuse(PlanGraph& g, std::vector<PassPlan>& list, size_t ia) {
 int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
     const uint64_t N = job.N;
     const int sc_ops = (job.scale != 1.0) ? B2_OP_SCALE : 0;
-    std::vector<Dim> m = merge_dims(job.lines);
+    std::vector<Dim> sliced = job.lines;
+    int64_t slice_in = 0, slice_out = 0;
+    if (job.line_world > 1) {
+        // the outermost dimension with more than one line that divides evenly (never the batch entry, which is 1 here)
+        bool done = false;
+        for (size_t i = sliced.size(); i-- > 0 && !done;) {
+            uint64_t first;
+            if (sliced[i].n > 1 && sliced[i].n % job.line_world == 0) done = slice_dim(sliced[i], job.line_world, job.line_rank, slice_in, slice_out, first);
+        }
+        if (!done) return R_UNSUPPORTED_FFT_LENGTH;
+    }
+    std::vector<Dim> m = merge_dims(sliced);
     const bool contiguous = (job.es_in == 1 && job.es_out == 1);
     const int kind = job.unit_lines ? B2_KIND_COLS : B2_KIND_ROWS;
+    const size_t first_launch = list.size();
+    struct SyncMark {     // marks the first launch this job emits (whatever branch emits it)
+        std::vector<PassPlan>& l; size_t at; bool on;
+        ~SyncMark() { if (on && l.size() > at) l[at].sync_before = true; }
+    } sync_mark{list, first_launch, job.sync_first};
 
     if (N == 1) return R_SUCCESS;   // length-1 transform is the identity
     const bool dist = job.world > 1;
@@ -711,7 +738,7 @@ int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
         }
         rq.outer = m;
         rq.in_role = job.in_role; rq.out_role = job.out_role;
-        rq.in_base = job.in_base; rq.out_base = job.out_base;
+        rq.in_base = job.in_base + slice_in; rq.out_base = job.out_base + slice_out;
         rq.scale = job.scale;
         rq.what = job.unit_lines ? "strided axis" : "single-pass";
         return emit(g, list, rq);
@@ -745,7 +772,7 @@ int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
         a.tw_outer = 0;
         for (const Dim& d : rest) a.outer.push_back(Dim{d.n, d.is, d.os});
         a.in_role = job.in_role; a.out_role = ROLE_TEMP;
-        a.in_base = job.in_base; a.out_base = job.tmp_base;
+        a.in_base = job.in_base + slice_in; a.out_base = job.tmp_base + slice_out;
         a.twM = N;
         a.what = "strided four-step 1/2";
         int rc2 = emit(g, list, a);
@@ -757,7 +784,7 @@ int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
         b.outer.push_back(Dim{N1, job.es_out * (int64_t)N2, job.es_out});
         for (const Dim& d : rest) b.outer.push_back(Dim{d.n, d.os, d.os});
         b.in_role = ROLE_TEMP; b.out_role = job.out_role;
-        b.in_base = job.tmp_base; b.out_base = job.out_base;
+        b.in_base = job.tmp_base + slice_out; b.out_base = job.out_base + slice_out;
         b.scale = job.scale;
         b.what = "strided four-step 2/2";
         return emit(g, list, b);
@@ -900,8 +927,10 @@ std::vector<Dim> other_dims(const PlanGraph& g, const uint64_t* size, uint32_t a
     return lines;
 }
 
+// slab: < 0 ordinary plan;  0: local axis of a distributed N-D plan (this rank's slab only: `size` already holds the slab's
+// extent of the last dimension, every base moves to the slab);  1: the axis that crosses the slabs (lines shared out over the ranks)
 int plan_c2c_axis(PlanGraph& g, std::vector<PassPlan>& list, const uint64_t* size, uint32_t axis, int inv,
-                  const Layout& in, const Layout& out, double scale) {
+                  const Layout& in, const Layout& out, double scale, int slab = -1, bool sync_first = false) {
     C2CJob job;
     job.N = size[axis]; job.inv = inv;
     job.es_in = axis == 0 ? 1 : (int64_t)in.stride[axis - 1];
@@ -910,7 +939,15 @@ int plan_c2c_axis(PlanGraph& g, std::vector<PassPlan>& list, const uint64_t* siz
     job.unit_lines = (axis != 0);
     job.in_role = in.role; job.out_role = out.role;
     job.scale = scale;
-    if (g.distributed) { job.world = g.desc.dist_world; job.rank = g.desc.dist_rank; }
+    job.sync_first = sync_first;
+    if (slab < 0) {
+        if (g.distributed) { job.world = g.desc.dist_world; job.rank = g.desc.dist_rank; }
+    } else if (slab == 0) {
+        const int64_t base = (int64_t)((uint64_t)g.desc.dist_rank * (g.total_elems / g.desc.dist_world));
+        job.in_base = job.out_base = job.tmp_base = base;
+    } else {
+        job.line_world = g.desc.dist_world; job.line_rank = g.desc.dist_rank;
+    }
     return plan_c2c(g, list, job);
 }
 
@@ -951,7 +988,25 @@ int plan_direction_c2c(PlanGraph& g, std::vector<PassPlan>& list, int inv) {
             if (last && d.is_input_formatted && d.inverse_return_to_input) out = inl;
         }
         const size_t before = list.size();
-        int rc = plan_c2c_axis(g, list, d.size, axes[i], inv, in, out, last ? norm : 1.0);
+        int rc;
+        if (g.distributed && d.fft_dim > 1) {
+            // slab decomposition along the last dimension: the lower axes are transformed inside this rank's
+            // slab; the last axis is a strided pass over the whole window whose lines are shared out over the ranks -- its loads
+            // and stores are the exchange (NVLink reads / writes from inside the FFT launch, as in the 1-D distributed plan).
+            // Barriers: before the first launch that reads other ranks' slabs and before the first one that follows it.
+            const uint32_t la = d.fft_dim - 1;
+            if (axes[i] == la) {
+                rc = plan_c2c_axis(g, list, d.size, la, inv, in, out, last ? norm : 1.0, 1, true);
+            } else {
+                uint64_t lsize[B200FFT_MAX_DIMS];
+                for (int a = 0; a < B200FFT_MAX_DIMS; ++a) lsize[a] = d.size[a];
+                lsize[la] = d.size[la] / d.dist_world;
+                const bool after_cross = inv && i > 0 && axes[i - 1] == la;
+                rc = plan_c2c_axis(g, list, lsize, axes[i], inv, in, out, last ? norm : 1.0, 0, after_cross);
+            }
+        } else {
+            rc = plan_c2c_axis(g, list, d.size, axes[i], inv, in, out, last ? norm : 1.0);
+        }
         if (rc != R_SUCCESS) return rc;
         g.axis_uploads[inv ? 1 : 0][axes[i]] += (uint32_t)(list.size() - before);
     }
@@ -1409,9 +1464,18 @@ static int build_plan_impl(const b200fft_desc& din, PlanGraph& g) {
     if (d.dist_world > 1) {
         // one long in-place C2C sequence over peer windows: nothing else is defined for a distributed plan
         if (d.dist_rank >= d.dist_world) return R_INVALID_DEVICE;
-        if (d.fft_dim != 1 || d.number_batches * d.coordinate_features != 1 || d.perform_r2c || d.perform_dct || d.perform_dst ||
+        // 1-D: one long sequence (Four-Step over the window).  2-D / 3-D: slabs along the last dimension, default strides.
+        if (d.fft_dim > 3 || d.number_batches * d.coordinate_features != 1 || d.perform_r2c || d.perform_dct || d.perform_dst ||
             d.is_input_formatted || d.is_output_formatted || d.buffer_stride[0] != d.size[0] || d.omit_dimension[0])
             return R_UNSUPPORTED_FFT_LENGTH;
+        if (d.fft_dim > 1) {
+            uint64_t st = 1;
+            for (uint32_t a = 0; a < d.fft_dim; ++a) {
+                st *= d.size[a];
+                if (d.buffer_stride[a] != st || d.omit_dimension[a]) return R_UNSUPPORTED_FFT_LENGTH;
+            }
+            if (d.size[d.fft_dim - 1] % d.dist_world) return R_UNSUPPORTED_FFT_LENGTH;
+        }
         if (!d.user_temp_buffer) return R_EMPTY_TEMPBUFFER;
     } else {
         d.dist_world = 1; d.dist_rank = 0;

@@ -5,6 +5,7 @@
 // (vkFFT_UpdateBuffers.h:776-1199) and teardown (vkFFT_DeletePlan.h:59-69, vkFFT_DeleteApp.h:28-324).
 // There is no NVRTC / module loading: every kernel is compiled ahead of time for sm_100a and found through
 // the registry.  There is no CPU fallback either: if the device or the kernels are missing the call fails.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -45,6 +46,34 @@ struct b200fft_plan {
 };
 
 namespace {
+
+// cuTensorMapEncodeTiled through the runtime's driver entry-point lookup (the library links the CUDA runtime only)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+// pass A of a fused Four-Step: the input as [sequences * n1 rows][2 * n2 floats], tiles = boxes of 2*qa floats x min(n1,256) rows
+bool encode_pass_a_map(b2_fused_params& F, uint32_t n1, uint32_t n2, uint32_t qa) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return false;
+    static_assert(sizeof(CUtensorMap) == sizeof(F.tmap_a), "CUtensorMap is 128 bytes");
+    const cuuint64_t dims[2] = {2ull * n2, (cuuint64_t)F.nseq * n1};
+    const cuuint64_t strides[1] = {(cuuint64_t)n2 * 8};                  // bytes between rows
+    const cuuint32_t box[2] = {2u * qa, n1 < 256 ? n1 : 256u};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc((CUtensorMap*)F.tmap_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(F.A.in), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 struct DeviceGuard {
     int prev = -1;
@@ -245,10 +274,16 @@ static int exec_impl(b200fft_plan* p, int inverse, const b200fft_buffers* b, std
             if (const char* e = getenv("B200FFT_FUSED_FLAGS")) F.B.aux_u1 |= (uint32_t)strtoul(e, nullptr, 10);   // tuning: 1 = no discard
             F.ctl = (uint32_t*)p->d_ctl;
             F.nseq = pp.fz_nseq; F.U = pp.fz_U; F.NU = pp.fz_NU; F.R = pp.fz_R; F.TA = pp.fz_TA; F.TB = pp.fz_TB; F.reserved = pp.fz_L;
-            if (!F.ctl || pp.fused->launch(&F, fused_max_ctas, (void*)st) != 0) return fail(R_FAILED_TO_LAUNCH_KERNEL);
-            ++ip;
-            continue;
+            // the tiles arrive by TMA: 16-byte aligned sources and a dense batch (checked at plan time); otherwise the two
+            // launches run on their own
+            const bool aligned = ((((uintptr_t)F.A.in) | ((uintptr_t)F.B.in)) & 15) == 0;
+            if (aligned && F.ctl && encode_pass_a_map(F, F.A.n, F.B.n, (uint32_t)pp.fused->qa)) {
+                if (pp.fused->launch(&F, fused_max_ctas, (void*)st) != 0) return fail(R_FAILED_TO_LAUNCH_KERNEL);
+                ++ip;
+                continue;
+            }
         }
+
         if (pp.sync_before) {
             mark(0);
             int brc = b200fft_window_barrier(p->window, (void*)st);
@@ -257,6 +292,8 @@ static int exec_impl(b200fft_plan* p, int inverse, const b200fft_buffers* b, std
         mark(1);
         b2_pass_params P;
         resolve(pp, P);
+        // un-fused execution of a fusable pair (unaligned buffers): the stand-alone kernels use their own stage tables
+        if (pp.lut_id_plain >= 0) P.lut = p->d_luts[pp.lut_id_plain];
         const b2_kernel_info* k = pp.k;
         if (k->pipelined && ((((uintptr_t)P.in) | (uintptr_t)(P.in_gs * (int64_t)esz) | (uintptr_t)(P.in_bs[0] * (int64_t)esz) |
                               (uintptr_t)(P.in_bs[1] * (int64_t)esz) | (uintptr_t)(P.in_bs[2] * (int64_t)esz)) & 15))

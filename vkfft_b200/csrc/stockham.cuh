@@ -123,12 +123,16 @@ struct KCfg {
     static constexpr int QP = Q;  // elem-major row pitch
     // 3: DCT-II, 4: DCT-III with two real lines per complex line (contiguous real lines, or neighbouring real columns
     //    viewed as one complex column on strided axes) -- vkFFT_R2R.h:193-229, :784-859 as fused load/store stages
-    static constexpr int SMEM_ELEMS = (Sch::ns <= 1 && RMODE != 1 && RMODE != 3 && RMODE != 4) ? 0 : ((LAYOUT == LAY_LINE) ? Q * LS : N * QP);
+    // 10: short contiguous lines, one thread per line, staged through shared memory so that HBM is read and written in
+    //     whole consecutive segments (thread q alone would walk its line in 8-byte steps N*8 bytes apart from its neighbour)
+    static constexpr int SMEM_ELEMS = RMODE == 10 ? Q * (N + 1)
+                                    : ((Sch::ns <= 1 && RMODE != 1 && RMODE != 3 && RMODE != 4) ? 0 : ((LAYOUT == LAY_LINE) ? Q * LS : N * QP));
     static constexpr int SMEM_BYTES = SMEM_ELEMS * 2 * (int)sizeof(T);
-    // stage twiddles w^k generated from w^1, w^2, w^4, w^8 (Engine::compute).  Measured per kernel on B200
-    // (profiles/r1/ktune_f32_tw_chain.log): -1...-10 % for most shapes (N = 4096: 687 -> 655 us per 2 GiB pass), but
-    // +9 % for the contiguous 8192-point kernels, which keep one table load per twiddle.
-    static constexpr bool TWCHAIN = !(N == 8192 && LAYOUT_ == 0 && sizeof(T_) == 4 && REGS_ != 127);
+    // stage twiddles w^k generated from w^1, w^2, w^4, w^8 (Engine::compute): 4 table loads instead of 15 per radix-16
+    // butterfly.  Measured per kernel on B200: round 1 (scalar FP32) -1...-10 % for most shapes but +9 % for the contiguous
+    // 8192-point kernels; with the packed FP32 arithmetic of round 2 the 8192-point kernel gains as well (807 -> 750 us per
+    // 2 GiB pass, profiles/r2/ktune_f32_8192_twchain.log), so every kernel generates them now.
+    static constexpr bool TWCHAIN = true;
 };
 
 // XF (extra flags, fused Four-Step kernel):
@@ -779,7 +783,42 @@ struct Engine {
 
         const X* __restrict__ rw = (const X*)P.aux0;   // e^{-2 pi i k/2n} for the fused real transforms
         const uint32_t psel = (P.tw_sel == 1 ? o0 : (P.tw_sel == 2 ? o1 : o2));   // n2 / k1 of the long strided DCT launches
-        if constexpr (C::RMODE == 9) {
+        if constexpr (C::RMODE == 10) {
+            // ---- short lines (N <= 32), one thread per line --------------------------------------------------------------------
+            // A warp reading "its" 32 lines directly touches 32 segments N*8 bytes apart with every load instruction; here the
+            // CTA copies its Q lines as ONE contiguous run (consecutive lanes, consecutive elements) into the tile, every thread
+            // transforms the line it owns out of shared memory (line pitch N+1: conflict free), and the run goes back the same way.
+            static_assert(NS == 1 && TPL == 1 && V == 1 && C::LAYOUT == LAY_LINE && C::IN_UNIT && C::OUT_UNIT, "staged short lines");
+            const uint32_t g0 = grp * Q;
+            const uint32_t nv = (P.G - g0) < (uint32_t)Q ? (P.G - g0) : (uint32_t)Q;
+            const X* __restrict__ src = (const X*)P.in + obase_in + (int64_t)g0 * P.in_gs;
+            X* __restrict__ dst = (X*)P.out + obase_out + (int64_t)g0 * P.out_gs;
+            const bool dense_in = P.in_gs == (int64_t)N, dense_out = P.out_gs == (int64_t)N;
+            for (uint32_t i = tid; i < nv * (uint32_t)N; i += C::THREADS) {
+                const uint32_t l = i / N, p = i % N;
+                X a = dense_in ? src[i] : src[(int64_t)l * P.in_gs + p];
+                B2_SMEM_ST(sm, l * (N + 1) + p, C::INV ? swp(a) : a);
+            }
+            __syncthreads();
+            if ((uint32_t)tid < nv) {
+                X x[N];
+#pragma unroll
+                for (int p = 0; p < N; ++p) x[p] = B2_SMEM_LD(sm, tid * (N + 1) + p);
+                dft<N, T>(x);
+#pragma unroll
+                for (int p = 0; p < N; ++p) B2_SMEM_ST(sm, tid * (N + 1) + p, x[p]);
+            }
+            __syncthreads();
+            const bool do_scale = (P.ops & B2_OP_SCALE) != 0;
+            const T sc = (T)P.scale;
+            for (uint32_t i = tid; i < nv * (uint32_t)N; i += C::THREADS) {
+                const uint32_t l = i / N, p = i % N;
+                X a = B2_SMEM_LD(sm, l * (N + 1) + p);
+                if (do_scale) a = a * sc;
+                if (C::INV) a = swp(a);
+                if (dense_out) dst[i] = a; else dst[(int64_t)l * P.out_gs + p] = a;
+            }
+        } else if constexpr (C::RMODE == 9) {
             // ---- fused convolution (vkFFT_Convolution.h:125 fuses the same three steps into the last-axis kernel) ----------
             // forward transform; the last stage leaves element p = b + k*NB in the registers of the thread that would read
             // exactly these legs for the first stage of another transform, because the schedule starts and ends with the

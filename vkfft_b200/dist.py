@@ -230,3 +230,46 @@ class FusedDistributedFFT1D:
             if getattr(self, w, None) is not None:
                 getattr(self, w).close()
                 setattr(self, w, None)
+
+
+class FusedDistributedFFTND(FusedDistributedFFT1D):
+    """A 2-D or 3-D C2C transform whose array is spread over the GPUs of a box in SLABS along its last (slowest) dimension
+    (SURVEY.md section 8 f4).
+
+    `shape_xyz` = (nx, ny[, nz]) with x fastest, as VkFFT counts; rank g holds the planes [g*n_last/R, (g+1)*n_last/R) of the
+    array, contiguous, in `self.local` (shape (n_last/R, ..., nx)).  The lower axes are transformed inside every rank's own slab;
+    the last axis runs as strided launches over the peer window whose lines are shared out over the ranks -- their loads gather
+    a line from all slabs and their stores scatter it back, which IS the exchange of the textbook slab algorithm (no transposes,
+    no collective; planner.cpp plan_direction_c2c).  One device-side barrier separates the two parts.  In place, natural order."""
+
+    def __init__(self, shape_xyz, dist, device, double=False, normalize=False):
+        import torch
+        from . import api, _lib
+        from .window import PeerWindow
+        self.torch, self.dist, self.api = torch, dist, api
+        self.R, self.r = dist.get_world_size(), dist.get_rank()
+        shape_xyz = tuple(int(v) for v in shape_xyz)
+        if not 2 <= len(shape_xyz) <= 3:
+            raise ValueError("2-D or 3-D shapes; one long sequence is FusedDistributedFFT1D")
+        if shape_xyz[-1] % self.R:
+            raise ValueError("world size must divide the last dimension")
+        total = 1
+        for v in shape_xyz:
+            total *= v
+        esz = 16 if double else 8
+        self.n = total
+        self.shape_xyz = shape_xyz
+        self.seq = PeerWindow(total // self.R * esz, dist, device)
+        self.tmp = PeerWindow(total // self.R * esz, dist, device)
+        dt = torch.complex128 if double else torch.complex64
+        local_shape = (shape_xyz[-1] // self.R,) + tuple(reversed(shape_xyz[:-1]))
+        self.local = self.seq.tensor(torch, dt).reshape(local_shape)
+        cfg = api.VkFFTConfiguration(FFTdim=len(shape_xyz), size=list(shape_xyz), device=device, doublePrecision=int(double),
+                                     normalize=int(normalize), userTempBuffer=1, distWorld=self.R, distRank=self.r)
+        self.app = api.VkFFTApplication()
+        rc = api.initializeVkFFT(self.app, cfg)
+        if rc != 0:
+            self.close()
+            raise RuntimeError(api.getVkFFTErrorString(rc))
+        _lib.load().b200fft_plan_attach_window(self.app._plan, self.seq.handle)
+

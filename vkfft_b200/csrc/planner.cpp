@@ -73,14 +73,9 @@ const int RADER_MAX_PRIME = 127;
 const int RADER_DEFAULT_MAX_PRIME = 127;
 // largest prime factor the runtime-scheduled kernel takes as a Rader stage; lengths with a larger one go through Bluestein.
 // B200FFT_RADER_MAX_PRIME overrides it (tuning)
-// Measured on B200 (profiles/r2/rader_vs_bluestein.log, ~512 MiB per pair): the Rader stage of the runtime-scheduled kernel is
-// a direct O(p^2) product and loses to the two fused Bluestein launches for every length that has them (padded length
-// M <= 4096, i.e. N <= 2048: 34: 2.68 vs 2.03 ms, 323: 4.71 vs 1.85, 2032: 13.0 vs 1.38, 113: 10.2 vs 1.80); above that
-// Bluestein needs 5-7 launches and the two are comparable (4416: 4.31 vs 6.54, 12167: 8.77 vs 5.90).  So: no Rader stages up
-// to 2048 points (those lengths run as Bluestein unless a curated kernel with a direct prime butterfly exists), Rader above.
-int rader_max_prime(uint64_t n) {
+int rader_max_prime() {
     if (const char* e = getenv("B200FFT_RADER_MAX_PRIME")) { const int v = atoi(e); return v < 13 ? 13 : (v > RADER_MAX_PRIME ? RADER_MAX_PRIME : v); }
-    return n <= 2048 ? 13 : RADER_DEFAULT_MAX_PRIME;
+    return RADER_DEFAULT_MAX_PRIME;
 }
 std::vector<int> generic_radices(uint64_t n) {
     std::vector<int> r, primes;
@@ -90,8 +85,7 @@ std::vector<int> generic_radices(uint64_t n) {
     // split off prime factors > 13 first
     uint64_t m = n;
     for (int f : {2, 3, 5, 7, 11, 13}) while (m % f == 0) m /= f;
-    const uint64_t n_whole = n;
-    for (uint64_t f = 17; m > 1 && f <= (uint64_t)rader_max_prime(n_whole); f += 2)
+    for (uint64_t f = 17; m > 1 && f <= (uint64_t)rader_max_prime(); f += 2)
         while (m % f == 0) { primes.push_back((int)f); m /= f; n /= f; }
     if (m != 1) return {};
     // greedy factorisation per radix class; keep the leanest class that does not need more stages than the widest one
@@ -695,6 +689,18 @@ int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
     const bool dist = job.world > 1;
     if (dist && (!contiguous || job.unit_lines || count_lines(job.lines) != 1 || !is_smooth(N))) return R_UNSUPPORTED_FFT_LENGTH;
     if (!is_smooth(N)) return plan_bluestein(g, list, job);
+    // Measured on B200 (profiles/r2/rader_vs_bluestein.log, ~512 MiB per pair): the Rader stage of the runtime-scheduled kernel is
+    // a direct O(p^2) product and loses to the two fused Bluestein launches wherever those exist (padded length M <= 4096, i.e.
+    // N <= 2048: N = 34: 2.68 vs 2.03 ms, 323: 4.71 vs 1.85, 2032: 13.0 vs 1.38, 113: 10.2 vs 1.80); above that Bluestein needs
+    // 5-7 launches and the two are comparable (4416: 4.31 vs 6.54, 12167: 8.77 vs 5.90).  So a contiguous 1-D length up to 2048
+    // with a prime factor of 17 or more runs as Bluestein unless a curated kernel with a direct prime butterfly exists for it
+    // (the {17..31} * 2^k lengths).  Factors of a Four-Step split and strided axes keep the Rader stages.
+    if (contiguous && !job.unit_lines && !dist && N <= 2048 && !(job.extra_ops & B2_OP_CONV) && !getenv("B200FFT_RADER_MAX_PRIME") &&
+        !b2_find_kernel(kind, g.prec, (int)N, 0, 0)) {
+        uint64_t mm = N;
+        for (int f : {2, 3, 5, 7, 11, 13}) while (mm % f == 0) mm /= f;
+        if (mm > 1) return plan_bluestein(g, list, job);
+    }
 
     // a strided axis served only by the runtime-scheduled kernel with fewer than 8 neighbouring lines per CTA would
     // read 8..56-byte row fragments: split it instead (falls through to the strided Four-Step below)
@@ -1005,7 +1011,19 @@ int plan_direction_c2c(PlanGraph& g, std::vector<PassPlan>& list, int inv) {
                 rc = plan_c2c_axis(g, list, lsize, axes[i], inv, in, out, last ? norm : 1.0, 0, after_cross);
             }
         } else {
-            rc = plan_c2c_axis(g, list, d.size, axes[i], inv, in, out, last ? norm : 1.0);
+            // Zero padding at the END of a dimension b (an open system: fft_zeropad_right[b] == size[b], sample_4 / sample_51)
+            // makes whole lines of the LOWER axes trivial: forward, every line of axis a < b whose b-coordinate lies in the padded
+            // range is all zero (the ranges were cleared above) and stays zero; inverse, it only carries values of the padded
+            // range nobody reads.  Those lines are not transformed (the reference skips them the same way,
+            // vkFFT_KernelsLevel0/vkFFT_Zeropad.h).  Half-padded 3-D: 1/4 + 1/2 + 1 passes instead of 3.
+            uint64_t lsize[B200FFT_MAX_DIMS];
+            for (int a = 0; a < B200FFT_MAX_DIMS; ++a) lsize[a] = d.size[a];
+            if (!d.frequency_zeropadding && !d.perform_convolution && !d.is_input_formatted && !d.is_output_formatted)
+                for (uint32_t b = axes[i] + 1; b < d.fft_dim; ++b)
+                    if (d.perform_zeropadding[b] && d.zeropad_right[b] == d.size[b] && d.zeropad_left[b] > 0 && d.zeropad_left[b] < d.size[b] &&
+                        !d.omit_dimension[b])
+                        lsize[b] = d.zeropad_left[b];
+            rc = plan_c2c_axis(g, list, lsize, axes[i], inv, in, out, last ? norm : 1.0);
         }
         if (rc != R_SUCCESS) return rc;
         g.axis_uploads[inv ? 1 : 0][axes[i]] += (uint32_t)(list.size() - before);
@@ -1532,8 +1550,15 @@ static int build_plan_impl(const b200fft_desc& din, PlanGraph& g) {
                 z.out_base = (int64_t)L * stride_of(a);
                 lines.push_back(Dim{R - L, stride_of(a), stride_of(a)});
             }
+            // where a higher dimension b is padded at its end, its own clearing pass covers every point with a b-coordinate in
+            // the padded range: this pass only needs the rest (half-padded 3-D: 1/8 + 1/4 + 1/2 of the buffer instead of 3 x 1/2)
             for (uint32_t b = 1; b < d.fft_dim; ++b)
-                if (b != a) lines.push_back(Dim{d.size[b], stride_of(b), stride_of(b)});
+                if (b != a) {
+                    uint64_t nb_ = d.size[b];
+                    if (b > a && d.perform_zeropadding[b] && d.zeropad_right[b] == d.size[b] && d.zeropad_left[b] > 0 && d.zeropad_left[b] < d.size[b])
+                        nb_ = d.zeropad_left[b];
+                    lines.push_back(Dim{nb_, stride_of(b), stride_of(b)});
+                }
             const int64_t bstride = (int64_t)(d.buffer_stride[d.fft_dim - 1] * unit);
             lines.push_back(Dim{g.batches, bstride, bstride});
             z.in_base = z.out_base;

@@ -6,7 +6,7 @@ ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := -std=c++17 -O3 $(ARCH) -lineinfo -Xcompiler -fPIC -Ivkfft_b200/csrc -Iinclude
 CXXFLAGS  := -std=c++17 -O2 -fPIC -Ivkfft_b200/csrc -Iinclude
 SRC       := vkfft_b200/csrc
-SHARDS    := 0 1 2 3 4 5 6 7 8 9 10 11 12 13 14 15 16 17 18 19 20 21 22 23 24 25
+SHARDS    := 0 1 2 3 4 5 6 7 8 9 10 11 12 13 14 15 16 17 18 19 20 21 22 23 24 25 26 27
 SHARD_OBJ := $(foreach s,$(SHARDS),build/kernels_shard_$(s).o)
 HDRS      := $(wildcard $(SRC)/*.cuh $(SRC)/*.h $(SRC)/*.def include/*.h)
 LIB       := vkfft_b200/lib/libb200fft.so

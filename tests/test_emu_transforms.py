@@ -34,6 +34,53 @@ def test_bluestein_c2c(shape, b, prec, inv):
     assert orc.error_metrics(buf, orc.c2c(x, len(shape), inv == 1))["l2_rel"] < (T32 if prec == 0 else T64)
 
 
+def _one_launch_lengths():
+    """every padded length of kernel_list_blue1.def, reached from the largest N it serves and from the smallest one"""
+    ms = {0: sorted(k["n"] for k in emu.kernels() if k["ops"] == 1024 and k["prec"] == 0),
+          1: sorted(k["n"] for k in emu.kernels() if k["ops"] == 1024 and k["prec"] == 1)}
+    cases = []
+    for prec, lst in ms.items():
+        prev = 0
+        for m in lst:
+            hi, lo = (m + 1) // 2, prev // 2 + 1           # 2N-1 <= m  and  2N-1 > previous padded length
+            for n in sorted({hi, max(lo, 2)}):
+                cases.append((n, m, prec))
+            prev = m
+    return cases
+
+
+@pytest.mark.parametrize("n,m,prec", _one_launch_lengths())
+def test_bluestein_in_one_launch_every_padded_length(n, m, prec, monkeypatch):
+    """stockham.cuh RMODE 11 (chirp, FFT_M, filter in registers, IFFT_M, chirp in ONE launch, no scratch): every registered
+    padded length M in both precisions, forward and inverse with normalisation, ragged batch, against the oracle; the
+    generic route is forced (no curated kernel, no Rader stage) so that smooth N take the Bluestein path as well"""
+    monkeypatch.setenv("B200FFT_FORCE_BLUESTEIN", "1")
+    dt = np.complex64 if prec == 0 else np.complex128
+    b = 37 if m <= 256 else (5 if m <= 2048 else 2)
+    x = orc.random_input((b, n), dt, seed=n + m)
+    buf = x.copy()
+    rc, npass = emu.exec_plan(emu.make_desc((n,), b, prec), -1, buf)
+    assert rc == 0 and npass == 1
+    tol = T32 if prec == 0 else T64
+    assert orc.error_metrics(buf, orc.c2c(x, 1))["l2_rel"] < tol
+    d = emu.make_desc((n,), b, prec)
+    d.normalize = 1
+    rc, npass = emu.exec_plan(d, 1, buf)
+    assert rc == 0 and npass == 1
+    assert orc.error_metrics(buf, x)["l2_rel"] < 2 * tol
+
+
+def test_bluestein_one_launch_equals_two_launches(monkeypatch):
+    """same tables, same stage code: the one-launch kernel and the two-launch plan agree to rounding"""
+    x = orc.random_input((6, 509), np.complex64, seed=5)
+    a, b2 = x.copy(), x.copy()
+    rc, n1 = emu.exec_plan(emu.make_desc((509,), 6, 0), -1, a)
+    monkeypatch.setenv("B200FFT_NO_FUSED_BLUESTEIN", "1")
+    rc2, n2 = emu.exec_plan(emu.make_desc((509,), 6, 0), -1, b2)
+    assert rc == 0 and rc2 == 0 and n1 == 1 and n2 == 2
+    assert orc.error_metrics(a, b2)["l2_rel"] < 3e-7
+
+
 @pytest.mark.parametrize("shape,b,prec", [((17,), 5, 0), ((127,), 3, 1), ((1088,), 2, 0), ((2032,), 2, 0), ((94,), 3, 0), ((529,), 2, 0),
                                           ((323,), 2, 1), ((12167,), 1, 0), ((64, 17), 2, 0)])
 @pytest.mark.parametrize("inv", [-1, 1])
@@ -51,10 +98,10 @@ def test_rader_prime_radix_stages(shape, b, prec, inv, monkeypatch):
     assert orc.error_metrics(buf, orc.c2c(x, len(shape), inv == 1))["l2_rel"] < (T32 if prec == 0 else T64)
 
 
-@pytest.mark.parametrize("n,launches", [(127, 2), (2032, 2), (94, 2), (323, 2), (1088, 1), (136, 1), (12167, 2)])
+@pytest.mark.parametrize("n,launches", [(127, 1), (2032, 1), (94, 1), (323, 1), (1088, 1), (136, 1), (12167, 2)])
 def test_lengths_with_prime_factors_17_to_127_default_routing(n, launches):
-    """up to 2048 points: a curated kernel with a direct prime butterfly (1088 = 17.64, 136 = 17.8) or the two fused Bluestein
-    launches; longer ones keep the Rader stages (12167 = 23^3 in two passes)"""
+    """up to 2048 points: a curated kernel with a direct prime butterfly (1088 = 17.64, 136 = 17.8) or the one-launch Bluestein
+    kernel; longer ones keep the Rader stages (12167 = 23^3 in two passes)"""
     x = orc.random_input((3, n), np.complex64, seed=n)
     buf = x.copy()
     rc, npass = emu.exec_plan(emu.make_desc((n,), 3, 0), -1, buf)

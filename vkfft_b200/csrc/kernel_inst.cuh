@@ -146,7 +146,7 @@ struct Registrar {
     using KT = KindTraits<KIND>;
     using Sch = RList<Rs...>;
     static constexpr int RMODE = (OPS & B2_OP_REAL_EVEN) ? (INV ? 2 : 1)
-                               : ((OPS & B2_OP_DCT23) ? (INV ? 4 : 3) : ((OPS & B2_OP_PERM_IN) ? 5 : ((OPS & B2_OP_PERM_OUT) ? 6 : ((OPS & B2_OP_BLUESTEIN) ? (INV ? 8 : 7) : ((OPS & B2_OP_CONV) ? 9 : 0)))));
+                               : ((OPS & B2_OP_DCT23) ? (INV ? 4 : 3) : ((OPS & B2_OP_PERM_IN) ? 5 : ((OPS & B2_OP_PERM_OUT) ? 6 : ((OPS & B2_OP_BLUESTEIN) ? (INV ? 8 : 7) : ((OPS & B2_OP_CONV) ? 9 : ((OPS & B2_OP_BLUE_FUSED) ? 11 : 0))))));
     using C = KCfg<T, Sch, TPL, Q, V, KT::LMAP, KT::SMAP, KT::LAYOUT, INV, (OPS & B2_OP_TWIDDLE_OUT), KT::IN_UNIT, KT::OUT_UNIT,
                    MINB, RMODE>;
     b2_kernel_info info;
@@ -317,6 +317,22 @@ struct MaybeBlue<true, T, TPL, Q, V, MINB, Rs...> {
 #define B2_KB(shard, T, TPL, Q, V, MINB, ...)                                                              \
     static ::b200fft::MaybeBlue<B2_SHARD_ON(shard), T, TPL, Q, V, MINB, __VA_ARGS__>                      \
         B2_CAT(b2_regb_, __COUNTER__)("BLUESTEIN_ROWS<" #T "," #TPL "x" #Q ",V" #V ";" #__VA_ARGS__ ">");
+
+// the whole Bluestein transform in one launch (stockham.cuh RMODE 11) on a palindromic schedule
+namespace b200fft {
+template <bool EN, typename T, int TPL, int Q, int V, int MINB, int... Rs>
+struct MaybeBlue1 {
+    explicit MaybeBlue1(const char*) {}
+};
+template <typename T, int TPL, int Q, int V, int MINB, int... Rs>
+struct MaybeBlue1<true, T, TPL, Q, V, MINB, Rs...> {
+    Registrar<B2_KIND_ROWS, T, TPL, Q, V, MINB, false, B2_OP_BLUE_FUSED, Rs...> a;
+    explicit MaybeBlue1(const char* n) : a(n) {}
+};
+}  // namespace b200fft
+#define B2_KB1(shard, T, TPL, Q, V, MINB, ...)                                                             \
+    static ::b200fft::MaybeBlue1<B2_SHARD_ON(shard), T, TPL, Q, V, MINB, __VA_ARGS__>                     \
+        B2_CAT(b2_regb1_, __COUNTER__)("BLUESTEIN1_ROWS<" #T "," #TPL "x" #Q ",V" #V ";" #__VA_ARGS__ ">");
 
 // fused convolution (forward transform, kernel product, inverse transform in one launch) on a palindromic schedule
 namespace b200fft {

@@ -7,4 +7,5 @@
 
 #include "kernel_list.def"
 #include "kernel_list_nonpow2.def"
+#include "kernel_list_blue1.def"
 #include "kernel_list_fused.def"

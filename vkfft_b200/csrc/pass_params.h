@@ -36,6 +36,10 @@ enum {
     B2_OP_CONV = 512,        // specialised kernels, contiguous lines: forward transform, product with the kernel line
                              // (aux0, data offset modulo aux_u0 = features x plane elements; aux_u1 = B2_CONV_* option bits of ew.cuh), inverse
                              // transform, all in one launch -- needs a schedule whose first and last radix agree
+    B2_OP_BLUE_FUSED = 1024, // specialised kernels, contiguous lines: the WHOLE Bluestein transform of a line in one launch (stockham.cuh
+                             // RMODE 11) -- zero-pad to n + chirp aux0 on load, forward stages, filter aux1 in registers, the stages again
+                             // (inverse), chirp aux0 + scale + truncation to out_len on store.  One HBM read and one write of the N-point
+                             // line, no scratch.  Needs a schedule whose first and last radix agree; P.inverse = direction at run time
     B2_OP_PERM_OUT = 128,    // strided Four-Step last launch of a long DCT-III: result k1 + N1*p is scattered to row makhoul(k)
                              // (aux_u0 = full length, aux_u1 = N1, k1 = coordinate tw_sel)
 };

@@ -157,8 +157,8 @@ int emit(PlanGraph& g, std::vector<PassPlan>& list, const PassReq& rq) {
     const b2_kernel_info* k = nullptr;
     const bool plain = !rq.force_generic && rq.load_io == B2_IO_C2C && rq.store_io == B2_IO_C2C &&
                        !(rq.ops & (B2_OP_MUL_IN | B2_OP_MUL_OUT)) &&
-                       ((rq.in_len == 0 && rq.out_len == 0) || (rq.ops & B2_OP_BLUESTEIN)) && !rq.inner_inverse;
-    if (plain) k = b2_find_kernel(rq.kind, g.prec, rq.n, rq.inv, rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN | B2_OP_DCT23 | B2_OP_PERM_IN | B2_OP_PERM_OUT | B2_OP_BLUESTEIN | B2_OP_CONV));
+                       ((rq.in_len == 0 && rq.out_len == 0) || (rq.ops & (B2_OP_BLUESTEIN | B2_OP_BLUE_FUSED))) && !rq.inner_inverse;
+    if (plain) k = b2_find_kernel(rq.kind, g.prec, rq.n, rq.inv, rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN | B2_OP_DCT23 | B2_OP_PERM_IN | B2_OP_PERM_OUT | B2_OP_BLUESTEIN | B2_OP_CONV | B2_OP_BLUE_FUSED));
     std::vector<int> radices;
     bool generic = false;
     if (!k) {
@@ -227,12 +227,12 @@ int emit(PlanGraph& g, std::vector<PassPlan>& list, const PassReq& rq) {
         pp.k = k;
         if (k->pipelined) {   // TMA needs 16-byte aligned sources: keep the first non-pipelined kernel of the same key as a stand-in
             for (int v = 0; v < 16 && !pp.k_unaligned; ++v) {
-                const b2_kernel_info* alt = b2_find_kernel_variant(rq.kind, g.prec, rq.n, rq.inv, rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN | B2_OP_DCT23 | B2_OP_PERM_IN | B2_OP_PERM_OUT | B2_OP_BLUESTEIN | B2_OP_CONV), v);
+                const b2_kernel_info* alt = b2_find_kernel_variant(rq.kind, g.prec, rq.n, rq.inv, rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN | B2_OP_DCT23 | B2_OP_PERM_IN | B2_OP_PERM_OUT | B2_OP_BLUESTEIN | B2_OP_CONV | B2_OP_BLUE_FUSED), v);
                 if (alt && !alt->pipelined && alt->q == k->q) pp.k_unaligned = alt;
             }
             if (!pp.k_unaligned) {    // no drop-in with the same tile height: do not use the pipelined kernel at all
                 for (int v = 0; v < 16; ++v) {
-                    const b2_kernel_info* alt = b2_find_kernel_variant(rq.kind, g.prec, rq.n, rq.inv, rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN | B2_OP_DCT23 | B2_OP_PERM_IN | B2_OP_PERM_OUT | B2_OP_BLUESTEIN | B2_OP_CONV), v);
+                    const b2_kernel_info* alt = b2_find_kernel_variant(rq.kind, g.prec, rq.n, rq.inv, rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN | B2_OP_DCT23 | B2_OP_PERM_IN | B2_OP_PERM_OUT | B2_OP_BLUESTEIN | B2_OP_CONV | B2_OP_BLUE_FUSED), v);
                     if (alt && !alt->pipelined) { pp.k = k = alt; break; }
                 }
                 tpl = k->tpl; q = k->q;
@@ -492,6 +492,19 @@ uint64_t count_lines(const std::vector<Dim>& lines) {
     return c;
 }
 
+// smallest padded length >= 2N-1 with a one-launch Bluestein kernel (stockham.cuh RMODE 11), 0 if there is none
+uint64_t blue1_length(const PlanGraph& g, uint64_t N) {
+    if (getenv("B200FFT_NO_FUSED_BLUESTEIN")) return 0;
+    uint64_t M1 = 0;
+    for (int i = 0; i < b2_kernel_count(); ++i) {
+        const b2_kernel_info* k = b2_kernel_at(i);
+        if (k->kind != B2_KIND_ROWS || k->prec != g.prec || k->ops != B2_OP_BLUE_FUSED || k->inv != 0) continue;
+        const uint64_t n = (uint64_t)k->n;
+        if (n >= 2 * N - 1 && (M1 == 0 || n < M1)) M1 = n;
+    }
+    return M1;
+}
+
 int plan_bluestein(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
     // X[k] = conj(b_k) * sum_n (x_n conj(b_n)) b_{k-n},  b_n = e^{i pi n^2/N}   (API guide :465-493)
     const uint64_t N = job.N;
@@ -504,6 +517,25 @@ int plan_bluestein(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job)
             if (k->kind != B2_KIND_ROWS || k->prec != g.prec || k->ops != B2_OP_BLUESTEIN || k->inv != 0) continue;
             const uint64_t n = (uint64_t)k->n;
             if (n >= 2 * N - 1 && n < M && b2_find_kernel(B2_KIND_ROWS, g.prec, k->n, 1, B2_OP_BLUESTEIN)) M = n;
+        }
+    }
+    // contiguous lines: the whole transform in ONE launch (stockham.cuh RMODE 11: chirp, FFT_M, filter, IFFT_M, chirp with the
+    // padded line never leaving the SM) on the smallest padded length that has such a kernel.  No scratch, one HBM read and one
+    // write of the N-point line instead of 2 + 2 padded ones.  B200FFT_NO_FUSED_BLUESTEIN=1 keeps the two launches (A/B timing).
+    if (!job.unit_lines && job.es_in == 1 && job.es_out == 1) {
+        const uint64_t M1 = blue1_length(g, N);
+        if (M1) {
+            PassReq f1;
+            f1.kind = B2_KIND_ROWS; f1.n = (int)M1; f1.inv = 0; f1.runtime_inverse = job.inv;
+            f1.ops = B2_OP_BLUE_FUSED | (job.scale != 1.0 ? B2_OP_SCALE : 0); f1.scale = job.scale;
+            f1.in_es = f1.out_es = 1;
+            if (job.lines.empty()) f1.group = Dim{1, 0, 0};
+            else { f1.group = job.lines[0]; f1.outer.assign(job.lines.begin() + 1, job.lines.end()); }
+            f1.in_role = job.in_role; f1.out_role = job.out_role; f1.in_base = job.in_base; f1.out_base = job.out_base;
+            f1.in_len = (uint32_t)N; f1.out_len = (uint32_t)N;
+            f1.aux0 = aux_for(g, AUX_BLUE_CHIRP, N); f1.aux1 = aux_for(g, AUX_BLUE_FILTER, N, M1);
+            f1.what = "bluestein in one launch: chirp+fft+filter+ifft+chirp (specialised)";
+            return emit(g, list, f1);
         }
     }
     const uint64_t L = count_lines(job.lines);
@@ -695,12 +727,17 @@ int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
     // 5-7 launches and the two are comparable (4416: 4.31 vs 6.54, 12167: 8.77 vs 5.90).  So a contiguous 1-D length up to 2048
     // with a prime factor of 17 or more runs as Bluestein unless a curated kernel with a direct prime butterfly exists for it
     // (the {17..31} * 2^k lengths).  Factors of a Four-Step split and strided axes keep the Rader stages.
-    if (contiguous && !job.unit_lines && !dist && N <= 2048 && !(job.extra_ops & B2_OP_CONV) && !getenv("B200FFT_RADER_MAX_PRIME") &&
+    // Round 2, later: the whole Bluestein transform in ONE launch (blue1_length: padded lengths up to 8192 in FP32, 4096 in FP64)
+    // extends the rule to N <= 4096 / 2048.  B200FFT_FORCE_BLUESTEIN=1 sends every contiguous length that way
+    // (tests, and A/B timing against the runtime-scheduled kernel on smooth lengths).
+    if (contiguous && !job.unit_lines && !dist && (N <= 2048 || blue1_length(g, N)) && !(job.extra_ops & B2_OP_CONV) && !getenv("B200FFT_RADER_MAX_PRIME") &&
         !b2_find_kernel(kind, g.prec, (int)N, 0, 0)) {
         uint64_t mm = N;
         for (int f : {2, 3, 5, 7, 11, 13}) while (mm % f == 0) mm /= f;
         if (mm > 1) return plan_bluestein(g, list, job);
     }
+    if (contiguous && !job.unit_lines && !dist && !(job.extra_ops & B2_OP_CONV) && N > 1 && getenv("B200FFT_FORCE_BLUESTEIN") && blue1_length(g, N))
+        return plan_bluestein(g, list, job);
 
     // a strided axis served only by the runtime-scheduled kernel with fewer than 8 neighbouring lines per CTA would
     // read 8..56-byte row fragments: split it instead (falls through to the strided Four-Step below)

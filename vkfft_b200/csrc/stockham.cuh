@@ -884,6 +884,70 @@ struct Engine {
                     out_line[C::OUT_UNIT ? (int64_t)(b + k * NB) : (int64_t)(b + k * NB) * P.out_es] = a;
                 }
             }
+        } else if constexpr (C::RMODE == 11) {
+            // ---- the whole Bluestein transform of a line in ONE launch -----------------------------------------------------
+            //   X[k] = conj(b_k) sum_n (x_n conj(b_n)) b_{k-n}:  chirp + zero-pad to the padded length on load, forward stages,
+            //   product with the filter spectrum (aux1, one table for every line) in registers, swap, the stages again (= inverse),
+            //   chirp + scale + truncation on store.  Same register hand-over as the fused convolution above (equal first and last
+            //   radix); the two-launch form (RMODE 7 then 8) writes and re-reads a padded scratch line of n >= 2N-1 points in between,
+            //   here HBM sees the N-point line once in and once out.  The reference runs Bluestein as separate FFT / multiply / iFFT
+            //   dispatches through its temp buffer as well (vkFFT_Bluestein.h:32,201; vkFFT_Scheduler.h:2493-2578).
+            static_assert(Sch::r(0) == Sch::r(NS - 1), "fused Bluestein needs a schedule with equal first and last radix");
+            static_assert(C::LMAP == C::SMAP && V == 1 && C::IN_UNIT && C::OUT_UNIT, "contiguous lines, same thread map on both sides");
+            constexpr int s = NS - 1, r = Sch::r(0), NB = nbut<0>(), BPT = bpt<0>();
+            const bool valid = gl < P.G;
+            const X* __restrict__ filt = (const X*)P.aux1;
+            X* out_line = (X*)P.out + obase_out + (int64_t)gl * P.out_gs;
+            X x[BPT * r];
+            load_global_blue<0>(x, in_line, P, tl, valid);
+            compute<0>(x, lut, tl);
+            if constexpr (NS > 1) {
+                store_smem<0>(x, sm, ql, tl);
+                __syncthreads();
+                middle<1>(sm, lut, tid);
+                load_smem<s>(x, sm, ql, tl);
+                compute<s>(x, lut, tl);
+            }
+#pragma unroll
+            for (int m = 0; m < BPT; ++m) {
+                const int b = tl + m * TPL;
+                const bool ok = valid && (!guarded<0>() || b < NB);
+#pragma unroll
+                for (int k = 0; k < r; ++k) {
+                    X w = mk<T>(T(0), T(0));
+                    if (ok) w = ld_lut(filt + (b + k * NB));
+                    x[m * r + k] = swp(x[m * r + k] * w);
+                }
+            }
+            compute<0>(x, lut, tl);
+            if constexpr (NS > 1) {
+                __syncthreads();       // every last-stage read of the forward transform is done
+                store_smem<0>(x, sm, ql, tl);
+                __syncthreads();
+                middle<1>(sm, lut, tid);
+                load_smem<s>(x, sm, ql, tl);
+                compute<s>(x, lut, tl);
+            }
+            {
+                const bool do_scale = (P.ops & B2_OP_SCALE) != 0;
+                const T sc = (T)P.scale;
+                const bool oswap = P.inverse != 0;
+                const X* __restrict__ chirp = (const X*)P.aux0;
+#pragma unroll
+                for (int m = 0; m < BPT; ++m) {
+                    const int b = tl + m * TPL;
+                    if (!valid || (guarded<0>() && b >= NB)) continue;
+#pragma unroll
+                    for (int k = 0; k < r; ++k) {
+                        const int p = b + k * NB;
+                        if (p < (int)P.out_len) {
+                            X a = swp(x[m * r + k]) * ld_lut(chirp + p);
+                            if (do_scale) a = a * sc;
+                            out_line[p] = oswap ? swp(a) : a;
+                        }
+                    }
+                }
+            }
         } else if constexpr (C::RMODE == 4 && C::LAYOUT == LAY_LINE && B2_DCT3_STAGE_IN) {
             // real lines staged through the tile (see stage_in_dct); every stage reads its legs from shared memory
             stage_in_dct(sm, P, obase_in, gl, ql, tl, gl < P.G);

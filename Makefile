@@ -29,11 +29,18 @@ build/window.o: $(SRC)/window.cu $(HDRS)
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
+build/jit_headers.cpp: tools/embed_headers.py $(HDRS)
+	@mkdir -p build
+	python3 tools/embed_headers.py $@
+
+build/jit_headers.o: build/jit_headers.cpp
+	$(CXX) $(CXXFLAGS) -c $< -o $@
+
 build/%.o: $(SRC)/%.cpp $(HDRS)
 	@mkdir -p build
 	$(CXX) $(CXXFLAGS) -c $< -o $@
 
-$(LIB): $(SHARD_OBJ) build/kernels_generic.o build/runtime.o build/window.o build/planner.o build/kernel_registry.o
+$(LIB): $(SHARD_OBJ) build/kernels_generic.o build/runtime.o build/window.o build/planner.o build/kernel_registry.o build/jit.o build/jit_headers.o
 	@mkdir -p vkfft_b200/lib
 	$(NVCC) -shared $(ARCH) -o $@ $^ -lcudart_static -ldl -lrt -lpthread
 

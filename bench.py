@@ -12,6 +12,8 @@
   roofline the dominant kernel = the kernel with the LARGEST SHARE of the step's device time (per-launch CUDA events
            through b200fft_debug_exec_timed, aggregated by kernel over the sweep): algorithmic bytes per launch / mean
            launch time / measured peak; `kernel_shares` lists the top kernels, `step_frac` is the whole step.
+  other_lengths  lengths off the power-of-two sweep (curated kernels, templates instantiated at plan time, Bluestein): ms per
+              pair of ~512 MiB, roofline fraction, plan time, and the reference's CUDA backend beside it
   per_config  BASELINE configs 3-5 on one GPU (3-D FP64 256^3 / 512^3, 2-D R2C 4096^2, DCT-II 8192^2, 1-D 2^26): ms per
            forward+inverse pair, roofline fraction, and the unmodified reference's CUDA backend on the same GPU.
   sample0  the reference's own sample_0 benchmark binary (VkFFT_TestSuite -vkfft 0, "Benchmark score VkFFT") built from the
@@ -251,6 +253,60 @@ CONFIG_CASES = [
     ("config4: 2D DCT-II/III FP32 8192^2 x2", (8192, 8192), 2, False, dict(performDCT=2), dict(perform_dct=2), True),
     ("config5 (one GPU): 1D C2C FP32 2^26 x4", (1 << 26,), 4, False, {}, {}, False),
 ]
+
+
+OTHER_LENGTHS = [
+    # lengths off the power-of-two sweep, 1-D C2C FP32, ~512 MiB per transform: (N, which kind of kernel serves it)
+    (1000, "curated ahead-of-time kernel"), (2187, "curated ahead-of-time kernel (3^7)"), (1088, "curated, direct radix-17 butterfly"),
+    (1100, "template instantiated at plan time"), (2002, "template instantiated at plan time"), (34, "template instantiated at plan time (17 x 2)"),
+    (127, "Bluestein in one launch"), (509, "Bluestein in one launch"), (1019, "Bluestein in one launch"), (4093, "Bluestein, two launches"),
+]
+
+
+def bench_other_lengths(torch, vk, peak, dev, warm=2, reps=5):
+    """non power-of-two lengths: engine vs the unmodified reference's CUDA backend (which generates a kernel per plan)"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import vkfft_oracle as orc
+    rows = []
+    for n, what in OTHER_LENGTHS:
+        batch = max(1, (1 << 26) // n)
+        buf = torch.zeros(batch * n, dtype=torch.complex64, device=dev)
+        torch.view_as_real(buf).uniform_(-1, 1)
+        row = {"n": n, "batch": batch, "served_by": what}
+        app = vk.VkFFTApplication()
+        t0 = time.time()
+        rc = vk.initializeVkFFT(app, vk.VkFFTConfiguration(FFTdim=1, size=[n], numberBatches=batch, device=dev.index, normalize=1))
+        row["plan_seconds"] = round(time.time() - t0, 2)
+        if rc != 0:
+            row["error"] = vk.getVkFFTErrorString(rc)
+        else:
+            info = vk.planInfo(app)
+            lp = vk.VkFFTLaunchParams(buffer=buf)
+            for _ in range(warm):
+                vk.VkFFTAppend(app, -1, lp); vk.VkFFTAppend(app, 1, lp)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                vk.VkFFTAppend(app, -1, lp); vk.VkFFTAppend(app, 1, lp)
+            b.record(); torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / reps
+            alg = 4 * buf.numel() * 8                 # one read + one write of the lines per direction
+            row.update(ms_pair=round(ms, 4), launches_forward=len(launch_labels(info["forward"])), frac_of_peak=round(alg / (ms * 1e-3) / 1e9 / peak, 4))
+            vk.deleteVkFFT(app)
+        if orc.ref_available():
+            L = orc.ref_lib()
+            d = orc.ref_desc((n,), batch, False, device=dev.index)
+            h = ctypes.c_void_p()
+            if L.vkref_open(ctypes.byref(d), ctypes.byref(h)) == 0:
+                e, w = ctypes.c_double(), ctypes.c_double()
+                buf.uniform_(-1e-3, 1e-3) if False else None
+                if L.vkref_bench_pairs(h, buf.data_ptr(), warm, reps, ctypes.byref(e), ctypes.byref(w)) == 0:
+                    row["reference_ms_pair"] = round(e.value, 4)
+                L.vkref_close(h)
+        rows.append(row)
+        del buf
+        torch.cuda.empty_cache()
+    return rows
 
 
 def bench_configs(torch, vk, peak, dev, warm=2, reps=5):
@@ -689,6 +745,10 @@ def main():
             line["per_config"] = bench_configs(torch, vk, peak, dev)
         except Exception as e:
             line["per_config"] = {"error": repr(e)}
+        try:
+            line["other_lengths"] = bench_other_lengths(torch, vk, peak, dev)
+        except Exception as e:
+            line["other_lengths"] = {"error": repr(e)}
     if world == 1 and not args.no_sample0:
         line["sample0"] = sample0_scores(local_rank)
     print(json.dumps(line), flush=True)

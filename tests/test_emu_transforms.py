@@ -98,7 +98,7 @@ def test_rader_prime_radix_stages(shape, b, prec, inv, monkeypatch):
     assert orc.error_metrics(buf, orc.c2c(x, len(shape), inv == 1))["l2_rel"] < (T32 if prec == 0 else T64)
 
 
-@pytest.mark.parametrize("n,launches", [(127, 1), (2032, 1), (94, 1), (323, 1), (1088, 1), (136, 1), (12167, 2)])
+@pytest.mark.parametrize("n,launches", [(127, 1), (2032, 2), (94, 1), (323, 1), (1088, 1), (136, 1), (12167, 2)])
 def test_lengths_with_prime_factors_17_to_127_default_routing(n, launches):
     """up to 2048 points: a curated kernel with a direct prime butterfly (1088 = 17.64, 136 = 17.8) or the one-launch Bluestein
     kernel; longer ones keep the Rader stages (12167 = 23^3 in two passes)"""

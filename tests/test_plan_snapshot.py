@@ -39,7 +39,8 @@ def test_sweep_plan(log2n):
     (dict(shape=(8192, 8192), b=2, prec=0, perform_dct=2), 4),                  # fused DCT rows + long strided DCT (3 launches)
     (dict(shape=(1 << 26,), b=4, prec=0), 3),                                   # three-launch Four-Step
     (dict(shape=(1088,), b=1 << 17, prec=0), 1),                                # prime-radix specialised kernel
-    (dict(shape=(509,), b=1 << 18, prec=0), 2),                                 # Bluestein on the specialised kernels
+    (dict(shape=(509,), b=1 << 18, prec=0), 1),                                 # the whole Bluestein transform in one launch
+    (dict(shape=(4093,), b=1 << 14, prec=0), 2),                                # Bluestein, two launches on the specialised kernels
     (dict(shape=(4096,), b=1 << 16, prec=0, perform_convolution=1), 1),         # fused convolution
 ])
 def test_launch_counts_of_the_other_baseline_configurations(desc_kw, launches):

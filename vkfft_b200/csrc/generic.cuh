@@ -50,6 +50,98 @@ struct Generic {
         }
     }
 
+    // ---- first stage with its legs straight from HBM and/or last stage with its outputs straight to HBM ------------------
+    // (plain complex lines only).  The separate load / store phases cost one shared-memory write + read each per element; here
+    // the first butterflies read x[b + k n/R] from the line in global memory (consecutive threads, consecutive b: coalesced for
+    // every k) and the last butterflies write y[b + k S] (S = n/R, again consecutive b), with the load / store operators of
+    // load_line / store_line applied in registers.  FIN / FOUT: this stage is the first / the last one of the schedule.
+    template <int R, bool FIN, bool FOUT>
+    B2_D static void stage_io(const b2_pass_params& P, const X* src, X* dst, int S, const X* __restrict__ lut, int q, int t, int tpl,
+                              int ls, int64_t in_off, int64_t out_off, uint32_t twline, bool valid) {
+        const int n = (int)P.n, nb = n / R;
+        const bool inv = P.inverse != 0, inner = P.inner_inverse != 0;
+        const X zero = mk<T>(T(0), T(0));
+        const X* s = src + q * ls;
+        X* d = dst + q * ls;
+        const X* in = (const X*)P.in + in_off;
+        X* out = (X*)P.out + out_off;
+        const T sc = (T)P.scale;
+        const bool do_scale = (P.ops & B2_OP_SCALE) != 0;
+        const int lim = (int)P.out_len < n ? (int)P.out_len : n;
+        if (FOUT && !valid) return;
+        for (int b = t; b < nb; b += tpl) {
+            X x[R];
+            if constexpr (FIN) {
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
+                    const int p = b + k * nb;
+                    X v = zero;
+                    if (valid && p < (int)P.in_len) {
+                        v = in[(int64_t)p * P.in_es];
+                        if (inv) v = swp(v);
+                        if (P.ops & B2_OP_MUL_IN) v = v * ld_lut((const X*)P.aux0 + p);
+                        if (inner) v = swp(v);
+                    }
+                    x[k] = v;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < R; ++k) x[k] = B2_SMEM_LD(s, pad(b + k * nb));
+            }
+            const int j = b % S;
+            if (!FIN && S > 1) {
+#pragma unroll
+                for (int k = 1; k < R; ++k) x[k] = x[k] * ld_lut(lut + (k - 1) * S + j);
+            }
+            dft<R, T>(x);
+            const int base = (b - j) * R + j;
+            if constexpr (FOUT) {
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
+                    const int p = base + k * S;
+                    if (p >= lim) continue;
+                    X v = x[k];
+                    if (inner) v = swp(v);
+                    if (P.ops & B2_OP_MUL_OUT) v = v * ld_lut((const X*)P.aux1 + p);
+                    if (P.ops & B2_OP_TWIDDLE_OUT) {
+                        const uint64_t e = (uint64_t)twline * (uint64_t)p;
+                        v = v * twiddle2<T>((const X*)P.tw_hi, (const X*)P.tw_lo, P.tw_shift, e);
+                    }
+                    if (do_scale) v = v * sc;
+                    if (inv) v = swp(v);
+                    out[(int64_t)p * P.out_es] = v;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < R; ++k) B2_SMEM_ST(d, pad(base + k * S), x[k]);
+            }
+        }
+    }
+    template <bool FIN, bool FOUT>
+    B2_D static void run_stage_io(int r, const b2_pass_params& P, const X* src, X* dst, int S, const X* lut, int q, int t, int tpl, int ls,
+                                  int64_t in_off, int64_t out_off, uint32_t twline, bool valid) {
+#define B2_GEN_IO(RR) case RR: stage_io<RR, FIN, FOUT>(P, src, dst, S, lut, q, t, tpl, ls, in_off, out_off, twline, valid); break;
+        switch (r) {
+            B2_GEN_IO(2) B2_GEN_IO(3) B2_GEN_IO(4) B2_GEN_IO(5) B2_GEN_IO(6) B2_GEN_IO(7) B2_GEN_IO(8)
+            default:
+                if constexpr (RMAX > 8) {
+                    switch (r) {
+                        B2_GEN_IO(9) B2_GEN_IO(10) B2_GEN_IO(11)
+                        default:
+                            if constexpr (RMAX > 11) {
+                                switch (r) {
+                                    B2_GEN_IO(12) B2_GEN_IO(13) B2_GEN_IO(14) B2_GEN_IO(15) B2_GEN_IO(16)
+                                    default: break;
+                                }
+                            }
+                            break;
+                    }
+                }
+                break;
+        }
+#undef B2_GEN_IO
+    }
+
     // ---- Rader stage for a prime radix p > 16 ("mult" form: the length-(p-1) cyclic convolution is evaluated
     //      directly, vkFFT_RaderKernels.h:1278).  X_0 = sum of the legs;  X_{g^-q} = x_0 + sum_m a_m b_{(q-m) mod (p-1)},
     //      a_m = leg_{g^m}.  The legs are twiddled in place first (phase 1), then every thread produces outputs (phase 2).
@@ -447,14 +539,16 @@ struct Generic {
         const int in_mult = (P.load_io == B2_IO_DCT2 || P.load_io == B2_IO_DCT3 || P.load_io == B2_IO_DCT1 || P.load_io == B2_IO_DST1) ? 2 : 1;
         const int out_mult = (P.store_io == B2_IO_DCT2 || P.store_io == B2_IO_DCT3 || P.store_io == B2_IO_DCT1 || P.store_io == B2_IO_DST1) ? 2 : 1;
 
-        {   // load
-            int q, t, step;
-            if (P.load_qfast) { q = tid % Q; t = tid / Q; } else { t = tid % TPL; q = tid / TPL; }
-            step = TPL;
-            const uint32_t gl = grp * Q + q;
-            load_line(P, buf0 + q * ls, obase_in + (int64_t)gl * in_mult * P.in_gs, gl, gl < P.G, t, step);
+        // plain complex lines (B2_GEN_FUSE_IN / _OUT, set by the planner): no separate load / store phase, see stage_io
+        const bool fin = (P.gen_flags & B2_GEN_FUSE_IN) != 0, fout = (P.gen_flags & B2_GEN_FUSE_OUT) != 0;
+        int ql, tl, qs, ts;
+        if (P.load_qfast) { ql = tid % Q; tl = tid / Q; } else { tl = tid % TPL; ql = tid / TPL; }
+        if (P.store_qfast) { qs = tid % Q; ts = tid / Q; } else { ts = tid % TPL; qs = tid / TPL; }
+        const uint32_t gll = grp * Q + ql, gls = grp * Q + qs;
+        if (!fin) {   // load
+            load_line(P, buf0 + ql * ls, obase_in + (int64_t)gll * in_mult * P.in_gs, gll, gll < P.G, tl, TPL);
+            __syncthreads();
         }
-        __syncthreads();
         const X* lut = (const X*)P.lut;
         {   // stages (t fastest: neighbouring lanes take neighbouring butterflies of one line)
             const int t = tid % TPL, q = tid / TPL;
@@ -469,22 +563,28 @@ struct Generic {
             }
             for (uint32_t s = 0; s < P.nstages; ++s) {
                 const int r = (int)P.radix[s];
-                if (r > 16) { rader_stage(r, src, dst, n, S, lut, rader, q, t, TPL, ls); rader += 2 * (r - 1); }
+                const bool first = fin && s == 0, last = fout && s + 1 == P.nstages;
+                if (first && last) {       // one radix: HBM -> registers -> HBM, in the load-side thread map
+                    run_stage_io<true, true>(r, P, src, dst, S, lut, ql, tl, TPL, ls, obase_in + (int64_t)gll * P.in_gs,
+                                             obase_out + (int64_t)gll * P.out_gs, twbase + (twsel == 0 ? gll : 0), gll < P.G);
+                } else if (first) {
+                    run_stage_io<true, false>(r, P, src, dst, S, lut, ql, tl, TPL, ls, obase_in + (int64_t)gll * P.in_gs, 0, 0, gll < P.G);
+                } else if (last) {
+                    run_stage_io<false, true>(r, P, src, dst, S, lut, qs, ts, TPL, ls, 0, obase_out + (int64_t)gls * P.out_gs,
+                                              twbase + (twsel == 0 ? gls : 0), gls < P.G);
+                } else if (r > 16) { rader_stage(r, src, dst, n, S, lut, rader, q, t, TPL, ls); rader += 2 * (r - 1); }
                 else run_stage(r, src, dst, n, S, lut, q, t, TPL, ls);
                 if (s > 0) lut += (r - 1) * S;
                 S *= r;
+                if (last) return;
                 __syncthreads();
                 X* tmp = src; src = dst; dst = tmp;
             }
             buf0 = src;   // final data
         }
-        {   // store
-            int q, t;
-            if (P.store_qfast) { q = tid % Q; t = tid / Q; } else { t = tid % TPL; q = tid / TPL; }
-            const uint32_t gl = grp * Q + q;
-            store_line(P, buf0 + q * ls, obase_out + (int64_t)gl * out_mult * P.out_gs, gl,
-                       twbase + (twsel == 0 ? gl : 0), gl < P.G, t, TPL);
-        }
+        // store
+        store_line(P, buf0 + qs * ls, obase_out + (int64_t)gls * out_mult * P.out_gs, gls,
+                   twbase + (twsel == 0 ? gls : 0), gls < P.G, ts, TPL);
     }
 };
 

@@ -36,10 +36,13 @@ extern "C" void b2_register_kernel(const b2_kernel_info* k) {
     m->variant = v;
     table().push_back(m);
 }
+namespace { b2_kernel_provider g_provider = nullptr; }
+extern "C" void b2_set_kernel_provider(b2_kernel_provider p) { g_provider = p; }
 extern "C" const b2_kernel_info* b2_find_kernel_variant(int kind, int prec, int n, int inv, int ops, int variant) {
     for (const b2_kernel_info* k : table())
         if (k->kind == kind && k->prec == prec && k->n == n && k->inv == inv && k->ops == ops && k->variant == variant)
             return k;
+    if (variant == 0 && g_provider) return g_provider(kind, prec, n, inv, ops);
     return nullptr;
 }
 extern "C" const b2_kernel_info* b2_find_kernel(int kind, int prec, int n, int inv, int ops) {

@@ -1,6 +1,9 @@
-// Registry of ahead-of-time compiled kernel instantiations.  The planner looks kernels up by
-// (kind, precision, length, direction, fused-operator set); nothing is generated or compiled at run time
-// (the reference JIT-compiles every plan through NVRTC, vkFFT_CompileKernel.h:299-491).
+// Registry of kernel instantiations.  The planner looks kernels up by (kind, precision, length, direction, fused-operator
+// set).  The hot path -- powers of two, the curated lengths, every Four-Step factor of the BASELINE configurations -- is
+// compiled ahead of time for sm_100a.  A length that is 2..31-smooth but not in the ahead-of-time lists gets the SAME
+// hand-written templates (stockham.cuh) instantiated for it when its plan is created (jit.cpp, NVRTC -> cubin; the product
+// library only) instead of falling back to the runtime-scheduled kernel, which is 3-5x slower.  The reference compiles every
+// kernel of every plan that way (vkFFT_CompileKernel.h:299-491); here it is the exception, and B200FFT_NO_JIT=1 turns it off.
 #pragma once
 #include "pass_params.h"
 
@@ -30,7 +33,20 @@ typedef struct b2_kernel_info {
     int (*launch)(const b2_pass_params* P, unsigned grid, void* stream);
     int (*prepare)(void);              // one-time cudaFuncSetAttribute (max dynamic smem)
     const char* name;
+    void* jit;                         // != 0: instantiated at plan time (jit.cpp); launch / prepare are null, use b2_jit_prepare / b2_jit_launch
 } b2_kernel_info;
+
+// plan-time instantiation (jit.cpp installs the provider in the product library; absent in the CPU emulation): asked on a
+// registry miss, returns a kernel description (not compiled yet) or null when the key is not eligible
+typedef const b2_kernel_info* (*b2_kernel_provider)(int kind, int prec, int n, int inv, int ops);
+void b2_set_kernel_provider(b2_kernel_provider p);
+// jit.cpp (product library only): compile + load the kernel behind a plan-time description / enqueue it
+int b2_jit_prepare(const b2_kernel_info* k);
+void b2_jit_disable(const b2_kernel_info* k);   // after a failed prepare: stop offering the key (the plan is rebuilt without it)
+int b2_jit_launch(const b2_kernel_info* k, const b2_pass_params* P, unsigned grid, void* stream);
+long b2_jit_selftest(int kind, int prec, int n, int ops);   // no GPU needed: cubin size, 0 = not eligible, < 0 = compile error
+const char* b2_jit_last_log(void);
+int b2_jit_available(void);
 
 void b2_register_kernel(const b2_kernel_info* k);
 const b2_kernel_info* b2_find_kernel(int kind, int prec, int n, int inv, int ops);   // honours B200FFT_VARIANTS

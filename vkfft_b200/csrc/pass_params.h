@@ -103,7 +103,13 @@ typedef struct b2_pass_params {
     uint32_t inner_inverse;                // 1: the FFT inside this pass is an inverse one (swap around the stages only)
     uint32_t tw_sel;                       // which coordinate is the four-step "line": 0 group index, 1..3 outer dim 0..2
     uint32_t dst_flags;                    // B2_DST_* wrappers around the DCT operators
+    uint32_t gen_flags;                    // B2_GEN_*: first stage reads its legs from HBM / last stage writes its outputs to HBM
 } b2_pass_params;
+
+enum {
+    B2_GEN_FUSE_IN = 1,
+    B2_GEN_FUSE_OUT = 2,
+};
 
 // One launch of the fused Four-Step kernel (fused4.cuh): both passes of a two-factor split N = n1*n2 in ONE persistent
 // launch.  Pass A (strided n1-point transforms + phase) writes into a small ring of scratch "units" that stays in L2,

@@ -265,6 +265,12 @@ int emit(PlanGraph& g, std::vector<PassPlan>& list, const PassReq& rq) {
         for (size_t s = 0; s < radices.size(); ++s) P.radix[s] = radices[s];
         P.tpl = tpl; P.q = q; P.line_stride = ls;
         P.load_io = rq.load_io; P.store_io = rq.store_io;
+        if (generic && !getenv("B200FFT_GENERIC_STAGED")) {
+            // plain complex lines: the first butterflies read HBM and the last ones write it (generic.cuh stage_io) instead of
+            // separate copy phases through shared memory.  B200FFT_GENERIC_STAGED=1 keeps the copy phases (A/B timing)
+            if ((rq.load_io == B2_IO_C2C || rq.load_io == B2_IO_R2C_EVEN) && radices.front() <= 16) P.gen_flags |= B2_GEN_FUSE_IN;
+            if ((rq.store_io == B2_IO_C2C || rq.store_io == B2_IO_C2R_EVEN) && radices.back() <= 16) P.gen_flags |= B2_GEN_FUSE_OUT;
+        }
         P.in_len = rq.in_len ? rq.in_len : rq.n;
         P.out_len = rq.out_len ? rq.out_len : rq.n;
         P.load_qfast = qfast_l; P.store_qfast = qfast_s;
@@ -495,6 +501,12 @@ uint64_t count_lines(const std::vector<Dim>& lines) {
 // smallest padded length >= 2N-1 with a one-launch Bluestein kernel (stockham.cuh RMODE 11), 0 if there is none
 uint64_t blue1_length(const PlanGraph& g, uint64_t N) {
     if (getenv("B200FFT_NO_FUSED_BLUESTEIN")) return 0;
+    // measured on B200 (profiles/r2/bluestein_one_launch_vs_two.log, ms per pair of ~512 MiB): one launch wins up to a padded
+    // length of 3584 in FP32 (N = 113: 0.95 vs 1.80, 509: 1.08 vs 1.45, 1019: 1.17 vs 1.56, 1517: 1.72 vs 1.87) and ties or loses
+    // above (N = 2039, M = 4096: 1.43 vs 1.40; 4093, M = 8192: 2.24 vs 1.87 -- 32 points per thread at 2 CTAs per SM); in
+    // FP64 it wins at every length it exists for (2039: 1.79 vs 2.50)
+    const uint64_t limit = getenv("B200FFT_FORCE_BLUESTEIN") ? ~0ull : (g.prec == B2_PREC_F32 ? 3584 : 4096);
+    if (2 * N - 1 > limit) return 0;
     uint64_t M1 = 0;
     for (int i = 0; i < b2_kernel_count(); ++i) {
         const b2_kernel_info* k = b2_kernel_at(i);

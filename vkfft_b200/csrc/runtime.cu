@@ -165,6 +165,15 @@ extern "C" int b200fft_plan_create(const b200fft_desc* desc, b200fft_plan** out)
         if (a.prec == B2_PREC_F32) rc = upload(make_aux<float>(a.kind, a.a, a.b), &p->d_auxs[i], p->lut_bytes);
         else rc = upload(make_aux<double>(a.kind, a.a, a.b), &p->d_auxs[i], p->lut_bytes);
     }
+    // plan-time instantiated kernels (jit.cpp): compile + load.  One that fails is withdrawn from the registry and the plan is
+    // built again without it (the length then runs on the runtime-scheduled kernel): never an error of its own
+    if (rc == R_SUCCESS) {
+        bool withdrawn = false;
+        for (int dir = 0; dir < 2; ++dir)
+            for (const PassPlan& pp : (dir ? g.inv : g.fwd))
+                if (pp.k && pp.k->jit && b2_jit_prepare(pp.k) != 0) { b2_jit_disable(pp.k); withdrawn = true; }
+        if (withdrawn) { cudaGetLastError(); free_plan(p); return b200fft_plan_create(desc, out); }
+    }
     // one-time kernel attributes (dynamic shared memory above 48 KiB)
     for (int dir = 0; dir < 2 && rc == R_SUCCESS; ++dir)
         for (const PassPlan& pp : (dir ? g.inv : g.fwd))
@@ -301,7 +310,7 @@ static int exec_impl(b200fft_plan* p, int inverse, const b200fft_buffers* b, std
             k = pp.k_unaligned;
             if (pp.lut_id_unaligned >= 0) P.lut = p->d_luts[pp.lut_id_unaligned];
         }
-        if (!k || k->launch(&P, pp.grid, (void*)st) != 0) {
+        if (!k || (k->jit ? b2_jit_launch(k, &P, pp.grid, (void*)st) : k->launch(&P, pp.grid, (void*)st)) != 0) {
             // a distributed plan that stops half way would leave the peers spinning in their next barrier until the device-side
             // time-out: keep the barrier sequence complete (the data is lost either way, the error code says so)
             if (g.distributed) {
@@ -488,14 +497,16 @@ extern "C" int b200fft_debug_time_kernel(int index, void* in, void* out, uint64_
             P.tw_hi = d_hi; P.tw_lo = d_lo;
         }
     }
+    if (!rc && k->jit && b2_jit_prepare(k) != 0) rc = R_FAILED_TO_SET_DYNAMIC_SHARED_MEMORY;
     if (!rc && k->prepare && k->prepare() != 0) rc = R_FAILED_TO_SET_DYNAMIC_SHARED_MEMORY;
+    auto launch1 = [&]() { return k->jit ? b2_jit_launch(k, &P, (unsigned)grid, nullptr) : k->launch(&P, (unsigned)grid, nullptr); };
     float ms = 0;
     if (!rc) {
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0); cudaEventCreate(&e1);
-        for (int i = 0; i < 2 && !rc; ++i) rc = k->launch(&P, (unsigned)grid, nullptr);
+        for (int i = 0; i < 2 && !rc; ++i) rc = launch1();
         cudaEventRecord(e0, 0);
-        for (int i = 0; i < reps && !rc; ++i) rc = k->launch(&P, (unsigned)grid, nullptr);
+        for (int i = 0; i < reps && !rc; ++i) rc = launch1();
         cudaEventRecord(e1, 0);
         if (cudaDeviceSynchronize() != cudaSuccess) rc = R_FAILED_TO_SYNCHRONIZE;
         cudaEventElapsedTime(&ms, e0, e1);

@@ -265,9 +265,11 @@ int emit(PlanGraph& g, std::vector<PassPlan>& list, const PassReq& rq) {
         for (size_t s = 0; s < radices.size(); ++s) P.radix[s] = radices[s];
         P.tpl = tpl; P.q = q; P.line_stride = ls;
         P.load_io = rq.load_io; P.store_io = rq.store_io;
-        if (generic && !getenv("B200FFT_GENERIC_STAGED")) {
+        if (generic && getenv("B200FFT_GENERIC_FUSED_IO")) {
             // plain complex lines: the first butterflies read HBM and the last ones write it (generic.cuh stage_io) instead of
-            // separate copy phases through shared memory.  B200FFT_GENERIC_STAGED=1 keeps the copy phases (A/B timing)
+            // separate copy phases through shared memory.  Measured on B200 and REJECTED as the default
+            // (profiles/r2/other_lengths_plan_time_templates_ab.log: N = 154 2.34 vs 2.03 ms, 4004 2.87 vs 2.29, 1100 1.60 vs 1.56 --
+            // the strided first-stage legs of a runtime radix cost more than the two shared-memory passes they save); opt-in
             if ((rq.load_io == B2_IO_C2C || rq.load_io == B2_IO_R2C_EVEN) && radices.front() <= 16) P.gen_flags |= B2_GEN_FUSE_IN;
             if ((rq.store_io == B2_IO_C2C || rq.store_io == B2_IO_C2R_EVEN) && radices.back() <= 16) P.gen_flags |= B2_GEN_FUSE_OUT;
         }

@@ -29,7 +29,9 @@ extern "C" {
 #define B200FFT_MAX_DIMS 4
 #define B200FFT_VERSION 10000 /* engine version; VkFFTGetVersion() of the shim still reports 10304 */
 
-typedef enum b200fft_precision { B200FFT_F32 = 0, B200FFT_F64 = 1 } b200fft_precision;
+/* B200FFT_F16: half-precision STORAGE -- every buffer holds 32-bit complex elements (half re, half im), arithmetic and tables are
+   FP32 (the reference's halfPrecision, vkFFT_Structs.h:210; plain C2C transforms, kernels instantiated at plan time) */
+typedef enum b200fft_precision { B200FFT_F32 = 0, B200FFT_F64 = 1, B200FFT_F16 = 2 } b200fft_precision;
 
 /* Plan description: the subset of VkFFTConfiguration (vkFFT_Structs.h:93-324) the hot path consumes.
  * Zero means "default" for every field, exactly like the reference's zero-initialised configuration. */
@@ -39,7 +41,7 @@ typedef struct b200fft_desc {
     uint64_t size[B200FFT_MAX_DIMS];      /* size[]: logical transform lengths, x first */
     uint64_t number_batches;              /* numberBatches (0 -> 1) */
     uint64_t coordinate_features;         /* coordinateFeatures (0 -> 1); treated as one more batch level */
-    uint32_t precision;                   /* doublePrecision -> B200FFT_F64 */
+    uint32_t precision;                   /* doublePrecision -> B200FFT_F64, halfPrecision -> B200FFT_F16 */
     uint32_t perform_r2c;                 /* performR2C */
     uint32_t perform_dct;                 /* performDCT: 1..4 */
     uint32_t perform_dst;                 /* performDST: 1..4 */

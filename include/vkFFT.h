@@ -80,7 +80,8 @@ typedef struct {
 
     pfUINT doublePrecision;
     pfUINT quadDoubleDoublePrecision, quadDoubleDoublePrecisionDoubleMemory;   /* unsupported */
-    pfUINT halfPrecision, halfPrecisionMemoryOnly, doublePrecisionFloatMemory; /* unsupported */
+    pfUINT halfPrecision;                                       /* half storage, FP32 arithmetic: plain C2C transforms */
+    pfUINT halfPrecisionMemoryOnly, doublePrecisionFloatMemory; /* unsupported */
 
     pfUINT performR2C, performDCT, performDST;
     pfUINT disableMergeSequencesR2C, forceCallbackVersionRealTransforms;
@@ -262,8 +263,8 @@ static inline VkFFTResult initializeVkFFT(VkFFTApplication* app, VkFFTConfigurat
     if (c->FFTdim > VKFFT_MAX_FFT_DIMENSIONS) return VKFFT_ERROR_FFTdim_GT_MAX_FFT_DIMENSIONS;
     if (c->size[0] == 0) return VKFFT_ERROR_EMPTY_size;
     /* features of the reference outside this engine's hot path */
-    if (c->halfPrecision || c->halfPrecisionMemoryOnly || c->quadDoubleDoublePrecision ||
-        c->quadDoubleDoublePrecisionDoubleMemory || c->doublePrecisionFloatMemory)
+    if (c->halfPrecisionMemoryOnly || c->quadDoubleDoublePrecision ||
+        c->quadDoubleDoublePrecisionDoubleMemory || c->doublePrecisionFloatMemory || (c->halfPrecision && c->doublePrecision))
         return VKFFT_ERROR_UNSUPPORTED_FFT_LENGTH;
     if (c->bufferNum > 1 || c->tempBufferNum > 1 || c->inputBufferNum > 1 || c->outputBufferNum > 1)
         return VKFFT_ERROR_UNSUPPORTED_FFT_LENGTH;
@@ -287,7 +288,8 @@ static inline VkFFTResult initializeVkFFT(VkFFTApplication* app, VkFFTConfigurat
     d.frequency_zeropadding = (uint32_t)c->frequencyZeroPadding;
     d.number_batches = c->numberBatches;
     d.coordinate_features = c->coordinateFeatures;
-    d.precision = c->doublePrecision ? B200FFT_F64 : B200FFT_F32;
+    /* halfPrecision (vkFFT_Structs.h:210): every buffer holds half-precision complex elements, arithmetic in FP32 -- B200FFT_F16 */
+    d.precision = c->doublePrecision ? B200FFT_F64 : (c->halfPrecision ? B200FFT_F16 : B200FFT_F32);
     d.perform_r2c = (uint32_t)c->performR2C;
     d.perform_dct = (uint32_t)c->performDCT;
     d.perform_dst = (uint32_t)c->performDST;

@@ -93,8 +93,9 @@ static int emu_run_one(PlanGraph& g, PassPlan& pp, void* const* base) {
         else { a1d = make_aux<double>(a.kind, a.a, a.b); P.aux1 = a1d.data(); }
     }
     if (pp.aux0_role == ROLE_KERNEL) P.aux0 = g_emu_kernel;
-    P.in = (const unsigned char*)base[pp.in_role] + pp.in_off * (pp.in_scalar ? esz / 2 : esz);
-    P.out = (unsigned char*)base[pp.out_role] + pp.out_off * (pp.out_scalar ? esz / 2 : esz);
+    const size_t esz_in = g.role_half[pp.in_role] ? 4 : esz, esz_out = g.role_half[pp.out_role] ? 4 : esz;   // half-precision storage
+    P.in = (const unsigned char*)base[pp.in_role] + pp.in_off * (pp.in_scalar ? esz_in / 2 : esz_in);
+    P.out = (unsigned char*)base[pp.out_role] + pp.out_off * (pp.out_scalar ? esz_out / 2 : esz_out);
     return pp.k->launch(&P, pp.grid, nullptr) ? 4039 : 0;
 }
 

@@ -70,6 +70,7 @@ class VkFFTConfiguration:
     numberBatches: int = 0
     coordinateFeatures: int = 0
     doublePrecision: int = 0
+    halfPrecision: int = 0            # half-precision storage (complex32 buffers), FP32 arithmetic; plain C2C transforms
     performR2C: int = 0
     performDCT: int = 0
     performDST: int = 0
@@ -156,7 +157,7 @@ def _to_desc(cfg: VkFFTConfiguration) -> "_lib.b200fft_desc":
             dst[i] = int(s)
     d.number_batches = cfg.numberBatches
     d.coordinate_features = cfg.coordinateFeatures
-    d.precision = 1 if cfg.doublePrecision else 0
+    d.precision = 1 if cfg.doublePrecision else (2 if cfg.halfPrecision else 0)
     d.perform_r2c = cfg.performR2C
     d.perform_dct = cfg.performDCT
     d.perform_dst = cfg.performDST

@@ -107,18 +107,23 @@ std::vector<int> factor(int n, bool primes) {
 
 struct Shape {
     std::vector<int> r;
-    int tpl = 0, q = 0, regs = 0, smem = 0, lut = 0, rmode_f = 0, rmode_i = 0;
+    int tpl = 0, q = 0, regs = 0, smem = 0, lut = 0, rmode_f = 0, rmode_i = 0, st = 0;
 };
 
-bool choose(int kind, int prec, int n, int ops, Shape& s) {
+bool choose(int kind, int prec, int n, int ops_all, Shape& s) {
     const bool dbl = prec == B2_PREC_F64;
-    if (n < 18 || n > 4096) return false;
+    // half-precision storage (B2_OP_HALF_IN / _OUT -> KCfg::ST): FP32 plain complex transforms only; no ahead-of-time kernel
+    // exists for it, so every length from 2 up comes from here (one-radix kernels included)
+    const int half = ops_all & (B2_OP_HALF_IN | B2_OP_HALF_OUT), ops = ops_all & ~half;
+    if (half && (dbl || (ops & ~B2_OP_TWIDDLE_OUT))) return false;
+    s.st = ((half & B2_OP_HALF_IN) ? 1 : 0) | ((half & B2_OP_HALF_OUT) ? 2 : 0);
+    if (n < (half ? 2 : 18) || n > 4096) return false;
     if (kind == B2_KIND_ROWS) { if (ops != 0 && ops != B2_OP_REAL_EVEN) return false; }
     else if (kind == B2_KIND_COLS) { if (ops != 0 && ops != B2_OP_TWIDDLE_OUT) return false; if (n > (dbl ? 1024 : 2048)) return false; }
     else if (kind == B2_KIND_ROWS_TOUT) { if (ops != 0) return false; if (n > (dbl ? 1024 : 2048)) return false; }
     else return false;
     s.r = factor(n, kind == B2_KIND_ROWS && !dbl);
-    if (s.r.size() < 2 || s.r.size() > 8) return false;
+    if (s.r.size() < (half ? 1u : 2u) || s.r.size() > 8) return false;
     int rmax = 0;
     for (int r : s.r) rmax = r > rmax ? r : rmax;
     const int esz = dbl ? 16 : 8;
@@ -147,7 +152,7 @@ bool choose(int kind, int prec, int n, int ops, Shape& s) {
     const int pad_shift = dbl ? 3 : 4, npad = n + (n >> pad_shift);
     const bool line = kind != B2_KIND_COLS;
     const int ls = s.q == 1 ? npad : (npad | 1);
-    s.smem = (line ? s.q * ls : n * s.q) * esz;
+    s.smem = s.r.size() <= 1 && !(ops & B2_OP_REAL_EVEN) ? 0 : (line ? s.q * ls : n * s.q) * esz;
     int S = 1, lut = 0;
     for (size_t i = 0; i < s.r.size(); ++i) { if (i > 0) lut += (s.r[i] - 1) * S; S *= s.r[i]; }
     s.lut = lut;
@@ -184,8 +189,8 @@ std::string make_source(int kind, int prec, int ops, const Shape& s) {
              "#include \"stockham.cuh\"\n"
              "using namespace b200fft;\n"
              "using Sch = RList<%s>;\n"
-             "using CF = KCfg<%s, Sch, %d, %d, 1, %d, %d, %d, false, %d, %s, %s, %d, %d>;\n"
-             "using CI = KCfg<%s, Sch, %d, %d, 1, %d, %d, %d, true, %d, %s, %s, %d, %d>;\n"
+             "using CF = KCfg<%s, Sch, %d, %d, 1, %d, %d, %d, false, %d, %s, %s, %d, %d, %d>;\n"
+             "using CI = KCfg<%s, Sch, %d, %d, 1, %d, %d, %d, true, %d, %s, %s, %d, %d, %d>;\n"
              "static_assert(CF::SMEM_BYTES == %d && CI::SMEM_BYTES == %d, \"host copy of KCfg::SMEM_BYTES\");\n"
              "static_assert(Sch::lut_size == %d, \"host copy of RList::lut_size\");\n"
              "extern \"C\" __global__ void __launch_bounds__(CF::THREADS, CF::MINB) b2_jit_fwd(const __grid_constant__ b2_pass_params P) {\n"
@@ -196,8 +201,8 @@ std::string make_source(int kind, int prec, int ops, const Shape& s) {
              "    extern __shared__ __align__(16) unsigned char b2_smem_raw[];\n"
              "    Engine<CI>::run(P, b2_smem_raw);\n"
              "}\n",
-             rl.c_str(), T, s.tpl, s.q, lmap, smap, layout, ops & B2_OP_TWIDDLE_OUT, in_unit, out_unit, s.regs, s.rmode_f, T, s.tpl, s.q, lmap,
-             smap, layout, ops & B2_OP_TWIDDLE_OUT, in_unit, out_unit, s.regs, s.rmode_i, s.smem, s.smem, s.lut);
+             rl.c_str(), T, s.tpl, s.q, lmap, smap, layout, ops & B2_OP_TWIDDLE_OUT, in_unit, out_unit, s.regs, s.rmode_f, s.st, T, s.tpl, s.q,
+             lmap, smap, layout, ops & B2_OP_TWIDDLE_OUT, in_unit, out_unit, s.regs, s.rmode_i, s.st, s.smem, s.smem, s.lut);
     return buf;
 }
 
@@ -245,7 +250,9 @@ const b2_kernel_info* provide(int kind, int prec, int n, int inv, int ops) {
     std::string rl;
     for (size_t i = 0; i < s.r.size(); ++i) rl += (i ? ", " : "") + std::to_string(s.r[i]);
     const char* kn = kind == B2_KIND_ROWS ? "ROWS" : (kind == B2_KIND_COLS ? "COLS" : "ROWS_TOUT");
-    e->name = std::string("JIT_") + kn + "<" + (prec == B2_PREC_F64 ? "double" : "float") + "," + std::to_string(s.tpl) + "x" + std::to_string(s.q) + ",V1;" + rl + ">";
+    const char* stn[] = {"", ",half in+out", ",half in", ",half out"};
+    e->name = std::string("JIT_") + kn + "<" + (prec == B2_PREC_F64 ? "double" : "float") + "," + std::to_string(s.tpl) + "x" + std::to_string(s.q) + ",V1;" + rl +
+              stn[s.st == 3 ? 1 : (s.st == 1 ? 2 : (s.st == 2 ? 3 : 0))] + ">";
     b2_kernel_info& k = e->info;
     memset(&k, 0, sizeof k);
     k.kind = kind; k.prec = prec; k.n = n; k.inv = inv; k.ops = ops;

@@ -147,8 +147,9 @@ struct Registrar {
     using Sch = RList<Rs...>;
     static constexpr int RMODE = (OPS & B2_OP_REAL_EVEN) ? (INV ? 2 : 1)
                                : ((OPS & B2_OP_DCT23) ? (INV ? 4 : 3) : ((OPS & B2_OP_PERM_IN) ? 5 : ((OPS & B2_OP_PERM_OUT) ? 6 : ((OPS & B2_OP_BLUESTEIN) ? (INV ? 8 : 7) : ((OPS & B2_OP_CONV) ? 9 : ((OPS & B2_OP_BLUE_FUSED) ? 11 : 0))))));
+    static constexpr int ST = ((OPS & B2_OP_HALF_IN) ? 1 : 0) | ((OPS & B2_OP_HALF_OUT) ? 2 : 0);   // half-precision storage
     using C = KCfg<T, Sch, TPL, Q, V, KT::LMAP, KT::SMAP, KT::LAYOUT, INV, (OPS & B2_OP_TWIDDLE_OUT), KT::IN_UNIT, KT::OUT_UNIT,
-                   MINB, RMODE>;
+                   MINB, RMODE, ST>;
     b2_kernel_info info;
     explicit Registrar(const char* name) {
         info = b2_kernel_info{};
@@ -317,6 +318,29 @@ struct MaybeBlue<true, T, TPL, Q, V, MINB, Rs...> {
 #define B2_KB(shard, T, TPL, Q, V, MINB, ...)                                                              \
     static ::b200fft::MaybeBlue<B2_SHARD_ON(shard), T, TPL, Q, V, MINB, __VA_ARGS__>                      \
         B2_CAT(b2_regb_, __COUNTER__)("BLUESTEIN_ROWS<" #T "," #TPL "x" #Q ",V" #V ";" #__VA_ARGS__ ">");
+
+// half-precision storage variants of one schedule: (half in, half out), (half in, float out), (float in, half out); forward and
+// inverse; OPS = 0 or B2_OP_TWIDDLE_OUT.  The product library instantiates these at plan time (jit.cpp); the CPU emulation
+// registers a handful ahead of time so that the load / store conversions are exercised by the CPU suite
+namespace b200fft {
+template <bool EN, int KIND, typename T, int TPL, int Q, int V, int MINB, int OPS, int... Rs>
+struct MaybeHalf {
+    explicit MaybeHalf(const char*) {}
+};
+template <int KIND, typename T, int TPL, int Q, int V, int MINB, int OPS, int... Rs>
+struct MaybeHalf<true, KIND, T, TPL, Q, V, MINB, OPS, Rs...> {
+    Registrar<KIND, T, TPL, Q, V, MINB, false, OPS | B2_OP_HALF_IN | B2_OP_HALF_OUT, Rs...> a;
+    Registrar<KIND, T, TPL, Q, V, MINB, true, OPS | B2_OP_HALF_IN | B2_OP_HALF_OUT, Rs...> b;
+    Registrar<KIND, T, TPL, Q, V, MINB, false, OPS | B2_OP_HALF_IN, Rs...> c;
+    Registrar<KIND, T, TPL, Q, V, MINB, true, OPS | B2_OP_HALF_IN, Rs...> d;
+    Registrar<KIND, T, TPL, Q, V, MINB, false, OPS | B2_OP_HALF_OUT, Rs...> e;
+    Registrar<KIND, T, TPL, Q, V, MINB, true, OPS | B2_OP_HALF_OUT, Rs...> f;
+    explicit MaybeHalf(const char* n) : a(n), b(n), c(n), d(n), e(n), f(n) {}
+};
+}  // namespace b200fft
+#define B2_KH(shard, KIND, OPS, TPL, Q, V, MINB, ...)                                                      \
+    static ::b200fft::MaybeHalf<B2_SHARD_ON(shard), B2_KIND_##KIND, float, TPL, Q, V, MINB, OPS, __VA_ARGS__> \
+        B2_CAT(b2_regh_, __COUNTER__)("HALF_" #KIND "<float," #TPL "x" #Q ",V" #V ";" #__VA_ARGS__ ">");
 
 // the whole Bluestein transform in one launch (stockham.cuh RMODE 11) on a palindromic schedule
 namespace b200fft {

@@ -40,6 +40,8 @@ enum {
                              // RMODE 11) -- zero-pad to n + chirp aux0 on load, forward stages, filter aux1 in registers, the stages again
                              // (inverse), chirp aux0 + scale + truncation to out_len on store.  One HBM read and one write of the N-point
                              // line, no scratch.  Needs a schedule whose first and last radix agree; P.inverse = direction at run time
+    B2_OP_HALF_IN = 2048,    // the lines this pass READS are stored in half precision (32-bit complex elements, cplx.cuh); plain complex
+    B2_OP_HALF_OUT = 4096,   // the lines it WRITES are                                   transforms, FP32 arithmetic, KCfg::ST
     B2_OP_PERM_OUT = 128,    // strided Four-Step last launch of a long DCT-III: result k1 + N1*p is scattered to row makhoul(k)
                              // (aux_u0 = full length, aux_u1 = N1, k1 = coordinate tw_sel)
 };

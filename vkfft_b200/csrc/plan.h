@@ -103,6 +103,9 @@ struct PlanGraph {
     uint32_t axis_uploads[2][B200FFT_MAX_DIMS] = {{0, 0, 0, 0}, {0, 0, 0, 0}};   // launches per axis, [0] forward / [1] inverse (the reference's numAxisUploads)
     int skip_axis = -1;          // convolution plans: this axis is transformed by the fused kernel, the direction planners leave it out
     uint64_t ctl_words = 0;      // control block of the fused Four-Step launches (largest one of the plan)
+    // half-precision storage (desc.precision = B200FFT_F16: the reference's halfPrecision, vkFFT_Structs.h:210): arithmetic, tables
+    // and g.prec are FP32, the elements of the flagged buffer roles are 32-bit (half re, half im); strides / offsets count elements
+    bool role_half[ROLE_COUNT] = {false, false, false, false, false};
     bool distributed = false;    // desc.dist_world > 1: one more barrier follows the last launch of a direction
 };
 

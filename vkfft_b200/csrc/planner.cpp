@@ -112,7 +112,9 @@ std::vector<int> generic_radices(uint64_t n) {
     return r;
 }
 
-uint64_t esize(const PlanGraph& g) { return g.prec == B2_PREC_F64 ? 16 : 8; }
+uint64_t esize(const PlanGraph& g) { return g.prec == B2_PREC_F64 ? 16 : 8; }      // element size of the ARITHMETIC (tiles in shared memory)
+uint64_t role_esize(const PlanGraph& g, int role) { return g.role_half[role] ? 4 : esize(g); }   // element size in HBM
+bool half_plan(const PlanGraph& g) { return g.role_half[ROLE_BUFFER]; }
 int pad_of(const PlanGraph& g, uint64_t n) { return (int)(n + (n >> (g.prec == B2_PREC_F64 ? 3 : 4))); }
 const uint64_t GENERIC_SMEM_LIMIT = 200 * 1024;
 
@@ -158,7 +160,12 @@ int emit(PlanGraph& g, std::vector<PassPlan>& list, const PassReq& rq) {
     const bool plain = !rq.force_generic && rq.load_io == B2_IO_C2C && rq.store_io == B2_IO_C2C &&
                        !(rq.ops & (B2_OP_MUL_IN | B2_OP_MUL_OUT)) &&
                        ((rq.in_len == 0 && rq.out_len == 0) || (rq.ops & (B2_OP_BLUESTEIN | B2_OP_BLUE_FUSED))) && !rq.inner_inverse;
-    if (plain) k = b2_find_kernel(rq.kind, g.prec, rq.n, rq.inv, rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN | B2_OP_DCT23 | B2_OP_PERM_IN | B2_OP_PERM_OUT | B2_OP_BLUESTEIN | B2_OP_CONV | B2_OP_BLUE_FUSED));
+    // half-precision storage on either side: the conversion lives in the specialised kernels' HBM load / store (KCfg::ST),
+    // instantiated at plan time (jit.cpp); the runtime-scheduled kernel and the operator launches have no such variant
+    const int hops = (g.role_half[rq.in_role] ? B2_OP_HALF_IN : 0) | (g.role_half[rq.out_role] ? B2_OP_HALF_OUT : 0);
+    const int key_ops = (rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN | B2_OP_DCT23 | B2_OP_PERM_IN | B2_OP_PERM_OUT | B2_OP_BLUESTEIN | B2_OP_CONV | B2_OP_BLUE_FUSED)) | hops;
+    if (plain) k = b2_find_kernel(rq.kind, g.prec, rq.n, rq.inv, key_ops);
+    if (hops && !k) return R_UNSUPPORTED_FFT_LENGTH;
     std::vector<int> radices;
     bool generic = false;
     if (!k) {
@@ -227,12 +234,12 @@ int emit(PlanGraph& g, std::vector<PassPlan>& list, const PassReq& rq) {
         pp.k = k;
         if (k->pipelined) {   // TMA needs 16-byte aligned sources: keep the first non-pipelined kernel of the same key as a stand-in
             for (int v = 0; v < 16 && !pp.k_unaligned; ++v) {
-                const b2_kernel_info* alt = b2_find_kernel_variant(rq.kind, g.prec, rq.n, rq.inv, rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN | B2_OP_DCT23 | B2_OP_PERM_IN | B2_OP_PERM_OUT | B2_OP_BLUESTEIN | B2_OP_CONV | B2_OP_BLUE_FUSED), v);
+                const b2_kernel_info* alt = b2_find_kernel_variant(rq.kind, g.prec, rq.n, rq.inv, key_ops, v);
                 if (alt && !alt->pipelined && alt->q == k->q) pp.k_unaligned = alt;
             }
             if (!pp.k_unaligned) {    // no drop-in with the same tile height: do not use the pipelined kernel at all
                 for (int v = 0; v < 16; ++v) {
-                    const b2_kernel_info* alt = b2_find_kernel_variant(rq.kind, g.prec, rq.n, rq.inv, rq.ops & (B2_OP_TWIDDLE_OUT | B2_OP_REAL_EVEN | B2_OP_DCT23 | B2_OP_PERM_IN | B2_OP_PERM_OUT | B2_OP_BLUESTEIN | B2_OP_CONV | B2_OP_BLUE_FUSED), v);
+                    const b2_kernel_info* alt = b2_find_kernel_variant(rq.kind, g.prec, rq.n, rq.inv, key_ops, v);
                     if (alt && !alt->pipelined) { pp.k = k = alt; break; }
                 }
                 tpl = k->tpl; q = k->q;
@@ -338,7 +345,7 @@ std::vector<uint64_t> split_four_step(const PlanGraph& g, uint64_t N, bool dist 
         }
         if (prod == N && f.size() >= 2 && f.size() <= 3) return f;
     }
-    const uint64_t cap = std::min<uint64_t>(max_single_env(), 4096);
+    const uint64_t cap = std::min<uint64_t>(max_single_env(), half_plan(g) ? 2048 : 4096);   // (plan-time kernels with transposed / strided access stop at 2048)
     auto fast = [&](int kind, uint64_t n, int ops) { return b2_find_kernel(kind, g.prec, (int)n, 0, ops) != nullptr; };
     // measured cost of one full pass over a 2 GiB FP32 buffer on B200, microseconds (profiles/r2/ktune_f32.log);
     // used to rank factorizations.  Unknown sizes / FP64 fall back to "balanced factors".
@@ -457,7 +464,7 @@ int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job);
 // elementwise helper launch over `lines` (every line dimension, any order)
 int emit_ew(PlanGraph& g, std::vector<PassPlan>& list, PassReq rq, const std::vector<Dim>& lines) {
     const b2_kernel_info* k = b2_find_kernel(B2_KIND_ELEMENTWISE, g.prec, 0, 0, 0);
-    if (!k) return R_UNSUPPORTED_FFT_LENGTH;
+    if (!k || g.role_half[rq.in_role] || g.role_half[rq.out_role]) return R_UNSUPPORTED_FFT_LENGTH;
     std::vector<Dim> m = merge_dims(lines);
     if (m.size() > 1 + B2_MAX_OUTER) return R_UNSUPPORTED_FFT_LENGTH;
     PassPlan pp;
@@ -670,7 +677,7 @@ int plan_bluestein(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job)
 // kernel exists for (n1, n2).  B200FFT_NO_FUSED4=1 keeps the two launches; B200FFT_FUSED_UNIT_KB / B200FFT_FUSED_RING /
 // B200FFT_FUSED_RING_MB tune the ring (unit size, slots, total size).
 void try_fuse(PlanGraph& g, std::vector<PassPlan>& list, size_t ia) {
-    if (!fused4_enabled() || ia + 2 != list.size()) return;
+    if (!fused4_enabled() || ia + 2 != list.size() || half_plan(g)) return;
     PassPlan& a = list[ia];
     PassPlan& b = list[ia + 1];
     if (a.out_role != ROLE_TEMP || b.in_role != ROLE_TEMP || a.sync_before || b.sync_before) return;
@@ -766,7 +773,7 @@ int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
         const b2_kernel_info* kk = b2_find_kernel(kind, g.prec, (int)std::min<uint64_t>(N, 0x7fffffff), 0, 0);
         if (kk && kk->q < 8 && N >= 2048) poor_strided = true;
     }
-    bool try_single = !dist && N <= max_single_env() && single_ok(g, kind, N, 0);
+    bool try_single = !dist && N <= max_single_env() && single_ok(g, kind, N, 0) && (!half_plan(g) || N <= (job.unit_lines ? 2048u : 4096u));
     if (job.extra_ops & B2_OP_CONV) {
         if (!b2_find_kernel(kind, g.prec, (int)std::min<uint64_t>(N, 0x7fffffff), 0, B2_OP_CONV)) return R_UNSUPPORTED_FFT_LENGTH;
         try_single = true; poor_strided = false;
@@ -1513,7 +1520,11 @@ static int build_plan_impl(const b200fft_desc& din, PlanGraph& g) {
         if (d.size[a] == 0 || a >= d.fft_dim) d.size[a] = 1;
     if (d.number_batches == 0) d.number_batches = 1;
     if (d.coordinate_features == 0) d.coordinate_features = 1;
-    if (d.precision > B200FFT_F64) return R_UNSUPPORTED_FFT_LENGTH;
+    if (d.precision > B200FFT_F16) return R_UNSUPPORTED_FFT_LENGTH;
+    // half-precision storage: plain complex transforms (the conversion is fused into the first-stage load / last-stage store of the
+    // specialised kernels); the real-data operators, convolution and zero padding have no half variant
+    if (d.precision == B200FFT_F16 && (d.perform_r2c || d.perform_dct || d.perform_dst || d.perform_convolution || d.dist_world > 1))
+        return R_UNSUPPORTED_FFT_LENGTH;
     if (d.perform_dct > 4 || d.perform_dst > 4) return R_UNSUPPORTED_FFT_LENGTH_R2R;
     if ((d.perform_r2c && (d.perform_dct || d.perform_dst)) || (d.perform_dct && d.perform_dst)) return R_UNSUPPORTED_FFT_LENGTH_R2R;
     if (d.omit_dimension[0] && d.perform_r2c) return R_UNSUPPORTED_FFT_OMIT;
@@ -1551,7 +1562,9 @@ static int build_plan_impl(const b200fft_desc& din, PlanGraph& g) {
     }
     g.desc = d;
     g.distributed = d.dist_world > 1;
-    g.prec = (int)d.precision;
+    g.prec = d.precision == B200FFT_F16 ? B2_PREC_F32 : (int)d.precision;
+    if (d.precision == B200FFT_F16)
+        for (int r : {ROLE_BUFFER, ROLE_TEMP, ROLE_INPUT, ROLE_OUTPUT}) g.role_half[r] = true;
     for (int a = 0; a < B200FFT_MAX_DIMS; ++a) g.stride[a] = d.buffer_stride[a];
     g.batches = d.number_batches * d.coordinate_features;
     g.batch_stride = d.buffer_stride[d.fft_dim - 1];
@@ -1567,7 +1580,7 @@ static int build_plan_impl(const b200fft_desc& din, PlanGraph& g) {
         const double n = (double)d.size[a];
         g.flops += (real_tf ? 2.5 : 5.0) * (double)g.total_elems * std::log2(n);
     }
-    const uint64_t esz = esize(g);
+    const uint64_t esz = role_esize(g, ROLE_BUFFER);
     // algorithmic bytes: one read + one write of every point per transformed axis (real data: half the bytes)
     g.algorithmic_bytes = 2 * (real_tf ? esz / 2 : esz) * g.total_elems * naxes;
 
@@ -1726,7 +1739,7 @@ int build_plan(const b200fft_desc& din, PlanGraph& g) {
     // tempBufferSize the reference's contract applies ("same size as buffer"): the buffer size stands in.  The required
     // size is published through b200fft_plan_get_info().temp_bytes either way.
     if (g.desc.user_temp_buffer && g.temp_elems) {
-        const uint64_t need = g.temp_elems * esize(g);
+        const uint64_t need = g.temp_elems * role_esize(g, ROLE_TEMP);
         const uint64_t have = din.temp_buffer_size ? din.temp_buffer_size : din.buffer_size;
         if (have != 0 && need > have) return R_USER_TEMP_TOO_SMALL;
     }

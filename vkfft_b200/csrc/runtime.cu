@@ -188,7 +188,7 @@ extern "C" int b200fft_plan_create(const b200fft_desc* desc, b200fft_plan** out)
     if (rc == R_SUCCESS && g.ctl_words && cudaMalloc(&p->d_ctl, g.ctl_words * 4) != cudaSuccess) rc = R_FAILED_TO_ALLOCATE;
     // scratch for Four-Step (the reference auto-allocates tempBuffer the same way, vkFFT_InitializeApp.h:1603-1637)
     if (rc == R_SUCCESS && g.temp_elems && !g.desc.user_temp_buffer) {
-        p->temp_bytes = g.temp_elems * (g.prec == B2_PREC_F64 ? 16 : 8);
+        p->temp_bytes = g.temp_elems * (g.role_half[ROLE_TEMP] ? 4 : (g.prec == B2_PREC_F64 ? 16 : 8));
         if (cudaMalloc(&p->d_temp, p->temp_bytes) != cudaSuccess) rc = R_FAILED_TO_ALLOCATE;
     }
     if (rc != R_SUCCESS) { cudaGetLastError(); free_plan(p); return rc; }
@@ -258,8 +258,9 @@ static int exec_impl(b200fft_plan* p, int inverse, const b200fft_buffers* b, std
     };
     auto resolve = [&](const PassPlan& pp, b2_pass_params& P) {
         P = pp.P;
-        P.in = base[pp.in_role] + pp.in_off * (int64_t)(pp.in_scalar ? esz / 2 : esz);
-        P.out = base[pp.out_role] + pp.out_off * (int64_t)(pp.out_scalar ? esz / 2 : esz);
+        const size_t esz_in = g.role_half[pp.in_role] ? 4 : esz, esz_out = g.role_half[pp.out_role] ? 4 : esz;   // half-precision storage
+        P.in = base[pp.in_role] + pp.in_off * (int64_t)(pp.in_scalar ? esz_in / 2 : esz_in);
+        P.out = base[pp.out_role] + pp.out_off * (int64_t)(pp.out_scalar ? esz_out / 2 : esz_out);
         if (pp.aux0_id >= 0) P.aux0 = p->d_auxs[pp.aux0_id];
         if (pp.aux1_id >= 0) P.aux1 = p->d_auxs[pp.aux1_id];
         if (pp.aux0_role >= 0) P.aux0 = base[pp.aux0_role];
@@ -344,7 +345,7 @@ extern "C" int b200fft_plan_get_info(const b200fft_plan* p, b200fft_plan_info* i
     if (!p || !info) return R_EMPTY_APP;
     info->num_passes_forward = (uint32_t)p->g.fwd.size();
     info->num_passes_inverse = (uint32_t)p->g.inv.size();
-    info->temp_bytes = p->g.temp_elems * (p->g.prec == B2_PREC_F64 ? 16 : 8);   // required scratch, whoever owns it
+    info->temp_bytes = p->g.temp_elems * (p->g.role_half[ROLE_TEMP] ? 4 : (p->g.prec == B2_PREC_F64 ? 16 : 8));   // required scratch, whoever owns it
     info->lut_bytes = p->lut_bytes;
     info->algorithmic_bytes = p->g.algorithmic_bytes;
     info->flops = p->g.flops;
@@ -383,7 +384,7 @@ extern "C" int b200fft_exec_host(b200fft_plan* p, int inverse, const void* host_
     // the staging buffer always covers the plan's own layout (strides x batches, counted in complex elements: an upper
     // bound for the real-data layouts), whatever byte counts the caller passes: a short count can then neither make a
     // kernel read or write past the allocation nor leave uninitialised input behind (the tail is cleared)
-    const uint64_t extent = p->g.batch_stride * p->g.batches * (p->g.prec == B2_PREC_F64 ? 16 : 8);
+    const uint64_t extent = p->g.batch_stride * p->g.batches * (p->g.role_half[ROLE_BUFFER] ? 4 : (p->g.prec == B2_PREC_F64 ? 16 : 8));
     uint64_t need = bytes_in > bytes_out ? bytes_in : bytes_out;
     if (extent > need) need = extent;
     if (need > p->stage_bytes) {

@@ -9,7 +9,8 @@
 //   so the output of the last stage is in natural order with no bit reversal.
 // What is different from the reference: twiddles are correctly-rounded LUT entries (never __sincosf),
 // thread<->line mapping can differ between the load side and the store side (so the four-step transposed
-// write is coalesced), all shapes are template constants (AOT for sm_100a, nothing is JIT-compiled), and the
+// write is coalesced), all shapes are template constants (compiled ahead of time for sm_100a; lengths outside those lists get
+// the same templates instantiated when their plan is created, jit.cpp -- there is no code GENERATOR), and the
 // inverse transform is the forward code with re/im swapped at the HBM boundary.
 #pragma once
 #include <math.h>
@@ -94,8 +95,11 @@ B2_D cpx<T> twiddle2(const cpx<T>* hi, const cpx<T>* lo, uint32_t shift, uint64_
 // ------------------------------------------------------------------------------------------------
 // Kernel configuration (all compile-time)
 template <typename T_, class Sch_, int TPL_, int Q_, int V_, int LMAP_, int SMAP_, int LAYOUT_, bool INV_,
-          int OPS_, bool IN_UNIT_, bool OUT_UNIT_, int REGS_ = 128, int RMODE_ = 0>
+          int OPS_, bool IN_UNIT_, bool OUT_UNIT_, int REGS_ = 128, int RMODE_ = 0, int ST_ = 0>
 struct KCfg {
+    // storage in HBM: 0 = elements of T on both sides; bit 0 = the lines READ are half precision (32-bit complex elements),
+    // bit 1 = the lines WRITTEN are (cplx.cuh; plain complex transforms only).  Strides and offsets count elements either way
+    static constexpr int ST = ST_;
     using T = T_;
     using Sch = Sch_;
     static constexpr int N = Sch::N;
@@ -171,6 +175,17 @@ struct Engine {
     static constexpr int N = C::N, TPL = C::TPL, Q = C::Q, V = C::V, NS = Sch::ns;
     static constexpr bool RUNNING_IN = !C::IN_UNIT && ESI == 0;      // strides only known at run time
     static constexpr bool RUNNING_OUT = !C::OUT_UNIT && ESO == 0;
+    // element types in HBM (half-precision storage: one 32-bit word per complex element, converted in the load / store)
+    static constexpr bool HIN = (C::ST & 1) != 0, HOUT = (C::ST & 2) != 0;
+    static_assert(C::ST == 0 || (C::RMODE == 0 && V == 1 && sizeof(T) == 4 && XF == 0), "half storage: plain FP32 complex transforms");
+    template <bool H, class A, class B> struct Sel { using type = A; };
+    template <class A, class B> struct Sel<true, A, B> { using type = B; };
+    using XI = typename Sel<HIN, X, uint32_t>::type;
+    using XO = typename Sel<HOUT, X, uint32_t>::type;
+    B2_D static X ldx(const X* p) { return *p; }
+    B2_D static X ldx(const uint32_t* p) { float re, im; b2_h2_to_f2(*p, re, im); return mk<T>((T)re, (T)im); }
+    B2_D static void stx(X* p, X a) { *p = a; }
+    B2_D static void stx(uint32_t* p, X a) { *p = b2_f2_to_h2((float)a.x, (float)a.y); }
 
     B2_D static int sidx(int q, int p) {
         if constexpr (C::LAYOUT == LAY_LINE) return q * C::LS + p + (p >> C::PAD_SHIFT);
@@ -186,7 +201,7 @@ struct Engine {
 
     // ---- HBM load of first-stage legs --------------------------------------------------------------
     template <int s>
-    B2_D static void load_global(X* x, const X* __restrict__ line, int64_t es_rt, int t, bool valid) {
+    B2_D static void load_global(X* x, const XI* __restrict__ line, int64_t es_rt, int t, bool valid) {
         constexpr int r = Sch::r(s), NB = nbut<s>(), BPT = bpt<s>();
         // element stride: 1 (contiguous kinds), a compile-time constant (fused kernel) or the descriptor's value; the legs
         // of one butterfly are `step` apart, so one multiply per butterfly and additions from there (the per-leg 64-bit
@@ -197,15 +212,15 @@ struct Engine {
         for (int m = 0; m < BPT; ++m) {
             const int b0 = V * (t + m * TPL);
             const bool ok = valid && (!guarded<s>() || b0 < NB);
-            const X* src = line + (int64_t)b0 * es;
+            const XI* src = line + (int64_t)b0 * es;
 #pragma unroll
             for (int k = 0; k < r; ++k) {
                 // runtime stride: walk the legs with a running pointer the compiler may not re-associate into
                 // (b0 + k*NB) * es (it does otherwise: a 64-bit multiply + two LEA per leg); constant stride: immediates
-                const X* lp = src;
+                const XI* lp = src;
                 if constexpr (RUNNING_IN) { if (k + 1 < r) { int64_t st = step; B2_OPAQUE64(st); src += st; } }
                 else lp = src + k * step;
-                if constexpr (V == 2 && C::IN_UNIT) {
+                if constexpr (V == 2 && C::IN_UNIT && !HIN) {
                     using G = typename gvec<T, 2>::type;
                     G g = ok ? *reinterpret_cast<const G*>(lp) : G{};
                     X a = mk<T>(g.x, g.y), c = mk<T>(g.z, g.w);
@@ -216,8 +231,8 @@ struct Engine {
                     for (int v = 0; v < V; ++v) {
                         X a = mk<T>(T(0), T(0));
                         if (ok) {
-                            const X* q = lp + (int64_t)v * es;
-                            if constexpr ((XF & XF_LDCG) != 0) a = ld_cg(q); else a = *q;
+                            const XI* q = lp + (int64_t)v * es;
+                            if constexpr ((XF & XF_LDCG) != 0 && !HIN) a = ld_cg(q); else a = ldx(q);
                         }
                         x[(m * V + v) * r + k] = C::INV ? swp(a) : a;
                     }
@@ -652,7 +667,7 @@ struct Engine {
     // of these kernels.  Also measured on B200 and rejected (profiles/r1/README.md): a tile-factored scheme with
     // coalesced table reads and the reference-style full M-entry table.
     template <int s>
-    B2_D static void store_global(const X* x, X* __restrict__ line, int64_t es_rt, int t, bool valid,
+    B2_D static void store_global(const X* x, XO* __restrict__ line, int64_t es_rt, int t, bool valid,
                                   const b2_pass_params& P, uint32_t gline, uint32_t qline) {
         constexpr int r = Sch::r(s), NB = nbut<s>(), BPT = bpt<s>();
         static_assert(s == NS - 1, "global store only after the last stage");
@@ -673,11 +688,11 @@ struct Engine {
             const int b0 = V * (t + m * TPL);
             const bool ok = valid && (!guarded<s>() || b0 < NB);
             if (!ok) continue;                     // one branch per butterfly, not one per output
-            X* dst = line + (int64_t)b0 * es;
+            XO* dst = line + (int64_t)b0 * es;
             X w0[V], w2[V], w4[V], w6[V];
 #pragma unroll
             for (int k = 0; k < r; ++k) {
-                X* sp = dst;
+                XO* sp = dst;
                 if constexpr (RUNNING_OUT) { if (k + 1 < r) { int64_t st = step; B2_OPAQUE64(st); dst += st; } }
                 else sp = dst + k * step;
                 X o[V];
@@ -701,14 +716,14 @@ struct Engine {
                     if (do_scale) a = a * sc;
                     o[v] = C::INV ? swp(a) : a;
                 }
-                if constexpr (V == 2 && C::OUT_UNIT) {
+                if constexpr (V == 2 && C::OUT_UNIT && !HOUT) {
                     using G = typename gvec<T, 2>::type;
                     G g;
                     g.x = o[0].x; g.y = o[0].y; g.z = o[1].x; g.w = o[1].y;
                     *reinterpret_cast<G*>(sp) = g;
                 } else {
 #pragma unroll
-                    for (int v = 0; v < V; ++v) sp[(int64_t)v * es] = o[v];
+                    for (int v = 0; v < V; ++v) stx(sp + (int64_t)v * es, o[v]);
                 }
             }
         }
@@ -779,7 +794,7 @@ struct Engine {
         int ql, tl;
         tmap<C::LMAP>(tid, ql, tl);
         const uint32_t gl = grp * Q + ql;
-        const X* in_line = (const X*)P.in + obase_in + (int64_t)gl * P.in_gs;
+        const XI* in_line = (const XI*)P.in + obase_in + (int64_t)gl * P.in_gs;
 
         const X* __restrict__ rw = (const X*)P.aux0;   // e^{-2 pi i k/2n} for the fused real transforms
         const uint32_t psel = (P.tw_sel == 1 ? o0 : (P.tw_sel == 2 ? o1 : o2));   // n2 / k1 of the long strided DCT launches
@@ -988,7 +1003,7 @@ struct Engine {
             else if constexpr (C::RMODE == 7) load_global_blue<0>(x, in_line, P, tl, gl < P.G);
             else load_global<0>(x, in_line, P.in_es, tl, gl < P.G);
             compute<0>(x, lut, tl);
-            X* out_line = (X*)P.out + obase_out + (int64_t)gl * P.out_gs;
+            XO* out_line = (XO*)P.out + obase_out + (int64_t)gl * P.out_gs;
             if constexpr (C::RMODE == 1) store_global_r2c<0>(x, sm, out_line, rw, ql, tl, gl < P.G, P);
             else if constexpr (C::RMODE == 3 || C::RMODE == 4) store_global_dct<0>(x, sm, P, obase_out, gl, ql, tl, gl < P.G);
             else if constexpr (C::RMODE == 6) store_global_perm<0>(x, out_line, P.out_es / P.aux_u1, psel, P.aux_u1, P.aux_u0, tl, gl < P.G, P);
@@ -1017,7 +1032,7 @@ struct Engine {
                 X x[bpt<s>() * V * Sch::r(s)];
                 load_smem<s>(x, sm, qs, ts);
                 compute<s>(x, lut, ts);
-                X* out_line = (X*)P.out + obase_out + (int64_t)gs * P.out_gs;
+                XO* out_line = (XO*)P.out + obase_out + (int64_t)gs * P.out_gs;
                 if constexpr (C::RMODE == 1) {
                     __syncthreads();     // every last-stage read of the tile is done before it is overwritten
                     store_global_r2c<s>(x, sm, out_line, rw, qs, ts, gs < P.G, P);

@@ -108,7 +108,6 @@ class VkFFTConfiguration:
     kernel: Any = None
     kernelOffset: int = 0
     # reference features outside the engine's scope: accepted here so that setting them fails like the C shim
-    halfPrecision: int = 0
     performZeropadding: List[int] = field(default_factory=list)
     fft_zeropad_left: List[int] = field(default_factory=list)
     fft_zeropad_right: List[int] = field(default_factory=list)
@@ -206,7 +205,7 @@ def initializeVkFFT(app: VkFFTApplication, inputLaunchConfiguration: VkFFTConfig
         return VKFFT_ERROR_FFTdim_GT_MAX_FFT_DIMENSIONS
     if not cfg.size or cfg.size[0] == 0:
         return VKFFT_ERROR_EMPTY_size
-    if cfg.halfPrecision:
+    if cfg.halfPrecision and cfg.doublePrecision:
         return VKFFT_ERROR_UNSUPPORTED_FFT_LENGTH
     L = _lib.load()
     d = _to_desc(cfg)

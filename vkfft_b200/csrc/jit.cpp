@@ -143,6 +143,8 @@ bool choose(int kind, int prec, int n, int ops_all, Shape& s) {
         int regs = e * 2 > 40 ? 128 : (e * 2 > 24 ? 96 : 80);
         int q = n <= 256 ? 16 : 8;
         if (dbl) { regs = regs * 2 > 168 ? 168 : regs * 2; q /= 2; }
+        // half-precision storage: q neighbouring lines are q * 4 bytes in HBM -- twice the lines for the same 64...128-byte runs
+        if (half) q = n <= 128 ? 32 : (n <= 512 ? 16 : 8);
         s.tpl = tpl; s.q = q; s.regs = regs;
     }
     if (s.tpl * s.q > 1024) return false;

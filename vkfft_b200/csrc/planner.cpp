@@ -345,7 +345,7 @@ std::vector<uint64_t> split_four_step(const PlanGraph& g, uint64_t N, bool dist 
         }
         if (prod == N && f.size() >= 2 && f.size() <= 3) return f;
     }
-    const uint64_t cap = std::min<uint64_t>(max_single_env(), half_plan(g) ? 2048 : 4096);   // (plan-time kernels with transposed / strided access stop at 2048)
+    const uint64_t cap = std::min<uint64_t>(max_single_env(), half_plan(g) ? 512 : 4096);   // (half storage: factors up to 512 keep 16+ lines = 64-byte runs per tile of the strided / transposed side)
     auto fast = [&](int kind, uint64_t n, int ops) { return b2_find_kernel(kind, g.prec, (int)n, 0, ops) != nullptr; };
     // measured cost of one full pass over a 2 GiB FP32 buffer on B200, microseconds (profiles/r2/ktune_f32.log);
     // used to rank factorizations.  Unknown sizes / FP64 fall back to "balanced factors".

@@ -260,6 +260,9 @@ OTHER_LENGTHS = [
     (1000, "curated ahead-of-time kernel"), (2187, "curated ahead-of-time kernel (3^7)"), (1088, "curated, direct radix-17 butterfly"),
     (1100, "template instantiated at plan time"), (2002, "template instantiated at plan time"), (34, "template instantiated at plan time (17 x 2)"),
     (127, "Bluestein in one launch"), (509, "Bluestein in one launch"), (1019, "Bluestein in one launch"), (4093, "Bluestein, two launches"),
+    # halfPrecision = 1: the same number of points in half-precision storage (256 MiB per transform), FP32 arithmetic
+    (-4096, "half-precision storage, plan-time variant of the tuned 4096-point kernel"),
+    (-(1 << 20), "half-precision storage, Four-Step (factors up to 512, scratch in half as well)"),
 ]
 
 
@@ -269,13 +272,18 @@ def bench_other_lengths(torch, vk, peak, dev, warm=2, reps=5):
     import vkfft_oracle as orc
     rows = []
     for n, what in OTHER_LENGTHS:
+        half = n < 0
+        n = abs(n)
         batch = max(1, (1 << 26) // n)
-        buf = torch.zeros(batch * n, dtype=torch.complex64, device=dev)
-        torch.view_as_real(buf).uniform_(-1, 1)
+        if half:
+            buf = torch.zeros(batch * n, dtype=torch.int32, device=dev)       # (half re, half im) per element, all zero
+        else:
+            buf = torch.zeros(batch * n, dtype=torch.complex64, device=dev)
+            torch.view_as_real(buf).uniform_(-1, 1)
         row = {"n": n, "batch": batch, "served_by": what}
         app = vk.VkFFTApplication()
         t0 = time.time()
-        rc = vk.initializeVkFFT(app, vk.VkFFTConfiguration(FFTdim=1, size=[n], numberBatches=batch, device=dev.index, normalize=1))
+        rc = vk.initializeVkFFT(app, vk.VkFFTConfiguration(FFTdim=1, size=[n], numberBatches=batch, device=dev.index, normalize=1, halfPrecision=int(half)))
         row["plan_seconds"] = round(time.time() - t0, 2)
         if rc != 0:
             row["error"] = vk.getVkFFTErrorString(rc)
@@ -290,10 +298,10 @@ def bench_other_lengths(torch, vk, peak, dev, warm=2, reps=5):
                 vk.VkFFTAppend(app, -1, lp); vk.VkFFTAppend(app, 1, lp)
             b.record(); torch.cuda.synchronize()
             ms = a.elapsed_time(b) / reps
-            alg = 4 * buf.numel() * 8                 # one read + one write of the lines per direction
+            alg = 4 * buf.numel() * (4 if half else 8)      # one read + one write of the lines per direction
             row.update(ms_pair=round(ms, 4), launches_forward=len(launch_labels(info["forward"])), frac_of_peak=round(alg / (ms * 1e-3) / 1e9 / peak, 4))
             vk.deleteVkFFT(app)
-        if orc.ref_available():
+        if orc.ref_available() and not half:
             L = orc.ref_lib()
             d = orc.ref_desc((n,), batch, False, device=dev.index)
             h = ctypes.c_void_p()

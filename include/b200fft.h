@@ -31,7 +31,9 @@ extern "C" {
 
 /* B200FFT_F16: half-precision STORAGE -- every buffer holds 32-bit complex elements (half re, half im), arithmetic and tables are
    FP32 (the reference's halfPrecision, vkFFT_Structs.h:210; plain C2C transforms, kernels instantiated at plan time) */
-typedef enum b200fft_precision { B200FFT_F32 = 0, B200FFT_F64 = 1, B200FFT_F16 = 2 } b200fft_precision;
+/* B200FFT_F16_IO: halfPrecisionMemoryOnly -- only the caller's inputBuffer (is_input_formatted = 1) is half: the forward transform
+   reads it, the inverse transform (inverse_return_to_input = 1) writes it; buffer / tempBuffer / outputBuffer are FP32 */
+typedef enum b200fft_precision { B200FFT_F32 = 0, B200FFT_F64 = 1, B200FFT_F16 = 2, B200FFT_F16_IO = 3 } b200fft_precision;
 
 /* Plan description: the subset of VkFFTConfiguration (vkFFT_Structs.h:93-324) the hot path consumes.
  * Zero means "default" for every field, exactly like the reference's zero-initialised configuration. */

@@ -81,7 +81,8 @@ typedef struct {
     pfUINT doublePrecision;
     pfUINT quadDoubleDoublePrecision, quadDoubleDoublePrecisionDoubleMemory;   /* unsupported */
     pfUINT halfPrecision;                                       /* half storage, FP32 arithmetic: plain C2C transforms */
-    pfUINT halfPrecisionMemoryOnly, doublePrecisionFloatMemory; /* unsupported */
+    pfUINT halfPrecisionMemoryOnly;                             /* half inputBuffer (isInputFormatted), FP32 everywhere else */
+    pfUINT doublePrecisionFloatMemory;                          /* unsupported */
 
     pfUINT performR2C, performDCT, performDST;
     pfUINT disableMergeSequencesR2C, forceCallbackVersionRealTransforms;
@@ -263,8 +264,8 @@ static inline VkFFTResult initializeVkFFT(VkFFTApplication* app, VkFFTConfigurat
     if (c->FFTdim > VKFFT_MAX_FFT_DIMENSIONS) return VKFFT_ERROR_FFTdim_GT_MAX_FFT_DIMENSIONS;
     if (c->size[0] == 0) return VKFFT_ERROR_EMPTY_size;
     /* features of the reference outside this engine's hot path */
-    if (c->halfPrecisionMemoryOnly || c->quadDoubleDoublePrecision ||
-        c->quadDoubleDoublePrecisionDoubleMemory || c->doublePrecisionFloatMemory || (c->halfPrecision && c->doublePrecision))
+    if (c->quadDoubleDoublePrecision || c->quadDoubleDoublePrecisionDoubleMemory || c->doublePrecisionFloatMemory ||
+        ((c->halfPrecision || c->halfPrecisionMemoryOnly) && c->doublePrecision))
         return VKFFT_ERROR_UNSUPPORTED_FFT_LENGTH;
     if (c->bufferNum > 1 || c->tempBufferNum > 1 || c->inputBufferNum > 1 || c->outputBufferNum > 1)
         return VKFFT_ERROR_UNSUPPORTED_FFT_LENGTH;
@@ -289,7 +290,8 @@ static inline VkFFTResult initializeVkFFT(VkFFTApplication* app, VkFFTConfigurat
     d.number_batches = c->numberBatches;
     d.coordinate_features = c->coordinateFeatures;
     /* halfPrecision (vkFFT_Structs.h:210): every buffer holds half-precision complex elements, arithmetic in FP32 -- B200FFT_F16 */
-    d.precision = c->doublePrecision ? B200FFT_F64 : (c->halfPrecision ? B200FFT_F16 : B200FFT_F32);
+    /* halfPrecisionMemoryOnly (:211): half only in the caller's formatted inputBuffer (forward reads it, the inverse returns to it) */
+    d.precision = c->doublePrecision ? B200FFT_F64 : (c->halfPrecisionMemoryOnly ? B200FFT_F16_IO : (c->halfPrecision ? B200FFT_F16 : B200FFT_F32));
     d.perform_r2c = (uint32_t)c->performR2C;
     d.perform_dct = (uint32_t)c->performDCT;
     d.perform_dst = (uint32_t)c->performDST;

@@ -31,7 +31,8 @@ def _need_nvrtc(L):
 
 @pytest.mark.parametrize("kind,prec,n,ops", [(KIND_ROWS, 0, 1100, 0), (KIND_ROWS, 0, 1430, OP_REAL_EVEN), (KIND_COLS, 0, 770, OP_TW),
                                              (KIND_COLS, 1, 154, 0), (KIND_TOUT, 0, 1100, 0), (KIND_ROWS, 1, 2002, 0),
-                                             (KIND_ROWS, 0, 2 * 3 * 17, 0), (KIND_ROWS, 0, 4004, 0)])
+                                             (KIND_ROWS, 0, 2 * 3 * 17, 0), (KIND_ROWS, 0, 4004, 0),
+                                             (KIND_ROWS, 0, 1100, 32), (KIND_COLS, 1, 286, 32)])      # 32 = B2_OP_DCT23
 def test_templates_compile_at_plan_time_without_a_gpu(kind, prec, n, ops):
     """the generated translation unit static_asserts the host-side copies of KCfg::SMEM_BYTES and RList::lut_size"""
     L = _lib()
@@ -156,3 +157,34 @@ def test_switch_keeps_the_runtime_scheduled_kernel(gpu, monkeypatch):
         assert orc.error_metrics(t.cpu().numpy(), orc.c2c(x, 1))["l2_rel"] < 1e-6
     finally:
         vk.deleteVkFFT(app)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,batch,double", [((1100,), 6, False), ((770, 154), 2, False), ((286, 22), 3, True), ((2310,), 2, False)])
+@pytest.mark.parametrize("kind", [2, 3])
+def test_dct_2_and_3_lengths_without_ahead_of_time_kernels(gpu, shape, batch, double, kind):
+    """DCT-II / DCT-III fused into the plan-time kernels (two real lines per complex line; strided axes: pairs of columns)"""
+    import torch
+    import vkfft_b200 as vk
+    L = _lib()
+    _need_nvrtc(L)
+    rdt = np.float64 if double else np.float32
+    x = np.random.default_rng(sum(shape) + kind).uniform(-1, 1, (batch,) + tuple(reversed(shape))).astype(rdt)
+    t = torch.from_numpy(x.copy()).cuda()
+    app = vk.VkFFTApplication()
+    rc = vk.initializeVkFFT(app, vk.VkFFTConfiguration(FFTdim=len(shape), size=list(shape), numberBatches=batch, device=0,
+                                                       doublePrecision=int(double), performDCT=kind))
+    assert rc == 0, vk.getVkFFTErrorString(rc)
+    try:
+        assert "JIT_" in _describe(vk, app)
+        assert vk.VkFFTAppend(app, -1, vk.VkFFTLaunchParams(buffer=t)) == 0
+        torch.cuda.synchronize()
+        got = t.cpu().numpy()
+    finally:
+        vk.deleteVkFFT(app)
+    ref = orc.dct(x, kind, len(shape))
+    if double:
+        assert orc.error_metrics(got, ref)["l2_rel"] < 1e-12
+    else:      # 1e-6, or -- where the transform's conditioning puts both engines beyond it -- at least as close as the reference
+        from gpu_util import assert_f32_parity, ref_inplace
+        assert_f32_parity(got, ref, lambda: ref_inplace(x, shape, batch, -1, perform_dct=kind))

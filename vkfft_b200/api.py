@@ -71,6 +71,7 @@ class VkFFTConfiguration:
     coordinateFeatures: int = 0
     doublePrecision: int = 0
     halfPrecision: int = 0            # half-precision storage (complex32 buffers), FP32 arithmetic; plain C2C transforms
+    halfPrecisionMemoryOnly: int = 0  # only inputBuffer (isInputFormatted = 1) is half; buffer / tempBuffer / outputBuffer FP32
     performR2C: int = 0
     performDCT: int = 0
     performDST: int = 0
@@ -156,7 +157,7 @@ def _to_desc(cfg: VkFFTConfiguration) -> "_lib.b200fft_desc":
             dst[i] = int(s)
     d.number_batches = cfg.numberBatches
     d.coordinate_features = cfg.coordinateFeatures
-    d.precision = 1 if cfg.doublePrecision else (2 if cfg.halfPrecision else 0)
+    d.precision = 1 if cfg.doublePrecision else (3 if cfg.halfPrecisionMemoryOnly else (2 if cfg.halfPrecision else 0))
     d.perform_r2c = cfg.performR2C
     d.perform_dct = cfg.performDCT
     d.perform_dst = cfg.performDST
@@ -205,7 +206,7 @@ def initializeVkFFT(app: VkFFTApplication, inputLaunchConfiguration: VkFFTConfig
         return VKFFT_ERROR_FFTdim_GT_MAX_FFT_DIMENSIONS
     if not cfg.size or cfg.size[0] == 0:
         return VKFFT_ERROR_EMPTY_size
-    if cfg.halfPrecision and cfg.doublePrecision:
+    if (cfg.halfPrecision or cfg.halfPrecisionMemoryOnly) and cfg.doublePrecision:
         return VKFFT_ERROR_UNSUPPORTED_FFT_LENGTH
     L = _lib.load()
     d = _to_desc(cfg)

@@ -110,6 +110,18 @@ struct Shape {
     int tpl = 0, q = 0, regs = 0, smem = 0, lut = 0, rmode_f = 0, rmode_i = 0, st = 0;
 };
 
+// the tuned ahead-of-time kernel of the same transform (half-storage variants copy its schedule and CTA shape)
+const b2_kernel_info* tuned_base(int kind, int prec, int n, int ops) {
+    const b2_kernel_info* best = nullptr;
+    for (int i = 0; i < b2_kernel_count(); ++i) {
+        const b2_kernel_info* k = b2_kernel_at(i);
+        if (k->kind != kind || k->prec != prec || k->n != n || k->inv != 0 || k->ops != ops) continue;
+        if (k->pipelined || k->v != 1 || k->regs <= 0 || k->jit || !k->name || !strncmp(k->name, "STAGED", 6)) continue;
+        if (!best || k->variant < best->variant) best = k;
+    }
+    return best;
+}
+
 bool choose(int kind, int prec, int n, int ops_all, Shape& s) {
     const bool dbl = prec == B2_PREC_F64;
     // half-precision storage (B2_OP_HALF_IN / _OUT -> KCfg::ST): FP32 plain complex transforms only; no ahead-of-time kernel
@@ -117,9 +129,12 @@ bool choose(int kind, int prec, int n, int ops_all, Shape& s) {
     const int half = ops_all & (B2_OP_HALF_IN | B2_OP_HALF_OUT), ops = ops_all & ~half;
     if (half && (dbl || (ops & ~B2_OP_TWIDDLE_OUT))) return false;
     s.st = ((half & B2_OP_HALF_IN) ? 1 : 0) | ((half & B2_OP_HALF_OUT) ? 2 : 0);
-    if (n < (half ? 2 : 18) || n > 4096) return false;
-    if (kind == B2_KIND_ROWS) { if (ops != 0 && ops != B2_OP_REAL_EVEN) return false; }
-    else if (kind == B2_KIND_COLS) { if (ops != 0 && ops != B2_OP_TWIDDLE_OUT) return false; if (n > (dbl ? 1024 : 2048)) return false; }
+    const b2_kernel_info* base = half ? tuned_base(kind, prec, n, ops) : nullptr;
+    if (n < (half ? 2 : 18) || n > ((base && kind == B2_KIND_ROWS) ? 8192 : 4096)) return false;
+    // B2_OP_DCT23: DCT-II (forward kernel) / DCT-III (inverse kernel) fused into the load and store, two real lines (or two
+    // neighbouring real columns) per complex line -- the B2_KD variants of the curated lists, same shapes
+    if (kind == B2_KIND_ROWS) { if (ops != 0 && ops != B2_OP_REAL_EVEN && ops != B2_OP_DCT23) return false; }
+    else if (kind == B2_KIND_COLS) { if (ops != 0 && ops != B2_OP_TWIDDLE_OUT && ops != B2_OP_DCT23) return false; if (n > (dbl ? 1024 : 2048)) return false; }
     else if (kind == B2_KIND_ROWS_TOUT) { if (ops != 0) return false; if (n > (dbl ? 1024 : 2048)) return false; }
     else return false;
     s.r = factor(n, kind == B2_KIND_ROWS && !dbl);
@@ -147,9 +162,17 @@ bool choose(int kind, int prec, int n, int ops_all, Shape& s) {
         if (half) q = n <= 128 ? 32 : (n <= 512 ? 16 : 8);
         s.tpl = tpl; s.q = q; s.regs = regs;
     }
+    if (base) {
+        // powers of two and curated lengths: the measured-best schedule and CTA shape of the FP32-storage kernel; along strided /
+        // transposed sides at least the tile width of the half rule above (64...128-byte runs) where the tile still fits
+        const int qh = s.q;
+        s.r.assign(base->radices, base->radices + base->ns);
+        s.tpl = base->tpl; s.q = base->q; s.regs = base->regs;
+        if (kind != B2_KIND_ROWS && qh > s.q && s.tpl * qh <= 512 && n * qh * esz <= 96 * 1024) s.q = qh;
+    }
     if (s.tpl * s.q > 1024) return false;
-    s.rmode_f = (ops & B2_OP_REAL_EVEN) ? 1 : 0;
-    s.rmode_i = (ops & B2_OP_REAL_EVEN) ? 2 : 0;
+    s.rmode_f = (ops & B2_OP_REAL_EVEN) ? 1 : ((ops & B2_OP_DCT23) ? 3 : 0);
+    s.rmode_i = (ops & B2_OP_REAL_EVEN) ? 2 : ((ops & B2_OP_DCT23) ? 4 : 0);
     // KCfg::SMEM_BYTES and RList::lut_size (stockham.cuh); the generated source static_asserts both
     const int pad_shift = dbl ? 3 : 4, npad = n + (n >> pad_shift);
     const bool line = kind != B2_KIND_COLS;

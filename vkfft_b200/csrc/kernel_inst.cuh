@@ -158,6 +158,7 @@ struct Registrar {
         info.ns = Sch::ns;
         for (int s = 0; s < Sch::ns; ++s) info.radices[s] = Sch::r(s);
         info.lut_size = Sch::lut_size;
+        info.regs = MINB;                  // (the template parameter is the register budget; KCfg turns it into min blocks per SM)
         info.launch = &launch_impl<C>;
         info.prepare = &prepare_impl<C>;
         info.name = name;

@@ -33,6 +33,7 @@ typedef struct b2_kernel_info {
     int (*launch)(const b2_pass_params* P, unsigned grid, void* stream);
     int (*prepare)(void);              // one-time cudaFuncSetAttribute (max dynamic smem)
     const char* name;
+    int regs;                          // register budget per thread the kernel was compiled with (0 = not recorded)
     void* jit;                         // != 0: instantiated at plan time (jit.cpp); launch / prepare are null, use b2_jit_prepare / b2_jit_launch
 } b2_kernel_info;
 

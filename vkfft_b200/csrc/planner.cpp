@@ -114,7 +114,7 @@ std::vector<int> generic_radices(uint64_t n) {
 
 uint64_t esize(const PlanGraph& g) { return g.prec == B2_PREC_F64 ? 16 : 8; }      // element size of the ARITHMETIC (tiles in shared memory)
 uint64_t role_esize(const PlanGraph& g, int role) { return g.role_half[role] ? 4 : esize(g); }   // element size in HBM
-bool half_plan(const PlanGraph& g) { return g.role_half[ROLE_BUFFER]; }
+bool half_plan(const PlanGraph& g) { return g.role_half[ROLE_BUFFER] || g.role_half[ROLE_INPUT]; }   // some launch converts: plan-time kernels only
 int pad_of(const PlanGraph& g, uint64_t n) { return (int)(n + (n >> (g.prec == B2_PREC_F64 ? 3 : 4))); }
 const uint64_t GENERIC_SMEM_LIMIT = 200 * 1024;
 
@@ -773,7 +773,7 @@ int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
         const b2_kernel_info* kk = b2_find_kernel(kind, g.prec, (int)std::min<uint64_t>(N, 0x7fffffff), 0, 0);
         if (kk && kk->q < 8 && N >= 2048) poor_strided = true;
     }
-    bool try_single = !dist && N <= max_single_env() && single_ok(g, kind, N, 0) && (!half_plan(g) || N <= (job.unit_lines ? 2048u : 4096u));
+    bool try_single = !dist && N <= max_single_env() && single_ok(g, kind, N, 0) && (!half_plan(g) || N <= (job.unit_lines ? 2048u : 8192u));
     if (job.extra_ops & B2_OP_CONV) {
         if (!b2_find_kernel(kind, g.prec, (int)std::min<uint64_t>(N, 0x7fffffff), 0, B2_OP_CONV)) return R_UNSUPPORTED_FFT_LENGTH;
         try_single = true; poor_strided = false;
@@ -1520,10 +1520,14 @@ static int build_plan_impl(const b200fft_desc& din, PlanGraph& g) {
         if (d.size[a] == 0 || a >= d.fft_dim) d.size[a] = 1;
     if (d.number_batches == 0) d.number_batches = 1;
     if (d.coordinate_features == 0) d.coordinate_features = 1;
-    if (d.precision > B200FFT_F16) return R_UNSUPPORTED_FFT_LENGTH;
+    if (d.precision > B200FFT_F16_IO) return R_UNSUPPORTED_FFT_LENGTH;
+    // B200FFT_F16_IO (the reference's halfPrecisionMemoryOnly, vkFFT_InitAPIParameters.h:153-172: half only where the forward
+    // transform first reads and where the inverse transform last writes): the caller's inputBuffer is half, buffer / tempBuffer /
+    // outputBuffer are FP32 -- forward inputBuffer -> buffer, inverse (inverseReturnToInputBuffer) buffer -> inputBuffer
+    if (d.precision == B200FFT_F16_IO && !d.is_input_formatted) return R_UNSUPPORTED_FFT_LENGTH;
     // half-precision storage: plain complex transforms (the conversion is fused into the first-stage load / last-stage store of the
     // specialised kernels); the real-data operators, convolution and zero padding have no half variant
-    if (d.precision == B200FFT_F16 && (d.perform_r2c || d.perform_dct || d.perform_dst || d.perform_convolution || d.dist_world > 1))
+    if ((d.precision == B200FFT_F16 || d.precision == B200FFT_F16_IO) && (d.perform_r2c || d.perform_dct || d.perform_dst || d.perform_convolution || d.dist_world > 1))
         return R_UNSUPPORTED_FFT_LENGTH;
     if (d.perform_dct > 4 || d.perform_dst > 4) return R_UNSUPPORTED_FFT_LENGTH_R2R;
     if ((d.perform_r2c && (d.perform_dct || d.perform_dst)) || (d.perform_dct && d.perform_dst)) return R_UNSUPPORTED_FFT_LENGTH_R2R;
@@ -1562,7 +1566,8 @@ static int build_plan_impl(const b200fft_desc& din, PlanGraph& g) {
     }
     g.desc = d;
     g.distributed = d.dist_world > 1;
-    g.prec = d.precision == B200FFT_F16 ? B2_PREC_F32 : (int)d.precision;
+    g.prec = (d.precision == B200FFT_F16 || d.precision == B200FFT_F16_IO) ? B2_PREC_F32 : (int)d.precision;
+    if (d.precision == B200FFT_F16_IO) g.role_half[ROLE_INPUT] = true;
     if (d.precision == B200FFT_F16)
         for (int r : {ROLE_BUFFER, ROLE_TEMP, ROLE_INPUT, ROLE_OUTPUT}) g.role_half[r] = true;
     for (int a = 0; a < B200FFT_MAX_DIMS; ++a) g.stride[a] = d.buffer_stride[a];

@@ -170,7 +170,23 @@ bool choose(int kind, int prec, int n, int ops_all, Shape& s) {
         s.tpl = base->tpl; s.q = base->q; s.regs = base->regs;
         if (kind != B2_KIND_ROWS && qh > s.q && s.tpl * qh <= 512 && n * qh * esz <= 96 * 1024) s.q = qh;
     }
-    if (s.tpl * s.q > 1024) return false;
+    // tuning experiments (tools/jit_shape_sweep.py): B200FFT_JIT_SHAPE="tpl,q,regs[,r0,r1,...]" overrides the rule for contiguous lines
+    if (const char* ov = getenv("B200FFT_JIT_SHAPE")) {
+        if (kind == B2_KIND_ROWS && !half) {
+            std::vector<int> v;
+            for (const char* p = ov; *p;) { char* e; long x = strtol(p, &e, 10); if (e == p) break; v.push_back((int)x); p = (*e == ',') ? e + 1 : e; }
+            if (v.size() >= 3) {
+                s.tpl = v[0]; s.q = v[1]; s.regs = v[2];
+                if (v.size() > 3) {
+                    long prod = 1;
+                    for (size_t i = 3; i < v.size(); ++i) prod *= v[i];
+                    if (prod != n || v.size() - 3 > 8) return false;
+                    s.r.assign(v.begin() + 3, v.end());
+                }
+            }
+        }
+    }
+    if (s.tpl < 1 || s.q < 1 || s.tpl * s.q > 1024) return false;
     s.rmode_f = (ops & B2_OP_REAL_EVEN) ? 1 : ((ops & B2_OP_DCT23) ? 3 : 0);
     s.rmode_i = (ops & B2_OP_REAL_EVEN) ? 2 : ((ops & B2_OP_DCT23) ? 4 : 0);
     // KCfg::SMEM_BYTES and RList::lut_size (stockham.cuh); the generated source static_asserts both
@@ -262,13 +278,19 @@ const b2_kernel_info* provide(int kind, int prec, int n, int inv, int ops) {
     if (getenv("B200FFT_NO_JIT")) return nullptr;
     if (!api().have_nvrtc) return nullptr;
     std::lock_guard<std::mutex> lk(g_mu);
+    // (with a shape override in the environment nothing is cached: every plan gets the shape of the moment, forward and
+    // inverse of one plan still share a program through the override string in the key)
+    const char* ov = getenv("B200FFT_JIT_SHAPE");
+    static std::map<std::string, std::pair<std::map<std::tuple<int, int, int, int, int>, Entry*>, std::map<PKey, Program*>>> per_override;
+    auto& entries = ov ? per_override[ov].first : g_entries;
+    auto& programs = ov ? per_override[ov].second : g_programs;
     auto ek = std::make_tuple(kind, prec, n, inv, ops);
-    auto it = g_entries.find(ek);
-    if (it != g_entries.end()) return it->second ? &it->second->info : nullptr;
+    auto it = entries.find(ek);
+    if (it != entries.end()) return it->second ? &it->second->info : nullptr;
     Shape s;
-    if (!choose(kind, prec, n, ops, s)) { g_entries[ek] = nullptr; return nullptr; }
+    if (!choose(kind, prec, n, ops, s)) { entries[ek] = nullptr; return nullptr; }
     PKey pk = std::make_tuple(kind, prec, n, ops);
-    Program*& prog = g_programs[pk];
+    Program*& prog = programs[pk];
     if (!prog) { prog = new Program; prog->source = make_source(kind, prec, ops, s); }
     Entry* e = new Entry;
     e->shape = s; e->prog = prog;
@@ -287,7 +309,7 @@ const b2_kernel_info* provide(int kind, int prec, int n, int inv, int ops) {
     k.lut_size = s.lut;
     k.name = e->name.c_str();
     k.jit = e;
-    g_entries[ek] = e;
+    entries[ek] = e;
     return &k;
 }
 

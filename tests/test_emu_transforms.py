@@ -34,6 +34,25 @@ def test_bluestein_c2c(shape, b, prec, inv):
     assert orc.error_metrics(buf, orc.c2c(x, len(shape), inv == 1))["l2_rel"] < (T32 if prec == 0 else T64)
 
 
+@pytest.mark.parametrize("shape,b,prec", [((77,), 5, 0), ((1430,), 2, 0), ((2 * 3 * 5 * 7 * 11,), 1, 1), ((66, 26), 2, 0), ((13,), 9, 0)])
+@pytest.mark.parametrize("inv", [-1, 1])
+def test_runtime_scheduled_kernel_first_and_last_stage_from_registers(shape, b, prec, inv, monkeypatch):
+    """generic.cuh::stage_io (opt-in, B200FFT_GENERIC_FUSED_IO=1: measured slower than the separate copy phases on B200, kept
+    for the record): the first butterflies read the lines from global memory, the last ones write them, operators in registers"""
+    monkeypatch.setenv("B200FFT_GENERIC_FUSED_IO", "1")
+    dt = np.complex64 if prec == 0 else np.complex128
+    x = orc.random_input((b,) + tuple(reversed(shape)), dt, seed=sum(shape) + 17)
+    buf = x.copy()
+    d = emu.make_desc(shape, b, prec)
+    d.normalize = 1
+    rc, npass = emu.exec_plan(d, inv, buf)
+    assert rc == 0
+    ref = orc.c2c(x, len(shape), inv == 1)
+    if inv == 1:
+        ref = ref / np.prod(shape)
+    assert orc.error_metrics(buf, ref)["l2_rel"] < (T32 if prec == 0 else T64)
+
+
 def _one_launch_lengths():
     """every padded length of kernel_list_blue1.def, reached from the largest N it serves and from the smallest one"""
     ms = {0: sorted(k["n"] for k in emu.kernels() if k["ops"] == 1024 and k["prec"] == 0),

@@ -278,8 +278,8 @@ const b2_kernel_info* provide(int kind, int prec, int n, int inv, int ops) {
     if (getenv("B200FFT_NO_JIT")) return nullptr;
     if (!api().have_nvrtc) return nullptr;
     std::lock_guard<std::mutex> lk(g_mu);
-    // (with a shape override in the environment nothing is cached: every plan gets the shape of the moment, forward and
-    // inverse of one plan still share a program through the override string in the key)
+    // (tuning experiments: descriptions and programs are kept per value of B200FFT_JIT_SHAPE, so a sweep over shapes in one process
+    // gets a fresh kernel per shape while the forward and inverse kernel of one plan still share a program)
     const char* ov = getenv("B200FFT_JIT_SHAPE");
     static std::map<std::string, std::pair<std::map<std::tuple<int, int, int, int, int>, Entry*>, std::map<PKey, Program*>>> per_override;
     auto& entries = ov ? per_override[ov].first : g_entries;

@@ -257,8 +257,8 @@ int compile(Program& p, const char* arch) {
         return -1;
     }
     const std::string archopt = std::string("--gpu-architecture=") + arch;
-    const char* opts[] = {archopt.c_str(), "-std=c++17", "-w"};
-    const nvrtcResult rc = a.CompileProgram(prog, 3, opts);
+    const char* opts[] = {archopt.c_str(), "-std=c++17", "-w", "-lineinfo"};      // -lineinfo: ncu's source page maps to the templates
+    const nvrtcResult rc = a.CompileProgram(prog, 4, opts);
     size_t ln = 0;
     if (a.GetProgramLogSize && a.GetProgramLog && a.GetProgramLogSize(prog, &ln) == 0 && ln > 1) {
         p.log.resize(ln);

@@ -46,7 +46,8 @@ def test_templates_compile_at_plan_time_without_a_gpu(kind, prec, n, ops):
                                              (KIND_ROWS, 1, 34, 0),          # prime butterflies above 13 are FP32 only
                                              (KIND_COLS, 0, 4004, 0),        # strided tiles stop at 2048 points
                                              (KIND_ROWS, 0, 1100, 256),      # Bluestein launches are ahead-of-time only
-                                             (KIND_ROWS, 0, 8190, 0)])       # beyond one shared-memory pass
+                                             (KIND_ROWS, 0, 8200, 0),        # beyond one launch (8192 points)
+                                             (KIND_ROWS, 1, 5000, 0)])       # FP64 stops at 4096
 def test_keys_that_are_not_instantiated(kind, prec, n, ops):
     L = _lib()
     _need_nvrtc(L)
@@ -80,7 +81,8 @@ def _describe(vk, app):
                                                 ((2002,), 5, False), ((3003,), 3, False), ((4004,), 3, False), ((34,), 501, False),
                                                 ((51,), 100, False), ((2 * 3 * 19 * 4,), 7, False), ((770,), 13, True), ((2002,), 3, True),
                                                 ((1100, 154), 2, False), ((154, 66, 22), 2, False), ((286, 182), 2, True),
-                                                ((1100 * 1430,), 1, False), ((2002 * 66,), 2, False)])
+                                                ((1100 * 1430,), 1, False), ((2002 * 66,), 2, False),
+                                                ((5000,), 3, False), ((6000,), 2, False), ((8190,), 2, False)])      # 4097...8192 points: one launch
 @pytest.mark.parametrize("inverse", [-1, 1])
 def test_c2c_lengths_without_ahead_of_time_kernels(gpu, shape, batch, double, inverse):
     """contiguous lines (ROWS), strided axes (COLS), Four-Step with such factors (COLS + phase, ROWS with transposed store)"""
@@ -107,7 +109,7 @@ def test_c2c_lengths_without_ahead_of_time_kernels(gpu, shape, batch, double, in
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape,batch,double", [((1100,), 5, False), ((2002, 6), 2, False), ((154, 22), 3, True), ((1430,), 4, True)])
+@pytest.mark.parametrize("shape,batch,double", [((1100,), 5, False), ((2002, 6), 2, False), ((154, 22), 3, True), ((1430,), 4, True), ((14000,), 2, False)])
 def test_r2c_c2r_lengths_without_ahead_of_time_kernels(gpu, shape, batch, double):
     """even-length real transforms: the Hermitian pass is fused into the plan-time kernel like into the ahead-of-time ones"""
     import torch

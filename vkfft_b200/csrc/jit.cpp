@@ -130,7 +130,8 @@ bool choose(int kind, int prec, int n, int ops_all, Shape& s) {
     if (half && (dbl || (ops & ~B2_OP_TWIDDLE_OUT))) return false;
     s.st = ((half & B2_OP_HALF_IN) ? 1 : 0) | ((half & B2_OP_HALF_OUT) ? 2 : 0);
     const b2_kernel_info* base = half ? tuned_base(kind, prec, n, ops) : nullptr;
-    if (n < (half ? 2 : 18) || n > ((base && kind == B2_KIND_ROWS) ? 8192 : 4096)) return false;
+    // contiguous FP32 lines up to 8192 points in one launch (64 KiB tile, up to 32 points per thread), everything else up to 4096
+    if (n < (half ? 2 : 18) || n > ((kind == B2_KIND_ROWS && !dbl && (base || !half)) ? 8192 : 4096)) return false;
     // B2_OP_DCT23: DCT-II (forward kernel) / DCT-III (inverse kernel) fused into the load and store, two real lines (or two
     // neighbouring real columns) per complex line -- the B2_KD variants of the curated lists, same shapes
     if (kind == B2_KIND_ROWS) { if (ops != 0 && ops != B2_OP_REAL_EVEN && ops != B2_OP_DCT23) return false; }

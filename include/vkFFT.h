@@ -9,8 +9,9 @@
  *     VkFFTAppend(&app, -1, &launchParams); // reference: vkFFT_RunApp.h:79   (-1 forward, +1 inverse)
  *     deleteVkFFT(&app);                   // reference: vkFFT_DeleteApp.h:28
  *
- * What changes underneath: nothing is generated or JIT-compiled; the three calls forward to the C ABI in
- * b200fft.h (plain pointers and sizes), which launches ahead-of-time compiled sm_100a kernels.
+ * What changes underneath: no kernel text is generated; the three calls forward to the C ABI in b200fft.h (plain
+ * pointers and sizes), which launches hand-written sm_100a kernels -- compiled ahead of time for the powers of two and the
+ * curated lengths, instantiated from the same templates at plan time for other smooth lengths (csrc/jit.cpp).
  * VkFFTConfiguration / VkFFTLaunchParams keep the reference's member names, order and types for
  * VKFFT_BACKEND==1 (vkFFT_Structs.h:93-379) so that sizeof/offsetof agree with the reference build
  * (1168 and 80 bytes on x86-64; checked in tests/test_abi.py).  Members that configure the reference's
@@ -360,7 +361,7 @@ static inline VkFFTResult initializeVkFFT(VkFFTApplication* app, VkFFTConfigurat
         }
         if (dir) app->localFFTPlan_inverse = pl; else app->localFFTPlan = pl;
     }
-    if (c->saveApplicationToString) {   /* nothing is compiled at plan time, so the "binary" is a tag */
+    if (c->saveApplicationToString) {   /* the plan holds no generated binary worth saving, so the "binary" is a tag */
         static const char tag[] = "b200fft:aot:sm_100a";
         app->saveApplicationString = malloc(sizeof tag);
         if (!app->saveApplicationString) { deleteVkFFT(app); return VKFFT_ERROR_MALLOC_FAILED; }

@@ -310,6 +310,9 @@ int emit(PlanGraph& g, std::vector<PassPlan>& list, const PassReq& rq) {
 bool single_ok(const PlanGraph& g, int kind, uint64_t n, int ops) {
     if (n > 0x7fffffffull) return false;
     if (n == 1) return false;
+    // half-precision storage: only the specialised kernels convert, and only as plan-time variants (jit.cpp) -- their limits
+    // differ from the FP32 kernels' (e.g. a non-curated 5000-point line is one FP32 launch but has no half variant: Four-Step)
+    if (half_plan(g)) return b2_find_kernel(kind, g.prec, (int)n, 0, ops | B2_OP_HALF_IN | B2_OP_HALF_OUT) != nullptr;
     if (b2_find_kernel(kind, g.prec, (int)n, 0, ops)) return true;
     return generic_fits(g, n);
 }
@@ -524,6 +527,16 @@ uint64_t blue1_length(const PlanGraph& g, uint64_t N) {
         if (n >= 2 * N - 1 && (M1 == 0 || n < M1)) M1 = n;
     }
     return M1;
+}
+
+// is there a pair of specialised two-launch Bluestein kernels (RMODE 7 / 8) for some padded length >= 2N-1 ?
+bool blue2_available(const PlanGraph& g, uint64_t N) {
+    for (int i = 0; i < b2_kernel_count(); ++i) {
+        const b2_kernel_info* k = b2_kernel_at(i);
+        if (k->kind != B2_KIND_ROWS || k->prec != g.prec || k->ops != B2_OP_BLUESTEIN || k->inv != 0) continue;
+        if ((uint64_t)k->n >= 2 * N - 1 && b2_find_kernel(B2_KIND_ROWS, g.prec, k->n, 1, B2_OP_BLUESTEIN)) return true;
+    }
+    return false;
 }
 
 int plan_bluestein(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
@@ -751,7 +764,10 @@ int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
     // Round 2, later: the whole Bluestein transform in ONE launch (blue1_length: padded lengths up to 8192 in FP32, 4096 in FP64)
     // extends the rule to N <= 4096 / 2048.  B200FFT_FORCE_BLUESTEIN=1 sends every contiguous length that way
     // (tests, and A/B timing against the runtime-scheduled kernel on smooth lengths).
-    if (contiguous && !job.unit_lines && !dist && (N <= 2048 || blue1_length(g, N)) && !(job.extra_ops & B2_OP_CONV) && !getenv("B200FFT_RADER_MAX_PRIME") &&
+    // ... and to every length whose padded transform still has the two specialised launches (FP32: padded length 8192, N <= 4096):
+    // N = 4093 runs in 1.86 ms per pair of 512 MiB that way, the Rader stages of the runtime-scheduled kernel took 2.9-13 ms on
+    // the lengths measured (1377: 2.91, 1900: 3.23, 1517: 8.25, 2032: 13.0; profiles/r2/rader_vs_bluestein.log)
+    if (contiguous && !job.unit_lines && !dist && (N <= 2048 || blue1_length(g, N) || blue2_available(g, N)) && !(job.extra_ops & B2_OP_CONV) && !getenv("B200FFT_RADER_MAX_PRIME") &&
         !b2_find_kernel(kind, g.prec, (int)N, 0, 0)) {
         uint64_t mm = N;
         for (int f : {2, 3, 5, 7, 11, 13}) while (mm % f == 0) mm /= f;

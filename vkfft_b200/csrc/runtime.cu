@@ -374,6 +374,30 @@ extern "C" size_t b200fft_plan_describe(const b200fft_plan* p, int inverse, char
     return n;
 }
 
+// Planner only, no device: the launch list the engine WOULD build for `desc` (same text as b200fft_plan_describe), with the
+// plan-time kernel descriptions of jit.cpp offered but nothing compiled.  Lets the CPU tests check the product library's
+// planning -- which, unlike the emulation's, sees the plan-time kernels.  Returns the planner's VkFFTResult code.
+extern "C" int b200fft_debug_plan_text(const b200fft_desc* desc, int inverse, char* dst, size_t cap) {
+    if (!desc || !dst || cap == 0) return R_EMPTY_APP;
+    b200fft_desc full;
+    memset(&full, 0, sizeof full);
+    const size_t have = (desc->struct_size >= 64 && desc->struct_size <= sizeof full) ? desc->struct_size : sizeof full;
+    memcpy(&full, desc, have);
+    PlanGraph g;
+    const int rc = build_plan(full, g);
+    dst[0] = 0;
+    if (rc != R_SUCCESS) return rc;
+    std::string s;
+    const std::vector<PassPlan>& list = (inverse == 1) ? g.inv : g.fwd;
+    static const char* role[] = {"buffer", "temp", "input", "output", "kernel"};
+    for (size_t i = 0; i < list.size(); ++i)
+        s += "pass " + std::to_string(i) + ": " + list[i].note + "  " + role[list[i].in_role] + " -> " + role[list[i].out_role] + "\n";
+    const size_t n = s.size() < cap - 1 ? s.size() : cap - 1;
+    memcpy(dst, s.data(), n);
+    dst[n] = 0;
+    return R_SUCCESS;
+}
+
 extern "C" int b200fft_exec_host(b200fft_plan* p, int inverse, const void* host_in, void* host_out,
                                  uint64_t bytes_in, uint64_t bytes_out) {
     if (!p) return R_EMPTY_APP;

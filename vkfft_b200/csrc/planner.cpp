@@ -765,8 +765,8 @@ int plan_c2c(PlanGraph& g, std::vector<PassPlan>& list, const C2CJob& job) {
     // extends the rule to N <= 4096 / 2048.  B200FFT_FORCE_BLUESTEIN=1 sends every contiguous length that way
     // (tests, and A/B timing against the runtime-scheduled kernel on smooth lengths).
     // ... and to every length whose padded transform still has the two specialised launches (FP32: padded length 8192, N <= 4096):
-    // N = 4093 runs in 1.86 ms per pair of 512 MiB that way, the Rader stages of the runtime-scheduled kernel took 2.9-13 ms on
-    // the lengths measured (1377: 2.91, 1900: 3.23, 1517: 8.25, 2032: 13.0; profiles/r2/rader_vs_bluestein.log)
+    // measured against the Rader stages of the runtime-scheduled kernel (profiles/r2/bluestein_2049_4096_vs_rader.log, ms per pair
+    // of 512 MiB): N = 2050 3.15 vs 5.34, 3526 2.04 vs 9.72, 4094 1.86 vs 12.6
     if (contiguous && !job.unit_lines && !dist && (N <= 2048 || blue1_length(g, N) || blue2_available(g, N)) && !(job.extra_ops & B2_OP_CONV) && !getenv("B200FFT_RADER_MAX_PRIME") &&
         !b2_find_kernel(kind, g.prec, (int)N, 0, 0)) {
         uint64_t mm = N;

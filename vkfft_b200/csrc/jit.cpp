@@ -258,8 +258,9 @@ int compile(Program& p, const char* arch) {
         return -1;
     }
     const std::string archopt = std::string("--gpu-architecture=") + arch;
-    const char* opts[] = {archopt.c_str(), "-std=c++17", "-w", "-lineinfo"};      // -lineinfo: ncu's source page maps to the templates
-    const nvrtcResult rc = a.CompileProgram(prog, 4, opts);
+    // B200FFT_JIT_LINEINFO=1: line tables so that ncu's source page maps to the templates (cubins grow from ~70 KB to 0.3-1 MB)
+    const char* opts[] = {archopt.c_str(), "-std=c++17", "-w", "-lineinfo"};
+    const nvrtcResult rc = a.CompileProgram(prog, getenv("B200FFT_JIT_LINEINFO") ? 4 : 3, opts);
     size_t ln = 0;
     if (a.GetProgramLogSize && a.GetProgramLog && a.GetProgramLogSize(prog, &ln) == 0 && ln > 1) {
         p.log.resize(ln);

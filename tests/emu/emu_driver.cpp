@@ -203,3 +203,8 @@ extern "C" int emu_selftest_checkers(int mode) {
     s.hazards = 0; s.smem_oob = false;
     return r;
 }
+
+// host versions of the half <-> float conversions the emulated half-storage kernels use (cplx.cuh); the device uses cvt.f32.f16 /
+// cvt.rn.f16x2.f32 -- both are IEEE round-to-nearest-even, tests/test_half_storage.py pins the host ones to numpy
+extern "C" unsigned short emu_float_to_half_bits(float f) { return b200fft::b2_float_to_half_bits(f); }
+extern "C" float emu_half_bits_to_float(unsigned short h) { return b200fft::b2_half_bits_to_float(h); }

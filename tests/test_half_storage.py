@@ -33,6 +33,34 @@ def _unpack(packed):
 
 
 # ------------------------------------------------------------ CPU emulation ------------------------------------------------------------
+def test_host_half_conversions_match_ieee_round_to_nearest_even():
+    """the conversions behind the emulated kernels: every half value survives half -> float -> half, and float -> half agrees
+    with numpy (ties to even, subnormals, overflow to infinity) on random values, on every midpoint and next to it"""
+    import emu
+    L = emu.lib()
+    L.emu_half_bits_to_float.restype = ctypes.c_float
+    L.emu_half_bits_to_float.argtypes = [ctypes.c_ushort]
+    L.emu_float_to_half_bits.restype = ctypes.c_ushort
+    L.emu_float_to_half_bits.argtypes = [ctypes.c_float]
+    allh = np.arange(65536, dtype=np.uint16)
+    vals = allh.view(np.float16).astype(np.float32)
+    for h, v in zip(allh[::7].tolist(), vals[::7].tolist()):
+        if np.isnan(v):
+            continue
+        assert L.emu_half_bits_to_float(h) == v or (v == 0 and L.emu_half_bits_to_float(h) == 0), h
+        assert L.emu_float_to_half_bits(v) == h, h
+    rng = np.random.default_rng(0)
+    finite = vals[np.isfinite(vals)]
+    mids = ((finite[:-1].astype(np.float64) + np.roll(finite, -1)[:-1].astype(np.float64)) / 2).astype(np.float32)[::13]
+    cases = np.concatenate([rng.uniform(-70000, 70000, 3000).astype(np.float32), rng.uniform(-1e-4, 1e-4, 3000).astype(np.float32),
+                            mids, np.nextafter(mids, np.float32(np.inf)), np.nextafter(mids, np.float32(-np.inf))])
+    with np.errstate(over="ignore"):
+        want = cases.astype(np.float16).view(np.uint16)
+    for c, w in zip(cases.tolist(), want.tolist()):
+        assert L.emu_float_to_half_bits(c) == w, (c, w)
+
+
+
 @pytest.mark.parametrize("n,b", [(64, 37), (100, 5), (1024, 3), (8, 200)])
 @pytest.mark.parametrize("inv", [-1, 1])
 def test_emulated_single_pass(n, b, inv):

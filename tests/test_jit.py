@@ -63,6 +63,25 @@ def test_plan_uses_a_plan_time_kernel_and_the_switch_turns_it_off(monkeypatch):
     assert L.b2_jit_available() == 0 and L.b2_jit_selftest(KIND_ROWS, 0, 1100, 0) == 0
 
 
+def test_disk_cache_of_compiled_kernels(tmp_path):
+    """B200FFT_JIT_CACHE=<dir>: the first process compiles and stores the cubin, the second one reads it back (same bytes, no
+    compile) -- the saving the reference offers through saveApplicationToString / loadApplicationFromString"""
+    import subprocess
+    _need_nvrtc(_lib())
+    code = ("import ctypes, sys, time; sys.path.insert(0, %r); from vkfft_b200 import _lib; L = _lib.load(); "
+            "L.b2_jit_selftest.restype = ctypes.c_long; L.b2_jit_selftest(0, 0, 154, 0); t = time.time(); "
+            "print(L.b2_jit_selftest(0, 0, 1430, 0), time.time() - t)") % os.path.join(os.path.dirname(__file__), "..")
+    env = dict(os.environ, B200FFT_JIT_CACHE=str(tmp_path))
+    first = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True).stdout.split()
+    files = sorted(os.listdir(tmp_path))
+    assert len(files) == 2 and all(f.endswith(".cubin") for f in files)
+    sizes = {os.path.getsize(os.path.join(tmp_path, f)) for f in files}
+    second = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True).stdout.split()
+    assert int(first[0]) == int(second[0]) and int(first[0]) in sizes
+    assert float(second[1]) < 0.25 * float(first[1]) + 0.05, (first, second)
+    assert sorted(os.listdir(tmp_path)) == files
+
+
 # ---------------------------------------------------------------- GPU ----------------------------------------------------------------
 @pytest.fixture(scope="module")
 def gpu():

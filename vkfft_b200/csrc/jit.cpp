@@ -13,6 +13,7 @@
 // libnvrtc and libcuda are opened with dlopen: the library itself links neither.
 #include <dlfcn.h>
 #include <stdint.h>
+#include <unistd.h>
 
 #include <cstdio>
 #include <cstdlib>
@@ -248,9 +249,43 @@ std::string make_source(int kind, int prec, int ops, const Shape& s) {
     return buf;
 }
 
+// optional on-disk cache of the compiled kernels (B200FFT_JIT_CACHE=<directory>): one file per (templates, translation unit,
+// architecture, options), so that a second process does not pay the ~1-2 s per length again.  The reference offers the same
+// saving through saveApplicationToString / loadApplicationFromString (vkFFT_InitializeApp.h:1603-1637).
+uint64_t fnv1a(const char* s, uint64_t h = 1469598103934665603ull) {
+    for (; *s; ++s) { h ^= (unsigned char)*s; h *= 1099511628211ull; }
+    return h;
+}
+std::string cache_path(const Program& p, const char* arch, bool lineinfo) {
+    const char* dir = getenv("B200FFT_JIT_CACHE");
+    if (!dir || !*dir) return std::string();
+    static uint64_t hdr = 0;
+    if (!hdr) { hdr = 1469598103934665603ull; for (int i = 0; i < b2_jit_header_count; ++i) hdr = fnv1a(b2_jit_header_sources[i], hdr); }
+    uint64_t h = fnv1a(p.source.c_str(), hdr);
+    h = fnv1a(arch, h);
+    h = fnv1a(lineinfo ? "L" : "-", h);
+    char name[64];
+    snprintf(name, sizeof name, "/b200fft_%016llx.cubin", (unsigned long long)h);
+    return std::string(dir) + name;
+}
+
 // NVRTC -> cubin for `arch` ("sm_100a"); no GPU needed
 int compile(Program& p, const char* arch) {
     Api& a = api();
+    const bool lineinfo = getenv("B200FFT_JIT_LINEINFO") != nullptr;
+    const std::string cached = cache_path(p, arch, lineinfo);
+    if (!cached.empty()) {
+        if (FILE* f = fopen(cached.c_str(), "rb")) {
+            fseek(f, 0, SEEK_END);
+            const long sz = ftell(f);
+            fseek(f, 0, SEEK_SET);
+            bool ok = sz > 0;
+            if (ok) { p.cubin.resize((size_t)sz); ok = fread(p.cubin.data(), 1, (size_t)sz, f) == (size_t)sz; }
+            fclose(f);
+            if (ok) { p.log = "from " + cached; return 0; }
+            p.cubin.clear();
+        }
+    }
     if (!a.have_nvrtc) { p.log = "libnvrtc not found"; return -1; }
     nvrtcProgram prog = nullptr;
     if (a.CreateProgram(&prog, p.source.c_str(), "b200fft_jit.cu", b2_jit_header_count, b2_jit_header_sources, b2_jit_header_names) != 0) {
@@ -260,7 +295,7 @@ int compile(Program& p, const char* arch) {
     const std::string archopt = std::string("--gpu-architecture=") + arch;
     // B200FFT_JIT_LINEINFO=1: line tables so that ncu's source page maps to the templates (cubins grow from ~70 KB to 0.3-1 MB)
     const char* opts[] = {archopt.c_str(), "-std=c++17", "-w", "-lineinfo"};
-    const nvrtcResult rc = a.CompileProgram(prog, getenv("B200FFT_JIT_LINEINFO") ? 4 : 3, opts);
+    const nvrtcResult rc = a.CompileProgram(prog, lineinfo ? 4 : 3, opts);
     size_t ln = 0;
     if (a.GetProgramLogSize && a.GetProgramLog && a.GetProgramLogSize(prog, &ln) == 0 && ln > 1) {
         p.log.resize(ln);
@@ -273,6 +308,14 @@ int compile(Program& p, const char* arch) {
         if (a.GetCUBIN(prog, p.cubin.data()) == 0) ret = 0;
     }
     a.DestroyProgram(&prog);
+    if (ret == 0 && !cached.empty()) {          // write next to the final name, then rename: readers never see a partial file
+        const std::string tmp = cached + ".tmp" + std::to_string((long)getpid());
+        if (FILE* f = fopen(tmp.c_str(), "wb")) {
+            const bool ok = fwrite(p.cubin.data(), 1, p.cubin.size(), f) == p.cubin.size();
+            fclose(f);
+            if (!ok || rename(tmp.c_str(), cached.c_str()) != 0) remove(tmp.c_str());
+        }
+    }
     return ret;
 }
 

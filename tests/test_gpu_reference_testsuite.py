@@ -41,3 +41,16 @@ def test_sample_0_benchmark_reports_a_score():
     out = _run(0)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "Benchmark score VkFFT" in out.stdout
+
+
+def test_sample_2_half_precision_benchmark_reports_a_score():
+    """sample_2: the reference's half-precision benchmark (halfPrecision = 1, N = 8 ... 2^26, 512 MiB buffers) on this engine; the
+    half-storage kernels are instantiated at plan time, so without libnvrtc the program stops with the unsupported-length code"""
+    from vkfft_b200 import _lib
+    if not _lib.load().b2_jit_available():
+        pytest.skip("half-storage kernels are instantiated at plan time: libnvrtc is not loadable here")
+    out = _run(2)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    m = re.search(r"Benchmark score VkFFT: (\d+)", out.stdout)
+    assert m and int(m.group(1)) > 100000, out.stdout[-1000:]
+    assert len(re.findall(r"VkFFT System: \d+ \d+x\d+", out.stdout)) == 24
